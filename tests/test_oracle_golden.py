@@ -1,0 +1,147 @@
+"""CPU: pin the oracle against the reference's own known-answer tests
+(core.spec.ts) and cross-check its two forms (string-level literal vs compiled
+int-level) by seeded fuzzing, including the closed-form tie-break of
+SURVEY.md Appendix A.2."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import kat_suite
+from oracle import LiteralTokenizer, compact_merge, utf16_len
+from oracle.int_oracle import IntOracleTokenizer
+
+IMPLS = {"literal": LiteralTokenizer, "int": IntOracleTokenizer}
+
+
+@pytest.mark.parametrize("impl", sorted(IMPLS))
+@pytest.mark.parametrize("kat", kat_suite.ALL, ids=lambda f: f.__name__)
+def test_reference_known_answers(impl, kat):
+    kat(IMPLS[impl])
+
+
+@pytest.mark.parametrize("impl", sorted(IMPLS))
+def test_reference_merge_log_resume(impl):
+    kat_suite.kat_merge_log_resume(IMPLS[impl], compact_merge)
+
+
+def _random_docs(rng, alphabet, n_docs, max_len):
+    return ["".join(rng.choice(alphabet) for _ in range(rng.randint(0, max_len))) for _ in range(n_docs)]
+
+
+def _closed_form_next_merge(t: LiteralTokenizer, min_weight, max_length):
+    """count with run parity, then
+    argmax (weight desc, a.index+b.index asc, position of last counted occurrence asc)."""
+    count, last = {}, {}
+    pos = 0
+    for doc in t.corpus_in_code:
+        toks = [t.code_to_token[c].index for c in doc]
+        run = 0  # number of pairs (x,x) seen so far in the current run of identical tokens
+        for i in range(1, len(toks)):
+            a, b = toks[i - 1], toks[i]
+            if a == b:
+                run = run + 1 if (i >= 2 and toks[i - 2] == a) else 1
+                counted = run % 2 == 1
+            else:
+                run = 0
+                counted = True
+            if max_length and utf16_len(t.token_table[a].chars) + utf16_len(t.token_table[b].chars) > max_length:
+                counted = False
+            if counted:
+                count[(a, b)] = count.get((a, b), 0) + 1
+                last[(a, b)] = pos + i
+        pos += len(toks) + 1
+    if not count:
+        return None
+    w = max(count.values())
+    if w < (min_weight or 2):
+        return None
+    a, b = min((k for k, v in count.items() if v == w), key=lambda k: (k[0] + k[1], last[k]))
+    return a, b, w
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_literal_vs_int_vs_closed_form(seed):
+    rng = random.Random(seed)
+    alphabet = "abc"[: rng.randint(1, 3)] if seed % 2 else "abcdefg"[: rng.randint(2, 7)]
+    docs = _random_docs(rng, alphabet, rng.randint(1, 4), rng.choice([6, 20, 60]))
+    max_length = rng.choice([None, None, 3, 4, 8])
+    min_weight = rng.choice([None, 2, 3])
+    lit, fast = LiteralTokenizer(), IntOracleTokenizer()
+    for d in docs:
+        lit.addToCorpus(d)
+        fast.addToCorpus(d)
+    for _ in range(200):
+        want = _closed_form_next_merge(lit, min_weight, max_length)
+        m1 = lit.find_next_merge(min_weight, max_length)
+        m2 = fast.find_next_merge(min_weight, max_length)
+        if m1 is None:
+            assert m2 is None and want is None
+            break
+        assert (m1[0].index, m1[1].index, m1[2].weight) == (m2[0].index, m2[1].index, m2[2].weight) == want
+        lit.apply_merge(m1)
+        fast.apply_merge(m2)
+        assert lit.corpus_in_code == fast.corpus_in_code
+    assert lit.to_json() == fast.to_json()
+    for d in docs + _random_docs(rng, alphabet, 3, 40):
+        try:
+            want_code = lit.encode_to_code(d)
+        except ValueError as e:
+            with pytest.raises(ValueError, match="unknown token, char"):
+                fast.encode_to_code(d)
+            continue
+        assert fast.encode_to_code(d) == want_code
+        ids = [lit.char_to_token[ch].index for ch in d]
+        assert "".join(chr(int(i) + 1) for i in fast.encode_ids(ids, fast=True)) == want_code
+
+
+def test_int_merge_until_matches_literal_loop():
+    rng = random.Random(7)
+    docs = _random_docs(rng, "abcd ", 6, 200)
+    lit, fast = LiteralTokenizer(), IntOracleTokenizer()
+    for d in docs:
+        lit.addToCorpus(d)
+        fast.addToCorpus(d)
+    n1 = lit.merge_until(min_weight=2, max_length=6)
+    n2 = fast.merge_until(min_weight=2, max_length=6)
+    assert n1 == n2 and n1 > 10
+    assert lit.to_json() == fast.to_json()
+    assert lit.corpus_in_code == fast.corpus_in_code
+
+
+def test_astral_characters_count_two_utf16_units():
+    # core.ts:272 uses chars.length (UTF-16); one astral char is one token (core.ts:185) of length 2
+    t = LiteralTokenizer()
+    t.addToCorpus("\U0001F600\U0001F600\U0001F600\U0001F600ab" * 3)
+    assert t.find_next_merge(max_length=3) is not None  # 'ab' (1+1) still allowed
+    m = t.find_next_merge(max_length=4)
+    assert m[2].chars in ("\U0001F600\U0001F600",)
+    u = IntOracleTokenizer()
+    u.addToCorpus("\U0001F600\U0001F600\U0001F600\U0001F600ab" * 3)
+    m2 = u.find_next_merge(max_length=3)
+    assert m2[2].chars == t.find_next_merge(max_length=3)[2].chars
+
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "literal_cases.json")
+
+
+def test_committed_golden_fixtures_still_match_literal_oracle():
+    with open(GOLDEN, encoding="utf-8") as f:
+        cases = json.load(f)
+    assert len(cases) >= 8
+    for case in cases:
+        for cls in (LiteralTokenizer, IntOracleTokenizer):
+            t = cls()
+            for d in case["docs"]:
+                t.addToCorpus(d)
+            t.mergeUntil(case["options"])
+            assert t.toJSON() == case["json"], case["name"]
+            assert [[a.index, b.index, c.weight] for a, b, c in t.merge_tokens] == case["merges"], case["name"]
+            for text, want in case["encode"]:
+                try:
+                    got = list(t.encodeToVector(text))
+                except ValueError as e:
+                    got = "throws: " + str(e)
+                assert got == want, (case["name"], text)
