@@ -1,0 +1,986 @@
+// bpe_b200.cu -- engine state, host orchestration and the C ABI declared in include/bpe_b200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (build.py).
+#include "../../include/bpe_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "encode_kernels.cuh"
+#include "train_kernels.cuh"
+
+using namespace bpe;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) {
+    o.p = nullptr;
+    o.cap = 0;
+  }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) {
+      release();
+      p = o.p;
+      cap = o.cap;
+      o.p = nullptr;
+      o.cap = 0;
+    }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  // grow to at least n elements; keep_n elements are preserved (stream-ordered copy)
+  cudaError_t reserve(size_t n, size_t keep_n = 0, cudaStream_t s = 0, double growth = 1.0) {
+    if (n <= cap) return cudaSuccess;
+    size_t want = std::max(n, (size_t)((double)cap * growth));
+    T* q = nullptr;
+    cudaError_t err = cudaMalloc(&q, want * sizeof(T));
+    if (err != cudaSuccess) {
+      want = n;
+      err = cudaMalloc(&q, want * sizeof(T));
+      if (err != cudaSuccess) return err;
+    }
+    if (p && keep_n) {
+      err = cudaMemcpyAsync(q, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, s);
+      if (err != cudaSuccess) {
+        cudaFree(q);
+        return err;
+      }
+      cudaStreamSynchronize(s);
+    }
+    if (p) cudaFree(p);
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
+};
+
+uint32_t pow2_at_least(uint64_t x) {
+  uint32_t p = 1;
+  while (p < x && p < 0x80000000u) p <<= 1;
+  return p;
+}
+int ilog2(uint32_t p) {
+  int l = 0;
+  while ((1u << l) < p) l++;
+  return l;
+}
+
+}  // namespace
+
+struct bpe_engine {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  std::string err;
+  bool profiling = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // corpus_in_code (core.ts:106): slots + document boundaries
+  DevBuf<uint32_t> slots;
+  uint64_t n_slots = 0;
+  std::vector<int64_t> doc_off{0};
+  uint64_t live_tokens = 0;
+
+  // vocabulary
+  std::vector<int32_t> h_len16;
+  DevBuf<uint32_t> d_len16;
+  int32_t n_tokens = 0;
+
+  // merge list (core.ts:88-91) + device lookup table for encode
+  std::vector<int32_t> h_merges;
+  bool mt_dirty = true;
+  DevBuf<unsigned long long> d_mt;
+  uint32_t mt_cap = 0;
+
+  // pair index
+  bool index_valid = false;
+  uint32_t tbl_cap = 0;
+  DevBuf<uint32_t> t_keys, t_cnt, t_start, t_len, t_fill;
+  DevBuf<uint32_t> pool;
+  DevBuf<DevState> d_st;
+  DevState* h_st = nullptr;  // pinned
+  DevBuf<Best> partials;
+  DevBuf<SiteRec> sites;
+  DevBuf<uint32_t> newslots;
+  DevBuf<uint32_t> hot;
+  bool hot_valid = false;
+  uint32_t hot_max_length = 0;
+  uint32_t hot_thresh = 0;
+  DevBuf<uint32_t> cands;
+  int scan_mode = 0;  // debug: walk all slots instead of occurrence lists
+
+  // scratch
+  DevBuf<int32_t> stage_ids;
+  DevBuf<int64_t> stage_off;
+
+  bpe_stats stats{};
+
+  PairTable table() const {
+    PairTable t;
+    t.keys = t_keys.p;
+    t.cnt = t_cnt.p;
+    t.occ_start = t_start.p;
+    t.occ_len = t_len.p;
+    t.occ_fill = t_fill.p;
+    t.mask = tbl_cap - 1;
+    t.shift = 32 - ilog2(tbl_cap);
+    return t;
+  }
+  int grid(int per_sm = 4) const { return sm_count * per_sm; }
+};
+
+namespace {
+
+int fail(bpe_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t _err = (call);                                                                                \
+    if (_err != cudaSuccess)                                                                                  \
+      return fail(e, _err == cudaErrorMemoryAllocation ? BPE_E_NOMEM : BPE_E_CUDA, "%s:%d %s: %s", __FILE__, \
+                  __LINE__, #call, cudaGetErrorString(_err));                                                 \
+  } while (0)
+
+#define CKL()                                \
+  do {                                       \
+    e->stats.kernel_launches++;              \
+    CK(cudaGetLastError());                  \
+  } while (0)
+
+#define TRY(call)             \
+  do {                        \
+    int _rc = (call);         \
+    if (_rc != BPE_OK) return _rc; \
+  } while (0)
+
+int fetch_state(bpe_engine* e) {
+  CK(cudaMemcpyAsync(e->h_st, e->d_st.p, sizeof(DevState), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return BPE_OK;
+}
+
+int check_dev_err(bpe_engine* e) {
+  uint32_t f = e->h_st->err & ~ERR_HOT_OVERFLOW;  // hot-list overflow is recoverable (rebuild), handled by the caller
+  if (!f) return BPE_OK;
+  if (f & ERR_POOL_FULL) return fail(e, BPE_E_INTERNAL, "occurrence pool exhausted (flags 0x%x)", f);
+  if (f & ERR_MISSING_KEY) return fail(e, BPE_E_INTERNAL, "pair missing from the table (flags 0x%x)", f);
+  if (f & ERR_SPAN_OVERFLOW) return fail(e, BPE_E_DOMAIN, "token span exceeds 2^29 positions");
+  return fail(e, BPE_E_INTERNAL, "device error flags 0x%x", f);
+}
+
+int sync_len16(bpe_engine* e) {
+  size_t n = e->h_len16.size();
+  CK(e->d_len16.reserve(std::max<size_t>(n + 1024, 4096), 0, e->stream, 2.0));
+  if (n) {
+    std::vector<uint32_t> tmp(e->h_len16.begin(), e->h_len16.end());
+    CK(cudaMemcpyAsync(e->d_len16.p, tmp.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return BPE_OK;
+}
+
+// ---- pair table allocation / growth -------------------------------------------------------------
+int alloc_table(bpe_engine* e, uint32_t cap) {
+  e->t_keys.release();
+  e->t_cnt.release();
+  e->t_start.release();
+  e->t_len.release();
+  e->t_fill.release();
+  CK(e->t_keys.reserve(cap));
+  CK(e->t_cnt.reserve(cap));
+  CK(e->t_start.reserve(cap));
+  CK(e->t_len.reserve(cap));
+  CK(e->t_fill.reserve(cap));
+  e->tbl_cap = cap;
+  CK(cudaMemsetAsync(e->t_keys.p, 0xFF, (size_t)cap * 4, e->stream));
+  CK(cudaMemsetAsync(e->t_cnt.p, 0, (size_t)cap * 4, e->stream));
+  CK(cudaMemsetAsync(e->t_start.p, 0, (size_t)cap * 4, e->stream));
+  CK(cudaMemsetAsync(e->t_len.p, 0, (size_t)cap * 4, e->stream));
+  CK(cudaMemsetAsync(e->t_fill.p, 0, (size_t)cap * 4, e->stream));
+  return BPE_OK;
+}
+
+__global__ void k_rehash(PairTable src, PairTable dst, DevState* st) {
+  uint32_t cap = src.mask + 1;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+    uint32_t key = src.keys[i];
+    if (key == EMPTY_KEY) continue;
+    uint32_t h = (key * 0x9E3779B1u) >> dst.shift;
+    for (;;) {
+      uint32_t old = atomicCAS(dst.keys + h, EMPTY_KEY, key);
+      if (old == EMPTY_KEY) break;
+      h = (h + 1) & dst.mask;
+    }
+    dst.cnt[h] = src.cnt[i];
+    dst.occ_start[h] = src.occ_start[i];
+    dst.occ_len[h] = src.occ_len[i];
+    dst.occ_fill[h] = src.occ_fill[i];
+  }
+}
+
+int grow_table(bpe_engine* e, uint32_t new_cap) {
+  PairTable old = e->table();
+  DevBuf<uint32_t> k, c, s, l, f;
+  std::swap(k, e->t_keys);
+  std::swap(c, e->t_cnt);
+  std::swap(s, e->t_start);
+  std::swap(l, e->t_len);
+  std::swap(f, e->t_fill);
+  TRY(alloc_table(e, new_cap));
+  k_rehash<<<e->grid(), 256, 0, e->stream>>>(old, e->table(), e->d_st.p);
+  CKL();
+  CK(cudaStreamSynchronize(e->stream));
+  e->hot_valid = false;  // slot numbers changed
+  return BPE_OK;
+}
+
+// ---- K1: build histogram + occurrence lists from the corpus -------------------------------------
+int build_index(bpe_engine* e) {
+  e->index_valid = false;
+  e->hot_valid = false;
+  if (!e->h_st) CK(cudaHostAlloc((void**)&e->h_st, sizeof(DevState), cudaHostAllocDefault));
+  CK(e->d_st.reserve(1));
+  CK(e->partials.reserve((size_t)e->grid(8)));
+  TRY(sync_len16(e));
+  uint64_t n = e->n_slots;
+  if (n >= 0xFFFFFFF0ull) return fail(e, BPE_E_DOMAIN, "corpus of %llu positions exceeds the 2^32 engine limit", (unsigned long long)n);
+  uint64_t pool_need = 3 * n + 1024;
+  if (pool_need > 0xFFFFFFF0ull) pool_need = 0xFFFFFFF0ull;
+  CK(e->pool.reserve((size_t)pool_need));
+  uint64_t t2 = (uint64_t)e->n_tokens * (uint64_t)e->n_tokens;
+  uint32_t cap = pow2_at_least(std::min<uint64_t>(std::max<uint64_t>(2 * std::min(n, t2), 1u << 16), 1u << 24));
+  if (e->tbl_cap > cap) cap = e->tbl_cap;
+  {
+    if (!e->ev0) {
+      CK(cudaEventCreate(&e->ev0));
+      CK(cudaEventCreate(&e->ev1));
+    }
+    CK(cudaEventRecord(e->ev0, e->stream));
+  }
+  for (;;) {
+    TRY(alloc_table(e, cap));
+    DevState init{};
+    init.live_tokens = e->live_tokens;
+    init.tie_pos = ~0ull;
+    CK(cudaMemcpyAsync(e->d_st.p, &init, sizeof init, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (n) {
+      k_hist<<<e->grid(4), K1_THREADS, 0, e->stream>>>(e->slots.p, (uint32_t)n, e->table(), e->d_st.p);
+      CKL();
+    }
+    TRY(fetch_state(e));
+    if (e->h_st->err & ERR_TABLE_FULL) {
+      if (cap >= 0x80000000u) return fail(e, BPE_E_NOMEM, "pair table cannot grow further");
+      cap <<= 2;
+      continue;
+    }
+    TRY(check_dev_err(e));
+    if ((uint64_t)e->h_st->n_keys * 2 > cap && cap < 0x80000000u) {  // keep the load factor <= 0.5
+      cap <<= 1;
+      continue;
+    }
+    break;
+  }
+  if (n) {
+    k_alloc_lists<<<e->grid(4), 256, 0, e->stream>>>(e->table(), e->d_st.p, (uint32_t)e->pool.cap);
+    CKL();
+    k_scatter<<<e->grid(8), K1_THREADS, 0, e->stream>>>(e->slots.p, (uint32_t)n, e->table(), e->pool.p, e->d_st.p);
+    CKL();
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  TRY(fetch_state(e));
+  TRY(check_dev_err(e));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->stats.ms_index_build += ms;
+  e->stats.index_builds++;
+  e->index_valid = true;
+  return BPE_OK;
+}
+
+int ensure_index(bpe_engine* e) {
+  if (e->index_valid) return BPE_OK;
+  return build_index(e);
+}
+
+// ---- hot list -----------------------------------------------------------------------------------
+constexpr uint32_t HOT_TARGET = 1u << 15;
+
+// returns found=0 when no pair with a count exists at all
+int rebuild_hot(bpe_engine* e, uint32_t max_length, bool* any) {
+  PairTable t = e->table();
+  CK(cudaMemsetAsync(&e->d_st.p->bins[0], 0, sizeof(uint32_t) * 36, e->stream));
+  k_count_bins<<<e->grid(4), 256, 0, e->stream>>>(t, e->d_len16.p, max_length, e->d_st.p);
+  CKL();
+  TRY(fetch_state(e));
+  uint64_t acc = 0;
+  int pick = 0;
+  for (int k = 32; k >= 1; k--) {
+    uint64_t nk = e->h_st->bins[k];
+    if (acc + nk > HOT_TARGET && acc > 0) break;
+    acc += nk;
+    if (nk) pick = k;
+    if (acc > HOT_TARGET) break;
+  }
+  *any = pick != 0;
+  e->hot_valid = false;
+  if (!pick) return BPE_OK;
+  // everything from bin `pick` up: counts >= 2^(pick-1); extend down to the lowest bin that adds nothing
+  int lo = pick;
+  while (lo > 1 && e->h_st->bins[lo - 1] == 0) lo--;
+  uint32_t thresh = 1u << (lo - 1);
+  CK(e->hot.reserve(std::max<size_t>((size_t)acc * 2 + 4096, 1u << 18)));
+  e->h_st->hot_n = 0;
+  e->h_st->hot_thresh = thresh;
+  uint32_t two[2] = {0, thresh};
+  CK(cudaMemcpyAsync(&e->d_st.p->hot_n, two, sizeof two, cudaMemcpyHostToDevice, e->stream));
+  k_build_hot<<<e->grid(4), 256, 0, e->stream>>>(t, e->d_len16.p, max_length, e->hot.p, (uint32_t)e->hot.cap, e->d_st.p);
+  CKL();
+  e->hot_thresh = thresh;
+  e->hot_max_length = max_length;
+  e->hot_valid = true;
+  e->stats.hot_rebuilds++;
+  return BPE_OK;
+}
+
+// ---- K2 driver: leaves the winner in h_st (best_primary == 0: none) -------------------------------
+int run_argmax(bpe_engine* e, uint32_t max_length, int use_hot) {
+  PairTable t = e->table();
+  int blocks = use_hot ? e->sm_count : e->grid(4);
+  k_argmax<<<blocks, AM_THREADS, 0, e->stream>>>(t, e->d_len16.p, max_length, use_hot, e->hot.p, e->partials.p, e->d_st.p);
+  CKL();
+  TRY(fetch_state(e));
+  TRY(check_dev_err(e));
+  if (e->h_st->best_primary && e->h_st->best_mult > 1 && !(use_hot && e->h_st->best_cnt < e->hot_thresh)) {
+    // tie on (weight, a.index + b.index): the pair whose last counted occurrence comes first wins (core.ts:294-305)
+    uint32_t mult = e->h_st->best_mult;
+    CK(e->cands.reserve(std::max<size_t>(mult, 1024), 0, e->stream, 2.0));
+    k_collect_cands<<<blocks, 256, 0, e->stream>>>(t, e->d_len16.p, max_length, use_hot, e->hot.p, e->cands.p, (uint32_t)e->cands.cap, e->d_st.p);
+    CKL();
+    k_tie_break<<<std::min<uint32_t>(mult, (uint32_t)e->grid(4)), 256, 0, e->stream>>>(e->slots.p, (uint32_t)e->n_slots, t, e->pool.p, e->cands.p, e->d_st.p);
+    CKL();
+    k_tie_finish<<<1, 32, 0, e->stream>>>(t, e->d_st.p);
+    CKL();
+    TRY(fetch_state(e));
+    TRY(check_dev_err(e));
+    e->stats.tie_breaks++;
+  }
+  return BPE_OK;
+}
+
+// ---- K3 driver ------------------------------------------------------------------------------------
+// bound = upper bound on the number of sites (count of the pair, or its list length)
+int run_apply(bpe_engine* e, uint32_t a, uint32_t b, uint32_t c, uint32_t bound) {
+  // capacity: new keys <= 2*bound, new list cells <= 2*bound
+  uint64_t keys_after = (uint64_t)e->h_st->n_keys + 2ull * bound + 2;
+  if (keys_after * 2 > e->tbl_cap) {
+    uint64_t want = keys_after * 4;
+    if (want > 0x80000000ull) want = 0x80000000ull;
+    if (keys_after >= want) return fail(e, BPE_E_NOMEM, "pair table cannot grow further");
+    TRY(grow_table(e, pow2_at_least(want)));
+  }
+  uint64_t pool_after = (uint64_t)e->h_st->pool_cursor + 2ull * bound;
+  if (pool_after > e->pool.cap) {
+    if (pool_after > 0xFFFFFFF0ull) return fail(e, BPE_E_DOMAIN, "occurrence pool exceeds 2^32 cells");
+    CK(e->pool.reserve((size_t)pool_after, e->h_st->pool_cursor, e->stream, 1.5));
+  }
+  CK(e->sites.reserve(std::max<size_t>(bound, 4096), 0, e->stream, 2.0));
+  CK(e->newslots.reserve(std::max<size_t>(2ull * bound + 2, 8192), 0, e->stream, 2.0));
+  if ((size_t)c + 1 > e->d_len16.cap) CK(e->d_len16.reserve((size_t)c + 1, (size_t)c, e->stream, 2.0));
+  PairTable t = e->table();
+  uint32_t work = e->scan_mode ? (uint32_t)e->n_slots : bound;
+  int blocks = (int)std::min<uint64_t>((uint64_t)e->grid(8), std::max<uint64_t>(1, (work + 255) / 256));
+  k_sites<<<blocks, 256, 0, e->stream>>>(e->slots.p, (uint32_t)e->n_slots, t, e->pool.p, e->d_st.p, a, b, c, e->scan_mode,
+                                         e->sites.p, (uint32_t)e->sites.cap, e->newslots.p, (uint32_t)e->newslots.cap,
+                                         e->d_len16.p);
+  CKL();
+  int blocks2 = (int)std::min<uint64_t>((uint64_t)e->grid(8), std::max<uint64_t>(1, (2ull * bound + 255) / 256));
+  k_alloc_new<<<blocks2, 256, 0, e->stream>>>(t, e->newslots.p, e->d_len16.p, e->hot_max_length, e->hot_valid ? 1 : 0, e->hot.p,
+                                              (uint32_t)e->hot.cap, (uint32_t)e->pool.cap, e->d_st.p);
+  CKL();
+  int blocks3 = (int)std::min<uint64_t>((uint64_t)e->grid(8), std::max<uint64_t>(1, ((uint64_t)bound + 255) / 256));
+  k_apply<<<blocks3, 256, 0, e->stream>>>(e->slots.p, (uint32_t)e->n_slots, t, e->pool.p, e->d_st.p, a, b, c, e->sites.p);
+  CKL();
+  e->h_len16.push_back(e->h_len16[a] + e->h_len16[b]);
+  e->h_merges.push_back((int32_t)a);
+  e->h_merges.push_back((int32_t)b);
+  e->h_merges.push_back((int32_t)c);
+  e->mt_dirty = true;
+  e->n_tokens++;
+  e->stats.merges_applied++;
+  return BPE_OK;
+}
+
+// ---- merge lookup table for encode ------------------------------------------------------------------
+int ensure_merge_table(bpe_engine* e) {
+  if (!e->mt_dirty && e->d_mt.p) return BPE_OK;
+  size_t m = e->h_merges.size() / 3;
+  uint32_t cap = pow2_at_least(std::max<size_t>(4 * m, 1024));
+  std::vector<unsigned long long> h(cap, MT_EMPTY);
+  int shift = 32 - ilog2(cap);
+  for (size_t r = 0; r < m; r++) {
+    uint32_t a = (uint32_t)e->h_merges[3 * r], b = (uint32_t)e->h_merges[3 * r + 1], c = (uint32_t)e->h_merges[3 * r + 2];
+    uint32_t key = pair_key(a, b);
+    uint32_t i = (key * 0x9E3779B1u) >> shift;
+    bool dup = false;
+    while (h[i] != MT_EMPTY) {
+      if ((uint32_t)(h[i] >> 32) == key) {
+        dup = true;  // a second rule for the same pair can never fire (the first one removed every occurrence)
+        break;
+      }
+      i = (i + 1) & (cap - 1);
+    }
+    if (!dup) h[i] = ((unsigned long long)key << 32) | ((unsigned long long)(uint32_t)r << 16) | c;
+  }
+  CK(e->d_mt.reserve(cap));
+  CK(cudaMemcpyAsync(e->d_mt.p, h.data(), (size_t)cap * 8, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->mt_cap = cap;
+  e->mt_dirty = false;
+  return BPE_OK;
+}
+
+struct EncodeScratch {
+  DevBuf<int32_t> out_tmp;
+  DevBuf<uint32_t> out_len;
+  DevBuf<uint64_t> out_off;
+  DevBuf<uint32_t> g_tok, g_rk;
+};
+
+// device-resident encode; leaves compacted output in dev_out / dev_out_offsets
+int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const int64_t* dev_doc_off, int64_t n_docs,
+               int64_t n_ids, int64_t max_doc_len, const int32_t* dev_tvi, int32_t n_tvi, int32_t* dev_out,
+               int64_t* dev_out_offsets, int64_t* dev_first_bad, int64_t* n_out) {
+  TRY(ensure_merge_table(e));
+  if (e->h_merges.size() / 3 > 65534) return fail(e, BPE_E_DOMAIN, "merge list too long");
+  CK(sc.out_tmp.reserve((size_t)std::max<int64_t>(n_ids, 1)));
+  CK(sc.out_len.reserve((size_t)n_docs + 1));
+  CK(sc.out_off.reserve((size_t)n_docs + 2));
+  if (max_doc_len > ENC_WARP_MAX) {
+    CK(sc.g_tok.reserve((size_t)n_ids));
+    CK(sc.g_rk.reserve((size_t)n_ids));
+  }
+  MergeTable mt{e->d_mt.p, e->mt_cap - 1, (uint32_t)(32 - ilog2(e->mt_cap))};
+  if (!e->ev0) {
+    CK(cudaEventCreate(&e->ev0));
+    CK(cudaEventCreate(&e->ev1));
+  }
+  CK(cudaEventRecord(e->ev0, e->stream));
+  if (n_docs > 0) {
+    int64_t blocks = std::min<int64_t>((n_docs + ENC_WARPS - 1) / ENC_WARPS, (int64_t)e->sm_count * 16);
+    k_encode<<<(int)blocks, ENC_THREADS, 0, e->stream>>>(dev_ids, dev_doc_off, n_docs, mt, sc.out_tmp.p, sc.out_len.p, sc.g_tok.p, sc.g_rk.p);
+    CKL();
+  }
+  k_scan_counts<<<1, 1024, 0, e->stream>>>(sc.out_len.p, sc.out_off.p, (uint32_t)n_docs);
+  CKL();
+  {
+    int64_t warps = n_docs + 1;
+    int64_t blocks = std::min<int64_t>((warps + ENC_WARPS - 1) / ENC_WARPS, (int64_t)e->sm_count * 16);
+    k_gather_map<<<(int)blocks, ENC_THREADS, 0, e->stream>>>(sc.out_tmp.p, dev_doc_off, sc.out_off.p, n_docs, dev_tvi, n_tvi, dev_out, dev_out_offsets, dev_first_bad);
+    CKL();
+  }
+  CK(cudaEventRecord(e->ev1, e->stream));
+  uint64_t total = 0;
+  CK(cudaMemcpyAsync(&total, sc.out_off.p + n_docs, sizeof total, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->stats.ms_encode = ms;
+  *n_out = (int64_t)total;
+  return BPE_OK;
+}
+
+int check_offsets(bpe_engine* e, const int64_t* off, int64_t n_docs) {
+  if (n_docs < 0 || (!off && n_docs > 0)) return fail(e, BPE_E_INVALID, "bad document offsets");
+  for (int64_t d = 0; d < n_docs; d++)
+    if (off[d + 1] < off[d]) return fail(e, BPE_E_INVALID, "document offsets must be non-decreasing (doc %lld)", (long long)d);
+  return BPE_OK;
+}
+
+// append ids (device pointer, already merged or raw) as documents
+int append_docs_dev(bpe_engine* e, const int32_t* dev_ids, const int64_t* host_off, int64_t n_docs) {
+  int64_t base_in = host_off[0];
+  int64_t total = host_off[n_docs] - base_in;
+  uint64_t new_n = e->n_slots + (uint64_t)total;
+  if (new_n >= 0xFFFFFFF0ull) return fail(e, BPE_E_DOMAIN, "corpus exceeds 2^32 positions per engine");
+  CK(e->slots.reserve((size_t)new_n + 4, (size_t)e->n_slots, e->stream, 1.5));
+  CK(e->d_st.reserve(1));
+  if (total > 0) {
+    CK(cudaMemsetAsync(&e->d_st.p->err, 0, sizeof(uint32_t), e->stream));
+    int blocks = (int)std::min<int64_t>((total / 4 + 255) / 256 + 1, (int64_t)e->grid(8));
+    k_ingest_ids<<<blocks, 256, 0, e->stream>>>(dev_ids + base_in, e->slots.p + e->n_slots, (uint64_t)total, (uint32_t)e->n_tokens, &e->d_st.p->err);
+    CKL();
+    CK(e->stage_off.reserve((size_t)n_docs + 1, 0, e->stream, 1.5));
+    CK(cudaMemcpyAsync(e->stage_off.p, host_off, (size_t)(n_docs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
+    int blocks2 = (int)std::min<int64_t>((n_docs + 255) / 256, (int64_t)e->grid(8));
+    k_mark_docstarts<<<blocks2, 256, 0, e->stream>>>(e->slots.p, e->stage_off.p, n_docs, (int64_t)e->n_slots - base_in);
+    CKL();
+    uint32_t bad = 0;
+    CK(cudaMemcpyAsync(&bad, &e->d_st.p->err, sizeof bad, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (bad) {
+      CK(cudaMemsetAsync(&e->d_st.p->err, 0, sizeof(uint32_t), e->stream));
+      return fail(e, BPE_E_INVALID, "document holds a token index >= n_tokens (%d); call bpe_set_tokens first", e->n_tokens);
+    }
+  }
+  for (int64_t d = 0; d < n_docs; d++) e->doc_off.push_back((int64_t)e->n_slots + (host_off[d + 1] - base_in));
+  e->n_slots = new_n;
+  e->live_tokens += (uint64_t)total;
+  e->index_valid = false;
+  e->hot_valid = false;
+  return BPE_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int bpe_abi_version(void) { return BPE_ABI_VERSION; }
+
+int bpe_create(int device, bpe_engine** out) {
+  if (!out) return BPE_E_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return BPE_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return BPE_E_CUDA;
+  bpe_engine* e = new bpe_engine();
+  e->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete e;
+    return BPE_E_CUDA;
+  }
+  e->stream = e->own_stream;
+  *out = e;
+  return BPE_OK;
+}
+
+void bpe_destroy(bpe_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  if (e->h_st) cudaFreeHost(e->h_st);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+const char* bpe_last_error(bpe_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int bpe_set_stream(bpe_engine* e, void* cuda_stream) {
+  if (!e) return BPE_E_INVALID;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  return BPE_OK;
+}
+
+int bpe_synchronize(bpe_engine* e) {
+  if (!e) return BPE_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  return BPE_OK;
+}
+
+int bpe_set_profiling(bpe_engine* e, int enabled) {
+  if (!e) return BPE_E_INVALID;
+  e->profiling = enabled != 0;
+  e->scan_mode = (enabled & 2) ? 1 : 0;  // bit 1: debug full-scan site discovery
+  return BPE_OK;
+}
+
+int bpe_get_stats(bpe_engine* e, bpe_stats* out) {
+  if (!e || !out) return BPE_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  if (e->index_valid && e->d_st.p) {
+    TRY(fetch_state(e));
+    e->live_tokens = e->h_st->live_tokens;
+    e->stats.distinct_pairs = e->h_st->n_keys;
+    e->stats.pool_used = e->h_st->pool_cursor;
+  }
+  e->stats.corpus_positions = (int64_t)e->n_slots;
+  e->stats.corpus_tokens = (int64_t)e->live_tokens;
+  *out = e->stats;
+  return BPE_OK;
+}
+
+int bpe_set_tokens(bpe_engine* e, const int32_t* utf16_len, int32_t n_tokens) {
+  if (!e || n_tokens < 0 || (!utf16_len && n_tokens > 0)) return fail(e, BPE_E_INVALID, "bad token table");
+  if (n_tokens > BPE_MAX_TOKENS) return fail(e, BPE_E_DOMAIN, "token table of %d exceeds %d", n_tokens, BPE_MAX_TOKENS);
+  for (int32_t i = 0; i < n_tokens; i++)
+    if (utf16_len[i] < 0) return fail(e, BPE_E_INVALID, "negative token length");
+  CK(cudaSetDevice(e->device));
+  e->h_len16.assign(utf16_len, utf16_len + n_tokens);
+  e->n_tokens = n_tokens;
+  TRY(sync_len16(e));
+  e->hot_valid = false;
+  return BPE_OK;
+}
+
+int bpe_num_tokens(bpe_engine* e, int32_t* n_tokens) {
+  if (!e || !n_tokens) return BPE_E_INVALID;
+  *n_tokens = e->n_tokens;
+  return BPE_OK;
+}
+
+int bpe_load_merges(bpe_engine* e, const int32_t* abc, int64_t n_merges) {
+  if (!e || n_merges < 0 || (!abc && n_merges > 0)) return fail(e, BPE_E_INVALID, "bad merge list");
+  for (int64_t i = 0; i < 3 * n_merges; i++)
+    if (abc[i] < 0 || abc[i] >= BPE_MAX_TOKENS) return fail(e, BPE_E_INVALID, "merge %lld holds index %d", (long long)(i / 3), abc[i]);
+  e->h_merges.assign(abc, abc + 3 * n_merges);
+  e->mt_dirty = true;
+  return BPE_OK;
+}
+
+int bpe_add_documents_dev(bpe_engine* e, const int32_t* dev_ids, const int64_t* host_doc_offsets, int64_t n_docs) {
+  if (!e) return BPE_E_INVALID;
+  TRY(check_offsets(e, host_doc_offsets, n_docs));
+  if (n_docs == 0) return BPE_OK;
+  if (!dev_ids && host_doc_offsets[n_docs] > host_doc_offsets[0]) return fail(e, BPE_E_INVALID, "null ids");
+  CK(cudaSetDevice(e->device));
+  return append_docs_dev(e, dev_ids, host_doc_offsets, n_docs);
+}
+
+int bpe_add_documents(bpe_engine* e, const int32_t* ids, const int64_t* doc_offsets, int64_t n_docs) {
+  if (!e) return BPE_E_INVALID;
+  TRY(check_offsets(e, doc_offsets, n_docs));
+  if (n_docs == 0) return BPE_OK;
+  int64_t base = doc_offsets[0], total = doc_offsets[n_docs] - base;
+  if (!ids && total > 0) return fail(e, BPE_E_INVALID, "null ids");
+  CK(cudaSetDevice(e->device));
+  CK(e->stage_ids.reserve((size_t)std::max<int64_t>(total, 1)));
+  if (total > 0) CK(cudaMemcpyAsync(e->stage_ids.p, ids + base, (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  std::vector<int64_t> rel((size_t)n_docs + 1);
+  for (int64_t d = 0; d <= n_docs; d++) rel[d] = doc_offsets[d] - base;
+  int rc = append_docs_dev(e, e->stage_ids.p, rel.data(), n_docs);
+  if (total > (64 << 20)) e->stage_ids.release();  // do not sit on GBs of staging
+  return rc;
+}
+
+int bpe_clear_corpus(bpe_engine* e) {
+  if (!e) return BPE_E_INVALID;
+  e->n_slots = 0;
+  e->doc_off.assign(1, 0);
+  e->live_tokens = 0;
+  e->index_valid = false;
+  e->hot_valid = false;
+  return BPE_OK;
+}
+
+int bpe_corpus_size(bpe_engine* e, int64_t* n_docs, int64_t* n_tokens) {
+  if (!e) return BPE_E_INVALID;
+  CK(cudaSetDevice(e->device));
+  if (e->index_valid && e->d_st.p) {
+    TRY(fetch_state(e));
+    e->live_tokens = e->h_st->live_tokens;
+  }
+  if (n_docs) *n_docs = (int64_t)e->doc_off.size() - 1;
+  if (n_tokens) *n_tokens = (int64_t)e->live_tokens;
+  return BPE_OK;
+}
+
+int bpe_get_corpus(bpe_engine* e, int64_t doc_begin, int64_t doc_end, int32_t* out, int64_t out_cap, int64_t* out_offsets,
+                   int64_t* n_out) {
+  if (!e || !n_out) return BPE_E_INVALID;
+  int64_t nd = (int64_t)e->doc_off.size() - 1;
+  if (doc_begin < 0 || doc_end < doc_begin || doc_end > nd) return fail(e, BPE_E_INVALID, "document range [%lld,%lld) outside [0,%lld)", (long long)doc_begin, (long long)doc_end, (long long)nd);
+  CK(cudaSetDevice(e->device));
+  uint64_t begin = (uint64_t)e->doc_off[doc_begin], end = (uint64_t)e->doc_off[doc_end];
+  int64_t n_bounds = doc_end - doc_begin + 1;
+  uint64_t span = end - begin;
+  uint32_t nblk = (uint32_t)((span + CP_TILE - 1) / CP_TILE);
+  DevBuf<uint32_t> bc;
+  DevBuf<uint64_t> bo;
+  DevBuf<int64_t> dpos, doffs;
+  DevBuf<int32_t> dout;
+  CK(bc.reserve(nblk + 1));
+  CK(bo.reserve(nblk + 2));
+  CK(dpos.reserve((size_t)n_bounds));
+  CK(doffs.reserve((size_t)n_bounds));
+  if (nblk) {
+    k_count_ids<<<nblk, CP_THREADS, 0, e->stream>>>(e->slots.p, begin, end, bc.p);
+    CKL();
+  }
+  k_scan_counts<<<1, 1024, 0, e->stream>>>(bc.p, bo.p, nblk);
+  CKL();
+  uint64_t total = 0;
+  CK(cudaMemcpyAsync(&total, bo.p + nblk, sizeof total, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  *n_out = (int64_t)total;
+  if ((int64_t)total > out_cap || (!out && total) || !out_offsets) {
+    if (!out_offsets || (!out && total)) return fail(e, BPE_E_CAPACITY, "output buffers missing; need %llu values", (unsigned long long)total);
+    return fail(e, BPE_E_CAPACITY, "output buffer holds %lld values, need %llu", (long long)out_cap, (unsigned long long)total);
+  }
+  CK(cudaMemcpyAsync(dpos.p, e->doc_off.data() + doc_begin, (size_t)n_bounds * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
+  k_doc_ranks<<<(int)std::min<int64_t>((n_bounds * 32 + 255) / 256, (int64_t)e->grid(8)), 256, 0, e->stream>>>(e->slots.p, begin, bo.p, dpos.p, n_bounds, doffs.p);
+  CKL();
+  CK(cudaMemcpyAsync(out_offsets, doffs.p, (size_t)n_bounds * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+  if (total) {
+    CK(dout.reserve((size_t)total));
+    k_compact_ids<<<nblk, CP_THREADS, 0, e->stream>>>(e->slots.p, begin, end, bo.p, dout.p);
+    CKL();
+    CK(cudaMemcpyAsync(out, dout.p, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  return BPE_OK;
+}
+
+int bpe_find_next_merge(bpe_engine* e, int64_t min_weight, int32_t max_length, bpe_merge* out, int* found) {
+  if (!e || !out || !found) return BPE_E_INVALID;
+  *found = 0;
+  CK(cudaSetDevice(e->device));
+  if (e->n_slots == 0) return BPE_OK;
+  TRY(ensure_index(e));
+  uint32_t ml = max_length > 0 ? (uint32_t)max_length : 0;
+  int64_t mw = min_weight > 0 ? min_weight : 2;  // core.ts:256
+  TRY(run_argmax(e, ml, 0));
+  if (!e->h_st->best_primary) return BPE_OK;            // core.ts:312
+  if ((int64_t)e->h_st->best_cnt < mw) return BPE_OK;   // core.ts:313
+  out->a = (int32_t)e->h_st->best_a;
+  out->b = (int32_t)e->h_st->best_b;
+  out->c = e->n_tokens;
+  out->reserved = 0;
+  out->weight = (int64_t)e->h_st->best_cnt;
+  *found = 1;
+  return BPE_OK;
+}
+
+int bpe_apply_merge(bpe_engine* e, int32_t a, int32_t b, int32_t c, int64_t* n_replaced) {
+  if (!e) return BPE_E_INVALID;
+  if (a < 0 || b < 0 || a >= e->n_tokens || b >= e->n_tokens) return fail(e, BPE_E_INVALID, "merge operands (%d,%d) outside the token table (%d)", a, b, e->n_tokens);
+  if (c != e->n_tokens) return fail(e, BPE_E_INVALID, "new token index must be %d, got %d", e->n_tokens, c);
+  if (c >= BPE_MAX_TOKENS) return fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
+  CK(cudaSetDevice(e->device));
+  if (n_replaced) *n_replaced = 0;
+  if (e->n_slots == 0) {  // no corpus: only the vocabulary grows (example/import-merge-log-to-ram.ts:22-31)
+    e->h_len16.push_back(e->h_len16[a] + e->h_len16[b]);
+    e->h_merges.push_back(a);
+    e->h_merges.push_back(b);
+    e->h_merges.push_back(c);
+    e->mt_dirty = true;
+    e->n_tokens++;
+    e->index_valid = false;
+    return BPE_OK;
+  }
+  TRY(ensure_index(e));
+  k_lookup_pair<<<1, 32, 0, e->stream>>>(e->table(), (uint32_t)a, (uint32_t)b, e->d_st.p);
+  CKL();
+  TRY(fetch_state(e));
+  TRY(run_apply(e, (uint32_t)a, (uint32_t)b, (uint32_t)c, e->h_st->list_len));
+  TRY(fetch_state(e));
+  TRY(check_dev_err(e));
+  e->stats.sites_merged += e->h_st->n_sites;
+  if (n_replaced) *n_replaced = e->h_st->n_sites;
+  return BPE_OK;
+}
+
+int bpe_merge_until(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations, bpe_merge* log,
+                    int64_t log_cap, int64_t* n_done) {
+  if (!e || !n_done || (log_cap > 0 && !log) || log_cap < 0) return BPE_E_INVALID;
+  *n_done = 0;
+  CK(cudaSetDevice(e->device));
+  if (e->n_slots == 0) return BPE_OK;
+  TRY(ensure_index(e));
+  uint32_t ml = max_length > 0 ? (uint32_t)max_length : 0;
+  int64_t mw = min_weight > 0 ? min_weight : 2;
+  if (!e->ev0) {
+    CK(cudaEventCreate(&e->ev0));
+    CK(cudaEventCreate(&e->ev1));
+  }
+  cudaEvent_t t0, t1;
+  CK(cudaEventCreate(&t0));
+  CK(cudaEventCreate(&t1));
+  CK(cudaEventRecord(t0, e->stream));
+  int rc = BPE_OK;
+  int64_t done = 0;
+  // core.ts:374-382: for (iteration = 1; !max_iterations || iteration <= max_iterations; iteration++)
+  while ((max_iterations <= 0 || done < max_iterations) && done < log_cap) {
+    if (!e->hot_valid || e->hot_max_length != ml) {
+      bool any = false;
+      if ((rc = rebuild_hot(e, ml, &any)) != BPE_OK) break;
+      if (!any) break;  // nothing countable left (core.ts:312)
+    }
+    if ((rc = run_argmax(e, ml, 1)) != BPE_OK) break;
+    if (e->h_st->err & ERR_HOT_OVERFLOW) {
+      e->hot_valid = false;
+      CK(cudaMemsetAsync(&e->d_st.p->err, 0, sizeof(uint32_t), e->stream));
+      continue;
+    }
+    if (!e->h_st->best_primary || e->h_st->best_cnt < e->hot_thresh) {
+      if (e->hot_thresh <= 1 && !e->h_st->best_primary) break;
+      e->hot_valid = false;  // the maximum fell below the list's threshold: rebuild lower
+      continue;
+    }
+    uint32_t a = e->h_st->best_a, b = e->h_st->best_b, w = e->h_st->best_cnt;
+    if ((int64_t)w < mw) break;  // core.ts:313
+    int32_t c = e->n_tokens;
+    if (c >= BPE_MAX_TOKENS) {
+      rc = fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
+      break;
+    }
+    if ((rc = run_apply(e, a, b, (uint32_t)c, e->scan_mode ? w : e->h_st->list_len)) != BPE_OK) break;
+    log[done].a = (int32_t)a;
+    log[done].b = (int32_t)b;
+    log[done].c = c;
+    log[done].reserved = 0;
+    log[done].weight = (int64_t)w;
+    e->stats.sites_merged += w;
+    done++;
+  }
+  *n_done = done;
+  if (rc != BPE_OK) return rc;
+  CK(cudaEventRecord(t1, e->stream));
+  TRY(fetch_state(e));
+  TRY(check_dev_err(e));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, t0, t1));
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  e->stats.ms_last_merge_until = ms;
+  e->live_tokens = e->h_st->live_tokens;
+  return BPE_OK;
+}
+
+int bpe_pair_counts(bpe_engine* e, int32_t* a, int32_t* b, int64_t* count, int64_t cap, int64_t* n) {
+  if (!e || !n || cap < 0) return BPE_E_INVALID;
+  *n = 0;
+  CK(cudaSetDevice(e->device));
+  if (e->n_slots == 0) return BPE_OK;
+  TRY(ensure_index(e));
+  DevBuf<int32_t> da, db;
+  DevBuf<int64_t> dc;
+  DevBuf<uint32_t> dn;
+  size_t c = (size_t)std::max<int64_t>(cap, 1);
+  CK(da.reserve(c));
+  CK(db.reserve(c));
+  CK(dc.reserve(c));
+  CK(dn.reserve(1));
+  CK(cudaMemsetAsync(dn.p, 0, 4, e->stream));
+  k_dump_pairs<<<e->grid(4), 256, 0, e->stream>>>(e->table(), da.p, db.p, dc.p, (uint32_t)std::min<int64_t>(cap, 0x7FFFFFFF), dn.p);
+  CKL();
+  uint32_t cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, dn.p, 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  *n = cnt;
+  if ((int64_t)cnt > cap) return fail(e, BPE_E_CAPACITY, "need room for %u pairs", cnt);
+  if (cnt) {
+    CK(cudaMemcpy(a, da.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b, db.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(count, dc.p, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  }
+  return BPE_OK;
+}
+
+int bpe_encode_batch_dev(bpe_engine* e, const int32_t* dev_ids, const int64_t* dev_doc_offsets, int64_t n_docs, int64_t n_ids,
+                         int64_t max_doc_len, const int32_t* dev_to_vector_index, int32_t n_tvi, int32_t* dev_out,
+                         int64_t* dev_out_offsets, int64_t* dev_first_bad, int64_t* n_out) {
+  if (!e || !n_out || n_docs < 0 || n_ids < 0 || !dev_doc_offsets || !dev_out_offsets || (n_ids > 0 && (!dev_ids || !dev_out)))
+    return fail(e, BPE_E_INVALID, "bad encode arguments");
+  CK(cudaSetDevice(e->device));
+  static thread_local EncodeScratch* tls = nullptr;  // reused across calls so steady-state encode does not allocate
+  if (!tls) tls = new EncodeScratch();
+  return encode_dev(e, *tls, dev_ids, dev_doc_offsets, n_docs, n_ids, max_doc_len, dev_to_vector_index, n_tvi, dev_out,
+                    dev_out_offsets, dev_first_bad, n_out);
+}
+
+int bpe_encode_batch(bpe_engine* e, const int32_t* ids, const int64_t* doc_offsets, int64_t n_docs, const int32_t* to_vector_index,
+                     int32_t n_tvi, int32_t* out, int64_t out_cap, int64_t* out_offsets, int64_t* first_bad, int64_t* n_out) {
+  if (!e || !n_out || !out_offsets) return fail(e, BPE_E_INVALID, "bad encode arguments");
+  TRY(check_offsets(e, doc_offsets, n_docs));
+  CK(cudaSetDevice(e->device));
+  int64_t base = n_docs ? doc_offsets[0] : 0, total = n_docs ? doc_offsets[n_docs] - base : 0;
+  if (total > 0 && !ids) return fail(e, BPE_E_INVALID, "null ids");
+  int64_t max_len = 0;
+  std::vector<int64_t> rel((size_t)n_docs + 1, 0);
+  for (int64_t d = 0; d < n_docs; d++) {
+    rel[d + 1] = doc_offsets[d + 1] - base;
+    max_len = std::max(max_len, doc_offsets[d + 1] - doc_offsets[d]);
+  }
+  for (int64_t i = 0; i < total; i++)
+    if (ids[base + i] < 0 || ids[base + i] >= e->n_tokens) return fail(e, BPE_E_INVALID, "id %d at %lld outside the token table", ids[base + i], (long long)i);
+  DevBuf<int32_t> d_ids, d_out, d_tvi;
+  DevBuf<int64_t> d_off, d_ooff, d_bad;
+  CK(d_ids.reserve((size_t)std::max<int64_t>(total, 1)));
+  CK(d_out.reserve((size_t)std::max<int64_t>(total, 1)));
+  CK(d_off.reserve((size_t)n_docs + 1));
+  CK(d_ooff.reserve((size_t)n_docs + 1));
+  if (first_bad) CK(d_bad.reserve((size_t)std::max<int64_t>(n_docs, 1)));
+  if (to_vector_index && n_tvi > 0) {
+    CK(d_tvi.reserve((size_t)n_tvi));
+    CK(cudaMemcpyAsync(d_tvi.p, to_vector_index, (size_t)n_tvi * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  if (total) CK(cudaMemcpyAsync(d_ids.p, ids + base, (size_t)total * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(d_off.p, rel.data(), (size_t)(n_docs + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  EncodeScratch sc;
+  TRY(encode_dev(e, sc, d_ids.p, d_off.p, n_docs, total, max_len, to_vector_index ? d_tvi.p : nullptr, n_tvi, d_out.p, d_ooff.p,
+                 first_bad ? d_bad.p : nullptr, n_out));
+  CK(cudaMemcpyAsync(out_offsets, d_ooff.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (first_bad && n_docs) CK(cudaMemcpyAsync(first_bad, d_bad.p, (size_t)n_docs * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (*n_out > out_cap || (*n_out && !out)) {
+    CK(cudaStreamSynchronize(e->stream));
+    return fail(e, BPE_E_CAPACITY, "output buffer holds %lld values, need %lld", (long long)out_cap, (long long)*n_out);
+  }
+  if (*n_out) CK(cudaMemcpyAsync(out, d_out.p, (size_t)*n_out * 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return BPE_OK;
+}
+
+int bpe_restore_documents(bpe_engine* e, const int32_t* ids, const int64_t* doc_offsets, int64_t n_docs) {
+  if (!e) return BPE_E_INVALID;
+  TRY(check_offsets(e, doc_offsets, n_docs));
+  if (n_docs == 0) return BPE_OK;
+  CK(cudaSetDevice(e->device));
+  int64_t base = doc_offsets[0], total = doc_offsets[n_docs] - base;
+  if (total > 0 && !ids) return fail(e, BPE_E_INVALID, "null ids");
+  int64_t max_len = 0;
+  std::vector<int64_t> rel((size_t)n_docs + 1, 0);
+  for (int64_t d = 0; d < n_docs; d++) {
+    rel[d + 1] = doc_offsets[d + 1] - base;
+    max_len = std::max(max_len, doc_offsets[d + 1] - doc_offsets[d]);
+  }
+  for (int64_t i = 0; i < total; i++)
+    if (ids[base + i] < 0 || ids[base + i] >= e->n_tokens) return fail(e, BPE_E_INVALID, "id %d at %lld outside the token table", ids[base + i], (long long)i);
+  DevBuf<int32_t> d_ids, d_out;
+  DevBuf<int64_t> d_off, d_ooff;
+  CK(d_ids.reserve((size_t)std::max<int64_t>(total, 1)));
+  CK(d_out.reserve((size_t)std::max<int64_t>(total, 1)));
+  CK(d_off.reserve((size_t)n_docs + 1));
+  CK(d_ooff.reserve((size_t)n_docs + 1));
+  if (total) CK(cudaMemcpyAsync(d_ids.p, ids + base, (size_t)total * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(d_off.p, rel.data(), (size_t)(n_docs + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  EncodeScratch sc;
+  int64_t n_out = 0;
+  TRY(encode_dev(e, sc, d_ids.p, d_off.p, n_docs, total, max_len, nullptr, 0, d_out.p, d_ooff.p, nullptr, &n_out));
+  std::vector<int64_t> ooff((size_t)n_docs + 1);
+  CK(cudaMemcpyAsync(ooff.data(), d_ooff.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return append_docs_dev(e, d_out.p, ooff.data(), n_docs);
+}
+
+}  // extern "C"

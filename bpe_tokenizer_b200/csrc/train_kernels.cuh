@@ -1,0 +1,775 @@
+// train_kernels.cuh -- K1 (pair histogram + occurrence lists), K2 (arg-max with the reference's exact
+// tie-break) and K3 (apply merge in place with count deltas) for sm_100a.
+//
+// Reference semantics restated (all citations are /root/reference/core.ts):
+//   counting  :265-310  every adjacent pair inside a document; for a == b only every other pair of a
+//                       run is counted (:285-290), i.e. count(X,X) = sum over runs floor(len/2)
+//   arg-max   :294-305  running max => winner = max weight, then min a.index+b.index, then the pair
+//                       whose LAST counted occurrence comes first in scan order
+//   filter    :270-273  utf16len(a)+utf16len(b) <= max_length when max_length is truthy
+//   apply     :356-359  replaceAll: left to right, non-overlapping
+//
+// Key structural fact used by the occurrence lists: all instances of a token index are created by the
+// one merge that created the index, so every adjacency (p,q) is born in iteration max(birth p, birth q)
+// -- each pair's occurrence list is written exactly once (contiguous in `pool`) and afterwards only
+// goes stale, which is detected by re-reading the corpus.
+#pragma once
+#include "common.cuh"
+
+namespace bpe {
+
+struct DevState {
+  // persistent
+  uint32_t n_keys;
+  uint32_t pool_cursor;
+  uint32_t err;
+  uint32_t hot_n;
+  uint32_t hot_thresh;
+  // per iteration
+  uint32_t n_sites;
+  uint32_t n_new;
+  uint32_t n_cand;
+  uint32_t blocks_done;
+  uint32_t _pad0;
+  // arg-max result
+  unsigned long long best_primary;  // (count << 20) | (0xFFFFF - (a+b)); 0 = nothing
+  uint32_t best_slot;
+  uint32_t best_mult;  // number of pairs sharing best_primary
+  uint32_t best_a, best_b, best_cnt;
+  uint32_t list_len;
+  unsigned long long tie_pos;  // (lastpos << 32 | slot) min over candidates
+  unsigned long long live_tokens;
+  uint32_t bins[36];  // histogram of bit lengths of counts (hot-list threshold selection)
+};
+
+struct SiteRec {
+  uint32_t p;      // position of the `a` being merged
+  uint32_t lpos;   // position of the left token of the new left adjacency (NOPOS if none)
+  uint32_t lslot;  // table slot of the new left adjacency's pair (NOSLOT if none)
+  uint32_t rslot;  // table slot of the new right adjacency's pair (NOSLOT if none)
+};
+
+__device__ __forceinline__ unsigned long long make_primary(uint32_t cnt, uint32_t a, uint32_t b) {
+  return ((unsigned long long)cnt << 20) | (unsigned long long)(0xFFFFFu - (a + b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingest: int32 ids -> slots (vectorised 128-bit), then DOCSTART flags per document
+// ------------------------------------------------------------------------------------------------
+__global__ void k_ingest_ids(const int32_t* __restrict__ ids, uint32_t* __restrict__ slots, uint64_t n,
+                             uint32_t max_id, uint32_t* __restrict__ err) {
+  uint64_t i4 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t n4 = n >> 2;
+  bool aligned = ((((uintptr_t)ids) | ((uintptr_t)slots)) & 15) == 0;
+  uint32_t bad = 0;
+  if (aligned) {
+    for (uint64_t i = i4; i < n4; i += stride) {
+      int4 v = __ldg(reinterpret_cast<const int4*>(ids) + i);
+      bad |= ((uint32_t)v.x >= max_id) | ((uint32_t)v.y >= max_id) | ((uint32_t)v.z >= max_id) | ((uint32_t)v.w >= max_id);
+      reinterpret_cast<uint4*>(slots)[i] = make_uint4((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w);
+    }
+    for (uint64_t i = (n4 << 2) + i4; i < n; i += stride) {
+      uint32_t v = (uint32_t)ids[i];
+      bad |= v >= max_id;
+      slots[i] = v;
+    }
+  } else {
+    for (uint64_t i = i4; i < n; i += stride) {
+      uint32_t v = (uint32_t)ids[i];
+      bad |= v >= max_id;
+      slots[i] = v;
+    }
+  }
+  if (bad) atomicOr(err, 1u);
+}
+
+__global__ void k_mark_docstarts(uint32_t* __restrict__ slots, const int64_t* __restrict__ doc_off, int64_t n_docs,
+                                 int64_t base) {
+  int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; d < n_docs; d += stride) {
+    int64_t s = doc_off[d], e = doc_off[d + 1];
+    if (e > s) slots[base + s] |= DOCSTART;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: pair histogram.  128-bit coalesced loads of the slots, block-local shared-memory open-addressing
+// hash for the counts (one global atomic per distinct pair per block instead of one per position).
+// ------------------------------------------------------------------------------------------------
+constexpr int K1_THREADS = 256;
+constexpr int K1_SMEM_SLOTS = 2048;  // 24 KB
+constexpr int K1_MAX_PROBE = 8;
+
+struct SmemHist {
+  uint32_t key[K1_SMEM_SLOTS];
+  uint32_t cnt[K1_SMEM_SLOTS];
+  uint32_t occ[K1_SMEM_SLOTS];
+};
+
+__device__ __forceinline__ void k1_add(SmemHist& sh, const PairTable& t, DevState* st, uint32_t key, uint32_t counted) {
+  uint32_t h = (key * 0x9E3779B1u) >> (32 - 11);
+#pragma unroll 1
+  for (int probe = 0; probe < K1_MAX_PROBE; probe++) {
+    uint32_t k = sh.key[h];
+    if (k == EMPTY_KEY) {
+      uint32_t old = atomicCAS(&sh.key[h], EMPTY_KEY, key);
+      k = (old == EMPTY_KEY) ? key : old;
+    }
+    if (k == key) {
+      if (counted) atomicAdd(&sh.cnt[h], 1u);
+      atomicAdd(&sh.occ[h], 1u);
+      return;
+    }
+    h = (h + 1) & (K1_SMEM_SLOTS - 1);
+  }
+  // shared table crowded: straight to the global table
+  uint32_t g = tbl_find_or_insert(t, key, &st->n_keys);
+  if (g == NOSLOT) {
+    atomicOr(&st->err, ERR_TABLE_FULL);
+    return;
+  }
+  if (counted) atomicAdd(t.cnt + g, 1u);
+  atomicAdd(t.occ_len + g, 1u);
+}
+
+// One adjacency starting at position p (slot value w).  Returns false when p starts no adjacency.
+__device__ __forceinline__ bool edge_at(const uint32_t* __restrict__ slots, uint32_t n, uint32_t p, uint32_t w,
+                                        uint32_t wnext_hint, bool have_hint, uint32_t* key, uint32_t* counted) {
+  if (!slot_is_id(w)) return false;
+  uint32_t a = slot_val(w);
+  int b;
+  if (have_hint && slot_is_id(wnext_hint)) {
+    b = (wnext_hint & DOCSTART) ? NOTOK : (int)slot_val(wnext_hint);
+  } else {
+    uint32_t q;
+    b = right_token(slots, n, p, &q);
+  }
+  if (b == NOTOK) return false;
+  *key = pair_key(a, (uint32_t)b);
+  *counted = 1;
+  if ((uint32_t)b == a) *counted = (run_left(slots, p, w, (int)a) & 1u) ? 0u : 1u;
+  return true;
+}
+
+__global__ void __launch_bounds__(K1_THREADS) k_hist(const uint32_t* __restrict__ slots, uint32_t n, PairTable t,
+                                                      DevState* st) {
+  __shared__ SmemHist sh;
+  for (int i = threadIdx.x; i < K1_SMEM_SLOTS; i += K1_THREADS) {
+    sh.key[i] = EMPTY_KEY;
+    sh.cnt[i] = 0;
+    sh.occ[i] = 0;
+  }
+  __syncthreads();
+  // contiguous chunk of 4-slot groups per block, so the shared table sees as few distinct pairs as possible
+  uint32_t n4 = (n + 3) >> 2;
+  uint32_t per_block = (n4 + gridDim.x - 1) / gridDim.x;
+  uint32_t g_begin = blockIdx.x * per_block;
+  uint32_t g_end = min(n4, g_begin + per_block);
+  for (uint32_t g = g_begin + threadIdx.x; g < g_end; g += K1_THREADS) {
+    uint32_t p0 = g << 2;
+    uint32_t v[5];
+    if (p0 + 4 <= n) {
+      uint4 q = __ldg(reinterpret_cast<const uint4*>(slots) + g);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = (p0 + j < n) ? __ldg(slots + p0 + j) : mk_hole();
+    }
+    v[4] = (p0 + 4 < n) ? __ldg(slots + p0 + 4) : (DOCSTART);  // DOCSTART|ID(0): "no right neighbour"
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t key, counted;
+      if (p0 + j < n && edge_at(slots, n, p0 + j, v[j], v[j + 1], true, &key, &counted)) k1_add(sh, t, st, key, counted);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K1_SMEM_SLOTS; i += K1_THREADS) {
+    uint32_t key = sh.key[i];
+    if (key == EMPTY_KEY) continue;
+    uint32_t g = tbl_find_or_insert(t, key, &st->n_keys);
+    if (g == NOSLOT) {
+      atomicOr(&st->err, ERR_TABLE_FULL);
+      continue;
+    }
+    if (sh.cnt[i]) atomicAdd(t.cnt + g, sh.cnt[i]);
+    if (sh.occ[i]) atomicAdd(t.occ_len + g, sh.occ[i]);
+  }
+}
+
+// carve every pair's occurrence list out of the pool
+__global__ void k_alloc_lists(PairTable t, DevState* st, uint32_t pool_cap) {
+  uint32_t cap = t.mask + 1;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+    if (t.keys[i] == EMPTY_KEY) continue;
+    uint32_t len = t.occ_len[i];
+    t.occ_fill[i] = 0;
+    if (len == 0) continue;
+    uint32_t start = atomicAdd(&st->pool_cursor, len);
+    if (start > pool_cap || len > pool_cap - start) atomicOr(&st->err, ERR_POOL_FULL);
+    t.occ_start[i] = start;
+  }
+}
+
+// K1b: scatter every adjacency's position into its pair's list (warp-aggregated cursor atomics)
+__global__ void __launch_bounds__(K1_THREADS) k_scatter(const uint32_t* __restrict__ slots, uint32_t n, PairTable t,
+                                                         uint32_t* __restrict__ pool, DevState* st) {
+  uint32_t n4 = (n + 3) >> 2;
+  uint32_t lane = threadIdx.x & 31;
+  uint32_t n4_round = (n4 + 31) & ~31u;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n4_round; g += gridDim.x * blockDim.x) {
+    uint32_t p0 = g << 2;
+    uint32_t v[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) v[j] = (p0 + j < n) ? __ldg(slots + p0 + j) : (j == 4 ? DOCSTART : mk_hole());
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t key = EMPTY_KEY - 1 - lane, counted;  // per-lane dummy: matches nobody
+      bool has = (p0 + j < n) && edge_at(slots, n, p0 + j, v[j], v[j + 1], true, &key, &counted);
+      uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+      uint32_t leader = __ffs(peers) - 1;
+      uint32_t rank = __popc(peers & ((1u << lane) - 1));
+      uint32_t base = 0;
+      if (has && lane == leader) {
+        uint32_t s = tbl_find(t, key);
+        if (s == NOSLOT) {
+          atomicOr(&st->err, ERR_MISSING_KEY);
+          base = NOPOS;
+        } else {
+          base = t.occ_start[s] + atomicAdd(t.occ_fill + s, (uint32_t)__popc(peers));
+        }
+      }
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (has && base != NOPOS) pool[base + rank] = p0 + j;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: arg-max.  primary = (count, -(a+b)); the position tie-break runs only when best_mult > 1.
+// ------------------------------------------------------------------------------------------------
+struct Best {
+  unsigned long long primary;
+  uint32_t slot;
+  uint32_t mult;
+};
+
+__device__ __forceinline__ Best best_merge(Best x, Best y) {
+  if (x.primary > y.primary) return x;
+  if (y.primary > x.primary) return y;
+  Best r;
+  r.primary = x.primary;
+  r.slot = min(x.slot, y.slot);
+  r.mult = x.mult + y.mult;
+  return r;
+}
+
+__device__ __forceinline__ Best best_warp_reduce(Best v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best w;
+    w.primary = __shfl_xor_sync(0xFFFFFFFFu, v.primary, o);
+    w.slot = __shfl_xor_sync(0xFFFFFFFFu, v.slot, o);
+    w.mult = __shfl_xor_sync(0xFFFFFFFFu, v.mult, o);
+    v = best_merge(v, w);
+  }
+  return v;
+}
+
+__device__ __forceinline__ unsigned long long slot_primary(const PairTable& t, const uint32_t* __restrict__ len16,
+                                                           uint32_t s, uint32_t max_length) {
+  uint32_t key = t.keys[s];
+  if (key == EMPTY_KEY) return 0ull;
+  uint32_t c = t.cnt[s];
+  if (c == 0) return 0ull;
+  uint32_t a = key >> 16, b = key & 0xFFFFu;
+  if (max_length && len16[a] + len16[b] > max_length) return 0ull;
+  return make_primary(c, a, b);
+}
+
+constexpr int AM_THREADS = 256;
+
+// use_hot = 0: scan the whole table; 1: scan the hot list (pairs with count >= hot_thresh).
+// The last block to finish folds the per-block partials and resets the per-iteration counters.
+__global__ void __launch_bounds__(AM_THREADS) k_argmax(PairTable t, const uint32_t* __restrict__ len16,
+                                                        uint32_t max_length, int use_hot,
+                                                        const uint32_t* __restrict__ hot, Best* __restrict__ partials,
+                                                        DevState* st) {
+  __shared__ Best s_best[AM_THREADS / 32];
+  __shared__ bool s_last;
+  Best mine{0ull, NOSLOT, 0};
+  uint32_t n = use_hot ? st->hot_n : (t.mask + 1);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t s = use_hot ? hot[i] : i;
+    unsigned long long pr = slot_primary(t, len16, s, max_length);
+    if (pr) mine = best_merge(mine, Best{pr, s, 1});
+  }
+  mine = best_warp_reduce(mine);
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    Best v = (threadIdx.x < AM_THREADS / 32) ? s_best[threadIdx.x] : Best{0ull, NOSLOT, 0};
+    v = best_warp_reduce(v);
+    if (threadIdx.x == 0) {
+      partials[blockIdx.x] = v;
+      __threadfence();
+      uint32_t done = atomicAdd(&st->blocks_done, 1u);
+      s_last = (done == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  Best v{0ull, NOSLOT, 0};
+  for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) v = best_merge(v, partials[i]);
+  v = best_warp_reduce(v);
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    Best u = (threadIdx.x < AM_THREADS / 32) ? s_best[threadIdx.x] : Best{0ull, NOSLOT, 0};
+    u = best_warp_reduce(u);
+    if (threadIdx.x == 0) {
+      st->best_primary = u.primary;
+      st->best_slot = u.slot;
+      st->best_mult = u.mult;
+      if (u.primary) {
+        uint32_t key = t.keys[u.slot];
+        st->best_a = key >> 16;
+        st->best_b = key & 0xFFFFu;
+        st->best_cnt = t.cnt[u.slot];
+        st->list_len = t.occ_len[u.slot];
+      } else {
+        st->best_a = st->best_b = st->best_cnt = st->list_len = 0;
+      }
+      st->blocks_done = 0;
+      st->n_sites = 0;
+      st->n_new = 0;
+      st->n_cand = 0;
+      st->tie_pos = ~0ull;
+    }
+  }
+}
+
+// candidates = pairs whose primary equals best_primary
+__global__ void k_collect_cands(PairTable t, const uint32_t* __restrict__ len16, uint32_t max_length, int use_hot,
+                                const uint32_t* __restrict__ hot, uint32_t* __restrict__ cands, uint32_t cand_cap,
+                                DevState* st) {
+  unsigned long long best = st->best_primary;
+  uint32_t n = use_hot ? st->hot_n : (t.mask + 1);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t s = use_hot ? hot[i] : i;
+    if (slot_primary(t, len16, s, max_length) == best) {
+      uint32_t k = atomicAdd(&st->n_cand, 1u);
+      if (k < cand_cap) cands[k] = s;
+      else atomicOr(&st->err, ERR_CAND_OVERFLOW);
+    }
+  }
+}
+
+// Is position p a *counted* occurrence of (a,b) right now?
+__device__ __forceinline__ bool counted_occurrence(const uint32_t* __restrict__ slots, uint32_t n, uint32_t p, uint32_t a,
+                                                   uint32_t b) {
+  uint32_t w = __ldg(slots + p);
+  if (!slot_is_id(w) || slot_val(w) != a) return false;
+  uint32_t q;
+  if (right_token(slots, n, p, &q) != (int)b) return false;
+  if (a == b && (run_left(slots, p, w, (int)a) & 1u)) return false;
+  return true;
+}
+
+// one block per candidate: scan position of its last counted occurrence; global min of (pos, slot) wins
+__global__ void __launch_bounds__(256) k_tie_break(const uint32_t* __restrict__ slots, uint32_t n, PairTable t,
+                                                    const uint32_t* __restrict__ pool,
+                                                    const uint32_t* __restrict__ cands, DevState* st) {
+  __shared__ uint32_t s_max[8];
+  uint32_t n_cand = st->n_cand;
+  for (uint32_t c = blockIdx.x; c < n_cand; c += gridDim.x) {
+    uint32_t s = cands[c];
+    uint32_t key = t.keys[s];
+    uint32_t a = key >> 16, b = key & 0xFFFFu;
+    uint32_t start = t.occ_start[s], len = t.occ_len[s];
+    uint32_t best = 0;
+    bool any = false;
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+      uint32_t p = pool[start + i];
+      if (counted_occurrence(slots, n, p, a, b)) {
+        best = max(best, p);
+        any = true;
+      }
+    }
+    uint32_t v = any ? best + 1 : 0;  // 0 = none
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t m = 0;
+      for (int i = 0; i < 8; i++) m = max(m, s_max[i]);
+      if (m) atomicMin(&st->tie_pos, ((unsigned long long)(m - 1) << 32) | s);
+    }
+  }
+}
+
+__global__ void k_tie_finish(PairTable t, DevState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && st->tie_pos != ~0ull) {
+    uint32_t s = (uint32_t)(st->tie_pos & 0xFFFFFFFFu);
+    uint32_t key = t.keys[s];
+    st->best_slot = s;
+    st->best_a = key >> 16;
+    st->best_b = key & 0xFFFFu;
+    st->best_cnt = t.cnt[s];
+    st->list_len = t.occ_len[s];
+  }
+}
+
+// look a pair up for bpe_apply_merge called on its own (restoreMerge path)
+__global__ void k_lookup_pair(PairTable t, uint32_t a, uint32_t b, DevState* st) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint32_t s = tbl_find(t, pair_key(a, b));
+    st->best_slot = s;
+    st->best_a = a;
+    st->best_b = b;
+    st->best_cnt = (s == NOSLOT) ? 0 : t.cnt[s];
+    st->list_len = (s == NOSLOT) ? 0 : t.occ_len[s];
+    st->n_sites = 0;
+    st->n_new = 0;
+    st->n_cand = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hot list: pairs with count >= hot_thresh (and passing the length filter).  Counts of existing pairs
+// never grow under merging, so between rebuilds only pairs created by a merge can enter.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_count_bins(PairTable t, const uint32_t* __restrict__ len16, uint32_t max_length, DevState* st) {
+  __shared__ uint32_t s_bins[36];
+  if (threadIdx.x < 36) s_bins[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t cap = t.mask + 1;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+    unsigned long long pr = slot_primary(t, len16, i, max_length);
+    if (pr) atomicAdd(&s_bins[32 - __clz((uint32_t)(pr >> 20))], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 36 && s_bins[threadIdx.x]) atomicAdd(&st->bins[threadIdx.x], s_bins[threadIdx.x]);
+}
+
+__global__ void k_build_hot(PairTable t, const uint32_t* __restrict__ len16, uint32_t max_length,
+                            uint32_t* __restrict__ hot, uint32_t hot_cap, DevState* st) {
+  uint32_t cap = t.mask + 1;
+  uint32_t thresh = st->hot_thresh;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+    unsigned long long pr = slot_primary(t, len16, i, max_length);
+    if (pr && (uint32_t)(pr >> 20) >= thresh) {
+      uint32_t k = atomicAdd(&st->hot_n, 1u);
+      if (k < hot_cap) hot[k] = i;
+      else atomicOr(&st->err, ERR_HOT_OVERFLOW);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 phase 1: find the merge sites of (a,b) -> c, emit count deltas and size the new pairs' lists.
+// Reads the corpus only (all writes happen in k_apply), so every thread sees the pre-merge state.
+// scan_mode = 1 walks every slot instead of the pair's occurrence list (cross-check / fallback).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void delta_dec(const PairTable& t, DevState* st, uint32_t key, uint32_t d) {
+  uint32_t s = tbl_find(t, key);
+  if (s == NOSLOT) {
+    atomicOr(&st->err, ERR_MISSING_KEY);
+    return;
+  }
+  atomicSub(t.cnt + s, d);
+}
+
+__device__ __forceinline__ uint32_t new_adjacency(const PairTable& t, DevState* st, uint32_t key, bool counted,
+                                                  uint32_t* __restrict__ newslots, uint32_t new_cap) {
+  uint32_t s = tbl_find_or_insert(t, key, &st->n_keys);
+  if (s == NOSLOT) {
+    atomicOr(&st->err, ERR_TABLE_FULL);
+    return NOSLOT;
+  }
+  if (counted) atomicAdd(t.cnt + s, 1u);
+  if (atomicAdd(t.occ_len + s, 1u) == 0) {  // first adjacency of a pair born in this iteration
+    uint32_t k = atomicAdd(&st->n_new, 1u);
+    if (k < new_cap) newslots[k] = s;
+    else atomicOr(&st->err, ERR_SITE_OVERFLOW);
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(256) k_sites(const uint32_t* __restrict__ slots, uint32_t n, PairTable t,
+                                                const uint32_t* __restrict__ pool, DevState* st, uint32_t a, uint32_t b,
+                                                uint32_t c, int scan_mode, SiteRec* __restrict__ sites,
+                                                uint32_t sites_cap, uint32_t* __restrict__ newslots, uint32_t new_cap,
+                                                uint32_t* __restrict__ len16) {
+  uint32_t list_start = 0, total = n;
+  if (!scan_mode) {
+    uint32_t s = tbl_find(t, pair_key(a, b));
+    total = (s == NOSLOT) ? 0 : t.occ_len[s];
+    list_start = (s == NOSLOT) ? 0 : t.occ_start[s];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) len16[c] = len16[a] + len16[b];  // chars = a.chars + b.chars (:318)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t p = scan_mode ? i : pool[list_start + i];
+    uint32_t w = __ldg(slots + p);
+    if (!slot_is_id(w) || slot_val(w) != a) continue;
+    uint32_t q;
+    if (right_token(slots, n, p, &q) != (int)b) continue;
+    uint32_t koff = 0;
+    if (a == b) {
+      koff = run_left(slots, p, w, (int)a);
+      if (koff & 1u) continue;  // overlaps the occurrence to its left (replaceAll is non-overlapping)
+    }
+    SiteRec rec{p, NOPOS, NOSLOT, NOSLOT};
+
+    // ---- adjacency on the left of the new token ----
+    uint32_t lpos;
+    int x = left_token(slots, p, w, &lpos);
+    if (x != NOTOK) {
+      bool chained = false;
+      uint32_t chain_j = 0, llpos = NOPOS;
+      if (a == b) {
+        chained = koff >= 2;
+        chain_j = koff >> 1;
+        if (chained) left_token(slots, lpos, __ldg(slots + lpos), &llpos);
+      } else if ((uint32_t)x == b) {
+        int xx = left_token(slots, lpos, __ldg(slots + lpos), &llpos);
+        if (xx == (int)a) {  // the pair to the left is itself a site: ... a b a b
+          chained = true;
+          chain_j = 1;
+          uint32_t cur = llpos;
+          for (;;) {  // index of this site within its chain of back-to-back sites
+            uint32_t l1, l2;
+            if (left_token(slots, cur, __ldg(slots + cur), &l1) != (int)b) break;
+            if (left_token(slots, l1, __ldg(slots + l1), &l2) != (int)a) break;
+            chain_j++;
+            cur = l2;
+          }
+        }
+      }
+      if (chained) {
+        if (a != b) delta_dec(t, st, pair_key(b, a), 1);
+        // new adjacency (c,c); runs of c count every other pair (:285-290)
+        rec.lslot = new_adjacency(t, st, pair_key(c, c), (chain_j & 1u) != 0, newslots, new_cap);
+        rec.lpos = llpos;
+      } else {
+        if ((uint32_t)x == a) {  // (a != b here) the run of a's ending at p loses its last element
+          uint32_t L = 1 + run_left(slots, p, w, (int)a);
+          if ((L & 1u) == 0) delta_dec(t, st, pair_key(a, a), 1);
+        } else {
+          delta_dec(t, st, pair_key((uint32_t)x, a), 1);
+        }
+        rec.lslot = new_adjacency(t, st, pair_key((uint32_t)x, c), true, newslots, new_cap);
+        rec.lpos = lpos;
+      }
+    }
+
+    // ---- adjacency on the right of the new token (left to the next site when that one is chained) ----
+    uint32_t r;
+    int y = right_token(slots, n, q, &r);
+    if (y != NOTOK) {
+      bool chained_right = false;
+      if ((uint32_t)y == a) {
+        uint32_t r2;
+        chained_right = right_token(slots, n, r, &r2) == (int)b;
+      }
+      if (!chained_right) {
+        if ((uint32_t)y == b && a != b) {  // the run of b's starting at q loses its first element
+          uint32_t L = 1 + run_right(slots, n, q, (int)b);
+          if ((L & 1u) == 0) delta_dec(t, st, pair_key(b, b), 1);
+        } else if (!(a == b && (uint32_t)y == a)) {  // (a,a) itself is zeroed by k_apply
+          delta_dec(t, st, pair_key(b, (uint32_t)y), 1);
+        }
+        rec.rslot = new_adjacency(t, st, pair_key(c, (uint32_t)y), true, newslots, new_cap);
+      }
+    }
+    uint32_t k = atomicAdd(&st->n_sites, 1u);
+    if (k < sites_cap) reinterpret_cast<uint4*>(sites)[k] = make_uint4(rec.p, rec.lpos, rec.lslot, rec.rslot);
+    else atomicOr(&st->err, ERR_SITE_OVERFLOW);
+  }
+}
+
+// K3 phase 2: allocate the lists of the pairs born in this iteration; feed the hot list.
+__global__ void k_alloc_new(PairTable t, const uint32_t* __restrict__ newslots, const uint32_t* __restrict__ len16,
+                            uint32_t max_length, int hot_valid, uint32_t* __restrict__ hot, uint32_t hot_cap,
+                            uint32_t pool_cap, DevState* st) {
+  uint32_t n_new = st->n_new;
+  uint32_t thresh = st->hot_thresh;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
+    uint32_t s = newslots[i];
+    uint32_t len = t.occ_len[s];
+    uint32_t start = atomicAdd(&st->pool_cursor, len);
+    if (start > pool_cap || len > pool_cap - start) {
+      atomicOr(&st->err, ERR_POOL_FULL);
+      start = 0;
+      t.occ_len[s] = 0;
+    }
+    t.occ_start[s] = start;
+    t.occ_fill[s] = 0;
+    if (hot_valid) {
+      unsigned long long pr = slot_primary(t, len16, s, max_length);
+      if (pr && (uint32_t)(pr >> 20) >= thresh) {
+        uint32_t k = atomicAdd(&st->hot_n, 1u);
+        if (k < hot_cap) hot[k] = s;
+        else atomicOr(&st->err, ERR_HOT_OVERFLOW);
+      }
+    }
+  }
+}
+
+// K3 phase 3: rewrite the corpus in place and fill the new pairs' occurrence lists.
+__global__ void __launch_bounds__(256) k_apply(uint32_t* __restrict__ slots, uint32_t n, PairTable t,
+                                                uint32_t* __restrict__ pool, DevState* st, uint32_t a, uint32_t b,
+                                                uint32_t c, const SiteRec* __restrict__ sites) {
+  uint32_t n_sites = st->n_sites;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    uint32_t s = tbl_find(t, pair_key(a, b));
+    if (s != NOSLOT) t.cnt[s] = 0;  // every counted occurrence was replaced
+    st->live_tokens -= n_sites;
+  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_sites; i += gridDim.x * blockDim.x) {
+    uint4 rv = __ldg(reinterpret_cast<const uint4*>(sites) + i);
+    uint32_t p = rv.x, lpos = rv.y, lslot = rv.z, rslot = rv.w;
+    if (lslot != NOSLOT && t.occ_len[lslot]) pool[t.occ_start[lslot] + atomicAdd(t.occ_fill + lslot, 1u)] = lpos;
+    if (rslot != NOSLOT && t.occ_len[rslot]) pool[t.occ_start[rslot] + atomicAdd(t.occ_fill + rslot, 1u)] = p;
+    // own slots only: [p, e] where e is the last slot of b
+    uint32_t q = next_pos(slots, n, p);
+    uint32_t e = next_pos(slots, n, q) - 1;
+    uint32_t span = e - p + 1;
+    uint32_t w = slots[p];
+    if (span > VAL_MASK) atomicOr(&st->err, ERR_SPAN_OVERFLOW);
+    slots[p] = (w & DOCSTART) | c;
+    if (span == 2) {
+      slots[p + 1] = mk_back(1);
+    } else {
+      if (q != p + 1 && q != e) slots[q] = mk_hole();
+      slots[p + 1] = mk_span(span);
+      slots[e] = mk_back(span - 1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// corpus read-back: compact ID slots of a slot range (two passes: count per block, then scatter)
+// ------------------------------------------------------------------------------------------------
+constexpr int CP_THREADS = 256;
+constexpr int CP_ITEMS = 8;  // slots per thread
+constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
+
+__global__ void __launch_bounds__(CP_THREADS) k_count_ids(const uint32_t* __restrict__ slots, uint64_t begin,
+                                                           uint64_t end, uint32_t* __restrict__ block_counts) {
+  __shared__ uint32_t s_w[CP_THREADS / 32];
+  uint64_t base = begin + (uint64_t)blockIdx.x * CP_TILE;
+  uint32_t c = 0;
+#pragma unroll
+  for (int j = 0; j < CP_ITEMS; j++) {
+    uint64_t p = base + (uint64_t)j * CP_THREADS + threadIdx.x;
+    if (p < end && slot_is_id(__ldg(slots + p))) c++;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+    for (int i = 0; i < CP_THREADS / 32; i++) s += s_w[i];
+    block_counts[blockIdx.x] = s;
+  }
+}
+
+// single-block exclusive scan of up to a few million block counts (u32 -> u64 offsets)
+__global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                       uint32_t n) {
+  __shared__ uint64_t s_part[1024];
+  uint32_t per = (n + 1023) / 1024;
+  uint32_t lo = threadIdx.x * per, hi = min(n, lo + per);
+  uint64_t s = 0;
+  for (uint32_t i = lo; i < hi; i++) s += in[i];
+  s_part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t acc = 0;
+    for (int i = 0; i < 1024; i++) {
+      uint64_t v = s_part[i];
+      s_part[i] = acc;
+      acc += v;
+    }
+    out[n] = acc;
+  }
+  __syncthreads();
+  uint64_t acc = s_part[threadIdx.x];
+  for (uint32_t i = lo; i < hi; i++) {
+    out[i] = acc;
+    acc += in[i];
+  }
+}
+
+__global__ void __launch_bounds__(CP_THREADS) k_compact_ids(const uint32_t* __restrict__ slots, uint64_t begin,
+                                                             uint64_t end, const uint64_t* __restrict__ block_off,
+                                                             int32_t* __restrict__ out) {
+  __shared__ uint32_t s_w[CP_THREADS / 32];
+  uint64_t base = begin + (uint64_t)blockIdx.x * CP_TILE;
+  uint64_t off = block_off[blockIdx.x];
+  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // order-preserving: item j of the tile is slot base + j*CP_THREADS + tid, processed j-major
+  for (int j = 0; j < CP_ITEMS; j++) {
+    uint64_t p = base + (uint64_t)j * CP_THREADS + threadIdx.x;
+    uint32_t w = (p < end) ? __ldg(slots + p) : mk_hole();
+    bool is = slot_is_id(w);
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, is);
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (int i = 0; i < CP_THREADS / 32; i++) {
+      uint32_t v = s_w[i];
+      if (i < (int)warp) before += v;
+      total += v;
+    }
+    if (is) out[off + before + __popc(m & ((1u << lane) - 1))] = (int32_t)slot_val(w);
+    off += total;
+    __syncthreads();
+  }
+}
+
+// number of ID slots in [begin, pos) for each document boundary `pos`
+__global__ void k_doc_ranks(const uint32_t* __restrict__ slots, uint64_t begin, const uint64_t* __restrict__ block_off,
+                            const int64_t* __restrict__ doc_pos, int64_t n_bounds, int64_t* __restrict__ out_offsets) {
+  // one warp per boundary
+  int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t lane = threadIdx.x & 31;
+  int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t d = wid; d < n_bounds; d += nw) {
+    uint64_t pos = (uint64_t)doc_pos[d];
+    uint64_t blk = (pos - begin) / CP_TILE;
+    uint64_t tile0 = begin + blk * CP_TILE;
+    uint32_t c = 0;
+    for (uint64_t p = tile0 + lane; p < pos; p += 32)
+      if (slot_is_id(__ldg(slots + p))) c++;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if (lane == 0) out_offsets[d] = (int64_t)(block_off[blk] + c);
+  }
+}
+
+// pair-count dump (debug / parity)
+__global__ void k_dump_pairs(PairTable t, int32_t* __restrict__ a, int32_t* __restrict__ b, int64_t* __restrict__ cnt,
+                             uint32_t cap, uint32_t* __restrict__ n_out) {
+  uint32_t tcap = t.mask + 1;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < tcap; i += gridDim.x * blockDim.x) {
+    uint32_t key = t.keys[i];
+    if (key == EMPTY_KEY) continue;
+    uint32_t c = t.cnt[i];
+    if (c == 0) continue;
+    uint32_t k = atomicAdd(n_out, 1u);
+    if (k < cap) {
+      a[k] = (int32_t)(key >> 16);
+      b[k] = (int32_t)(key & 0xFFFFu);
+      cnt[k] = (int64_t)c;
+    }
+  }
+}
+
+}  // namespace bpe

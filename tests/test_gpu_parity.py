@@ -1,0 +1,297 @@
+"""GPU: the CUDA path (through the C ABI) against the CPU oracle -- the reference's known answers,
+the committed golden fixtures, seeded fuzzing step by step, and MB-scale Zipf corpora."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import kat_suite
+from oracle import LiteralTokenizer, compact_merge
+from oracle.int_oracle import IntOracleTokenizer
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "literal_cases.json")
+
+
+def make():
+    from bpe_tokenizer_b200 import BPETokenizer
+
+    return BPETokenizer()
+
+
+def rows(t):
+    return [(x.chars, x.weight, x.original_weight, x.code, x.index) for x in t.token_table]
+
+
+@pytest.mark.parametrize("kat", kat_suite.ALL, ids=lambda f: f.__name__)
+def test_reference_known_answers(kat):
+    kat(make)
+
+
+def test_reference_merge_log_resume():
+    from bpe_tokenizer_b200 import compactMerge
+
+    kat_suite.kat_merge_log_resume(make, compactMerge)
+
+
+def test_committed_golden_fixtures():
+    with open(GOLDEN, encoding="utf-8") as f:
+        cases = json.load(f)
+    for case in cases:
+        t = make()
+        for d in case["docs"]:
+            t.addToCorpus(d)
+        t.mergeUntil(case["options"])
+        assert [[a.index, b.index, c.weight] for a, b, c in t.merge_tokens] == case["merges"], case["name"]
+        assert t.toJSON() == case["json"], case["name"]
+        for text, want in case["encode"]:
+            try:
+                got = list(t.encodeToVector(text))
+            except ValueError as e:
+                got = "throws: " + str(e)
+            assert got == want, (case["name"], text)
+
+
+def _random_docs(rng, alphabet, n_docs, max_len):
+    return ["".join(rng.choice(alphabet) for _ in range(rng.randint(0, max_len))) for _ in range(n_docs)]
+
+
+@pytest.mark.parametrize("scan_mode", [0, 1])
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_step_by_step_against_literal(seed, scan_mode):
+    """findNextMerge / applyMerge one at a time: same winner (tie-breaks included), same corpus,
+    same pair histogram after every merge.  scan_mode=1 discovers sites by a full scan instead of the
+    occurrence lists; both must agree with the literal restatement."""
+    rng = random.Random(1000 + seed)
+    alphabet = "abc"[: 1 + seed % 3] if seed % 2 else "abcdefgh"[: 2 + seed % 7]
+    docs = _random_docs(rng, alphabet, rng.randint(1, 5), rng.choice([8, 30, 120]))
+    max_length = rng.choice([None, None, 3, 4, 8])
+    min_weight = rng.choice([None, 2, 3])
+    lit, gpu = LiteralTokenizer(), make()
+    gpu._lib.bpe_set_profiling(gpu._h, 2 if scan_mode else 0)
+    for d in docs:
+        lit.addToCorpus(d)
+        gpu.addToCorpus(d)
+    assert gpu.corpus_in_code == lit.corpus_in_code
+    opts = {"min_weight": min_weight, "max_length": max_length}
+    for step in range(300):
+        m1 = lit.findNextMerge(opts)
+        m2 = gpu.findNextMerge(opts)
+        if m1 is None:
+            assert m2 is None
+            break
+        assert (m2[0].index, m2[1].index, m2[2].weight, m2[2].chars) == (m1[0].index, m1[1].index, m1[2].weight, m1[2].chars), step
+        lit.applyMerge(m1)
+        gpu.applyMerge(m2)
+        assert gpu.corpus_in_code == lit.corpus_in_code, step
+    assert gpu.toJSON() == lit.toJSON()
+    for d in docs + _random_docs(rng, alphabet, 3, 60):
+        assert gpu.encodeToCode(d) == lit.encodeToCode(d)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_merge_until_against_literal(seed):
+    rng = random.Random(2000 + seed)
+    alphabet = "ab" if seed % 3 == 0 else "abcde "
+    docs = _random_docs(rng, alphabet, rng.randint(1, 8), rng.choice([20, 100, 400]))
+    opts = {"min_weight": rng.choice([None, 2, 4]), "max_length": rng.choice([None, 5, 9]), "max_iterations": rng.choice([None, None, 7])}
+    lit, gpu = LiteralTokenizer(), make()
+    for d in docs:
+        lit.addToCorpus(d)
+        gpu.addToCorpus(d)
+    lit.mergeUntil(opts)
+    gpu.mergeUntil(opts)
+    assert [[a.index, b.index, c.weight] for a, b, c in gpu.merge_tokens] == [[a.index, b.index, c.weight] for a, b, c in lit.merge_tokens]
+    assert gpu.toJSON() == lit.toJSON()
+    assert gpu.corpus_in_code == lit.corpus_in_code
+    for d in docs:
+        try:
+            want = lit.encodeToVector(d)
+        except ValueError as e:
+            with pytest.raises(ValueError, match=str(e)):
+                gpu.encodeToVector(d)
+            continue
+        assert gpu.encodeToVector(d) == want
+        assert gpu.decodeVector(want) == d
+
+
+def test_long_runs_and_chains():
+    for text in ["x" * 1000, "ab" * 700, "aab" * 300 + "a" * 77, "x" * 33 + "y" + "x" * 64]:
+        lit, gpu = LiteralTokenizer(), make()
+        lit.addToCorpus(text)
+        gpu.addToCorpus(text)
+        lit.mergeUntil({})
+        gpu.mergeUntil({})
+        assert gpu.toJSON() == lit.toJSON(), text[:10]
+        assert gpu.corpus_in_code == lit.corpus_in_code
+        assert gpu.encodeToVector(text) == lit.encodeToVector(text)
+
+
+def test_pair_histogram_matches_oracle_counts():
+    import ctypes as C
+    from bpe_tokenizer_b200 import _abi
+    from bpe_tokenizer_b200.synth import synth_corpus
+
+    text, off = synth_corpus(300000)
+    docs = [bytes(text[off[d]:off[d + 1]]).decode() for d in range(len(off) - 1)]
+    lit, gpu = LiteralTokenizer(), make()
+    for d in docs:
+        lit.addToCorpus(d)
+        gpu.addToCorpus(d)
+    gpu._flush()
+    cap = 1 << 16
+    a = np.zeros(cap, dtype=np.int32)
+    b = np.zeros(cap, dtype=np.int32)
+    c = np.zeros(cap, dtype=np.int64)
+    n = C.c_int64()
+    gpu._check(gpu._lib.bpe_pair_counts(gpu._h, _abi.p32(a), _abi.p32(b), _abi.p64(c), cap, C.byref(n)))
+    got = {(int(a[i]), int(b[i])): int(c[i]) for i in range(n.value)}
+    want = {}
+    for doc in lit.corpus_in_code:
+        toks = [ord(ch) - 1 for ch in doc]
+        run = 0
+        for i in range(1, len(toks)):
+            x, y = toks[i - 1], toks[i]
+            if x == y:
+                run = run + 1 if (i >= 2 and toks[i - 2] == x) else 1
+                if run % 2 == 0:
+                    continue
+            else:
+                run = 0
+            want[(x, y)] = want.get((x, y), 0) + 1
+    assert got == want
+
+
+def _zipf_pair(n_bytes, seed=43):
+    from bpe_tokenizer_b200.synth import synth_corpus, first_appearance_ids
+
+    text, off = synth_corpus(n_bytes, seed=seed)
+    ids, alphabet = first_appearance_ids(text)
+    return text, off, ids, alphabet
+
+
+def _seed_tables(tok_gpu, tok_orc, alphabet):
+    # register the single-character tokens in first-appearance order (what addToCorpus would do)
+    for t in (tok_gpu, tok_orc):
+        t.addToCorpus("".join(chr(c) for c in alphabet))
+        if hasattr(t, "_pending"):
+            t._pending = []
+        else:
+            t._o.clear_corpus()
+        for tk in t.token_table:
+            tk.weight = 0
+            tk.original_weight = 0
+
+
+def test_zipf_1mb_500_merges_bit_exact():
+    text, off, ids, alphabet = _zipf_pair(1_000_000)
+    gpu, orc = make(), IntOracleTokenizer()
+    _seed_tables(gpu, orc, alphabet)
+    gpu.addDocuments(ids, off)
+    orc.add_ids(ids, off)
+    assert rows(gpu) == rows(orc)
+    n1 = gpu.mergeUntil({"max_iterations": 500})
+    n2 = orc.mergeUntil({"max_iterations": 500})
+    assert n1 == n2 == 500
+    assert [[a.index, b.index, c.weight] for a, b, c in gpu.merge_tokens] == [[a.index, b.index, c.weight] for a, b, c in orc.merge_tokens]
+    assert gpu.toJSON() == orc.toJSON()
+    got_ids, got_off = gpu.corpusIds()
+    want = np.concatenate([orc._o.document(d) for d in range(orc._o.num_documents())])
+    assert np.array_equal(got_ids, want)
+    # token.weight == live occurrences of the token in the corpus (core.ts:201,345-346 bookkeeping)
+    assert np.array_equal(np.bincount(got_ids, minlength=len(gpu.token_table)), np.array([t.weight for t in gpu.token_table]))
+    # encode unseen text (seed 44): vectors or the same throw
+    text2, off2, _, _ = _zipf_pair(60_000, seed=44)
+    lut = np.full(256, -1, dtype=np.int32)
+    lut[alphabet] = np.arange(len(alphabet))
+    ids2 = lut[text2]
+    vals, ooff, bad = gpu.encodeBatch(ids2, off2, vector=True)
+    raw, roff, _ = gpu.encodeBatch(ids2, off2, vector=False)
+    orc.compactVectorIndex()
+    for d in range(len(off2) - 1):
+        want_raw = orc.encode_ids(ids2[off2[d]:off2[d + 1]])
+        assert np.array_equal(raw[roff[d]:roff[d + 1]], want_raw), d
+        holes = [i for i, x in enumerate(want_raw.tolist()) if x not in orc.to_vector_index]
+        assert bad[d] == (holes[0] if holes else -1)
+        if not holes:
+            assert vals[ooff[d]:ooff[d + 1]].tolist() == [orc.to_vector_index[x] for x in want_raw.tolist()]
+
+
+def test_resume_routes_equal_uninterrupted_run():
+    """cfg5 shape at test size: max_length=8, split run resumed (a) via toJSON -> fromJSON -> restoreToCorpus and
+    (b) via addToCorpus + restoreMerge(compactMerge(...)); both must equal the uninterrupted run."""
+    from bpe_tokenizer_b200 import compactMerge
+    from bpe_tokenizer_b200.synth import synth_corpus
+
+    text, off = synth_corpus(200_000)
+    docs = [bytes(text[off[d]:off[d + 1]]).decode() for d in range(len(off) - 1)]
+    opts = {"max_length": 8, "max_iterations": 60}
+    full = make()
+    for d in docs:
+        full.addToCorpus(d)
+    full.mergeUntil({"max_length": 8, "max_iterations": 120})
+    first = make()
+    for d in docs:
+        first.addToCorpus(d)
+    first.mergeUntil(opts)
+    snap = json.loads(json.dumps(first.toJSON()))
+    log = [compactMerge(m) for m in first.merge_tokens]
+    # route (a)
+    a = make()
+    a.fromJSON(snap)
+    for d in docs:
+        a.restoreToCorpus(d)
+    assert a.corpus_in_code == first.corpus_in_code
+    a.mergeUntil(opts)
+    assert a.toJSON() == full.toJSON()
+    assert a.corpus_in_code == full.corpus_in_code
+    # route (b)
+    b = make()
+    for d in docs:
+        b.addToCorpus(d)
+    for m in log:
+        b.restoreMerge(m)
+    assert b.toJSON() == first.toJSON()
+    b.mergeUntil(opts)
+    assert b.toJSON() == full.toJSON()
+    # merge log replay with the corpus emptied (example/import-merge-log-to-ram.ts:22-31)
+    c = make()
+    for d in docs[:50]:
+        c.addToCorpus(d)
+    c.corpus_in_code = []
+    for m in log:
+        c.restoreMerge(m)
+    assert [t.chars for t in c.token_table] == [t.chars for t in first.token_table]
+
+
+def test_encode_edge_cases():
+    t, lit = make(), LiteralTokenizer()
+    docs = ["", "a", "ab" * 10, "hello world " * 200, "", "zzz"]
+    for d in docs:
+        t.addToCorpus(d)
+        lit.addToCorpus(d)
+    t.mergeUntil({})
+    lit.mergeUntil({})
+    assert t.toJSON() == lit.toJSON()
+    assert t.corpus_in_code == lit.corpus_in_code  # empty documents are kept (core.ts:206)
+    long_text = "hello world " * 500  # > 1024 tokens: the global-scratch encode path
+    assert t.encodeToCode(long_text) == lit.encodeToCode(long_text)
+    assert t.encodeToCode("") == ""
+    assert t.encodeToVector("") == []
+    with pytest.raises(ValueError, match="unknown token, char"):
+        t.encodeToVector("hello?")
+    assert t.decodeVector(t.encodeToVector("world hello")) == "world hello"
+
+
+def test_add_to_corpus_after_merges_appends_raw_ids():
+    t, lit = make(), LiteralTokenizer()
+    for x in (t, lit):
+        x.addToCorpus("abababab")
+        x.mergeUntil({})
+        x.addToCorpus("ababcab")  # core.ts:204 appends raw single-character codes; 'c' is a new token after the merges
+        x.mergeUntil({})
+    assert t.toJSON() == lit.toJSON()
+    assert t.corpus_in_code == lit.corpus_in_code
