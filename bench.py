@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline path on B200: `mergeUntil` merges/s and `encodeToVector` GB/s on
+seeded Zipf text (BASELINE.json), through the C ABI of include/bpe_b200.h.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+  python bench.py --impl reference --steps K --warmup W    # CPU restatement of core.ts (Node is not in the image)
+
+One step = one full pass of the hot path over the workload: ingest the corpus (addToCorpus -> K1 pair
+histogram + occurrence lists) and run mergeUntil to the configured number of merges.  `value` is measured
+with the corpus ids already resident in HBM; `e2e` runs the same step from pinned HOST buffers through
+bpe_add_documents / bpe_merge_until (H2D copy and log read-back inside the timed region).  The encode leg
+(bpe_encode_batch*) is timed the same way and reported under "encode".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (train bytes, merges, encode bytes)
+    "cfg2": (10_000_000, 4000, 10_000_000),
+    "cfg3": (1_000_000_000, 32000, 1_000_000_000),
+    "tiny": (200_000, 200, 200_000),
+}
+WORD_SEED, TRAIN_SEED, ENCODE_SEED, VOCAB = 42, 43, 44, 50000
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def synth(lib, target, seed):
+    from bpe_tokenizer_b200 import _abi
+
+    nb, nd = C.c_int64(), C.c_int64()
+    assert lib.bpe_synth_corpus(target, seed, VOCAB, WORD_SEED, None, 0, None, 0, C.byref(nb), C.byref(nd)) == 0
+    text = np.empty(nb.value, dtype=np.uint8)
+    off = np.empty(nd.value + 1, dtype=np.int64)
+    assert lib.bpe_synth_corpus(target, seed, VOCAB, WORD_SEED, text.ctypes.data_as(_abi.u8p), text.size, _abi.p64(off), off.size, C.byref(nb), C.byref(nd)) == 0
+    return text, off
+
+
+def alphabet_lut(text):
+    """first-appearance order, as addToCorpus assigns indices (core.ts:186-199)"""
+    first = np.full(256, np.iinfo(np.int64).max, dtype=np.int64)
+    step = 1 << 24
+    seen = np.zeros(256, dtype=bool)
+    for s in range(0, text.size, step):
+        chunk = text[s:s + step]
+        vals, idx = np.unique(chunk, return_index=True)
+        for v, i in zip(vals.tolist(), idx.tolist()):
+            if not seen[v]:
+                seen[v] = True
+                first[v] = s + i
+        if seen.sum() >= 29 and s > 0:
+            break
+    order = np.argsort(first, kind="stable")[: int(seen.sum())]
+    lut = np.full(256, -1, dtype=np.int32)
+    lut[order] = np.arange(order.size, dtype=np.int32)
+    return lut, [int(x) for x in order]
+
+
+class ClockSampler:
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.samples = []
+        self.reasons = set()
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append((float(out[0]), float(out[1])))
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples), "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def scan_equivalent_bytes(n0, weights):
+    """the reference algorithm reads N_t ids to count, reads N_t and writes N_{t+1} to replace."""
+    n, total = int(n0), 0
+    for w in weights:
+        total += 4 * (2 * n + (n - int(w)))
+        n -= int(w)
+    return total
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from bpe_tokenizer_b200 import _abi
+    from bpe_tokenizer_b200._abi import MERGE_DTYPE, bpe_stats, p32, p64
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _abi.load_library()
+    train_bytes, merges, encode_bytes = WORKLOADS[args.workload]
+    if args.merges:
+        merges = args.merges
+    peak, peak_src = measured_peak()
+
+    # ---- synthetic inputs: every rank owns its own shard of documents (weak scaling) ----------------
+    # rank r trains/encodes the text with seed (seed + 1000*r): independent document sets per GPU.
+    t0 = time.time()
+    text, off = synth(lib, train_bytes, TRAIN_SEED + 1000 * rank)
+    lut, alphabet = alphabet_lut(text)
+    ids_host = torch.from_numpy(lut[text]).pin_memory()
+    off_host = np.ascontiguousarray(off)
+    del text
+    text2, off2 = synth(lib, encode_bytes, ENCODE_SEED + 1000 * rank)
+    ids2_host = torch.from_numpy(lut[text2]).pin_memory()
+    del text2
+    n0, n_docs = ids_host.numel(), len(off_host) - 1
+    c2, n_docs2 = ids2_host.numel(), len(off2) - 1
+    gen_s = time.time() - t0
+    ids_dev = ids_host.cuda(non_blocking=True)
+    ids2_dev = ids2_host.cuda(non_blocking=True)
+    off2_dev = torch.from_numpy(off2).cuda()
+    max_doc2 = int(np.max(np.diff(off2))) if n_docs2 else 0
+    torch.cuda.synchronize()
+
+    h = C.c_void_p()
+    assert lib.bpe_create(local, C.byref(h)) == 0, "bpe_create failed"
+    stream = torch.cuda.current_stream()
+    assert lib.bpe_set_stream(h, C.c_void_p(stream.cuda_stream)) == 0
+    len16 = np.ones(len(alphabet), dtype=np.int32)
+    log = np.zeros(merges, dtype=MERGE_DTYPE)
+    n_done = C.c_int64()
+
+    def check(rc):
+        if rc != 0:
+            raise RuntimeError("bpe error %d: %s" % (rc, lib.bpe_last_error(h).decode()))
+
+    def reset():
+        check(lib.bpe_clear_corpus(h))
+        check(lib.bpe_set_tokens(h, p32(len16), len(len16)))
+        check(lib.bpe_load_merges(h, None, 0))
+
+    def train_step(from_host: bool):
+        reset()
+        if from_host:
+            check(lib.bpe_add_documents(h, C.cast(ids_host.data_ptr(), _abi.i32p), p64(off_host), n_docs))
+        else:
+            check(lib.bpe_add_documents_dev(h, C.c_void_p(ids_dev.data_ptr()), p64(off_host), n_docs))
+        check(lib.bpe_merge_until(h, 2, 0, merges, log.ctypes.data_as(C.c_void_p), merges, C.byref(n_done)))
+        return n_done.value
+
+    def stats():
+        s = bpe_stats()
+        check(lib.bpe_get_stats(h, C.byref(s)))
+        return s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    # ---- train: device-resident value ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        done = train_step(False)
+    l0 = stats().kernel_launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_train = timed(lambda: train_step(False), args.steps)
+    l1 = stats().kernel_launches
+    done = n_done.value
+    weights = log["weight"][:done].copy()
+    k1_ms = None
+    s_before = stats()
+    # K1 alone (ingest + histogram + lists), for its own roofline line
+    reset()
+    check(lib.bpe_add_documents_dev(h, C.c_void_p(ids_dev.data_ptr()), p64(off_host), n_docs))
+    m, found = _abi.bpe_merge(), C.c_int()
+    check(lib.bpe_find_next_merge(h, 2, 0, C.byref(m), C.byref(found)))
+    k1_ms = stats().ms_index_build - s_before.ms_index_build
+    # ---- train: end to end from host buffers ----------------------------------------------------------
+    e2e_steps = max(1, min(args.steps, 2))
+    train_step(True)
+    ms_train_e2e = timed(lambda: train_step(True), e2e_steps)
+
+    # ---- encode with the table just learned -------------------------------------------------------------
+    tvi = np.arange(len(alphabet) + done, dtype=np.int32)  # raw-index-equivalent map without holes
+    tvi_dev = torch.from_numpy(tvi).cuda()
+    out_dev = torch.empty(max(c2, 1), dtype=torch.int32, device="cuda")
+    ooff_dev = torch.empty(n_docs2 + 1, dtype=torch.int64, device="cuda")
+    n_out = C.c_int64()
+
+    def encode_step_dev():
+        check(lib.bpe_encode_batch_dev(h, C.c_void_p(ids2_dev.data_ptr()), C.c_void_p(off2_dev.data_ptr()), n_docs2, c2, max_doc2,
+                                       C.c_void_p(tvi_dev.data_ptr()), len(tvi), C.c_void_p(out_dev.data_ptr()),
+                                       C.c_void_p(ooff_dev.data_ptr()), None, C.byref(n_out)))
+
+    out_host = torch.empty(max(c2, 1), dtype=torch.int32).pin_memory()
+    ooff_host = np.zeros(n_docs2 + 1, dtype=np.int64)
+
+    def encode_step_host():
+        check(lib.bpe_encode_batch(h, C.cast(ids2_host.data_ptr(), _abi.i32p), p64(off2), n_docs2, p32(tvi), len(tvi),
+                                   C.cast(out_host.data_ptr(), _abi.i32p), out_host.numel(), p64(ooff_host), None, C.byref(n_out)))
+
+    for _ in range(args.warmup):
+        encode_step_dev()
+    le0 = stats().kernel_launches
+    ms_enc = timed(encode_step_dev, args.steps)
+    le1 = stats().kernel_launches
+    k_out = n_out.value
+    enc_kernel_ms = stats().ms_encode
+    encode_step_host()
+    ms_enc_e2e = timed(encode_step_host, e2e_steps)
+    clocks = sampler.stop()
+
+    # ---- aggregate over ranks -----------------------------------------------------------------------------
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    total_merges = allsum(done * args.steps)
+    step_s = ms_train / 1e3 / args.steps
+    value = total_merges / (ms_train / 1e3)
+    e2e_value = allsum(done * e2e_steps) / (ms_train_e2e / 1e3)
+    scan_bytes = scan_equivalent_bytes(n0, weights)
+    achieved = allsum(scan_bytes) / step_s / 1e9 / world  # per GPU
+    enc_gbs = allsum(c2 * args.steps) / (ms_enc / 1e3) / 1e9
+    enc_e2e_gbs = allsum(c2 * e2e_steps) / (ms_enc_e2e / 1e3) / 1e9
+    enc_alg_bytes = 4 * c2 + 4 * k_out
+    enc_achieved = enc_alg_bytes / (enc_kernel_ms / 1e3) / 1e9
+
+    if rank == 0:
+        cpu = cpu_baseline(args, merges_sample=8)
+        line = {
+            "metric": "mergeUntil merges/sec",
+            "value": value,
+            "unit": "merges/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_train / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "u32",
+            "data": "synthetic",
+            "config": {
+                "workload": "%s: %d B Zipf-word corpus per GPU (seed %d+1000*rank, %d docs), addToCorpus + mergeUntil to %d merges"
+                            % (args.workload, train_bytes, TRAIN_SEED, n_docs, merges),
+                "merges_done": done,
+                "sharding": "documents per GPU, independent shards" if world > 1 else "single GPU",
+                "l2": "corpus (4 B/char) and occurrence pool are larger than the 126 MB L2" if n0 * 4 > 126e6 else "inputs smaller than L2; every step re-ingests and rebuilds the index (cold tables)",
+            },
+            "e2e": {"value": e2e_value, "unit": "merges/s", "h2d_bytes_per_step": int(n0 * 4 + off_host.nbytes), "d2h_bytes_per_step": int(done * MERGE_DTYPE.itemsize),
+                    "ms_per_step": ms_train_e2e / e2e_steps},
+            "gpu_launches": int(l1 - l0),
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "mergeUntil step (host-driven loop of k_argmax/k_sites/k_alloc_new/k_apply)",
+                "note": "achieved = reference-algorithm bytes sum_t 4*(2*N_t+N_{t+1}) / step time ('x of reference-algorithm roofline', SURVEY 8d); "
+                        "an incremental design may exceed 1.0; peak from " + peak_src,
+            },
+            "roofline_k1": {"bound": "hbm", "achieved": 4 * n0 / (k1_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": 4 * n0 / (k1_ms / 1e3) / 1e9 / peak, "ms": k1_ms, "kernel": "k_hist + k_alloc_lists + k_scatter"},
+            "encode": {
+                "metric": "encodeToVector GB/s of input text", "value": enc_gbs, "unit": "GB/s", "ms_per_step": ms_enc / args.steps,
+                "chars": c2, "tokens_out": k_out, "docs": n_docs2, "gpu_launches": int(le1 - le0),
+                "e2e": {"value": enc_e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": int(c2 * 4 + off2.nbytes + tvi.nbytes), "d2h_bytes_per_step": int(k_out * 4 + off2.nbytes)},
+                "roofline": {"bound": "hbm", "achieved": enc_achieved, "peak": peak, "unit": "GB/s", "frac": enc_achieved / peak, "traffic": None,
+                             "kernel": "k_encode + k_scan_counts + k_gather_map", "alg_bytes": enc_alg_bytes},
+            },
+            "cpu_baseline": cpu,
+            "setup": {"synth_s": gen_s},
+        }
+        print(json.dumps(line))
+    lib.bpe_destroy(h)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_sample(args, merges_sample):
+    """The CPU restatement of core.ts (oracle/int_oracle.cpp, 1 thread) on a bounded slice of the same workload."""
+    from bpe_tokenizer_b200 import _abi
+    from oracle.int_oracle import IntOracle
+
+    lib = _abi.load_library()
+    train_bytes, merges, encode_bytes = WORKLOADS[args.workload]
+    sample_bytes = min(train_bytes, 16_000_000)
+    text, off = synth(lib, sample_bytes, TRAIN_SEED)
+    lut, alphabet = alphabet_lut(text)
+    ids = lut[text]
+    o = IntOracle()
+    o.set_len16(np.ones(len(alphabet) + merges_sample + 1, dtype=np.int32))
+    o.add_documents(ids, off)
+    t0 = time.perf_counter()
+    la, lb, lw = o.merge_until(2, 0, merges_sample, len(alphabet), merges_sample)
+    dt = time.perf_counter() - t0
+    rate_sample = len(la) / dt
+    scale = ids.size / train_bytes
+    return rate_sample, scale, ids.size, len(la), dt
+
+
+def cpu_baseline(args, merges_sample=8):
+    try:
+        rate, scale, n, done, dt = cpu_sample(args, merges_sample)
+    except Exception as e:  # the baseline must never take the GPU line down
+        return {"value": None, "unit": "merges/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+    return {
+        "value": rate * scale, "unit": "merges/s", "cores": 1, "kind": "port",
+        "sample": "C++ restatement of core.ts (Node/V8 absent), 1 thread of %d: first %d merges on the first %d chars took %.2f s (%.3f merges/s); "
+                  "per-merge cost is linear in corpus size, value = that x %.4f (sample/workload size)" % (os.cpu_count() or 1, done, n, dt, rate, scale),
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    train_bytes, merges, _ = WORKLOADS[args.workload]
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_sample(args, 2)
+    rates, info = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        info = cpu_sample(args, 8)
+        rates.append(info[0] * info[1])
+    wall = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    cpu = {"value": value, "unit": "merges/s", "cores": 1, "kind": "port",
+           "sample": "oracle/int_oracle.cpp (literal C++ restatement of core.ts; Node is not in the image), 1 thread of %d: first %d merges on the first %d chars, "
+                     "scaled by %.4f to the %d-char workload" % (os.cpu_count() or 1, info[3], info[2], info[1], train_bytes)}
+    print(json.dumps({
+        "impl": "reference", "metric": "mergeUntil merges/sec", "value": value, "unit": "merges/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "%s: %d B Zipf-word corpus, mergeUntil to %d merges (bounded CPU sample, see cpu_baseline.sample)" % (args.workload, train_bytes, merges)},
+        "cpu_baseline": cpu,
+        "e2e": {"value": value, "unit": "merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("BPE_BENCH_WORKLOAD", "cfg3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--merges", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -89,7 +89,14 @@ def test_fuzz_step_by_step_against_literal(seed, scan_mode):
         assert gpu.corpus_in_code == lit.corpus_in_code, step
     assert gpu.toJSON() == lit.toJSON()
     for d in docs + _random_docs(rng, alphabet, 3, 60):
-        assert gpu.encodeToCode(d) == lit.encodeToCode(d)
+        try:
+            want = lit.encodeToCode(d)
+        except ValueError as e:
+            with pytest.raises(ValueError) as ei:
+                gpu.encodeToCode(d)
+            assert str(ei.value) == str(e)
+            continue
+        assert gpu.encodeToCode(d) == want
 
 
 @pytest.mark.parametrize("seed", range(12))
@@ -238,7 +245,8 @@ def test_resume_routes_equal_uninterrupted_run():
         first.addToCorpus(d)
     first.mergeUntil(opts)
     snap = json.loads(json.dumps(first.toJSON()))
-    log = [compactMerge(m) for m in first.merge_tokens]
+    # the reference logs compactMerge(merge) at findNextMerge time, when c.weight is still its original weight
+    log = [[a.code, b.code, c.original_weight] for a, b, c in first.merge_tokens]
     # route (a)
     a = make()
     a.fromJSON(snap)
@@ -283,7 +291,16 @@ def test_encode_edge_cases():
     assert t.encodeToVector("") == []
     with pytest.raises(ValueError, match="unknown token, char"):
         t.encodeToVector("hello?")
-    assert t.decodeVector(t.encodeToVector("world hello")) == "world hello"
+    for text in ["world hello", "hello world ", "zzz", "a"]:
+        try:
+            want = lit.encodeToVector(text)
+        except ValueError as e:
+            with pytest.raises(ValueError) as ei:
+                t.encodeToVector(text)
+            assert str(ei.value) == str(e)
+            continue
+        assert t.encodeToVector(text) == want
+        assert t.decodeVector(want) == text
 
 
 def test_add_to_corpus_after_merges_appends_raw_ids():
