@@ -122,7 +122,10 @@ struct bpe_engine {
   uint32_t hot_max_length = 0;
   uint32_t hot_thresh = 0;
   DevBuf<uint32_t> cands;
-  int scan_mode = 0;  // debug: walk all slots instead of occurrence lists
+  DevBuf<MergeRec> dev_log;
+  int loop_blocks = 0;   // co-resident grid of k_merge_loop
+  int host_loop = 0;     // debug: drive mergeUntil from the host, one launch per phase
+  int scan_mode = 0;     // debug: walk all slots instead of occurrence lists
 
   // scratch
   DevBuf<int32_t> stage_ids;
@@ -391,6 +394,22 @@ int run_argmax(bpe_engine* e, uint32_t max_length, int use_hot) {
   return BPE_OK;
 }
 
+ApplyArgs apply_args(bpe_engine* e) {
+  ApplyArgs A;
+  A.slots = e->slots.p;
+  A.n = (uint32_t)e->n_slots;
+  A.t = e->table();
+  A.pool = e->pool.p;
+  A.st = e->d_st.p;
+  A.sites = e->sites.p;
+  A.sites_cap = (uint32_t)std::min<size_t>(e->sites.cap, 0xFFFFFFFFu);
+  A.newslots = e->newslots.p;
+  A.new_cap = (uint32_t)std::min<size_t>(e->newslots.cap, 0xFFFFFFFFu);
+  A.len16 = e->d_len16.p;
+  A.scan_mode = e->scan_mode;
+  return A;
+}
+
 // ---- K3 driver ------------------------------------------------------------------------------------
 // bound = upper bound on the number of sites (count of the pair, or its list length)
 int run_apply(bpe_engine* e, uint32_t a, uint32_t b, uint32_t c, uint32_t bound) {
@@ -413,16 +432,15 @@ int run_apply(bpe_engine* e, uint32_t a, uint32_t b, uint32_t c, uint32_t bound)
   PairTable t = e->table();
   uint32_t work = e->scan_mode ? (uint32_t)e->n_slots : bound;
   int blocks = (int)std::min<uint64_t>((uint64_t)e->grid(8), std::max<uint64_t>(1, (work + 255) / 256));
-  k_sites<<<blocks, 256, 0, e->stream>>>(e->slots.p, (uint32_t)e->n_slots, t, e->pool.p, e->d_st.p, a, b, c, e->scan_mode,
-                                         e->sites.p, (uint32_t)e->sites.cap, e->newslots.p, (uint32_t)e->newslots.cap,
-                                         e->d_len16.p);
+  ApplyArgs A = apply_args(e);
+  k_sites<<<blocks, 256, 0, e->stream>>>(A, a, b, c);
   CKL();
   int blocks2 = (int)std::min<uint64_t>((uint64_t)e->grid(8), std::max<uint64_t>(1, (2ull * bound + 255) / 256));
   k_alloc_new<<<blocks2, 256, 0, e->stream>>>(t, e->newslots.p, e->d_len16.p, e->hot_max_length, e->hot_valid ? 1 : 0, e->hot.p,
                                               (uint32_t)e->hot.cap, (uint32_t)e->pool.cap, e->d_st.p);
   CKL();
   int blocks3 = (int)std::min<uint64_t>((uint64_t)e->grid(8), std::max<uint64_t>(1, ((uint64_t)bound + 255) / 256));
-  k_apply<<<blocks3, 256, 0, e->stream>>>(e->slots.p, (uint32_t)e->n_slots, t, e->pool.p, e->d_st.p, a, b, c, e->sites.p);
+  k_apply<<<blocks3, 256, 0, e->stream>>>(A, a, b, c);
   CKL();
   e->h_len16.push_back(e->h_len16[a] + e->h_len16[b]);
   e->h_merges.push_back((int32_t)a);
@@ -553,6 +571,236 @@ int append_docs_dev(bpe_engine* e, const int32_t* dev_ids, const int64_t* host_o
   e->hot_valid = false;
   return BPE_OK;
 }
+
+
+// ---- mergeUntil: persistent cooperative kernel, the host only grows buffers / rebuilds the hot list -----------
+int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations, bpe_merge* log,
+                       int64_t log_cap, int64_t* n_done) {
+  *n_done = 0;
+  CK(cudaSetDevice(e->device));
+  if (e->n_slots == 0) return BPE_OK;
+  TRY(ensure_index(e));
+  uint32_t ml = max_length > 0 ? (uint32_t)max_length : 0;
+  int64_t mw = min_weight > 0 ? min_weight : 2;
+  if (!e->loop_blocks) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, ML_THREADS, 0));
+    if (per_sm < 1) return fail(e, BPE_E_CUDA, "k_merge_loop does not fit on an SM");
+    e->loop_blocks = e->sm_count * std::min(per_sm, 2);
+  }
+  CK(e->partials.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
+  CK(e->sites.reserve(1u << 16, 0, e->stream, 1.0));
+  CK(e->newslots.reserve(1u << 16, 0, e->stream, 1.0));
+  CK(e->cands.reserve(4096, 0, e->stream, 1.0));
+  cudaEvent_t t0, t1;
+  CK(cudaEventCreate(&t0));
+  CK(cudaEventCreate(&t1));
+  CK(cudaEventRecord(t0, e->stream));
+  int rc = BPE_OK;
+  int64_t done = 0;
+  std::vector<MergeRec> tmp;
+  for (;;) {
+    int64_t remaining = log_cap - done;
+    if (max_iterations > 0) remaining = std::min(remaining, max_iterations - done);  // core.ts:374-377
+    if (remaining <= 0) break;
+    if (!e->hot_valid || e->hot_max_length != ml) {
+      bool any = false;
+      if ((rc = rebuild_hot(e, ml, &any)) != BPE_OK) break;
+      if (!any) break;  // nothing countable left (core.ts:312)
+    }
+    uint32_t chunk = (uint32_t)std::min<int64_t>(remaining, 1 << 16);
+    if (e->n_tokens + (int64_t)chunk > BPE_MAX_TOKENS) chunk = (uint32_t)std::max<int64_t>(0, BPE_MAX_TOKENS - e->n_tokens);
+    if (chunk == 0) {
+      rc = fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
+      break;
+    }
+    cudaError_t ce;
+    if ((ce = e->dev_log.reserve(chunk)) != cudaSuccess ||
+        (ce = e->d_len16.reserve((size_t)e->n_tokens + chunk + 1, (size_t)e->n_tokens, e->stream, 1.5)) != cudaSuccess) {
+      rc = fail(e, BPE_E_NOMEM, "%s", cudaGetErrorString(ce));
+      break;
+    }
+    LoopArgs L;
+    L.A = apply_args(e);
+    L.pool_cap = (uint32_t)std::min<size_t>(e->pool.cap, 0xFFFFFFF0u);
+    L.len16_cap = (uint32_t)std::min<size_t>(e->d_len16.cap, 0xFFFFFFF0u);
+    L.hot = e->hot.p;
+    L.hot_cap = (uint32_t)std::min<size_t>(e->hot.cap, 0xFFFFFFF0u);
+    L.cands = e->cands.p;
+    L.cand_cap = (uint32_t)std::min<size_t>(e->cands.cap, 0xFFFFFFF0u);
+    L.partials = e->partials.p;
+    L.log = e->dev_log.p;
+    L.log_cap = chunk;
+    L.max_length = ml;
+    L.min_weight = (uint32_t)std::min<int64_t>(mw, 0xFFFFFFFFll);
+    L.max_tokens = BPE_MAX_TOKENS;
+    L.tbl_cap = e->tbl_cap;
+    k_loop_prepare<<<1, 32, 0, e->stream>>>(e->d_st.p, (uint32_t)e->n_tokens);
+    e->stats.kernel_launches++;
+    void* args[] = {&L};
+    ce = cudaLaunchCooperativeKernel((void*)k_merge_loop, dim3(e->loop_blocks), dim3(ML_THREADS), args, 0, e->stream);
+    if (ce != cudaSuccess) {
+      rc = fail(e, BPE_E_CUDA, "cooperative launch of k_merge_loop: %s", cudaGetErrorString(ce));
+      break;
+    }
+    e->stats.kernel_launches++;
+    if ((rc = fetch_state(e)) != BPE_OK) break;
+    uint32_t iters = e->h_st->iters_done;
+    if (iters) {
+      tmp.resize(iters);
+      ce = cudaMemcpyAsync(tmp.data(), e->dev_log.p, (size_t)iters * sizeof(MergeRec), cudaMemcpyDeviceToHost, e->stream);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+      if (ce != cudaSuccess) {
+        rc = fail(e, BPE_E_CUDA, "merge log read-back: %s", cudaGetErrorString(ce));
+        break;
+      }
+      for (uint32_t i = 0; i < iters; i++) {
+        const MergeRec& r = tmp[i];
+        log[done].a = r.a;
+        log[done].b = r.b;
+        log[done].c = r.c;
+        log[done].reserved = 0;
+        log[done].weight = r.weight;
+        done++;
+        e->h_len16.push_back(e->h_len16[r.a] + e->h_len16[r.b]);
+        e->h_merges.push_back(r.a);
+        e->h_merges.push_back(r.b);
+        e->h_merges.push_back(r.c);
+      }
+      e->n_tokens += (int32_t)iters;
+      e->mt_dirty = true;
+      e->stats.merges_applied += iters;
+    }
+    uint32_t status = e->h_st->status;
+    if (status == LOOP_DONE || status == LOOP_EMPTY) break;
+    if (status == LOOP_LIMIT) continue;
+    if (status == LOOP_NEED_REBUILD) {
+      e->hot_valid = false;
+      continue;
+    }
+    if (status == LOOP_ERROR) {
+      rc = check_dev_err(e);
+      if (rc == BPE_OK) rc = fail(e, BPE_E_INTERNAL, "merge loop stopped with an unexplained error (flags 0x%x)", e->h_st->err);
+      break;
+    }
+    if (status == LOOP_NEED_HOST) {
+      if (e->n_tokens >= BPE_MAX_TOKENS) {
+        rc = fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
+        break;
+      }
+      uint64_t w = e->h_st->best_cnt;
+      uint64_t new_keys = std::min<uint64_t>(2 * w + 2, 2 * ((uint64_t)e->n_tokens + 1) + 2);
+      uint64_t keys_after = (uint64_t)e->h_st->n_keys + new_keys;
+      if (keys_after * 2 > e->tbl_cap) {
+        uint64_t want = std::min<uint64_t>(keys_after * 4, 0x80000000ull);
+        if (keys_after * 2 > want) {
+          rc = fail(e, BPE_E_NOMEM, "pair table cannot grow further");
+          break;
+        }
+        if ((rc = grow_table(e, pow2_at_least(want))) != BPE_OK) break;
+      }
+      uint64_t pool_after = (uint64_t)e->h_st->pool_cursor + 2 * w;
+      if (pool_after > 0xFFFFFFF0ull) {
+        rc = fail(e, BPE_E_DOMAIN, "occurrence pool exceeds 2^32 cells");
+        break;
+      }
+      if ((ce = e->pool.reserve((size_t)pool_after, e->h_st->pool_cursor, e->stream, 1.5)) != cudaSuccess ||
+          (ce = e->sites.reserve((size_t)w, 0, e->stream, 1.25)) != cudaSuccess ||
+          (ce = e->newslots.reserve((size_t)new_keys, 0, e->stream, 1.25)) != cudaSuccess ||
+          (ce = e->hot.reserve((size_t)e->h_st->hot_n + new_keys, e->h_st->hot_n, e->stream, 1.5)) != cudaSuccess ||
+          (ce = e->cands.reserve((size_t)e->h_st->best_mult, 0, e->stream, 1.5)) != cudaSuccess) {
+        rc = fail(e, BPE_E_NOMEM, "growing merge buffers: %s", cudaGetErrorString(ce));
+        break;
+      }
+      continue;
+    }
+    rc = fail(e, BPE_E_INTERNAL, "merge loop returned status %u", status);
+    break;
+  }
+  *n_done = done;
+  if (rc == BPE_OK) {
+    CK(cudaEventRecord(t1, e->stream));
+    TRY(fetch_state(e));
+    TRY(check_dev_err(e));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, t0, t1));
+    e->stats.ms_last_merge_until = ms;
+    e->live_tokens = e->h_st->live_tokens;
+    e->stats.sites_merged = (int64_t)e->h_st->sites_total;
+    e->stats.tie_breaks = e->h_st->tie_breaks;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  return rc;
+}
+
+int merge_until_host(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations, bpe_merge* log,
+                            int64_t log_cap, int64_t* n_done) {
+  if (!e || !n_done || (log_cap > 0 && !log) || log_cap < 0) return BPE_E_INVALID;
+  *n_done = 0;
+  CK(cudaSetDevice(e->device));
+  if (e->n_slots == 0) return BPE_OK;
+  TRY(ensure_index(e));
+  uint32_t ml = max_length > 0 ? (uint32_t)max_length : 0;
+  int64_t mw = min_weight > 0 ? min_weight : 2;
+  if (!e->ev0) {
+    CK(cudaEventCreate(&e->ev0));
+    CK(cudaEventCreate(&e->ev1));
+  }
+  cudaEvent_t t0, t1;
+  CK(cudaEventCreate(&t0));
+  CK(cudaEventCreate(&t1));
+  CK(cudaEventRecord(t0, e->stream));
+  int rc = BPE_OK;
+  int64_t done = 0;
+  // core.ts:374-382: for (iteration = 1; !max_iterations || iteration <= max_iterations; iteration++)
+  while ((max_iterations <= 0 || done < max_iterations) && done < log_cap) {
+    if (!e->hot_valid || e->hot_max_length != ml) {
+      bool any = false;
+      if ((rc = rebuild_hot(e, ml, &any)) != BPE_OK) break;
+      if (!any) break;  // nothing countable left (core.ts:312)
+    }
+    if ((rc = run_argmax(e, ml, 1)) != BPE_OK) break;
+    if (e->h_st->err & ERR_HOT_OVERFLOW) {
+      e->hot_valid = false;
+      CK(cudaMemsetAsync(&e->d_st.p->err, 0, sizeof(uint32_t), e->stream));
+      continue;
+    }
+    if (!e->h_st->best_primary || e->h_st->best_cnt < e->hot_thresh) {
+      if (e->hot_thresh <= 1 && !e->h_st->best_primary) break;
+      e->hot_valid = false;  // the maximum fell below the list's threshold: rebuild lower
+      continue;
+    }
+    uint32_t a = e->h_st->best_a, b = e->h_st->best_b, w = e->h_st->best_cnt;
+    if ((int64_t)w < mw) break;  // core.ts:313
+    int32_t c = e->n_tokens;
+    if (c >= BPE_MAX_TOKENS) {
+      rc = fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
+      break;
+    }
+    if ((rc = run_apply(e, a, b, (uint32_t)c, e->scan_mode ? w : e->h_st->list_len)) != BPE_OK) break;
+    log[done].a = (int32_t)a;
+    log[done].b = (int32_t)b;
+    log[done].c = c;
+    log[done].reserved = 0;
+    log[done].weight = (int64_t)w;
+    e->stats.sites_merged += w;
+    done++;
+  }
+  *n_done = done;
+  if (rc != BPE_OK) return rc;
+  CK(cudaEventRecord(t1, e->stream));
+  TRY(fetch_state(e));
+  TRY(check_dev_err(e));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, t0, t1));
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  e->stats.ms_last_merge_until = ms;
+  e->live_tokens = e->h_st->live_tokens;
+  return BPE_OK;
+}
+
 
 }  // namespace
 
@@ -795,76 +1043,16 @@ int bpe_apply_merge(bpe_engine* e, int32_t a, int32_t b, int32_t c, int64_t* n_r
   TRY(run_apply(e, (uint32_t)a, (uint32_t)b, (uint32_t)c, e->h_st->list_len));
   TRY(fetch_state(e));
   TRY(check_dev_err(e));
-  e->stats.sites_merged += e->h_st->n_sites;
-  if (n_replaced) *n_replaced = e->h_st->n_sites;
+  e->stats.sites_merged += e->h_st->n_sites[0];
+  if (n_replaced) *n_replaced = e->h_st->n_sites[0];
   return BPE_OK;
 }
 
 int bpe_merge_until(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations, bpe_merge* log,
                     int64_t log_cap, int64_t* n_done) {
   if (!e || !n_done || (log_cap > 0 && !log) || log_cap < 0) return BPE_E_INVALID;
-  *n_done = 0;
-  CK(cudaSetDevice(e->device));
-  if (e->n_slots == 0) return BPE_OK;
-  TRY(ensure_index(e));
-  uint32_t ml = max_length > 0 ? (uint32_t)max_length : 0;
-  int64_t mw = min_weight > 0 ? min_weight : 2;
-  if (!e->ev0) {
-    CK(cudaEventCreate(&e->ev0));
-    CK(cudaEventCreate(&e->ev1));
-  }
-  cudaEvent_t t0, t1;
-  CK(cudaEventCreate(&t0));
-  CK(cudaEventCreate(&t1));
-  CK(cudaEventRecord(t0, e->stream));
-  int rc = BPE_OK;
-  int64_t done = 0;
-  // core.ts:374-382: for (iteration = 1; !max_iterations || iteration <= max_iterations; iteration++)
-  while ((max_iterations <= 0 || done < max_iterations) && done < log_cap) {
-    if (!e->hot_valid || e->hot_max_length != ml) {
-      bool any = false;
-      if ((rc = rebuild_hot(e, ml, &any)) != BPE_OK) break;
-      if (!any) break;  // nothing countable left (core.ts:312)
-    }
-    if ((rc = run_argmax(e, ml, 1)) != BPE_OK) break;
-    if (e->h_st->err & ERR_HOT_OVERFLOW) {
-      e->hot_valid = false;
-      CK(cudaMemsetAsync(&e->d_st.p->err, 0, sizeof(uint32_t), e->stream));
-      continue;
-    }
-    if (!e->h_st->best_primary || e->h_st->best_cnt < e->hot_thresh) {
-      if (e->hot_thresh <= 1 && !e->h_st->best_primary) break;
-      e->hot_valid = false;  // the maximum fell below the list's threshold: rebuild lower
-      continue;
-    }
-    uint32_t a = e->h_st->best_a, b = e->h_st->best_b, w = e->h_st->best_cnt;
-    if ((int64_t)w < mw) break;  // core.ts:313
-    int32_t c = e->n_tokens;
-    if (c >= BPE_MAX_TOKENS) {
-      rc = fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
-      break;
-    }
-    if ((rc = run_apply(e, a, b, (uint32_t)c, e->scan_mode ? w : e->h_st->list_len)) != BPE_OK) break;
-    log[done].a = (int32_t)a;
-    log[done].b = (int32_t)b;
-    log[done].c = c;
-    log[done].reserved = 0;
-    log[done].weight = (int64_t)w;
-    e->stats.sites_merged += w;
-    done++;
-  }
-  *n_done = done;
-  if (rc != BPE_OK) return rc;
-  CK(cudaEventRecord(t1, e->stream));
-  TRY(fetch_state(e));
-  TRY(check_dev_err(e));
-  float ms = 0;
-  CK(cudaEventElapsedTime(&ms, t0, t1));
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
-  e->stats.ms_last_merge_until = ms;
-  e->live_tokens = e->h_st->live_tokens;
-  return BPE_OK;
+  if (e->host_loop) return merge_until_host(e, min_weight, max_length, max_iterations, log, log_cap, n_done);
+  return merge_until_device(e, min_weight, max_length, max_iterations, log, log_cap, n_done);
 }
 
 int bpe_pair_counts(bpe_engine* e, int32_t* a, int32_t* b, int64_t* count, int64_t cap, int64_t* n) {

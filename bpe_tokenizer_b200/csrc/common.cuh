@@ -38,16 +38,22 @@ __host__ __device__ __forceinline__ uint32_t mk_back(uint32_t d) { return (KIND_
 __host__ __device__ __forceinline__ uint32_t mk_hole() { return (KIND_HOLE << KIND_SHIFT); }
 __host__ __device__ __forceinline__ uint32_t pair_key(uint32_t a, uint32_t b) { return (a << 16) | b; }
 
-struct Corpus {
-  const uint32_t* slots;
-  uint32_t n;  // number of slots
-};
+// Loads of data that other SMs rewrite during the SAME launch (the persistent mergeUntil kernel): go to L2
+// (ld.global.cg), never through the non-coherent path.
+__device__ __forceinline__ uint32_t ld_slot(const uint32_t* p) { return __ldcg(p); }
+__device__ __forceinline__ uint4 ld_slots4(const uint32_t* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ uint32_t ld_cg(const uint32_t* p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned long long ld_cg(const unsigned long long* p) { return __ldcg(p); }
+__device__ __forceinline__ uint4 ld_cg4(const uint4* p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
 
 // Position of the token after the one starting at p, or n when there is none in the array.
-__device__ __forceinline__ uint32_t next_pos(const uint32_t* __restrict__ slots, uint32_t n, uint32_t p) {
+__device__ __forceinline__ uint32_t next_pos(const uint32_t* slots, uint32_t n, uint32_t p) {
   uint32_t q = p + 1;
   if (q >= n) return n;
-  uint32_t w = __ldg(slots + q);
+  uint32_t w = ld_slot(slots + q);
   uint32_t k = slot_kind(w);
   if (k == KIND_ID) return q;
   if (k == KIND_BACK) return q + 1;  // span-2 token: its second slot is also its last
@@ -55,33 +61,33 @@ __device__ __forceinline__ uint32_t next_pos(const uint32_t* __restrict__ slots,
 }
 
 // Token index of the right neighbour of the token at p inside the same document, or NOTOK.
-__device__ __forceinline__ int right_token(const uint32_t* __restrict__ slots, uint32_t n, uint32_t p, uint32_t* pos) {
+__device__ __forceinline__ int right_token(const uint32_t* slots, uint32_t n, uint32_t p, uint32_t* pos) {
   uint32_t q = next_pos(slots, n, p);
   *pos = q;
   if (q >= n) return NOTOK;
-  uint32_t w = __ldg(slots + q);
+  uint32_t w = ld_slot(slots + q);
   if (w & DOCSTART) return NOTOK;
   return (int)slot_val(w);
 }
 
 // Token index of the left neighbour of the token at p (whose slot value is `wp`), or NOTOK.
-__device__ __forceinline__ int left_token(const uint32_t* __restrict__ slots, uint32_t p, uint32_t wp, uint32_t* pos) {
+__device__ __forceinline__ int left_token(const uint32_t* slots, uint32_t p, uint32_t wp, uint32_t* pos) {
   if ((wp & DOCSTART) || p == 0) {
     *pos = NOPOS;
     return NOTOK;
   }
-  uint32_t w = __ldg(slots + p - 1);
+  uint32_t w = ld_slot(slots + p - 1);
   uint32_t l = p - 1;
   if (slot_kind(w) == KIND_BACK) {
     l = p - 1 - slot_val(w);
-    w = __ldg(slots + l);
+    w = ld_slot(slots + l);
   }
   *pos = l;
   return (int)slot_val(w);
 }
 
 // Number of consecutive tokens equal to `t` immediately to the left of position p (same document).
-__device__ __forceinline__ uint32_t run_left(const uint32_t* __restrict__ slots, uint32_t p, uint32_t wp, int t) {
+__device__ __forceinline__ uint32_t run_left(const uint32_t* slots, uint32_t p, uint32_t wp, int t) {
   uint32_t k = 0;
   for (;;) {
     uint32_t l;
@@ -89,12 +95,12 @@ __device__ __forceinline__ uint32_t run_left(const uint32_t* __restrict__ slots,
     if (x != t) return k;
     k++;
     p = l;
-    wp = __ldg(slots + l);
+    wp = ld_slot(slots + l);
   }
 }
 
 // Number of consecutive tokens equal to `t` immediately to the right of the token at p.
-__device__ __forceinline__ uint32_t run_right(const uint32_t* __restrict__ slots, uint32_t n, uint32_t p, int t) {
+__device__ __forceinline__ uint32_t run_right(const uint32_t* slots, uint32_t n, uint32_t p, int t) {
   uint32_t k = 0;
   for (;;) {
     uint32_t q;

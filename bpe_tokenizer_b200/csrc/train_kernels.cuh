@@ -1,5 +1,6 @@
 // train_kernels.cuh -- K1 (pair histogram + occurrence lists), K2 (arg-max with the reference's exact
-// tie-break) and K3 (apply merge in place with count deltas) for sm_100a.
+// tie-break) and K3 (apply merge in place with count deltas) for sm_100a, plus the persistent
+// cooperative kernel that runs the whole mergeUntil loop on the device.
 //
 // Reference semantics restated (all citations are /root/reference/core.ts):
 //   counting  :265-310  every adjacent pair inside a document; for a == b only every other pair of a
@@ -13,6 +14,9 @@
 // one merge that created the index, so every adjacency (p,q) is born in iteration max(birth p, birth q)
 // -- each pair's occurrence list is written exactly once (contiguous in `pool`) and afterwards only
 // goes stale, which is detected by re-reading the corpus.
+//
+// Every phase is a __device__ function over (block id, block count) so that the same code runs as a
+// stand-alone kernel (findNextMerge / applyMerge called one at a time) and inside k_merge_loop.
 #pragma once
 #include "common.cuh"
 
@@ -25,12 +29,11 @@ struct DevState {
   uint32_t err;
   uint32_t hot_n;
   uint32_t hot_thresh;
-  // per iteration
-  uint32_t n_sites;
-  uint32_t n_new;
+  // per iteration (double-buffered by iteration parity inside k_merge_loop; index 0 otherwise)
+  uint32_t n_sites[2];
+  uint32_t n_new[2];
   uint32_t n_cand;
   uint32_t blocks_done;
-  uint32_t _pad0;
   // arg-max result
   unsigned long long best_primary;  // (count << 20) | (0xFFFFF - (a+b)); 0 = nothing
   uint32_t best_slot;
@@ -39,8 +42,18 @@ struct DevState {
   uint32_t list_len;
   unsigned long long tie_pos;  // (lastpos << 32 | slot) min over candidates
   unsigned long long live_tokens;
+  unsigned long long barrier;  // grid barrier arrival counter (k_merge_loop)
+  // k_merge_loop bookkeeping
+  uint32_t n_tokens;     // next free token index
+  uint32_t iters_done;   // merges applied by the current launch
+  uint32_t status;       // LOOP_* exit reason
+  uint32_t tie_breaks;
+  unsigned long long sites_total;
   uint32_t bins[36];  // histogram of bit lengths of counts (hot-list threshold selection)
 };
+
+constexpr uint32_t LOOP_RUNNING = 0, LOOP_DONE = 1, LOOP_NEED_REBUILD = 2, LOOP_NEED_HOST = 3, LOOP_EMPTY = 4,
+                   LOOP_ERROR = 5, LOOP_LIMIT = 6;
 
 struct SiteRec {
   uint32_t p;      // position of the `a` being merged
@@ -49,9 +62,16 @@ struct SiteRec {
   uint32_t rslot;  // table slot of the new right adjacency's pair (NOSLOT if none)
 };
 
+struct MergeRec {  // layout of bpe_merge (include/bpe_b200.h)
+  int32_t a, b, c, reserved;
+  long long weight;
+};
+
 __device__ __forceinline__ unsigned long long make_primary(uint32_t cnt, uint32_t a, uint32_t b) {
   return ((unsigned long long)cnt << 20) | (unsigned long long)(0xFFFFFu - (a + b));
 }
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
 // ------------------------------------------------------------------------------------------------
 // ingest: int32 ids -> slots (vectorised 128-bit), then DOCSTART flags per document
@@ -171,13 +191,13 @@ __global__ void __launch_bounds__(K1_THREADS) k_hist(const uint32_t* __restrict_
     uint32_t p0 = g << 2;
     uint32_t v[5];
     if (p0 + 4 <= n) {
-      uint4 q = __ldg(reinterpret_cast<const uint4*>(slots) + g);
+      uint4 q = ld_slots4(slots + p0);
       v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; j++) v[j] = (p0 + j < n) ? __ldg(slots + p0 + j) : mk_hole();
+      for (int j = 0; j < 4; j++) v[j] = (p0 + j < n) ? ld_slot(slots + p0 + j) : mk_hole();
     }
-    v[4] = (p0 + 4 < n) ? __ldg(slots + p0 + 4) : (DOCSTART);  // DOCSTART|ID(0): "no right neighbour"
+    v[4] = (p0 + 4 < n) ? ld_slot(slots + p0 + 4) : (DOCSTART);  // DOCSTART|ID(0): "no right neighbour"
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       uint32_t key, counted;
@@ -216,13 +236,13 @@ __global__ void k_alloc_lists(PairTable t, DevState* st, uint32_t pool_cap) {
 __global__ void __launch_bounds__(K1_THREADS) k_scatter(const uint32_t* __restrict__ slots, uint32_t n, PairTable t,
                                                          uint32_t* __restrict__ pool, DevState* st) {
   uint32_t n4 = (n + 3) >> 2;
-  uint32_t lane = threadIdx.x & 31;
+  uint32_t lane = lane_id();
   uint32_t n4_round = (n4 + 31) & ~31u;
   for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n4_round; g += gridDim.x * blockDim.x) {
     uint32_t p0 = g << 2;
     uint32_t v[5];
 #pragma unroll
-    for (int j = 0; j < 5; j++) v[j] = (p0 + j < n) ? __ldg(slots + p0 + j) : (j == 4 ? DOCSTART : mk_hole());
+    for (int j = 0; j < 5; j++) v[j] = (p0 + j < n) ? ld_slot(slots + p0 + j) : (j == 4 ? DOCSTART : mk_hole());
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       uint32_t key = EMPTY_KEY - 1 - lane, counted;  // per-lane dummy: matches nobody
@@ -277,8 +297,20 @@ __device__ __forceinline__ Best best_warp_reduce(Best v) {
   return v;
 }
 
-__device__ __forceinline__ unsigned long long slot_primary(const PairTable& t, const uint32_t* __restrict__ len16,
-                                                           uint32_t s, uint32_t max_length) {
+// block-wide reduction; the result is valid in every thread.  s_best must hold blockDim.x/32 entries.
+__device__ __forceinline__ Best best_block_reduce(Best v, Best* s_best) {
+  v = best_warp_reduce(v);
+  __syncthreads();
+  if (lane_id() == 0) s_best[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint32_t nw = blockDim.x >> 5;
+  Best u = (lane_id() < nw) ? s_best[lane_id()] : Best{0ull, NOSLOT, 0};
+  u = best_warp_reduce(u);
+  return u;
+}
+
+__device__ __forceinline__ unsigned long long slot_primary(const PairTable& t, const uint32_t* len16, uint32_t s,
+                                                           uint32_t max_length) {
   uint32_t key = t.keys[s];
   if (key == EMPTY_KEY) return 0ull;
   uint32_t c = t.cnt[s];
@@ -288,76 +320,71 @@ __device__ __forceinline__ unsigned long long slot_primary(const PairTable& t, c
   return make_primary(c, a, b);
 }
 
+// per-thread partial over this block's stripe of the hot list (use_hot) or of the whole table
+__device__ __forceinline__ Best argmax_stripe(const PairTable& t, const uint32_t* len16, uint32_t max_length, int use_hot,
+                                              const uint32_t* hot, uint32_t n, uint32_t bid, uint32_t nblk) {
+  Best mine{0ull, NOSLOT, 0};
+  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n; i += nblk * blockDim.x) {
+    uint32_t s = use_hot ? hot[i] : i;
+    unsigned long long pr = slot_primary(t, len16, s, max_length);
+    if (pr) mine = best_merge(mine, Best{pr, s, 1});
+  }
+  return mine;
+}
+
+__device__ __forceinline__ void publish_best(const PairTable& t, DevState* st, Best u) {
+  st->best_primary = u.primary;
+  st->best_slot = u.slot;
+  st->best_mult = u.mult;
+  if (u.primary) {
+    uint32_t key = t.keys[u.slot];
+    st->best_a = key >> 16;
+    st->best_b = key & 0xFFFFu;
+    st->best_cnt = t.cnt[u.slot];
+    st->list_len = t.occ_len[u.slot];
+  } else {
+    st->best_a = st->best_b = st->best_cnt = st->list_len = 0;
+  }
+}
+
 constexpr int AM_THREADS = 256;
 
-// use_hot = 0: scan the whole table; 1: scan the hot list (pairs with count >= hot_thresh).
-// The last block to finish folds the per-block partials and resets the per-iteration counters.
+// Stand-alone K2.  The last block to finish folds the per-block partials and resets the per-iteration counters.
 __global__ void __launch_bounds__(AM_THREADS) k_argmax(PairTable t, const uint32_t* __restrict__ len16,
                                                         uint32_t max_length, int use_hot,
                                                         const uint32_t* __restrict__ hot, Best* __restrict__ partials,
                                                         DevState* st) {
   __shared__ Best s_best[AM_THREADS / 32];
   __shared__ bool s_last;
-  Best mine{0ull, NOSLOT, 0};
   uint32_t n = use_hot ? st->hot_n : (t.mask + 1);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    uint32_t s = use_hot ? hot[i] : i;
-    unsigned long long pr = slot_primary(t, len16, s, max_length);
-    if (pr) mine = best_merge(mine, Best{pr, s, 1});
-  }
-  mine = best_warp_reduce(mine);
-  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = mine;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    Best v = (threadIdx.x < AM_THREADS / 32) ? s_best[threadIdx.x] : Best{0ull, NOSLOT, 0};
-    v = best_warp_reduce(v);
-    if (threadIdx.x == 0) {
-      partials[blockIdx.x] = v;
-      __threadfence();
-      uint32_t done = atomicAdd(&st->blocks_done, 1u);
-      s_last = (done == gridDim.x - 1);
-    }
+  Best v = best_block_reduce(argmax_stripe(t, len16, max_length, use_hot, hot, n, blockIdx.x, gridDim.x), s_best);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = v;
+    __threadfence();
+    uint32_t done = atomicAdd(&st->blocks_done, 1u);
+    s_last = (done == gridDim.x - 1);
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  Best v{0ull, NOSLOT, 0};
-  for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) v = best_merge(v, partials[i]);
-  v = best_warp_reduce(v);
-  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    Best u = (threadIdx.x < AM_THREADS / 32) ? s_best[threadIdx.x] : Best{0ull, NOSLOT, 0};
-    u = best_warp_reduce(u);
-    if (threadIdx.x == 0) {
-      st->best_primary = u.primary;
-      st->best_slot = u.slot;
-      st->best_mult = u.mult;
-      if (u.primary) {
-        uint32_t key = t.keys[u.slot];
-        st->best_a = key >> 16;
-        st->best_b = key & 0xFFFFu;
-        st->best_cnt = t.cnt[u.slot];
-        st->list_len = t.occ_len[u.slot];
-      } else {
-        st->best_a = st->best_b = st->best_cnt = st->list_len = 0;
-      }
-      st->blocks_done = 0;
-      st->n_sites = 0;
-      st->n_new = 0;
-      st->n_cand = 0;
-      st->tie_pos = ~0ull;
-    }
+  Best w{0ull, NOSLOT, 0};
+  for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) w = best_merge(w, partials[i]);
+  w = best_block_reduce(w, s_best);
+  if (threadIdx.x == 0) {
+    publish_best(t, st, w);
+    st->blocks_done = 0;
+    st->n_sites[0] = st->n_sites[1] = 0;
+    st->n_new[0] = st->n_new[1] = 0;
+    st->n_cand = 0;
+    st->tie_pos = ~0ull;
   }
 }
 
-// candidates = pairs whose primary equals best_primary
-__global__ void k_collect_cands(PairTable t, const uint32_t* __restrict__ len16, uint32_t max_length, int use_hot,
-                                const uint32_t* __restrict__ hot, uint32_t* __restrict__ cands, uint32_t cand_cap,
-                                DevState* st) {
-  unsigned long long best = st->best_primary;
-  uint32_t n = use_hot ? st->hot_n : (t.mask + 1);
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// candidates = pairs whose primary equals `best`
+__device__ __forceinline__ void phase_collect(const PairTable& t, const uint32_t* len16, uint32_t max_length, int use_hot,
+                                              const uint32_t* hot, uint32_t n, unsigned long long best, uint32_t* cands,
+                                              uint32_t cand_cap, DevState* st, uint32_t bid, uint32_t nblk) {
+  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n; i += nblk * blockDim.x) {
     uint32_t s = use_hot ? hot[i] : i;
     if (slot_primary(t, len16, s, max_length) == best) {
       uint32_t k = atomicAdd(&st->n_cand, 1u);
@@ -367,10 +394,16 @@ __global__ void k_collect_cands(PairTable t, const uint32_t* __restrict__ len16,
   }
 }
 
+__global__ void k_collect_cands(PairTable t, const uint32_t* __restrict__ len16, uint32_t max_length, int use_hot,
+                                const uint32_t* __restrict__ hot, uint32_t* __restrict__ cands, uint32_t cand_cap,
+                                DevState* st) {
+  uint32_t n = use_hot ? st->hot_n : (t.mask + 1);
+  phase_collect(t, len16, max_length, use_hot, hot, n, st->best_primary, cands, cand_cap, st, blockIdx.x, gridDim.x);
+}
+
 // Is position p a *counted* occurrence of (a,b) right now?
-__device__ __forceinline__ bool counted_occurrence(const uint32_t* __restrict__ slots, uint32_t n, uint32_t p, uint32_t a,
-                                                   uint32_t b) {
-  uint32_t w = __ldg(slots + p);
+__device__ __forceinline__ bool counted_occurrence(const uint32_t* slots, uint32_t n, uint32_t p, uint32_t a, uint32_t b) {
+  uint32_t w = ld_slot(slots + p);
   if (!slot_is_id(w) || slot_val(w) != a) return false;
   uint32_t q;
   if (right_token(slots, n, p, &q) != (int)b) return false;
@@ -379,37 +412,37 @@ __device__ __forceinline__ bool counted_occurrence(const uint32_t* __restrict__ 
 }
 
 // one block per candidate: scan position of its last counted occurrence; global min of (pos, slot) wins
-__global__ void __launch_bounds__(256) k_tie_break(const uint32_t* __restrict__ slots, uint32_t n, PairTable t,
-                                                    const uint32_t* __restrict__ pool,
-                                                    const uint32_t* __restrict__ cands, DevState* st) {
-  __shared__ uint32_t s_max[8];
-  uint32_t n_cand = st->n_cand;
-  for (uint32_t c = blockIdx.x; c < n_cand; c += gridDim.x) {
+__device__ __forceinline__ void phase_tie(const uint32_t* slots, uint32_t n, const PairTable& t, const uint32_t* pool,
+                                          const uint32_t* cands, uint32_t n_cand, DevState* st, uint32_t* s_max,
+                                          uint32_t bid, uint32_t nblk) {
+  for (uint32_t c = bid; c < n_cand; c += nblk) {
     uint32_t s = cands[c];
     uint32_t key = t.keys[s];
     uint32_t a = key >> 16, b = key & 0xFFFFu;
     uint32_t start = t.occ_start[s], len = t.occ_len[s];
-    uint32_t best = 0;
-    bool any = false;
+    uint32_t v = 0;  // 1 + max position, 0 = none
     for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
       uint32_t p = pool[start + i];
-      if (counted_occurrence(slots, n, p, a, b)) {
-        best = max(best, p);
-        any = true;
-      }
+      if (counted_occurrence(slots, n, p, a, b)) v = max(v, p + 1);
     }
-    uint32_t v = any ? best + 1 : 0;  // 0 = none
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = v;
+    if (lane_id() == 0) s_max[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t m = 0;
-      for (int i = 0; i < 8; i++) m = max(m, s_max[i]);
+      for (uint32_t i = 0; i < (blockDim.x >> 5); i++) m = max(m, s_max[i]);
       if (m) atomicMin(&st->tie_pos, ((unsigned long long)(m - 1) << 32) | s);
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_tie_break(const uint32_t* __restrict__ slots, uint32_t n, PairTable t,
+                                                    const uint32_t* __restrict__ pool,
+                                                    const uint32_t* __restrict__ cands, DevState* st) {
+  __shared__ uint32_t s_max[32];
+  phase_tie(slots, n, t, pool, cands, st->n_cand, st, s_max, blockIdx.x, gridDim.x);
 }
 
 __global__ void k_tie_finish(PairTable t, DevState* st) {
@@ -433,8 +466,8 @@ __global__ void k_lookup_pair(PairTable t, uint32_t a, uint32_t b, DevState* st)
     st->best_b = b;
     st->best_cnt = (s == NOSLOT) ? 0 : t.cnt[s];
     st->list_len = (s == NOSLOT) ? 0 : t.occ_len[s];
-    st->n_sites = 0;
-    st->n_new = 0;
+    st->n_sites[0] = st->n_sites[1] = 0;
+    st->n_new[0] = st->n_new[1] = 0;
     st->n_cand = 0;
   }
 }
@@ -472,133 +505,196 @@ __global__ void k_build_hot(PairTable t, const uint32_t* __restrict__ len16, uin
 
 // ------------------------------------------------------------------------------------------------
 // K3 phase 1: find the merge sites of (a,b) -> c, emit count deltas and size the new pairs' lists.
-// Reads the corpus only (all writes happen in k_apply), so every thread sees the pre-merge state.
-// scan_mode = 1 walks every slot instead of the pair's occurrence list (cross-check / fallback).
+// Reads the corpus only (all writes happen in phase_apply), so every thread sees the pre-merge state.
+// Count deltas and list sizing are warp-aggregated: lanes that touch the same pair elect one leader
+// (__match_any_sync) which issues a single atomic for all of them -- early merges hit a handful of
+// pairs millions of times.  scan_mode = 1 walks every slot instead of the pair's occurrence list.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void delta_dec(const PairTable& t, DevState* st, uint32_t key, uint32_t d) {
-  uint32_t s = tbl_find(t, key);
-  if (s == NOSLOT) {
-    atomicOr(&st->err, ERR_MISSING_KEY);
-    return;
+struct ApplyArgs {
+  uint32_t* slots;
+  uint32_t n;
+  PairTable t;
+  uint32_t* pool;
+  DevState* st;
+  SiteRec* sites;
+  uint32_t sites_cap;
+  uint32_t* newslots;
+  uint32_t new_cap;
+  uint32_t* len16;
+  int scan_mode;
+};
+
+// all 32 lanes call; lanes with has == false pass any key
+__device__ __forceinline__ void agg_dec(const PairTable& t, DevState* st, uint32_t key, bool has) {
+  uint32_t lane = lane_id();
+  uint32_t k = has ? key : (EMPTY_KEY - 1 - lane);
+  uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
+  if (has && lane == (uint32_t)(__ffs(peers) - 1)) {
+    uint32_t s = tbl_find(t, key);
+    if (s == NOSLOT) atomicOr(&st->err, ERR_MISSING_KEY);
+    else atomicSub(t.cnt + s, (uint32_t)__popc(peers));
   }
-  atomicSub(t.cnt + s, d);
 }
 
-__device__ __forceinline__ uint32_t new_adjacency(const PairTable& t, DevState* st, uint32_t key, bool counted,
-                                                  uint32_t* __restrict__ newslots, uint32_t new_cap) {
-  uint32_t s = tbl_find_or_insert(t, key, &st->n_keys);
-  if (s == NOSLOT) {
-    atomicOr(&st->err, ERR_TABLE_FULL);
-    return NOSLOT;
+// returns the table slot of `key` to every lane with has == true
+__device__ __forceinline__ uint32_t agg_new(const PairTable& t, DevState* st, uint32_t key, bool has, bool counted,
+                                            uint32_t* newslots, uint32_t new_cap, uint32_t par) {
+  uint32_t lane = lane_id();
+  uint32_t k = has ? key : (EMPTY_KEY - 1 - lane);
+  uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
+  uint32_t cmask = __ballot_sync(0xFFFFFFFFu, has && counted);
+  uint32_t leader = __ffs(peers) - 1;
+  uint32_t s = NOSLOT;
+  if (has && lane == leader) {
+    s = tbl_find_or_insert(t, key, &st->n_keys);
+    if (s == NOSLOT) {
+      atomicOr(&st->err, ERR_TABLE_FULL);
+    } else {
+      uint32_t nc = __popc(peers & cmask);
+      if (nc) atomicAdd(t.cnt + s, nc);
+      if (atomicAdd(t.occ_len + s, (uint32_t)__popc(peers)) == 0) {  // first adjacency of a pair born in this iteration
+        uint32_t i = atomicAdd(&st->n_new[par], 1u);
+        if (i < new_cap) newslots[i] = s;
+        else atomicOr(&st->err, ERR_SITE_OVERFLOW);
+      }
+    }
   }
-  if (counted) atomicAdd(t.cnt + s, 1u);
-  if (atomicAdd(t.occ_len + s, 1u) == 0) {  // first adjacency of a pair born in this iteration
-    uint32_t k = atomicAdd(&st->n_new, 1u);
-    if (k < new_cap) newslots[k] = s;
-    else atomicOr(&st->err, ERR_SITE_OVERFLOW);
-  }
-  return s;
+  return __shfl_sync(0xFFFFFFFFu, s, leader);
 }
 
-__global__ void __launch_bounds__(256) k_sites(const uint32_t* __restrict__ slots, uint32_t n, PairTable t,
-                                                const uint32_t* __restrict__ pool, DevState* st, uint32_t a, uint32_t b,
-                                                uint32_t c, int scan_mode, SiteRec* __restrict__ sites,
-                                                uint32_t sites_cap, uint32_t* __restrict__ newslots, uint32_t new_cap,
-                                                uint32_t* __restrict__ len16) {
+__device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint32_t b, uint32_t c, uint32_t par,
+                                            uint32_t bid, uint32_t nblk) {
+  const uint32_t* slots = A.slots;
+  const uint32_t n = A.n;
+  const PairTable& t = A.t;
+  DevState* st = A.st;
   uint32_t list_start = 0, total = n;
-  if (!scan_mode) {
+  if (!A.scan_mode) {
     uint32_t s = tbl_find(t, pair_key(a, b));
     total = (s == NOSLOT) ? 0 : t.occ_len[s];
     list_start = (s == NOSLOT) ? 0 : t.occ_start[s];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) len16[c] = len16[a] + len16[b];  // chars = a.chars + b.chars (:318)
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    uint32_t p = scan_mode ? i : pool[list_start + i];
-    uint32_t w = __ldg(slots + p);
-    if (!slot_is_id(w) || slot_val(w) != a) continue;
-    uint32_t q;
-    if (right_token(slots, n, p, &q) != (int)b) continue;
-    uint32_t koff = 0;
-    if (a == b) {
-      koff = run_left(slots, p, w, (int)a);
-      if (koff & 1u) continue;  // overlaps the occurrence to its left (replaceAll is non-overlapping)
+  uint32_t lane = lane_id();
+  uint32_t total_round = (total + 31u) & ~31u;
+  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < total_round; i += nblk * blockDim.x) {
+    bool site = false;
+    uint32_t p = 0, w = 0, q = 0, koff = 0;
+    if (i < total) {
+      p = A.scan_mode ? i : A.pool[list_start + i];
+      w = ld_slot(slots + p);
+      if (slot_is_id(w) && slot_val(w) == a && right_token(slots, n, p, &q) == (int)b) {
+        site = true;
+        if (a == b) {
+          koff = run_left(slots, p, w, (int)a);
+          if (koff & 1u) site = false;  // overlaps the occurrence to its left (replaceAll is non-overlapping)
+        }
+      }
     }
+    if (!__any_sync(0xFFFFFFFFu, site)) continue;
     SiteRec rec{p, NOPOS, NOSLOT, NOSLOT};
-
     // ---- adjacency on the left of the new token ----
-    uint32_t lpos;
-    int x = left_token(slots, p, w, &lpos);
-    if (x != NOTOK) {
-      bool chained = false;
-      uint32_t chain_j = 0, llpos = NOPOS;
-      if (a == b) {
-        chained = koff >= 2;
-        chain_j = koff >> 1;
-        if (chained) left_token(slots, lpos, __ldg(slots + lpos), &llpos);
-      } else if ((uint32_t)x == b) {
-        int xx = left_token(slots, lpos, __ldg(slots + lpos), &llpos);
-        if (xx == (int)a) {  // the pair to the left is itself a site: ... a b a b
-          chained = true;
-          chain_j = 1;
-          uint32_t cur = llpos;
-          for (;;) {  // index of this site within its chain of back-to-back sites
-            uint32_t l1, l2;
-            if (left_token(slots, cur, __ldg(slots + cur), &l1) != (int)b) break;
-            if (left_token(slots, l1, __ldg(slots + l1), &l2) != (int)a) break;
-            chain_j++;
-            cur = l2;
+    uint32_t dec1_key = 0, new1_key = 0;
+    bool dec1 = false, new1 = false, new1_counted = true;
+    if (site) {
+      uint32_t lpos;
+      int x = left_token(slots, p, w, &lpos);
+      if (x != NOTOK) {
+        bool chained = false;
+        uint32_t chain_j = 0, llpos = NOPOS;
+        if (a == b) {
+          chained = koff >= 2;
+          chain_j = koff >> 1;
+          if (chained) left_token(slots, lpos, ld_slot(slots + lpos), &llpos);
+        } else if ((uint32_t)x == b) {
+          int xx = left_token(slots, lpos, ld_slot(slots + lpos), &llpos);
+          if (xx == (int)a) {  // the pair to the left is itself a site: ... a b a b
+            chained = true;
+            chain_j = 1;
+            uint32_t cur = llpos;
+            for (;;) {  // index of this site within its chain of back-to-back sites
+              uint32_t l1, l2;
+              if (left_token(slots, cur, ld_slot(slots + cur), &l1) != (int)b) break;
+              if (left_token(slots, l1, ld_slot(slots + l1), &l2) != (int)a) break;
+              chain_j++;
+              cur = l2;
+            }
           }
         }
-      }
-      if (chained) {
-        if (a != b) delta_dec(t, st, pair_key(b, a), 1);
-        // new adjacency (c,c); runs of c count every other pair (:285-290)
-        rec.lslot = new_adjacency(t, st, pair_key(c, c), (chain_j & 1u) != 0, newslots, new_cap);
-        rec.lpos = llpos;
-      } else {
-        if ((uint32_t)x == a) {  // (a != b here) the run of a's ending at p loses its last element
-          uint32_t L = 1 + run_left(slots, p, w, (int)a);
-          if ((L & 1u) == 0) delta_dec(t, st, pair_key(a, a), 1);
+        new1 = true;
+        if (chained) {
+          if (a != b) {
+            dec1 = true;
+            dec1_key = pair_key(b, a);
+          }
+          new1_key = pair_key(c, c);  // runs of c count every other pair (:285-290)
+          new1_counted = (chain_j & 1u) != 0;
+          rec.lpos = llpos;
         } else {
-          delta_dec(t, st, pair_key((uint32_t)x, a), 1);
+          if ((uint32_t)x == a) {  // (a != b here) the run of a's ending at p loses its last element
+            uint32_t L = 1 + run_left(slots, p, w, (int)a);
+            dec1 = (L & 1u) == 0;
+            dec1_key = pair_key(a, a);
+          } else {
+            dec1 = true;
+            dec1_key = pair_key((uint32_t)x, a);
+          }
+          new1_key = pair_key((uint32_t)x, c);
+          rec.lpos = lpos;
         }
-        rec.lslot = new_adjacency(t, st, pair_key((uint32_t)x, c), true, newslots, new_cap);
-        rec.lpos = lpos;
       }
     }
+    agg_dec(t, st, dec1_key, dec1);
+    rec.lslot = agg_new(t, st, new1_key, new1, new1_counted, A.newslots, A.new_cap, par);
 
     // ---- adjacency on the right of the new token (left to the next site when that one is chained) ----
-    uint32_t r;
-    int y = right_token(slots, n, q, &r);
-    if (y != NOTOK) {
-      bool chained_right = false;
-      if ((uint32_t)y == a) {
-        uint32_t r2;
-        chained_right = right_token(slots, n, r, &r2) == (int)b;
-      }
-      if (!chained_right) {
-        if ((uint32_t)y == b && a != b) {  // the run of b's starting at q loses its first element
-          uint32_t L = 1 + run_right(slots, n, q, (int)b);
-          if ((L & 1u) == 0) delta_dec(t, st, pair_key(b, b), 1);
-        } else if (!(a == b && (uint32_t)y == a)) {  // (a,a) itself is zeroed by k_apply
-          delta_dec(t, st, pair_key(b, (uint32_t)y), 1);
+    uint32_t dec2_key = 0, new2_key = 0;
+    bool dec2 = false, new2 = false;
+    if (site) {
+      uint32_t r;
+      int y = right_token(slots, n, q, &r);
+      if (y != NOTOK) {
+        bool chained_right = false;
+        if ((uint32_t)y == a) {
+          uint32_t r2;
+          chained_right = right_token(slots, n, r, &r2) == (int)b;
         }
-        rec.rslot = new_adjacency(t, st, pair_key(c, (uint32_t)y), true, newslots, new_cap);
+        if (!chained_right) {
+          if ((uint32_t)y == b && a != b) {  // the run of b's starting at q loses its first element
+            uint32_t L = 1 + run_right(slots, n, q, (int)b);
+            dec2 = (L & 1u) == 0;
+            dec2_key = pair_key(b, b);
+          } else if (!(a == b && (uint32_t)y == a)) {  // (a,a) itself is zeroed by phase_apply
+            dec2 = true;
+            dec2_key = pair_key(b, (uint32_t)y);
+          }
+          new2 = true;
+          new2_key = pair_key(c, (uint32_t)y);
+        }
       }
     }
-    uint32_t k = atomicAdd(&st->n_sites, 1u);
-    if (k < sites_cap) reinterpret_cast<uint4*>(sites)[k] = make_uint4(rec.p, rec.lpos, rec.lslot, rec.rslot);
-    else atomicOr(&st->err, ERR_SITE_OVERFLOW);
+    agg_dec(t, st, dec2_key, dec2);
+    rec.rslot = agg_new(t, st, new2_key, new2, true, A.newslots, A.new_cap, par);
+
+    // ---- record the site (one counter atomic per warp) ----
+    uint32_t smask = __ballot_sync(0xFFFFFFFFu, site);
+    uint32_t base = 0;
+    if (lane == (uint32_t)(__ffs(smask) - 1)) base = atomicAdd(&st->n_sites[par], (uint32_t)__popc(smask));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(smask) - 1);
+    if (site) {
+      uint32_t k = base + __popc(smask & ((1u << lane) - 1u));
+      if (k < A.sites_cap) reinterpret_cast<uint4*>(A.sites)[k] = make_uint4(rec.p, rec.lpos, rec.lslot, rec.rslot);
+      else atomicOr(&st->err, ERR_SITE_OVERFLOW);
+    }
   }
 }
 
 // K3 phase 2: allocate the lists of the pairs born in this iteration; feed the hot list.
-__global__ void k_alloc_new(PairTable t, const uint32_t* __restrict__ newslots, const uint32_t* __restrict__ len16,
-                            uint32_t max_length, int hot_valid, uint32_t* __restrict__ hot, uint32_t hot_cap,
-                            uint32_t pool_cap, DevState* st) {
-  uint32_t n_new = st->n_new;
+__device__ __forceinline__ void phase_alloc_new(const PairTable& t, const uint32_t* newslots, uint32_t n_new,
+                                                const uint32_t* len16, uint32_t max_length, int hot_valid, uint32_t* hot,
+                                                uint32_t hot_cap, uint32_t pool_cap, DevState* st, uint32_t bid,
+                                                uint32_t nblk) {
   uint32_t thresh = st->hot_thresh;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
+  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n_new; i += nblk * blockDim.x) {
     uint32_t s = newslots[i];
     uint32_t len = t.occ_len[s];
     uint32_t start = atomicAdd(&st->pool_cursor, len);
@@ -621,26 +717,46 @@ __global__ void k_alloc_new(PairTable t, const uint32_t* __restrict__ newslots, 
 }
 
 // K3 phase 3: rewrite the corpus in place and fill the new pairs' occurrence lists.
-__global__ void __launch_bounds__(256) k_apply(uint32_t* __restrict__ slots, uint32_t n, PairTable t,
-                                                uint32_t* __restrict__ pool, DevState* st, uint32_t a, uint32_t b,
-                                                uint32_t c, const SiteRec* __restrict__ sites) {
-  uint32_t n_sites = st->n_sites;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+__device__ __forceinline__ uint32_t agg_cursor(const PairTable& t, uint32_t slot, bool has) {
+  uint32_t lane = lane_id();
+  uint32_t k = has ? slot : (0xFFFFFF00u + lane);
+  uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
+  uint32_t leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (has && lane == leader) base = t.occ_start[slot] + atomicAdd(t.occ_fill + slot, (uint32_t)__popc(peers));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void phase_apply(const ApplyArgs& A, uint32_t a, uint32_t b, uint32_t c, uint32_t n_sites,
+                                            uint32_t bid, uint32_t nblk) {
+  uint32_t* slots = A.slots;
+  const uint32_t n = A.n;
+  const PairTable& t = A.t;
+  if (bid == 0 && threadIdx.x == 0) {
     uint32_t s = tbl_find(t, pair_key(a, b));
     if (s != NOSLOT) t.cnt[s] = 0;  // every counted occurrence was replaced
-    st->live_tokens -= n_sites;
+    A.st->live_tokens -= n_sites;
+    A.st->sites_total += n_sites;
   }
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_sites; i += gridDim.x * blockDim.x) {
-    uint4 rv = __ldg(reinterpret_cast<const uint4*>(sites) + i);
+  uint32_t round = (n_sites + 31u) & ~31u;
+  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < round; i += nblk * blockDim.x) {
+    bool has = i < n_sites;
+    uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(A.sites) + i) : make_uint4(0, NOPOS, NOSLOT, NOSLOT);
     uint32_t p = rv.x, lpos = rv.y, lslot = rv.z, rslot = rv.w;
-    if (lslot != NOSLOT && t.occ_len[lslot]) pool[t.occ_start[lslot] + atomicAdd(t.occ_fill + lslot, 1u)] = lpos;
-    if (rslot != NOSLOT && t.occ_len[rslot]) pool[t.occ_start[rslot] + atomicAdd(t.occ_fill + rslot, 1u)] = p;
+    bool hl = has && lslot != NOSLOT && t.occ_len[lslot];
+    bool hr = has && rslot != NOSLOT && t.occ_len[rslot];
+    uint32_t il = agg_cursor(t, lslot, hl);
+    uint32_t ir = agg_cursor(t, rslot, hr);
+    if (hl) A.pool[il] = lpos;
+    if (hr) A.pool[ir] = p;
+    if (!has) continue;
     // own slots only: [p, e] where e is the last slot of b
     uint32_t q = next_pos(slots, n, p);
     uint32_t e = next_pos(slots, n, q) - 1;
     uint32_t span = e - p + 1;
-    uint32_t w = slots[p];
-    if (span > VAL_MASK) atomicOr(&st->err, ERR_SPAN_OVERFLOW);
+    uint32_t w = ld_slot(slots + p);
+    if (span > VAL_MASK) atomicOr(&A.st->err, ERR_SPAN_OVERFLOW);
     slots[p] = (w & DOCSTART) | c;
     if (span == 2) {
       slots[p + 1] = mk_back(1);
@@ -649,6 +765,190 @@ __global__ void __launch_bounds__(256) k_apply(uint32_t* __restrict__ slots, uin
       slots[p + 1] = mk_span(span);
       slots[e] = mk_back(span - 1);
     }
+  }
+}
+
+// ---- stand-alone K3 kernels (applyMerge / restoreMerge one at a time, and the host-driven loop) ----
+__global__ void __launch_bounds__(256) k_sites(ApplyArgs A, uint32_t a, uint32_t b, uint32_t c) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) A.len16[c] = A.len16[a] + A.len16[b];  // chars = a.chars + b.chars (:318)
+  phase_sites(A, a, b, c, 0, blockIdx.x, gridDim.x);
+}
+
+__global__ void k_alloc_new(PairTable t, const uint32_t* __restrict__ newslots, const uint32_t* __restrict__ len16,
+                            uint32_t max_length, int hot_valid, uint32_t* __restrict__ hot, uint32_t hot_cap,
+                            uint32_t pool_cap, DevState* st) {
+  phase_alloc_new(t, newslots, st->n_new[0], len16, max_length, hot_valid, hot, hot_cap, pool_cap, st, blockIdx.x, gridDim.x);
+}
+
+__global__ void __launch_bounds__(256) k_apply(ApplyArgs A, uint32_t a, uint32_t b, uint32_t c) {
+  phase_apply(A, a, b, c, A.st->n_sites[0], blockIdx.x, gridDim.x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// mergeUntil (core.ts:365-383) as ONE persistent cooperative kernel: every block runs the same loop,
+// phases are separated by a grid barrier (3 per merge), every block takes the same exit decision from
+// the same published state.  The host is only needed to grow buffers or rebuild the hot list.
+// ------------------------------------------------------------------------------------------------
+constexpr int ML_THREADS = 512;
+
+struct LoopArgs {
+  ApplyArgs A;
+  uint32_t pool_cap;
+  uint32_t len16_cap;
+  uint32_t* hot;
+  uint32_t hot_cap;
+  uint32_t* cands;
+  uint32_t cand_cap;
+  Best* partials;
+  MergeRec* log;       // device merge log for this launch
+  uint32_t log_cap;    // max merges this launch may apply
+  uint32_t max_length;
+  uint32_t min_weight;
+  uint32_t max_tokens;
+  uint32_t tbl_cap;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1ull);
+    while (ld_volatile_u64(ctr) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void k_loop_prepare(DevState* st, uint32_t n_tokens) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->status = LOOP_RUNNING;
+    st->barrier = 0;
+    st->n_tokens = n_tokens;
+    st->iters_done = 0;
+    st->n_sites[0] = st->n_sites[1] = 0;
+    st->n_new[0] = st->n_new[1] = 0;
+    st->n_cand = 0;
+    st->blocks_done = 0;
+    st->tie_pos = ~0ull;
+  }
+}
+
+__global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
+  __shared__ Best s_best[ML_THREADS / 32];
+  __shared__ uint32_t s_max[32];
+  const ApplyArgs& A = L.A;
+  DevState* st = A.st;
+  const PairTable& t = A.t;
+  const uint32_t bid = blockIdx.x, nblk = gridDim.x;
+  unsigned long long epoch = 0;
+  const uint32_t n_tokens0 = ld_cg(&st->n_tokens);
+  const uint32_t thresh = ld_cg(&st->hot_thresh);
+
+  // first arg-max partials
+  {
+    Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
+    if (threadIdx.x == 0) L.partials[bid] = v;
+  }
+  grid_barrier(&st->barrier, ++epoch * nblk);
+
+  for (uint32_t it = 0;; it++) {
+    const uint32_t par = it & 1u;
+    // ---- every block folds the partials and takes the same decision ----
+    Best w{0ull, NOSLOT, 0};
+    for (uint32_t i = threadIdx.x; i < nblk; i += blockDim.x) {
+      Best pb;
+      pb.primary = ld_cg(&L.partials[i].primary);
+      pb.slot = ld_cg(&L.partials[i].slot);
+      pb.mult = ld_cg(&L.partials[i].mult);
+      w = best_merge(w, pb);
+    }
+    w = best_block_reduce(w, s_best);
+    uint32_t status = LOOP_RUNNING;
+    uint32_t wa = 0, wb = 0, wcnt = 0;
+    if (w.primary) {
+      uint32_t key = t.keys[w.slot];
+      wa = key >> 16;
+      wb = key & 0xFFFFu;
+      wcnt = (uint32_t)(w.primary >> 20);
+    }
+    const uint32_t c = n_tokens0 + it;
+    if (ld_cg(&st->err)) status = LOOP_ERROR;
+    else if (!w.primary) status = (thresh <= 1) ? LOOP_EMPTY : LOOP_NEED_REBUILD;
+    else if (wcnt < thresh) status = LOOP_NEED_REBUILD;
+    else if (wcnt < L.min_weight) status = LOOP_DONE;  // core.ts:313
+    else if (it >= L.log_cap) status = LOOP_LIMIT;
+    else if (c >= L.max_tokens) status = LOOP_NEED_HOST;
+    if (status == LOOP_RUNNING && w.mult > 1) {
+      // tie on (weight, a.index+b.index): the pair whose last counted occurrence comes first wins (core.ts:294-305)
+      if (w.mult > L.cand_cap) status = LOOP_NEED_HOST;
+      else {
+        phase_collect(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), w.primary, L.cands, L.cand_cap, st, bid, nblk);
+        grid_barrier(&st->barrier, ++epoch * nblk);
+        phase_tie(A.slots, A.n, t, A.pool, L.cands, ld_cg(&st->n_cand), st, s_max, bid, nblk);
+        grid_barrier(&st->barrier, ++epoch * nblk);
+        unsigned long long tp = ld_cg(&st->tie_pos);
+        if (tp == ~0ull) status = LOOP_ERROR;
+        else {
+          uint32_t s = (uint32_t)(tp & 0xFFFFFFFFu);
+          uint32_t key = t.keys[s];
+          w.slot = s;
+          wa = key >> 16;
+          wb = key & 0xFFFFu;
+        }
+      }
+    }
+    if (status == LOOP_RUNNING) {
+      // capacity the host guarantees: sites = wcnt; new pairs are (x,c) or (c,y), so at most 2*(c+1) of them and
+      // at most 2 per site; new list cells <= 2 per site
+      unsigned long long new_keys = min(2ull * wcnt + 2ull, 2ull * (c + 1ull) + 2ull);
+      if ((unsigned long long)ld_cg(&st->n_keys) + new_keys > (unsigned long long)(L.tbl_cap >> 1)) status = LOOP_NEED_HOST;
+      else if ((unsigned long long)ld_cg(&st->pool_cursor) + 2ull * wcnt > L.pool_cap) status = LOOP_NEED_HOST;
+      else if (wcnt > A.sites_cap || new_keys > A.new_cap) status = LOOP_NEED_HOST;
+      else if ((unsigned long long)ld_cg(&st->hot_n) + new_keys > L.hot_cap) status = LOOP_NEED_HOST;
+      else if (c + 1 > L.len16_cap) status = LOOP_NEED_HOST;
+    }
+    if (status != LOOP_RUNNING) {
+      if (bid == 0 && threadIdx.x == 0) {
+        st->status = status;
+        st->iters_done = it;
+        st->n_tokens = n_tokens0 + it;
+        publish_best(t, st, w);
+        st->n_cand = 0;
+        st->tie_pos = ~0ull;
+      }
+      return;
+    }
+    // ---- P1: sites + deltas ----
+    if (bid == 0 && threadIdx.x == 0) {
+      A.len16[c] = A.len16[wa] + A.len16[wb];  // chars = a.chars + b.chars (:318)
+      MergeRec r;
+      r.a = (int32_t)wa;
+      r.b = (int32_t)wb;
+      r.c = (int32_t)c;
+      r.reserved = 0;
+      r.weight = (long long)wcnt;
+      L.log[it] = r;
+      st->n_sites[par ^ 1u] = 0;
+      st->n_new[par ^ 1u] = 0;
+      if (w.mult > 1) st->tie_breaks++;
+    }
+    phase_sites(A, wa, wb, c, par, bid, nblk);
+    grid_barrier(&st->barrier, ++epoch * nblk);
+    // ---- P2: lists of the new pairs, hot list ----
+    if (bid == 0 && threadIdx.x == 0) {
+      st->n_cand = 0;
+      st->tie_pos = ~0ull;
+    }
+    phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, 1, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);
+    grid_barrier(&st->barrier, ++epoch * nblk);
+    // ---- P3: rewrite + next arg-max partials ----
+    phase_apply(A, wa, wb, c, ld_cg(&st->n_sites[par]), bid, nblk);
+    {
+      Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
+      if (threadIdx.x == 0) L.partials[bid] = v;
+    }
+    grid_barrier(&st->barrier, ++epoch * nblk);
   }
 }
 
@@ -685,7 +985,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const uint32_t* __restrict
                                                        uint32_t n) {
   __shared__ uint64_t s_part[1024];
   uint32_t per = (n + 1023) / 1024;
-  uint32_t lo = threadIdx.x * per, hi = min(n, lo + per);
+  uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
   uint64_t s = 0;
   for (uint32_t i = lo; i < hi; i++) s += in[i];
   s_part[threadIdx.x] = s;
