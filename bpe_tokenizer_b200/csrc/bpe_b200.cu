@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -123,6 +124,7 @@ struct bpe_engine {
   uint32_t hot_thresh = 0;
   DevBuf<uint32_t> cands;
   DevBuf<MergeRec> dev_log;
+  DevBuf<unsigned long long> barrier;  // own 128-byte line
   int loop_blocks = 0;   // co-resident grid of k_merge_loop
   int host_loop = 0;     // debug: drive mergeUntil from the host, one launch per phase
   int scan_mode = 0;     // debug: walk all slots instead of occurrence lists
@@ -592,6 +594,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
   CK(e->sites.reserve(1u << 16, 0, e->stream, 1.0));
   CK(e->newslots.reserve(1u << 16, 0, e->stream, 1.0));
   CK(e->cands.reserve(4096, 0, e->stream, 1.0));
+  CK(e->barrier.reserve(64));
   cudaEvent_t t0, t1;
   CK(cudaEventCreate(&t0));
   CK(cudaEventCreate(&t1));
@@ -629,13 +632,14 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     L.cands = e->cands.p;
     L.cand_cap = (uint32_t)std::min<size_t>(e->cands.cap, 0xFFFFFFF0u);
     L.partials = e->partials.p;
+    L.barrier = e->barrier.p;
     L.log = e->dev_log.p;
     L.log_cap = chunk;
     L.max_length = ml;
     L.min_weight = (uint32_t)std::min<int64_t>(mw, 0xFFFFFFFFll);
     L.max_tokens = BPE_MAX_TOKENS;
     L.tbl_cap = e->tbl_cap;
-    k_loop_prepare<<<1, 32, 0, e->stream>>>(e->d_st.p, (uint32_t)e->n_tokens);
+    k_loop_prepare<<<1, 32, 0, e->stream>>>(e->d_st.p, (uint32_t)e->n_tokens, e->barrier.p);
     e->stats.kernel_launches++;
     void* args[] = {&L};
     ce = cudaLaunchCooperativeKernel((void*)k_merge_loop, dim3(e->loop_blocks), dim3(ML_THREADS), args, 0, e->stream);
@@ -824,6 +828,7 @@ int bpe_create(int device, bpe_engine** out) {
     return BPE_E_CUDA;
   }
   e->stream = e->own_stream;
+  if (getenv("BPE_HOST_LOOP")) e->host_loop = 1;
   *out = e;
   return BPE_OK;
 }
@@ -860,6 +865,7 @@ int bpe_set_profiling(bpe_engine* e, int enabled) {
   if (!e) return BPE_E_INVALID;
   e->profiling = enabled != 0;
   e->scan_mode = (enabled & 2) ? 1 : 0;  // bit 1: debug full-scan site discovery
+  e->host_loop = (enabled & 4) ? 1 : 0;  // bit 2: debug host-driven mergeUntil (one launch per phase)
   return BPE_OK;
 }
 
@@ -870,6 +876,7 @@ int bpe_get_stats(bpe_engine* e, bpe_stats* out) {
     TRY(fetch_state(e));
     e->live_tokens = e->h_st->live_tokens;
     e->stats.distinct_pairs = e->h_st->n_keys;
+    for (int i = 0; i < 8; i++) e->stats.ms_loop_phase[i] = (double)e->h_st->prof_ns[i] * 1e-6;
     e->stats.pool_used = e->h_st->pool_cursor;
   }
   e->stats.corpus_positions = (int64_t)e->n_slots;

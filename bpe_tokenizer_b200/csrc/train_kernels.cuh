@@ -42,13 +42,17 @@ struct DevState {
   uint32_t list_len;
   unsigned long long tie_pos;  // (lastpos << 32 | slot) min over candidates
   unsigned long long live_tokens;
-  unsigned long long barrier;  // grid barrier arrival counter (k_merge_loop)
+  unsigned long long _unused_barrier;
   // k_merge_loop bookkeeping
   uint32_t n_tokens;     // next free token index
   uint32_t iters_done;   // merges applied by the current launch
   uint32_t status;       // LOOP_* exit reason
   uint32_t tie_breaks;
   unsigned long long sites_total;
+  // snapshot taken by block 0 while nothing changes these (start of P3), read by every block for its exit decision:
+  // the decision must not depend on values a faster block may already be changing in the next phase
+  uint32_t snap_n_keys, snap_pool_cursor, snap_hot_n, snap_err;
+  unsigned long long prof_ns[8];  // block 0's view: decide, P1 work, P1 wait, P2 work, P2 wait, P3 work, P3 wait, tie path
   uint32_t bins[36];  // histogram of bit lengths of counts (hot-list threshold selection)
 };
 
@@ -729,13 +733,15 @@ __device__ __forceinline__ uint32_t agg_cursor(const PairTable& t, uint32_t slot
 }
 
 __device__ __forceinline__ void phase_apply(const ApplyArgs& A, uint32_t a, uint32_t b, uint32_t c, uint32_t n_sites,
-                                            uint32_t bid, uint32_t nblk) {
+                                            bool zero_count, uint32_t bid, uint32_t nblk) {
   uint32_t* slots = A.slots;
   const uint32_t n = A.n;
   const PairTable& t = A.t;
   if (bid == 0 && threadIdx.x == 0) {
-    uint32_t s = tbl_find(t, pair_key(a, b));
-    if (s != NOSLOT) t.cnt[s] = 0;  // every counted occurrence was replaced
+    if (zero_count) {
+      uint32_t s = tbl_find(t, pair_key(a, b));
+      if (s != NOSLOT) t.cnt[s] = 0;  // every counted occurrence was replaced
+    }
     A.st->live_tokens -= n_sites;
     A.st->sites_total += n_sites;
   }
@@ -781,7 +787,7 @@ __global__ void k_alloc_new(PairTable t, const uint32_t* __restrict__ newslots, 
 }
 
 __global__ void __launch_bounds__(256) k_apply(ApplyArgs A, uint32_t a, uint32_t b, uint32_t c) {
-  phase_apply(A, a, b, c, A.st->n_sites[0], blockIdx.x, gridDim.x);
+  phase_apply(A, a, b, c, A.st->n_sites[0], true, blockIdx.x, gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -800,6 +806,7 @@ struct LoopArgs {
   uint32_t* cands;
   uint32_t cand_cap;
   Best* partials;
+  unsigned long long* barrier;  // arrival counter, zeroed before the launch
   MergeRec* log;       // device merge log for this launch
   uint32_t log_cap;    // max merges this launch may apply
   uint32_t max_length;
@@ -808,22 +815,34 @@ struct LoopArgs {
   uint32_t tbl_cap;
 };
 
+// Grid barrier for the co-resident (cooperative) launch.  The arrival counter lives in its own 128-byte line, away
+// from the DevState counters the phases hit with atomics, and pollers back off so that they do not saturate the
+// L2 slice that owns it.
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(ctr, 1ull);
+    uint32_t ns = 32;
     while (ld_volatile_u64(ctr) < target) {
+      __nanosleep(ns);
+      if (ns < 256) ns <<= 1;
     }
     __threadfence();
   }
   __syncthreads();
 }
 
-__global__ void k_loop_prepare(DevState* st, uint32_t n_tokens) {
+__global__ void k_loop_prepare(DevState* st, uint32_t n_tokens, unsigned long long* barrier) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->status = LOOP_RUNNING;
-    st->barrier = 0;
+    *barrier = 0;
     st->n_tokens = n_tokens;
     st->iters_done = 0;
     st->n_sites[0] = st->n_sites[1] = 0;
@@ -846,12 +865,26 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
   const uint32_t thresh = ld_cg(&st->hot_thresh);
 
   // first arg-max partials
+  if (bid == 0 && threadIdx.x == 0) {
+    st->snap_n_keys = st->n_keys;
+    st->snap_pool_cursor = st->pool_cursor;
+    st->snap_hot_n = st->hot_n;
+    st->snap_err = st->err;
+  }
   {
     Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
     if (threadIdx.x == 0) L.partials[bid] = v;
   }
-  grid_barrier(&st->barrier, ++epoch * nblk);
+  grid_barrier(L.barrier, ++epoch * nblk);
 
+  const bool prof = (bid == 0 && threadIdx.x == 0);
+  unsigned long long tp0 = prof ? now_ns() : 0, tp1;
+#define PROF(i)                      \
+  if (prof) {                        \
+    tp1 = now_ns();                  \
+    st->prof_ns[i] += tp1 - tp0;     \
+    tp0 = tp1;                       \
+  }
   for (uint32_t it = 0;; it++) {
     const uint32_t par = it & 1u;
     // ---- every block folds the partials and takes the same decision ----
@@ -873,20 +906,21 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
       wcnt = (uint32_t)(w.primary >> 20);
     }
     const uint32_t c = n_tokens0 + it;
-    if (ld_cg(&st->err)) status = LOOP_ERROR;
+    if (ld_cg(&st->snap_err)) status = LOOP_ERROR;
     else if (!w.primary) status = (thresh <= 1) ? LOOP_EMPTY : LOOP_NEED_REBUILD;
     else if (wcnt < thresh) status = LOOP_NEED_REBUILD;
     else if (wcnt < L.min_weight) status = LOOP_DONE;  // core.ts:313
     else if (it >= L.log_cap) status = LOOP_LIMIT;
     else if (c >= L.max_tokens) status = LOOP_NEED_HOST;
+    PROF(0)
     if (status == LOOP_RUNNING && w.mult > 1) {
       // tie on (weight, a.index+b.index): the pair whose last counted occurrence comes first wins (core.ts:294-305)
       if (w.mult > L.cand_cap) status = LOOP_NEED_HOST;
       else {
         phase_collect(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), w.primary, L.cands, L.cand_cap, st, bid, nblk);
-        grid_barrier(&st->barrier, ++epoch * nblk);
+        grid_barrier(L.barrier, ++epoch * nblk);
         phase_tie(A.slots, A.n, t, A.pool, L.cands, ld_cg(&st->n_cand), st, s_max, bid, nblk);
-        grid_barrier(&st->barrier, ++epoch * nblk);
+        grid_barrier(L.barrier, ++epoch * nblk);
         unsigned long long tp = ld_cg(&st->tie_pos);
         if (tp == ~0ull) status = LOOP_ERROR;
         else {
@@ -898,14 +932,15 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
         }
       }
     }
+    PROF(7)
     if (status == LOOP_RUNNING) {
       // capacity the host guarantees: sites = wcnt; new pairs are (x,c) or (c,y), so at most 2*(c+1) of them and
       // at most 2 per site; new list cells <= 2 per site
       unsigned long long new_keys = min(2ull * wcnt + 2ull, 2ull * (c + 1ull) + 2ull);
-      if ((unsigned long long)ld_cg(&st->n_keys) + new_keys > (unsigned long long)(L.tbl_cap >> 1)) status = LOOP_NEED_HOST;
-      else if ((unsigned long long)ld_cg(&st->pool_cursor) + 2ull * wcnt > L.pool_cap) status = LOOP_NEED_HOST;
+      if ((unsigned long long)ld_cg(&st->snap_n_keys) + new_keys > (unsigned long long)(L.tbl_cap >> 1)) status = LOOP_NEED_HOST;
+      else if ((unsigned long long)ld_cg(&st->snap_pool_cursor) + 2ull * wcnt > L.pool_cap) status = LOOP_NEED_HOST;
       else if (wcnt > A.sites_cap || new_keys > A.new_cap) status = LOOP_NEED_HOST;
-      else if ((unsigned long long)ld_cg(&st->hot_n) + new_keys > L.hot_cap) status = LOOP_NEED_HOST;
+      else if ((unsigned long long)ld_cg(&st->snap_hot_n) + new_keys > L.hot_cap) status = LOOP_NEED_HOST;
       else if (c + 1 > L.len16_cap) status = LOOP_NEED_HOST;
     }
     if (status != LOOP_RUNNING) {
@@ -934,22 +969,37 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
       if (w.mult > 1) st->tie_breaks++;
     }
     phase_sites(A, wa, wb, c, par, bid, nblk);
-    grid_barrier(&st->barrier, ++epoch * nblk);
+    PROF(1)
+    grid_barrier(L.barrier, ++epoch * nblk);
+    PROF(2)
     // ---- P2: lists of the new pairs, hot list ----
     if (bid == 0 && threadIdx.x == 0) {
       st->n_cand = 0;
       st->tie_pos = ~0ull;
+      t.cnt[w.slot] = 0;  // every counted occurrence of the winner is being replaced; must be visible before the
+                          // next arg-max partials are taken in P3 (no delta of P1 touches the winner's own pair)
     }
     phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, 1, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);
-    grid_barrier(&st->barrier, ++epoch * nblk);
+    PROF(3)
+    grid_barrier(L.barrier, ++epoch * nblk);
+    PROF(4)
     // ---- P3: rewrite + next arg-max partials ----
-    phase_apply(A, wa, wb, c, ld_cg(&st->n_sites[par]), bid, nblk);
+    if (bid == 0 && threadIdx.x == 0) {
+      st->snap_n_keys = st->n_keys;
+      st->snap_pool_cursor = st->pool_cursor;
+      st->snap_hot_n = st->hot_n;
+      st->snap_err = st->err;
+    }
+    phase_apply(A, wa, wb, c, ld_cg(&st->n_sites[par]), false, bid, nblk);
     {
       Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
       if (threadIdx.x == 0) L.partials[bid] = v;
     }
-    grid_barrier(&st->barrier, ++epoch * nblk);
+    PROF(5)
+    grid_barrier(L.barrier, ++epoch * nblk);
+    PROF(6)
   }
+#undef PROF
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -177,7 +177,7 @@ class BPETokenizer:
     def stats(self) -> dict:
         s = bpe_stats()
         self._check(self._lib.bpe_get_stats(self._h, C.byref(s)))
-        return {n: getattr(s, n) for n, _ in bpe_stats._fields_}
+        return {n: (list(getattr(s, n)) if n == "ms_loop_phase" else getattr(s, n)) for n, _ in bpe_stats._fields_}
 
     # ---- snapshot (core.ts:112-171) ---------------------------------------------------------
     def toJSON(self) -> dict:

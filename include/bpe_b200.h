@@ -75,6 +75,8 @@ typedef struct bpe_stats {
   double ms_apply;             /* K3                                                              */
   double ms_encode;            /* K4 + K5, last bpe_encode_batch* call                            */
   double ms_last_merge_until;  /* device time of the last bpe_merge_until call                    */
+  double ms_loop_phase[8];     /* k_merge_loop as seen by block 0, cumulative since the last index build:
+                                  decide, P1 sites, P1 barrier wait, P2 alloc, P2 wait, P3 apply+argmax, P3 wait, tie path */
 } bpe_stats;
 
 int bpe_abi_version(void);

@@ -99,13 +99,15 @@ def test_fuzz_step_by_step_against_literal(seed, scan_mode):
         assert gpu.encodeToCode(d) == want
 
 
+@pytest.mark.parametrize("mode", [0, 4, 2])  # 0: persistent kernel, 4: host-driven loop, 2: persistent + full-scan sites
 @pytest.mark.parametrize("seed", range(12))
-def test_fuzz_merge_until_against_literal(seed):
+def test_fuzz_merge_until_against_literal(seed, mode):
     rng = random.Random(2000 + seed)
     alphabet = "ab" if seed % 3 == 0 else "abcde "
     docs = _random_docs(rng, alphabet, rng.randint(1, 8), rng.choice([20, 100, 400]))
     opts = {"min_weight": rng.choice([None, 2, 4]), "max_length": rng.choice([None, 5, 9]), "max_iterations": rng.choice([None, None, 7])}
     lit, gpu = LiteralTokenizer(), make()
+    gpu._lib.bpe_set_profiling(gpu._h, mode)
     for d in docs:
         lit.addToCorpus(d)
         gpu.addToCorpus(d)
