@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -122,6 +123,7 @@ struct bpe_engine {
   bool hot_valid = false;
   uint32_t hot_max_length = 0;
   uint32_t hot_thresh = 0;
+  uint32_t hot_limit = 0;
   DevBuf<uint32_t> cands;
   DevBuf<MergeRec> dev_log;
   DevBuf<unsigned long long> barrier;  // own 128-byte line
@@ -209,11 +211,13 @@ int sync_len16(bpe_engine* e) {
 
 // ---- pair table allocation / growth -------------------------------------------------------------
 int alloc_table(bpe_engine* e, uint32_t cap) {
-  e->t_keys.release();
-  e->t_cnt.release();
-  e->t_start.release();
-  e->t_len.release();
-  e->t_fill.release();
+  if (e->t_keys.cap < cap || e->t_keys.cap > 4ull * cap) {  // keep the buffers when they fit (cudaFree of GBs is slow)
+    e->t_keys.release();
+    e->t_cnt.release();
+    e->t_start.release();
+    e->t_len.release();
+    e->t_fill.release();
+  }
   CK(e->t_keys.reserve(cap));
   CK(e->t_cnt.reserve(cap));
   CK(e->t_start.reserve(cap));
@@ -277,7 +281,6 @@ int build_index(bpe_engine* e) {
   CK(e->pool.reserve((size_t)pool_need));
   uint64_t t2 = (uint64_t)e->n_tokens * (uint64_t)e->n_tokens;
   uint32_t cap = pow2_at_least(std::min<uint64_t>(std::max<uint64_t>(2 * std::min(n, t2), 1u << 16), 1u << 24));
-  if (e->tbl_cap > cap) cap = e->tbl_cap;
   {
     if (!e->ev0) {
       CK(cudaEventCreate(&e->ev0));
@@ -357,7 +360,7 @@ int rebuild_hot(bpe_engine* e, uint32_t max_length, bool* any) {
   int lo = pick;
   while (lo > 1 && e->h_st->bins[lo - 1] == 0) lo--;
   uint32_t thresh = 1u << (lo - 1);
-  CK(e->hot.reserve(std::max<size_t>((size_t)acc * 2 + 4096, 1u << 18)));
+  CK(e->hot.reserve(std::max<size_t>((size_t)acc * 2 + 4096 + 2 * (size_t)BPE_MAX_TOKENS, 1u << 18)));
   e->h_st->hot_n = 0;
   e->h_st->hot_thresh = thresh;
   uint32_t two[2] = {0, thresh};
@@ -365,6 +368,7 @@ int rebuild_hot(bpe_engine* e, uint32_t max_length, bool* any) {
   k_build_hot<<<e->grid(4), 256, 0, e->stream>>>(t, e->d_len16.p, max_length, e->hot.p, (uint32_t)e->hot.cap, e->d_st.p);
   CKL();
   e->hot_thresh = thresh;
+  e->hot_limit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(4ull * HOT_TARGET, 2 * acc + 4096), 0xFFFFFFF0u);
   e->hot_max_length = max_length;
   e->hot_valid = true;
   e->stats.hot_rebuilds++;
@@ -418,9 +422,9 @@ int run_apply(bpe_engine* e, uint32_t a, uint32_t b, uint32_t c, uint32_t bound)
   // capacity: new keys <= 2*bound, new list cells <= 2*bound
   uint64_t keys_after = (uint64_t)e->h_st->n_keys + 2ull * bound + 2;
   if (keys_after * 2 > e->tbl_cap) {
-    uint64_t want = keys_after * 4;
+    uint64_t want = keys_after * 5 / 2;
     if (want > 0x80000000ull) want = 0x80000000ull;
-    if (keys_after >= want) return fail(e, BPE_E_NOMEM, "pair table cannot grow further");
+    if (keys_after * 2 > pow2_at_least(want)) return fail(e, BPE_E_NOMEM, "pair table cannot grow further");
     TRY(grow_table(e, pow2_at_least(want)));
   }
   uint64_t pool_after = (uint64_t)e->h_st->pool_cursor + 2ull * bound;
@@ -487,7 +491,7 @@ struct EncodeScratch {
   DevBuf<int32_t> out_tmp;
   DevBuf<uint32_t> out_len;
   DevBuf<uint64_t> out_off;
-  DevBuf<uint32_t> g_tok, g_rk;
+  DevBuf<uint32_t> g_tok, g_nxt, g_prv, g_rk;
 };
 
 // device-resident encode; leaves compacted output in dev_out / dev_out_offsets
@@ -501,6 +505,8 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
   CK(sc.out_off.reserve((size_t)n_docs + 2));
   if (max_doc_len > ENC_WARP_MAX) {
     CK(sc.g_tok.reserve((size_t)n_ids));
+    CK(sc.g_nxt.reserve((size_t)n_ids));
+    CK(sc.g_prv.reserve((size_t)n_ids));
     CK(sc.g_rk.reserve((size_t)n_ids));
   }
   MergeTable mt{e->d_mt.p, e->mt_cap - 1, (uint32_t)(32 - ilog2(e->mt_cap))};
@@ -511,15 +517,15 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
   CK(cudaEventRecord(e->ev0, e->stream));
   if (n_docs > 0) {
     int64_t blocks = std::min<int64_t>((n_docs + ENC_WARPS - 1) / ENC_WARPS, (int64_t)e->sm_count * 16);
-    k_encode<<<(int)blocks, ENC_THREADS, 0, e->stream>>>(dev_ids, dev_doc_off, n_docs, mt, sc.out_tmp.p, sc.out_len.p, sc.g_tok.p, sc.g_rk.p);
+    k_encode<<<(int)blocks, ENC_THREADS, 0, e->stream>>>(dev_ids, dev_doc_off, n_docs, mt, sc.out_tmp.p, sc.out_len.p, sc.g_tok.p, sc.g_nxt.p, sc.g_prv.p, sc.g_rk.p);
     CKL();
   }
   k_scan_counts<<<1, 1024, 0, e->stream>>>(sc.out_len.p, sc.out_off.p, (uint32_t)n_docs);
   CKL();
   {
     int64_t warps = n_docs + 1;
-    int64_t blocks = std::min<int64_t>((warps + ENC_WARPS - 1) / ENC_WARPS, (int64_t)e->sm_count * 16);
-    k_gather_map<<<(int)blocks, ENC_THREADS, 0, e->stream>>>(sc.out_tmp.p, dev_doc_off, sc.out_off.p, n_docs, dev_tvi, n_tvi, dev_out, dev_out_offsets, dev_first_bad);
+    int64_t blocks = std::min<int64_t>((warps + 3) / 4, (int64_t)e->sm_count * 16);
+    k_gather_map<<<(int)blocks, 128, 0, e->stream>>>(sc.out_tmp.p, dev_doc_off, sc.out_off.p, n_docs, dev_tvi, n_tvi, dev_out, dev_out_offsets, dev_first_bad);
     CKL();
   }
   CK(cudaEventRecord(e->ev1, e->stream));
@@ -629,6 +635,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     L.len16_cap = (uint32_t)std::min<size_t>(e->d_len16.cap, 0xFFFFFFF0u);
     L.hot = e->hot.p;
     L.hot_cap = (uint32_t)std::min<size_t>(e->hot.cap, 0xFFFFFFF0u);
+    L.hot_limit = e->hot_limit;
     L.cands = e->cands.p;
     L.cand_cap = (uint32_t)std::min<size_t>(e->cands.cap, 0xFFFFFFF0u);
     L.partials = e->partials.p;
@@ -639,6 +646,8 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     L.min_weight = (uint32_t)std::min<int64_t>(mw, 0xFFFFFFFFll);
     L.max_tokens = BPE_MAX_TOKENS;
     L.tbl_cap = e->tbl_cap;
+    static const bool trace = getenv("BPE_TRACE") != nullptr;
+    auto tw0 = std::chrono::steady_clock::now();
     k_loop_prepare<<<1, 32, 0, e->stream>>>(e->d_st.p, (uint32_t)e->n_tokens, e->barrier.p);
     e->stats.kernel_launches++;
     void* args[] = {&L};
@@ -650,6 +659,11 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     e->stats.kernel_launches++;
     if ((rc = fetch_state(e)) != BPE_OK) break;
     uint32_t iters = e->h_st->iters_done;
+    if (trace) {
+      double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
+      fprintf(stderr, "[bpe] k_merge_loop: %u merges in %.2f ms, status %u, best_cnt %u, hot_n %u thresh %u, keys %u/%u\n", iters, ms,
+              e->h_st->status, e->h_st->best_cnt, e->h_st->hot_n, e->h_st->hot_thresh, e->h_st->n_keys, e->tbl_cap);
+    }
     if (iters) {
       tmp.resize(iters);
       ce = cudaMemcpyAsync(tmp.data(), e->dev_log.p, (size_t)iters * sizeof(MergeRec), cudaMemcpyDeviceToHost, e->stream);
@@ -765,7 +779,7 @@ int merge_until_host(bpe_engine* e, int64_t min_weight, int32_t max_length, int6
       if (!any) break;  // nothing countable left (core.ts:312)
     }
     if ((rc = run_argmax(e, ml, 1)) != BPE_OK) break;
-    if (e->h_st->err & ERR_HOT_OVERFLOW) {
+    if ((e->h_st->err & ERR_HOT_OVERFLOW) || e->h_st->hot_n > e->hot_limit) {
       e->hot_valid = false;
       CK(cudaMemsetAsync(&e->d_st.p->err, 0, sizeof(uint32_t), e->stream));
       continue;

@@ -38,10 +38,13 @@ __host__ __device__ __forceinline__ uint32_t mk_back(uint32_t d) { return (KIND_
 __host__ __device__ __forceinline__ uint32_t mk_hole() { return (KIND_HOLE << KIND_SHIFT); }
 __host__ __device__ __forceinline__ uint32_t pair_key(uint32_t a, uint32_t b) { return (a << 16) | b; }
 
-// Loads of data that other SMs rewrite during the SAME launch (the persistent mergeUntil kernel): go to L2
-// (ld.global.cg), never through the non-coherent path.
-__device__ __forceinline__ uint32_t ld_slot(const uint32_t* p) { return __ldcg(p); }
-__device__ __forceinline__ uint4 ld_slots4(const uint32_t* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+// Corpus slots are rewritten by other SMs during the SAME launch (persistent mergeUntil kernel), so they are never
+// read through the non-coherent path (no __ldg / ld.global.nc).  Plain loads may be served by L1: within a phase
+// nobody rewrites what a thread reads, and every grid barrier ends with a gpu-scope fence (which invalidates L1)
+// before the next phase starts -- the same contract cooperative-groups grid.sync() gives.
+// Control words polled or read right after a barrier use ld_cg (L2).
+__device__ __forceinline__ uint32_t ld_slot(const uint32_t* p) { return *p; }
+__device__ __forceinline__ uint4 ld_slots4(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t* p) { return __ldcg(p); }
 __device__ __forceinline__ unsigned long long ld_cg(const unsigned long long* p) { return __ldcg(p); }
 __device__ __forceinline__ uint4 ld_cg4(const uint4* p) { return __ldcg(p); }

@@ -125,46 +125,39 @@ __global__ void k_mark_docstarts(uint32_t* __restrict__ slots, const int64_t* __
 constexpr int K1_THREADS = 256;
 constexpr int K1_SMEM_SLOTS = 2048;  // 24 KB
 constexpr int K1_MAX_PROBE = 8;
+constexpr uint32_t K1B_CHUNK = 1u << 16;  // positions per block iteration of the scatter
 
 struct SmemHist {
   uint32_t key[K1_SMEM_SLOTS];
-  uint32_t cnt[K1_SMEM_SLOTS];
-  uint32_t occ[K1_SMEM_SLOTS];
+  uint32_t a[K1_SMEM_SLOTS];  // k_hist: adjacencies seen        k_scatter: ticket counter
+  uint32_t b[K1_SMEM_SLOTS];  // k_hist: of which NOT counted    k_scatter: base cell in the pool
 };
 
-__device__ __forceinline__ void k1_add(SmemHist& sh, const PairTable& t, DevState* st, uint32_t key, uint32_t counted) {
+// slot of `key` in the block-local table (inserting it), or -1 when the neighbourhood is crowded
+__device__ __forceinline__ int sh_slot(SmemHist& sh, uint32_t key, bool insert) {
   uint32_t h = (key * 0x9E3779B1u) >> (32 - 11);
 #pragma unroll 1
   for (int probe = 0; probe < K1_MAX_PROBE; probe++) {
     uint32_t k = sh.key[h];
     if (k == EMPTY_KEY) {
+      if (!insert) return -1;
       uint32_t old = atomicCAS(&sh.key[h], EMPTY_KEY, key);
       k = (old == EMPTY_KEY) ? key : old;
     }
-    if (k == key) {
-      if (counted) atomicAdd(&sh.cnt[h], 1u);
-      atomicAdd(&sh.occ[h], 1u);
-      return;
-    }
+    if (k == key) return (int)h;
     h = (h + 1) & (K1_SMEM_SLOTS - 1);
   }
-  // shared table crowded: straight to the global table
-  uint32_t g = tbl_find_or_insert(t, key, &st->n_keys);
-  if (g == NOSLOT) {
-    atomicOr(&st->err, ERR_TABLE_FULL);
-    return;
-  }
-  if (counted) atomicAdd(t.cnt + g, 1u);
-  atomicAdd(t.occ_len + g, 1u);
+  return -1;
 }
 
 // One adjacency starting at position p (slot value w).  Returns false when p starts no adjacency.
+// counted (optional): the run-parity rule of core.ts:285-290.
 __device__ __forceinline__ bool edge_at(const uint32_t* __restrict__ slots, uint32_t n, uint32_t p, uint32_t w,
-                                        uint32_t wnext_hint, bool have_hint, uint32_t* key, uint32_t* counted) {
+                                        uint32_t wnext_hint, uint32_t* key, uint32_t* counted) {
   if (!slot_is_id(w)) return false;
   uint32_t a = slot_val(w);
   int b;
-  if (have_hint && slot_is_id(wnext_hint)) {
+  if (slot_is_id(wnext_hint)) {
     b = (wnext_hint & DOCSTART) ? NOTOK : (int)slot_val(wnext_hint);
   } else {
     uint32_t q;
@@ -172,9 +165,24 @@ __device__ __forceinline__ bool edge_at(const uint32_t* __restrict__ slots, uint
   }
   if (b == NOTOK) return false;
   *key = pair_key(a, (uint32_t)b);
-  *counted = 1;
-  if ((uint32_t)b == a) *counted = (run_left(slots, p, w, (int)a) & 1u) ? 0u : 1u;
+  if (counted) {
+    *counted = 1;
+    if ((uint32_t)b == a) *counted = (run_left(slots, p, w, (int)a) & 1u) ? 0u : 1u;
+  }
   return true;
+}
+
+// loads the 4 slots of group g plus the slot after them
+__device__ __forceinline__ void load_group(const uint32_t* __restrict__ slots, uint32_t n, uint32_t g, uint32_t v[5]) {
+  uint32_t p0 = g << 2;
+  if (p0 + 4 <= n) {
+    uint4 q = ld_slots4(slots + p0);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = (p0 + j < n) ? ld_slot(slots + p0 + j) : mk_hole();
+  }
+  v[4] = (p0 + 4 < n) ? ld_slot(slots + p0 + 4) : (DOCSTART);  // DOCSTART|ID(0): "no right neighbour"
 }
 
 __global__ void __launch_bounds__(K1_THREADS) k_hist(const uint32_t* __restrict__ slots, uint32_t n, PairTable t,
@@ -182,8 +190,8 @@ __global__ void __launch_bounds__(K1_THREADS) k_hist(const uint32_t* __restrict_
   __shared__ SmemHist sh;
   for (int i = threadIdx.x; i < K1_SMEM_SLOTS; i += K1_THREADS) {
     sh.key[i] = EMPTY_KEY;
-    sh.cnt[i] = 0;
-    sh.occ[i] = 0;
+    sh.a[i] = 0;
+    sh.b[i] = 0;
   }
   __syncthreads();
   // contiguous chunk of 4-slot groups per block, so the shared table sees as few distinct pairs as possible
@@ -194,31 +202,38 @@ __global__ void __launch_bounds__(K1_THREADS) k_hist(const uint32_t* __restrict_
   for (uint32_t g = g_begin + threadIdx.x; g < g_end; g += K1_THREADS) {
     uint32_t p0 = g << 2;
     uint32_t v[5];
-    if (p0 + 4 <= n) {
-      uint4 q = ld_slots4(slots + p0);
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; j++) v[j] = (p0 + j < n) ? ld_slot(slots + p0 + j) : mk_hole();
-    }
-    v[4] = (p0 + 4 < n) ? ld_slot(slots + p0 + 4) : (DOCSTART);  // DOCSTART|ID(0): "no right neighbour"
+    load_group(slots, n, g, v);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       uint32_t key, counted;
-      if (p0 + j < n && edge_at(slots, n, p0 + j, v[j], v[j + 1], true, &key, &counted)) k1_add(sh, t, st, key, counted);
+      if (p0 + j < n && edge_at(slots, n, p0 + j, v[j], v[j + 1], &key, &counted)) {
+        int h = sh_slot(sh, key, true);
+        if (h >= 0) {
+          atomicAdd(&sh.a[h], 1u);
+          if (!counted) atomicAdd(&sh.b[h], 1u);
+        } else {  // shared table crowded: straight to the global table
+          uint32_t gs = tbl_find_or_insert(t, key, &st->n_keys);
+          if (gs == NOSLOT) {
+            atomicOr(&st->err, ERR_TABLE_FULL);
+          } else {
+            if (counted) atomicAdd(t.cnt + gs, 1u);
+            atomicAdd(t.occ_len + gs, 1u);
+          }
+        }
+      }
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < K1_SMEM_SLOTS; i += K1_THREADS) {
     uint32_t key = sh.key[i];
     if (key == EMPTY_KEY) continue;
-    uint32_t g = tbl_find_or_insert(t, key, &st->n_keys);
-    if (g == NOSLOT) {
+    uint32_t gs = tbl_find_or_insert(t, key, &st->n_keys);
+    if (gs == NOSLOT) {
       atomicOr(&st->err, ERR_TABLE_FULL);
       continue;
     }
-    if (sh.cnt[i]) atomicAdd(t.cnt + g, sh.cnt[i]);
-    if (sh.occ[i]) atomicAdd(t.occ_len + g, sh.occ[i]);
+    if (sh.a[i] != sh.b[i]) atomicAdd(t.cnt + gs, sh.a[i] - sh.b[i]);
+    if (sh.a[i]) atomicAdd(t.occ_len + gs, sh.a[i]);
   }
 }
 
@@ -236,37 +251,69 @@ __global__ void k_alloc_lists(PairTable t, DevState* st, uint32_t pool_cap) {
   }
 }
 
-// K1b: scatter every adjacency's position into its pair's list (warp-aggregated cursor atomics)
+// K1b: scatter every adjacency's position into its pair's list.  Per 64 Ki-position chunk a block counts its
+// adjacencies per pair in shared memory, reserves one contiguous range per pair with a single global atomic,
+// then hands out cells with shared-memory tickets (the chunk is re-read from L2).
 __global__ void __launch_bounds__(K1_THREADS) k_scatter(const uint32_t* __restrict__ slots, uint32_t n, PairTable t,
                                                          uint32_t* __restrict__ pool, DevState* st) {
-  uint32_t n4 = (n + 3) >> 2;
-  uint32_t lane = lane_id();
-  uint32_t n4_round = (n4 + 31) & ~31u;
-  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n4_round; g += gridDim.x * blockDim.x) {
-    uint32_t p0 = g << 2;
-    uint32_t v[5];
+  __shared__ SmemHist sh;
+  uint32_t n_chunks = (n + K1B_CHUNK - 1) / K1B_CHUNK;
+  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    for (int i = threadIdx.x; i < K1_SMEM_SLOTS; i += K1_THREADS) {
+      sh.key[i] = EMPTY_KEY;
+      sh.a[i] = 0;
+    }
+    __syncthreads();
+    uint32_t g_begin = chunk * (K1B_CHUNK >> 2);
+    uint32_t g_end = min((n + 3) >> 2, g_begin + (K1B_CHUNK >> 2));
+    for (uint32_t g = g_begin + threadIdx.x; g < g_end; g += K1_THREADS) {
+      uint32_t p0 = g << 2;
+      uint32_t v[5];
+      load_group(slots, n, g, v);
 #pragma unroll
-    for (int j = 0; j < 5; j++) v[j] = (p0 + j < n) ? ld_slot(slots + p0 + j) : (j == 4 ? DOCSTART : mk_hole());
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      uint32_t key = EMPTY_KEY - 1 - lane, counted;  // per-lane dummy: matches nobody
-      bool has = (p0 + j < n) && edge_at(slots, n, p0 + j, v[j], v[j + 1], true, &key, &counted);
-      uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-      uint32_t leader = __ffs(peers) - 1;
-      uint32_t rank = __popc(peers & ((1u << lane) - 1));
-      uint32_t base = 0;
-      if (has && lane == leader) {
-        uint32_t s = tbl_find(t, key);
-        if (s == NOSLOT) {
-          atomicOr(&st->err, ERR_MISSING_KEY);
-          base = NOPOS;
-        } else {
-          base = t.occ_start[s] + atomicAdd(t.occ_fill + s, (uint32_t)__popc(peers));
+      for (int j = 0; j < 4; j++) {
+        uint32_t key;
+        if (p0 + j < n && edge_at(slots, n, p0 + j, v[j], v[j + 1], &key, nullptr)) {
+          int h = sh_slot(sh, key, true);
+          if (h >= 0) atomicAdd(&sh.a[h], 1u);
         }
       }
-      base = __shfl_sync(0xFFFFFFFFu, base, leader);
-      if (has && base != NOPOS) pool[base + rank] = p0 + j;
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K1_SMEM_SLOTS; i += K1_THREADS) {
+      uint32_t key = sh.key[i];
+      if (key == EMPTY_KEY) continue;
+      uint32_t gs = tbl_find(t, key);
+      if (gs == NOSLOT) {
+        atomicOr(&st->err, ERR_MISSING_KEY);
+        sh.b[i] = NOPOS;
+      } else {
+        sh.b[i] = t.occ_start[gs] + atomicAdd(t.occ_fill + gs, sh.a[i]);
+      }
+      sh.a[i] = 0;
+    }
+    __syncthreads();
+    for (uint32_t g = g_begin + threadIdx.x; g < g_end; g += K1_THREADS) {
+      uint32_t p0 = g << 2;
+      uint32_t v[5];
+      load_group(slots, n, g, v);
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint32_t key;
+        if (p0 + j < n && edge_at(slots, n, p0 + j, v[j], v[j + 1], &key, nullptr)) {
+          int h = sh_slot(sh, key, false);
+          if (h >= 0) {
+            uint32_t base = sh.b[h];
+            if (base != NOPOS) pool[base + atomicAdd(&sh.a[h], 1u)] = p0 + j;
+          } else {  // pair did not fit the block-local table: one global cursor atomic
+            uint32_t gs = tbl_find(t, key);
+            if (gs == NOSLOT) atomicOr(&st->err, ERR_MISSING_KEY);
+            else pool[t.occ_start[gs] + atomicAdd(t.occ_fill + gs, 1u)] = p0 + j;
+          }
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -567,14 +614,14 @@ __device__ __forceinline__ uint32_t agg_new(const PairTable& t, DevState* st, ui
 }
 
 __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint32_t b, uint32_t c, uint32_t par,
-                                            uint32_t bid, uint32_t nblk) {
+                                            uint32_t pair_slot, uint32_t bid, uint32_t nblk) {
   const uint32_t* slots = A.slots;
   const uint32_t n = A.n;
   const PairTable& t = A.t;
   DevState* st = A.st;
   uint32_t list_start = 0, total = n;
   if (!A.scan_mode) {
-    uint32_t s = tbl_find(t, pair_key(a, b));
+    uint32_t s = pair_slot;
     total = (s == NOSLOT) ? 0 : t.occ_len[s];
     list_start = (s == NOSLOT) ? 0 : t.occ_start[s];
   }
@@ -777,7 +824,7 @@ __device__ __forceinline__ void phase_apply(const ApplyArgs& A, uint32_t a, uint
 // ---- stand-alone K3 kernels (applyMerge / restoreMerge one at a time, and the host-driven loop) ----
 __global__ void __launch_bounds__(256) k_sites(ApplyArgs A, uint32_t a, uint32_t b, uint32_t c) {
   if (blockIdx.x == 0 && threadIdx.x == 0) A.len16[c] = A.len16[a] + A.len16[b];  // chars = a.chars + b.chars (:318)
-  phase_sites(A, a, b, c, 0, blockIdx.x, gridDim.x);
+  phase_sites(A, a, b, c, 0, tbl_find(A.t, pair_key(a, b)), blockIdx.x, gridDim.x);
 }
 
 __global__ void k_alloc_new(PairTable t, const uint32_t* __restrict__ newslots, const uint32_t* __restrict__ len16,
@@ -803,6 +850,7 @@ struct LoopArgs {
   uint32_t len16_cap;
   uint32_t* hot;
   uint32_t hot_cap;
+  uint32_t hot_limit;  // rebuild the hot list with a higher threshold once it would pass this many entries
   uint32_t* cands;
   uint32_t cand_cap;
   Best* partials;
@@ -940,7 +988,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
       if ((unsigned long long)ld_cg(&st->snap_n_keys) + new_keys > (unsigned long long)(L.tbl_cap >> 1)) status = LOOP_NEED_HOST;
       else if ((unsigned long long)ld_cg(&st->snap_pool_cursor) + 2ull * wcnt > L.pool_cap) status = LOOP_NEED_HOST;
       else if (wcnt > A.sites_cap || new_keys > A.new_cap) status = LOOP_NEED_HOST;
-      else if ((unsigned long long)ld_cg(&st->snap_hot_n) + new_keys > L.hot_cap) status = LOOP_NEED_HOST;
+      else if ((unsigned long long)ld_cg(&st->snap_hot_n) + new_keys > min(L.hot_cap, L.hot_limit)) status = LOOP_NEED_REBUILD;
       else if (c + 1 > L.len16_cap) status = LOOP_NEED_HOST;
     }
     if (status != LOOP_RUNNING) {
@@ -968,7 +1016,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
       st->n_new[par ^ 1u] = 0;
       if (w.mult > 1) st->tie_breaks++;
     }
-    phase_sites(A, wa, wb, c, par, bid, nblk);
+    phase_sites(A, wa, wb, c, par, w.slot, bid, nblk);
     PROF(1)
     grid_barrier(L.barrier, ++epoch * nblk);
     PROF(2)
