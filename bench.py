@@ -316,7 +316,7 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "mergeUntil step (host-driven loop of k_argmax/k_sites/k_alloc_new/k_apply)",
+                "kernel": "k_merge_loop (persistent cooperative mergeUntil kernel; the step also contains k_ingest_ids + K1)",
                 "note": "achieved = reference-algorithm bytes sum_t 4*(2*N_t+N_{t+1}) / step time ('x of reference-algorithm roofline', SURVEY 8d); "
                         "an incremental design may exceed 1.0; peak from " + peak_src,
             },

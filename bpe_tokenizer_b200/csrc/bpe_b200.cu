@@ -107,6 +107,7 @@ struct bpe_engine {
   std::vector<int32_t> h_merges;
   bool mt_dirty = true;
   DevBuf<unsigned long long> d_mt;
+  DevBuf<uint32_t> d_minlr;  // per token: lowest rank as left operand << 16 | lowest rank as right operand
   uint32_t mt_cap = 0;
 
   // pair index
@@ -420,7 +421,7 @@ ApplyArgs apply_args(bpe_engine* e) {
 // bound = upper bound on the number of sites (count of the pair, or its list length)
 int run_apply(bpe_engine* e, uint32_t a, uint32_t b, uint32_t c, uint32_t bound) {
   // capacity: new keys <= 2*bound, new list cells <= 2*bound
-  uint64_t keys_after = (uint64_t)e->h_st->n_keys + 2ull * bound + 2;
+  uint64_t keys_after = (uint64_t)e->h_st->n_keys + std::min<uint64_t>(2ull * bound + 2, 2ull * ((uint64_t)e->n_tokens + 1) + 2);
   if (keys_after * 2 > e->tbl_cap) {
     uint64_t want = keys_after * 5 / 2;
     if (want > 0x80000000ull) want = 0x80000000ull;
@@ -479,6 +480,16 @@ int ensure_merge_table(bpe_engine* e) {
     }
     if (!dup) h[i] = ((unsigned long long)key << 32) | ((unsigned long long)(uint32_t)r << 16) | c;
   }
+  std::vector<uint32_t> minlr((size_t)std::max(e->n_tokens, 1), 0xFFFFFFFFu);
+  for (size_t r = 0; r < m; r++) {
+    uint32_t a = (uint32_t)e->h_merges[3 * r], b = (uint32_t)e->h_merges[3 * r + 1];
+    if (a >= minlr.size() || b >= minlr.size()) return fail(e, BPE_E_INVALID, "merge %zu refers to a token outside the table", r);
+    uint32_t rr = (uint32_t)std::min<size_t>(r, 0xFFFE);
+    if ((minlr[a] >> 16) > rr) minlr[a] = (minlr[a] & 0xFFFFu) | (rr << 16);
+    if ((minlr[b] & 0xFFFFu) > rr) minlr[b] = (minlr[b] & 0xFFFF0000u) | rr;
+  }
+  CK(e->d_minlr.reserve(minlr.size()));
+  CK(cudaMemcpyAsync(e->d_minlr.p, minlr.data(), minlr.size() * 4, cudaMemcpyHostToDevice, e->stream));
   CK(e->d_mt.reserve(cap));
   CK(cudaMemcpyAsync(e->d_mt.p, h.data(), (size_t)cap * 8, cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -491,7 +502,7 @@ struct EncodeScratch {
   DevBuf<int32_t> out_tmp;
   DevBuf<uint32_t> out_len;
   DevBuf<uint64_t> out_off;
-  DevBuf<uint32_t> g_tok, g_nxt, g_prv, g_rk;
+  DevBuf<uint32_t> g_tok, g_nxt, g_prv, g_rk, g_sel;
 };
 
 // device-resident encode; leaves compacted output in dev_out / dev_out_offsets
@@ -508,8 +519,9 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
     CK(sc.g_nxt.reserve((size_t)n_ids));
     CK(sc.g_prv.reserve((size_t)n_ids));
     CK(sc.g_rk.reserve((size_t)n_ids));
+    CK(sc.g_sel.reserve((size_t)n_ids));
   }
-  MergeTable mt{e->d_mt.p, e->mt_cap - 1, (uint32_t)(32 - ilog2(e->mt_cap))};
+  EncTables mt{MergeTable{e->d_mt.p, e->mt_cap - 1, (uint32_t)(32 - ilog2(e->mt_cap))}, e->d_minlr.p};
   if (!e->ev0) {
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
@@ -517,7 +529,7 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
   CK(cudaEventRecord(e->ev0, e->stream));
   if (n_docs > 0) {
     int64_t blocks = std::min<int64_t>((n_docs + ENC_WARPS - 1) / ENC_WARPS, (int64_t)e->sm_count * 16);
-    k_encode<<<(int)blocks, ENC_THREADS, 0, e->stream>>>(dev_ids, dev_doc_off, n_docs, mt, sc.out_tmp.p, sc.out_len.p, sc.g_tok.p, sc.g_nxt.p, sc.g_prv.p, sc.g_rk.p);
+    k_encode<<<(int)blocks, ENC_THREADS, 0, e->stream>>>(dev_ids, dev_doc_off, n_docs, mt, sc.out_tmp.p, sc.out_len.p, sc.g_tok.p, sc.g_nxt.p, sc.g_prv.p, sc.g_rk.p, sc.g_sel.p);
     CKL();
   }
   k_scan_counts<<<1, 1024, 0, e->stream>>>(sc.out_len.p, sc.out_off.p, (uint32_t)n_docs);
@@ -710,8 +722,8 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       uint64_t new_keys = std::min<uint64_t>(2 * w + 2, 2 * ((uint64_t)e->n_tokens + 1) + 2);
       uint64_t keys_after = (uint64_t)e->h_st->n_keys + new_keys;
       if (keys_after * 2 > e->tbl_cap) {
-        uint64_t want = std::min<uint64_t>(keys_after * 4, 0x80000000ull);
-        if (keys_after * 2 > want) {
+        uint64_t want = std::min<uint64_t>(keys_after * 5 / 2, 0x80000000ull);  // next power of two: load 0.2 .. 0.4
+        if (keys_after * 2 > pow2_at_least(want)) {
           rc = fail(e, BPE_E_NOMEM, "pair table cannot grow further");
           break;
         }
@@ -907,6 +919,7 @@ int bpe_set_tokens(bpe_engine* e, const int32_t* utf16_len, int32_t n_tokens) {
   CK(cudaSetDevice(e->device));
   e->h_len16.assign(utf16_len, utf16_len + n_tokens);
   e->n_tokens = n_tokens;
+  e->mt_dirty = true;
   TRY(sync_len16(e));
   e->hot_valid = false;
   return BPE_OK;

@@ -5,12 +5,9 @@
 // equivalent to "repeat: take the lowest-rank pair present, replace all its occurrences left to right
 // without overlap" (cross-checked against the literal form in tests).
 //
-// One warp owns one document.  Tokens never move: the document is a doubly linked list over its
-// original positions (tok/next/prev in shared memory) with the rank of every adjacent pair cached
-// (rk).  A round = warp-min over the cached ranks, then only the lanes that own an occurrence of that
-// pair do work: relink, write the new token, refresh the two ranks next to it (two L2-resident hash
-// probes).  Pairs with a == b (runs, core.ts:285-290 semantics of replaceAll) take a short serial path
-// on lane 0.  Documents longer than ENC_WARP_MAX use the same code over global scratch.
+// One warp owns one document (tokens + cached pair ranks in shared memory, global scratch above ENC_WARP_MAX
+// tokens).  Instead of one round per distinct merge, every round merges ALL pairs that are provably merged as they
+// stand by the sequential process (see below), then compacts the document in place.
 #pragma once
 #include "common.cuh"
 
@@ -39,109 +36,152 @@ __device__ __forceinline__ uint32_t mt_lookup(const MergeTable& mt, uint32_t a, 
   }
 }
 
-// IdxT: position type (uint16_t in shared memory, uint32_t in global scratch).  END = "no neighbour".
-template <typename TokT, typename IdxT>
-__device__ __forceinline__ void encode_doc(TokT* tok, IdxT* nxt, IdxT* prv, uint32_t* rk, uint32_t n,
-                                           const MergeTable& mt, uint32_t lane) {
-  const IdxT END = (IdxT)~(IdxT)0;
-  for (uint32_t i = lane; i < n; i += 32) {
-    nxt[i] = (i + 1 < n) ? (IdxT)(i + 1) : END;
-    prv[i] = (i > 0) ? (IdxT)(i - 1) : END;
-    rk[i] = (i + 1 < n) ? mt_lookup(mt, tok[i], tok[i + 1]) : RK_NONE;
+// ---- which pairs may be merged in the same round ---------------------------------------------------
+// The sequential process (core.ts:404-406) merges pair (x,y) of rank r at "time" r iff both tokens are still
+// there.  x can only disappear earlier by being consumed as the RIGHT operand of a lower-rank rule, y as the LEFT
+// operand.  Let
+//   SL[i] = largest r such that token i is certainly not consumed from its left strictly before time r
+//         = max(minAsRight[tok i], min(rank(i-1,i), SL[i-1])),   SL[0] = inf
+//   SR[i] = max(minAsLeft[tok i],  min(rank(i,i+1), SR[i+1])),   SR[n-1] = inf
+// (no rule can take it earlier, or the neighbouring pair fires no earlier and the neighbour itself is stable).
+// A pair with r <= SL[i] and r <= SR[i+1] is merged by the sequential process exactly as it stands, so it can be
+// merged now; merging early cannot enable anything earlier because every rule involving the new token has rank > r.
+// Runs x x x ... (replaceAll parity, core.ts:285-290) need both run ends stable and the run unable to GROW at its
+// left end before time r.  The lowest rank present always qualifies, so every round makes progress.
+// SL and SR are prefix scans of clamp functions x -> max(lo, min(hi, x)), which compose into clamps: one
+// warp-shuffle scan per 32 tokens.  After each round the document is compacted in place, so the work shrinks with
+// the token count.  Prototype + fuzz against the literal oracle: tools/proto_encode_safe.py.
+constexpr uint32_t RK_DIRTY = 0xFFFFFFFEu;
+constexpr uint32_t RINF = 0xFFFFu;
+
+struct EncTables {
+  MergeTable mt;
+  const uint32_t* minlr;  // per token: (lowest rank with the token as LEFT operand << 16) | lowest rank as RIGHT operand
+};
+
+constexpr int ENC_WALK = 16;  // bound of the stability walks
+
+// token j is not consumed from its left strictly before time r (see above); contiguous layout: neighbours are j-1, j+1
+template <typename TokT>
+__device__ __forceinline__ bool stable_left(const TokT* tok, const uint32_t* rk, const uint32_t* minlr, uint32_t j, uint32_t r) {
+#pragma unroll 1
+  for (int s = 0; s <= ENC_WALK; s++) {
+    if (j == 0 || (__ldg(minlr + tok[j]) & 0xFFFFu) >= r) return true;
+    if ((rk[j - 1] >> 16) < r) return false;
+    j--;
   }
+  return false;
+}
+
+template <typename TokT>
+__device__ __forceinline__ bool stable_right(const TokT* tok, const uint32_t* rk, const uint32_t* minlr, uint32_t j, uint32_t n,
+                                             uint32_t r) {
+#pragma unroll 1
+  for (int s = 0; s <= ENC_WALK; s++) {
+    if (j + 1 >= n || (__ldg(minlr + tok[j]) >> 16) >= r) return true;
+    if ((rk[j] >> 16) < r) return false;
+    j++;
+  }
+  return false;
+}
+
+// TokT/StT: uint16_t in shared memory (n <= ENC_WARP_MAX), uint32_t in global scratch.
+// take_g: per-position selection marks for the global-scratch path (the shared path keeps them in a register).
+template <typename TokT, typename StT>
+__device__ __forceinline__ uint32_t encode_doc(TokT* tok, uint32_t* rk, StT* sl, StT* sr, uint32_t* take_g, uint32_t n,
+                                               const EncTables& T, uint32_t lane) {
+  constexpr bool kSmem = sizeof(TokT) == 2;
+  const MergeTable& mt = T.mt;
+  for (uint32_t i = lane; i < n; i += 32) rk[i] = (i + 1 < n) ? mt_lookup(mt, tok[i], tok[i + 1]) : RK_NONE;
   __syncwarp();
   for (;;) {
+    const uint32_t rows = (n + 31) >> 5;
+    // lowest rank present: always mergeable (progress), and the loop ends when there is none
     uint32_t m = RK_NONE;
     for (uint32_t i = lane; i < n; i += 32) m = min(m, rk[i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
     if (m == RK_NONE) break;
-    const uint32_t c = m & 0xFFFFu;
-    // is this a run pair (a == b)?  every lane learns it from the first occurrence it can see
-    uint32_t first = 0xFFFFFFFFu;
-    for (uint32_t i = lane; i < n; i += 32)
-      if (rk[i] == m) {
-        first = i;
-        break;
-      }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, o));
-    const bool run_pair = tok[first] == tok[nxt[first]];
-    constexpr bool kSmem = sizeof(IdxT) == 2;  // shared-memory path: n <= ENC_WARP_MAX, <= 16 positions per lane
-    if (!run_pair || kSmem) {
-      // Select the occurrences to replace (replaceAll: left to right, non-overlapping, core.ts:405).
-      // a != b: occurrences cannot overlap, all are taken.  a == b: inside a run of matches only the even ones.
-      uint32_t sel = 0;  // bit k: position lane + 32*k (shared-memory path only)
-      if (run_pair) {
-        for (uint32_t i = lane, k = 0; i < n; i += 32, k++) {
-          if (rk[i] == m) {
-            uint32_t preds = 0;
-            IdxT p = prv[i];
-            while (p != END && rk[p] == m) {
-              preds++;
-              p = prv[p];
+    const uint32_t gmin = m >> 16;
+    // ---- select (read-only): bounded walks evaluate SL / SR lazily, "unknown" counts as unstable ----
+    uint32_t mask = 0;  // bit row: position 32*row + lane is merged with its right neighbour
+    for (uint32_t row = 0; row < rows; row++) {
+      uint32_t i = (row << 5) + lane;
+      bool take = false;
+      if (i + 1 < n) {
+        uint32_t r = rk[i] >> 16;
+        if (r != RINF) {
+          TokT x = tok[i];
+          if (x != tok[i + 1]) {
+            take = (r == gmin) || (stable_left<TokT>(tok, rk, T.minlr, i, r) && stable_right<TokT>(tok, rk, T.minlr, i + 1, n, r));
+          } else {
+            uint32_t s = i;
+            while (s > 0 && tok[s - 1] == x) s--;
+            if (((i - s) & 1u) == 0) {
+              if (r == gmin) {
+                take = true;
+              } else {
+                uint32_t e = i + 1;
+                while (e + 1 < n && tok[e + 1] == x) e++;
+                take = stable_left<TokT>(tok, rk, T.minlr, s, r) && (s == 0 || stable_left<TokT>(tok, rk, T.minlr, s - 1, r)) &&
+                       stable_right<TokT>(tok, rk, T.minlr, e, n, r);
+              }
             }
-            if ((preds & 1u) == 0) sel |= 1u << k;
           }
         }
-        __syncwarp();
       }
-      for (uint32_t i = lane, k = 0; i < n; i += 32, k++) {
-        if (run_pair ? ((sel >> k) & 1u) != 0 : rk[i] == m) {
-          uint32_t j = nxt[i];
-          IdxT jn = nxt[j];
-          tok[i] = (TokT)c;
-          nxt[i] = jn;
-          if (jn != END) prv[jn] = (IdxT)i;
-          rk[j] = RK_NONE;
-          rk[i] = RK_NONE - 1;  // marks "new token here" until the refresh below
-        }
+      if (kSmem) mask |= (take ? 1u : 0u) << row;
+      else if (i < n) take_g[i] = take ? 1u : 0u;
+    }
+    __syncwarp();
+    // ---- apply + compact in place (rows in order: writes never pass the row being read) ----
+    uint32_t wr = 0, carry_sel = 0;
+    for (uint32_t row = 0; row < rows; row++) {
+      uint32_t i = (row << 5) + lane;
+      uint32_t t = 0, v = RK_NONE;
+      bool take = false;
+      if (i < n) {
+        t = tok[i];
+        v = rk[i];
+        take = kSmem ? ((mask >> row) & 1u) != 0 : take_g[i] != 0;
       }
+      uint32_t S = __ballot_sync(0xFFFFFFFFu, take);
+      uint32_t removed = (S << 1) | carry_sel;
+      bool keep = (i < n) && !((removed >> lane) & 1u);
+      uint32_t K = __ballot_sync(0xFFFFFFFFu, keep);
+      if (keep) {
+        uint32_t j = wr + __popc(K & ((1u << lane) - 1u));
+        tok[j] = (TokT)(take ? (v & 0xFFFFu) : t);
+        rk[j] = take ? RK_DIRTY : v;
+      }
+      wr += __popc(K);
+      carry_sel = S >> 31;
       __syncwarp();
-      for (uint32_t i = lane; i < n; i += 32) {
-        if (rk[i] == RK_NONE - 1) {
-          IdxT jn = nxt[i], ip = prv[i];
-          // a neighbour that is a new token too already holds its final value (after the __syncwarp above)
-          if (ip != END && rk[ip] != RK_NONE - 1) rk[ip] = mt_lookup(mt, tok[ip], c);
-          rk[i] = (jn != END) ? mt_lookup(mt, c, tok[jn]) : RK_NONE;
-        }
-      }
+    }
+    n = wr;
+    // ---- refresh the ranks of pairs that touch a new token ----
+    for (uint32_t base = 0; base < n; base += 32) {
+      uint32_t i = base + lane;
+      uint32_t r = (i < n) ? rk[i] : RK_NONE;
+      uint32_t rn = (i + 1 < n) ? rk[i + 1] : RK_NONE;
       __syncwarp();
-    } else {
-      // a == b in a document too long for shared memory: walk the list once on lane 0
-      if (lane == 0) {
-        uint32_t i = first;
-        while (i != (uint32_t)END) {
-          IdxT jn = nxt[i];
-          if (rk[i] == m) {
-            uint32_t j = nxt[i];
-            IdxT ip = prv[i];
-            jn = nxt[j];
-            tok[i] = (TokT)c;
-            nxt[i] = jn;
-            if (jn != END) prv[jn] = (IdxT)i;
-            rk[j] = RK_NONE;
-            if (ip != END) rk[ip] = mt_lookup(mt, tok[ip], c);
-            rk[i] = (jn != END) ? mt_lookup(mt, c, tok[jn]) : RK_NONE;  // refreshed again if jn merges next
-          }
-          i = (jn != END) ? (uint32_t)jn : (uint32_t)END;
-        }
-      }
+      if (i < n && (r == RK_DIRTY || rn == RK_DIRTY)) rk[i] = (i + 1 < n) ? mt_lookup(mt, tok[i], tok[i + 1]) : RK_NONE;
       __syncwarp();
     }
   }
+  return n;
 }
 
 // One warp per document.  out_tmp holds each document's tokens at the document's INPUT offset.
 __global__ void __launch_bounds__(ENC_THREADS) k_encode(const int32_t* __restrict__ ids,
                                                          const int64_t* __restrict__ doc_off, int64_t n_docs,
-                                                         MergeTable mt, int32_t* __restrict__ out_tmp,
+                                                         EncTables T, int32_t* __restrict__ out_tmp,
                                                          uint32_t* __restrict__ out_len, uint32_t* __restrict__ g_tok,
-                                                         uint32_t* __restrict__ g_nxt, uint32_t* __restrict__ g_prv,
-                                                         uint32_t* __restrict__ g_rk) {
+                                                         uint32_t* __restrict__ g_sl, uint32_t* __restrict__ g_sr,
+                                                         uint32_t* __restrict__ g_rk, uint32_t* __restrict__ g_take) {
   __shared__ uint16_t s_tok[ENC_WARPS][ENC_WARP_MAX];
-  __shared__ uint16_t s_nxt[ENC_WARPS][ENC_WARP_MAX];
-  __shared__ uint16_t s_prv[ENC_WARPS][ENC_WARP_MAX];
+  __shared__ uint16_t s_sl[ENC_WARPS][ENC_WARP_MAX];
+  __shared__ uint16_t s_sr[ENC_WARPS][ENC_WARP_MAX];
   __shared__ uint32_t s_rk[ENC_WARPS][ENC_WARP_MAX];
   uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int64_t wid = (int64_t)blockIdx.x * ENC_WARPS + warp;
@@ -152,38 +192,19 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode(const int32_t* __restric
     uint32_t n = (uint32_t)(e - s);
     const int32_t* src = ids + s;
     int32_t* dst = out_tmp + s;
-    uint32_t wr = 0;
     if (n <= ENC_WARP_MAX) {
       for (uint32_t i = lane; i < n; i += 32) s_tok[warp][i] = (uint16_t)__ldg(src + i);
       __syncwarp();
-      encode_doc<uint16_t, uint16_t>(s_tok[warp], s_nxt[warp], s_prv[warp], s_rk[warp], n, mt, lane);
-      // survivors in position order: position 0 always survives; i survives iff it is still linked
-      for (uint32_t base = 0; base < n; base += 32) {
-        uint32_t i = base + lane;
-        bool keep = false;
-        if (i < n) keep = (i == 0) || (s_prv[warp][i] != 0xFFFFu && s_nxt[warp][s_prv[warp][i]] == i);
-        uint32_t K = __ballot_sync(0xFFFFFFFFu, keep);
-        if (keep) dst[wr + __popc(K & ((1u << lane) - 1u))] = (int32_t)s_tok[warp][i];
-        wr += __popc(K);
-      }
+      n = encode_doc<uint16_t, uint16_t>(s_tok[warp], s_rk[warp], s_sl[warp], s_sr[warp], nullptr, n, T, lane);
+      for (uint32_t i = lane; i < n; i += 32) dst[i] = (int32_t)s_tok[warp][i];
     } else {
       uint32_t* tok = g_tok + (s - base0);
-      uint32_t* nx = g_nxt + (s - base0);
-      uint32_t* pv = g_prv + (s - base0);
-      uint32_t* rk = g_rk + (s - base0);
       for (uint32_t i = lane; i < n; i += 32) tok[i] = (uint32_t)__ldg(src + i);
       __syncwarp();
-      encode_doc<uint32_t, uint32_t>(tok, nx, pv, rk, n, mt, lane);
-      for (uint32_t base = 0; base < n; base += 32) {
-        uint32_t i = base + lane;
-        bool keep = false;
-        if (i < n) keep = (i == 0) || (pv[i] != 0xFFFFFFFFu && nx[pv[i]] == i);
-        uint32_t K = __ballot_sync(0xFFFFFFFFu, keep);
-        if (keep) dst[wr + __popc(K & ((1u << lane) - 1u))] = (int32_t)tok[i];
-        wr += __popc(K);
-      }
+      n = encode_doc<uint32_t, uint32_t>(tok, g_rk + (s - base0), g_sl + (s - base0), g_sr + (s - base0), g_take + (s - base0), n, T, lane);
+      for (uint32_t i = lane; i < n; i += 32) dst[i] = (int32_t)tok[i];
     }
-    if (lane == 0) out_len[d] = wr;
+    if (lane == 0) out_len[d] = n;
     __syncwarp();
   }
 }
