@@ -114,6 +114,7 @@ struct bpe_engine {
   bool index_valid = false;
   uint32_t tbl_cap = 0;
   DevBuf<uint32_t> t_keys, t_cnt, t_start, t_len, t_fill;
+  DevBuf<uint32_t> u_keys, u_cnt, u_start, u_len, u_fill;  // second set, target of the next rehash (kept at high water)
   DevBuf<uint32_t> pool;
   DevBuf<DevState> d_st;
   DevState* h_st = nullptr;  // pinned
@@ -212,13 +213,7 @@ int sync_len16(bpe_engine* e) {
 
 // ---- pair table allocation / growth -------------------------------------------------------------
 int alloc_table(bpe_engine* e, uint32_t cap) {
-  if (e->t_keys.cap < cap || e->t_keys.cap > 4ull * cap) {  // keep the buffers when they fit (cudaFree of GBs is slow)
-    e->t_keys.release();
-    e->t_cnt.release();
-    e->t_start.release();
-    e->t_len.release();
-    e->t_fill.release();
-  }
+  // buffers only ever grow (cudaFree / cudaMalloc of GBs costs up to seconds); the logical capacity is `cap`
   CK(e->t_keys.reserve(cap));
   CK(e->t_cnt.reserve(cap));
   CK(e->t_start.reserve(cap));
@@ -253,13 +248,12 @@ __global__ void k_rehash(PairTable src, PairTable dst, DevState* st) {
 
 int grow_table(bpe_engine* e, uint32_t new_cap) {
   PairTable old = e->table();
-  DevBuf<uint32_t> k, c, s, l, f;
-  std::swap(k, e->t_keys);
-  std::swap(c, e->t_cnt);
-  std::swap(s, e->t_start);
-  std::swap(l, e->t_len);
-  std::swap(f, e->t_fill);
-  TRY(alloc_table(e, new_cap));
+  std::swap(e->t_keys, e->u_keys);
+  std::swap(e->t_cnt, e->u_cnt);
+  std::swap(e->t_start, e->u_start);
+  std::swap(e->t_len, e->u_len);
+  std::swap(e->t_fill, e->u_fill);
+  TRY(alloc_table(e, new_cap));  // the (former) alternate set becomes the live table
   k_rehash<<<e->grid(), 256, 0, e->stream>>>(old, e->table(), e->d_st.p);
   CKL();
   CK(cudaStreamSynchronize(e->stream));
@@ -569,7 +563,10 @@ int append_docs_dev(bpe_engine* e, const int32_t* dev_ids, const int64_t* host_o
   if (total > 0) {
     CK(cudaMemsetAsync(&e->d_st.p->err, 0, sizeof(uint32_t), e->stream));
     int blocks = (int)std::min<int64_t>((total / 4 + 255) / 256 + 1, (int64_t)e->grid(8));
-    k_ingest_ids<<<blocks, 256, 0, e->stream>>>(dev_ids + base_in, e->slots.p + e->n_slots, (uint64_t)total, (uint32_t)e->n_tokens, &e->d_st.p->err);
+    if (reinterpret_cast<const uint32_t*>(dev_ids + base_in) == e->slots.p + e->n_slots)
+      k_validate_ids<<<blocks, 256, 0, e->stream>>>(e->slots.p + e->n_slots, (uint64_t)total, (uint32_t)e->n_tokens, &e->d_st.p->err);
+    else
+      k_ingest_ids<<<blocks, 256, 0, e->stream>>>(dev_ids + base_in, e->slots.p + e->n_slots, (uint64_t)total, (uint32_t)e->n_tokens, &e->d_st.p->err);
     CKL();
     CK(e->stage_off.reserve((size_t)n_docs + 1, 0, e->stream, 1.5));
     CK(cudaMemcpyAsync(e->stage_off.p, host_off, (size_t)(n_docs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
@@ -956,13 +953,15 @@ int bpe_add_documents(bpe_engine* e, const int32_t* ids, const int64_t* doc_offs
   int64_t base = doc_offsets[0], total = doc_offsets[n_docs] - base;
   if (!ids && total > 0) return fail(e, BPE_E_INVALID, "null ids");
   CK(cudaSetDevice(e->device));
-  CK(e->stage_ids.reserve((size_t)std::max<int64_t>(total, 1)));
-  if (total > 0) CK(cudaMemcpyAsync(e->stage_ids.p, ids + base, (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  uint64_t new_n = e->n_slots + (uint64_t)total;
+  if (new_n >= 0xFFFFFFF0ull) return fail(e, BPE_E_DOMAIN, "corpus exceeds 2^32 positions per engine");
+  CK(e->slots.reserve((size_t)new_n + 4, (size_t)e->n_slots, e->stream, 1.5));
+  // int32 token ids ARE the slot encoding of single-slot tokens: copy them into place, then validate in place
+  if (total > 0)
+    CK(cudaMemcpyAsync(e->slots.p + e->n_slots, ids + base, (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
   std::vector<int64_t> rel((size_t)n_docs + 1);
   for (int64_t d = 0; d <= n_docs; d++) rel[d] = doc_offsets[d] - base;
-  int rc = append_docs_dev(e, e->stage_ids.p, rel.data(), n_docs);
-  if (total > (64 << 20)) e->stage_ids.release();  // do not sit on GBs of staging
-  return rc;
+  return append_docs_dev(e, reinterpret_cast<const int32_t*>(e->slots.p + e->n_slots), rel.data(), n_docs);
 }
 
 int bpe_clear_corpus(bpe_engine* e) {

@@ -108,6 +108,14 @@ __global__ void k_ingest_ids(const int32_t* __restrict__ ids, uint32_t* __restri
   if (bad) atomicOr(err, 1u);
 }
 
+// ids already sit in the slot array (host upload path): range check only
+__global__ void k_validate_ids(const uint32_t* __restrict__ slots, uint64_t n, uint32_t max_id, uint32_t* __restrict__ err) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint32_t bad = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) bad |= slots[i] >= max_id;
+  if (bad) atomicOr(err, 1u);
+}
+
 __global__ void k_mark_docstarts(uint32_t* __restrict__ slots, const int64_t* __restrict__ doc_off, int64_t n_docs,
                                  int64_t base) {
   int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
