@@ -9,9 +9,11 @@
 #include <chrono>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "encode_kernels.cuh"
+#include "encode_lanes.cuh"
 #include "train_kernels.cuh"
 
 using namespace bpe;
@@ -109,6 +111,14 @@ struct bpe_engine {
   DevBuf<unsigned long long> d_mt;
   DevBuf<uint32_t> d_minlr;  // per token: lowest rank as left operand << 16 | lowest rank as right operand
   uint32_t mt_cap = 0;
+  // lane path (encode_lanes.cuh): pair table with spine bounds, dense table of the low ids, token of each rank
+  bool lt_dirty = true;
+  DevBuf<uint4> d_lt;
+  DevBuf<uint2> d_lt_dense;
+  DevBuf<uint16_t> d_rule_c;
+  uint32_t lt_cap = 0;
+  int enc_lmax = 48;     // rows per lane of the lane path (32 or 48); BPE_ENC_LMAX overrides
+  int enc_force_old = 0; // debug: BPE_ENC_OLD=1 routes every document through the per-document kernel
 
   // pair index
   bool index_valid = false;
@@ -447,7 +457,7 @@ int run_apply(bpe_engine* e, uint32_t a, uint32_t b, uint32_t c, uint32_t bound)
   e->h_merges.push_back((int32_t)a);
   e->h_merges.push_back((int32_t)b);
   e->h_merges.push_back((int32_t)c);
-  e->mt_dirty = true;
+  e->mt_dirty = e->lt_dirty = true;
   e->n_tokens++;
   e->stats.merges_applied++;
   return BPE_OK;
@@ -492,38 +502,165 @@ int ensure_merge_table(bpe_engine* e) {
   return BPE_OK;
 }
 
+// ---- pair table of the lane path: rank + spine bounds per pair (see encode_lanes.cuh) ---------------------------
+int ensure_lane_tables(bpe_engine* e) {
+  if (!e->lt_dirty && e->d_lt.p) return BPE_OK;
+  size_t m = e->h_merges.size() / 3;
+  if (m > EL_MAX_RANK + 1) return fail(e, BPE_E_DOMAIN, "merge list too long");
+  const int32_t nt = std::max(e->n_tokens, 1);
+  struct Ent {
+    uint16_t rk = 0xFFFF, c = 0, rs = 0xFFFF, ls = 0xFFFF;
+  };
+  std::unordered_map<uint32_t, Ent> M;
+  M.reserve(m * 3 + 16);
+  // definition of every merged token (core.ts:315-325: c is a fresh index, so each c has one definition)
+  std::vector<int32_t> def_a((size_t)nt, -1), def_b((size_t)nt, -1);
+  std::vector<uint8_t> first(m, 0);
+  std::vector<uint16_t> rule_c(std::max<size_t>(m, 1), 0);
+  for (size_t r = 0; r < m; r++) {
+    int32_t a = e->h_merges[3 * r], b = e->h_merges[3 * r + 1], c = e->h_merges[3 * r + 2];
+    if (a < 0 || b < 0 || c < 0 || a >= nt || b >= nt || c >= nt)
+      return fail(e, BPE_E_INVALID, "merge %zu refers to a token outside the table", r);
+    rule_c[r] = (uint16_t)c;
+    if (def_a[c] < 0 && a < c && b < c) {
+      def_a[c] = a;
+      def_b[c] = b;
+    } else if (def_a[c] >= 0 && (def_a[c] != a || def_b[c] != b)) {
+      return fail(e, BPE_E_INVALID, "token %d is produced by two different merges", c);
+    }
+    Ent& x = M[pair_key((uint32_t)a, (uint32_t)b)];
+    if (x.rk == 0xFFFF) {  // a second rule for the same pair can never fire (the first one removed every occurrence)
+      x.rk = (uint16_t)r;
+      x.c = (uint16_t)c;
+      first[r] = 1;
+    }
+  }
+  for (size_t r = 0; r < m; r++) {
+    if (!first[r]) continue;
+    int32_t a = e->h_merges[3 * r], b = e->h_merges[3 * r + 1];
+    for (int32_t u = a;;) {  // every token on the right spine of a: anything ending in u may grow into a
+      Ent& x = M[pair_key((uint32_t)u, (uint32_t)b)];
+      if (x.rs > r) x.rs = (uint16_t)r;
+      if (def_a[u] < 0) break;
+      u = def_b[u];
+    }
+    for (int32_t w = b;;) {  // every token on the left spine of b
+      Ent& x = M[pair_key((uint32_t)a, (uint32_t)w)];
+      if (x.ls > r) x.ls = (uint16_t)r;
+      if (def_a[w] < 0) break;
+      w = def_a[w];
+    }
+  }
+  uint32_t cap = pow2_at_least(std::max<size_t>(2 * M.size(), 1024));
+  std::vector<uint4> h(cap, make_uint4(EMPTY_KEY, EL_NONE, 0xFFFFFFFFu, 0));
+  std::vector<uint2> dense((size_t)EL_DENSE * EL_DENSE, make_uint2(EL_NONE, 0xFFFFFFFFu));
+  int shift = 32 - ilog2(cap);
+  for (auto& kv : M) {
+    uint32_t key = kv.first;
+    const Ent& x = kv.second;
+    uint32_t y = (uint32_t)x.rk | ((uint32_t)x.c << 16), z = (uint32_t)x.rs | ((uint32_t)x.ls << 16);
+    uint32_t a = key >> 16, b = key & 0xFFFFu;
+    if (a < (uint32_t)EL_DENSE && b < (uint32_t)EL_DENSE) dense[a * EL_DENSE + b] = make_uint2(y, z);
+    uint32_t i = (key * 0x9E3779B1u) >> shift;
+    while (h[i].x != EMPTY_KEY) i = (i + 1) & (cap - 1);
+    h[i] = make_uint4(key, y, z, 0);
+  }
+  CK(e->d_lt.reserve(cap));
+  CK(cudaMemcpyAsync(e->d_lt.p, h.data(), (size_t)cap * sizeof(uint4), cudaMemcpyHostToDevice, e->stream));
+  CK(e->d_lt_dense.reserve(dense.size()));
+  CK(cudaMemcpyAsync(e->d_lt_dense.p, dense.data(), dense.size() * sizeof(uint2), cudaMemcpyHostToDevice, e->stream));
+  CK(e->d_rule_c.reserve(rule_c.size()));
+  CK(cudaMemcpyAsync(e->d_rule_c.p, rule_c.data(), rule_c.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->lt_cap = cap;
+  e->lt_dirty = false;
+  return BPE_OK;
+}
+
+template <int LMAX, int WARPS>
+int launch_encode_lanes(bpe_engine* e, const int32_t* dev_ids, const int64_t* dev_doc_off, int64_t n_docs, const uint32_t* range_first,
+                        uint32_t n_ranges, const LaneTables& lt, int32_t* out_tmp, uint32_t* out_len, uint32_t* n_long, uint32_t* err) {
+  size_t smem = (size_t)2 * EL_DENSE * EL_DENSE * 4 + (size_t)WARPS * (LMAX * 32 * 2 + LMAX * 16) * 4;
+  auto kern = k_encode_lanes<LMAX, WARPS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int per_sm = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+  per_sm = std::max(per_sm, 1);
+  int64_t blocks = std::min<int64_t>(((int64_t)n_ranges + WARPS - 1) / WARPS, (int64_t)e->sm_count * per_sm);
+  kern<<<(int)std::max<int64_t>(blocks, 1), WARPS * 32, smem, e->stream>>>(dev_ids, dev_doc_off, n_docs, range_first, n_ranges, lt, out_tmp,
+                                                                       out_len, n_long, err);
+  CKL();
+  return BPE_OK;
+}
+
 struct EncodeScratch {
   DevBuf<int32_t> out_tmp;
   DevBuf<uint32_t> out_len;
   DevBuf<uint64_t> out_off;
   DevBuf<uint32_t> g_tok, g_nxt, g_prv, g_rk, g_sel;
+  DevBuf<uint32_t> range_first;
+  DevBuf<uint32_t> flags;  // [0] long documents left for the per-document kernel, [1] error
 };
 
 // device-resident encode; leaves compacted output in dev_out / dev_out_offsets
 int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const int64_t* dev_doc_off, int64_t n_docs,
                int64_t n_ids, int64_t max_doc_len, const int32_t* dev_tvi, int32_t n_tvi, int32_t* dev_out,
                int64_t* dev_out_offsets, int64_t* dev_first_bad, int64_t* n_out) {
-  TRY(ensure_merge_table(e));
-  if (e->h_merges.size() / 3 > 65534) return fail(e, BPE_E_DOMAIN, "merge list too long");
+  if (e->h_merges.size() / 3 > EL_MAX_RANK + 1) return fail(e, BPE_E_DOMAIN, "merge list too long");
+  TRY(ensure_lane_tables(e));
   CK(sc.out_tmp.reserve((size_t)std::max<int64_t>(n_ids, 1)));
   CK(sc.out_len.reserve((size_t)n_docs + 1));
   CK(sc.out_off.reserve((size_t)n_docs + 2));
-  if (max_doc_len > ENC_WARP_MAX) {
-    CK(sc.g_tok.reserve((size_t)n_ids));
-    CK(sc.g_nxt.reserve((size_t)n_ids));
-    CK(sc.g_prv.reserve((size_t)n_ids));
-    CK(sc.g_rk.reserve((size_t)n_ids));
-    CK(sc.g_sel.reserve((size_t)n_ids));
-  }
-  EncTables mt{MergeTable{e->d_mt.p, e->mt_cap - 1, (uint32_t)(32 - ilog2(e->mt_cap))}, e->d_minlr.p};
+  CK(sc.flags.reserve(2));
   if (!e->ev0) {
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
   }
   CK(cudaEventRecord(e->ev0, e->stream));
-  if (n_docs > 0) {
+  bool run_old = e->enc_force_old != 0;
+  if (n_docs > 0 && !run_old) {
+    // lane path: one warp per batch of whole documents; position ranges of `stride` ids name the batches
+    const int lmax = e->enc_lmax;
+    const uint32_t cap = 32u * (uint32_t)((lmax & 1) ? lmax : lmax - 1);
+    uint32_t stride = cap - (uint32_t)std::min<int64_t>(std::max<int64_t>(max_doc_len, 1), cap / 2);
+    uint64_t nr64 = ((uint64_t)n_ids + stride - 1) / stride;
+    if (nr64 == 0) nr64 = 1;
+    if (nr64 > 0x7FFFFFF0ull || n_docs > 0x7FFFFFF0ll) return fail(e, BPE_E_DOMAIN, "batch too large for one encode call");
+    uint32_t n_ranges = (uint32_t)nr64;
+    CK(sc.range_first.reserve((size_t)n_ranges + 1));
+    CK(cudaMemsetAsync(sc.flags.p, 0, 2 * sizeof(uint32_t), e->stream));
+    k_range_starts<<<(int)std::min<uint32_t>((n_ranges + 256) / 256, (uint32_t)e->sm_count * 8), 256, 0, e->stream>>>(dev_doc_off, n_docs, stride, n_ranges,
+                                                                                                             sc.range_first.p);
+    CKL();
+    LaneTables lt{e->d_lt.p, e->lt_cap - 1, (uint32_t)(32 - ilog2(e->lt_cap)), e->d_lt_dense.p, e->d_rule_c.p};
+    if (lmax == 32)
+      TRY((launch_encode_lanes<32, 10>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1)));
+    else
+      TRY((launch_encode_lanes<48, 6>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1)));
+    uint32_t hf[2] = {0, 0};
+    CK(cudaMemcpyAsync(hf, sc.flags.p, sizeof hf, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (hf[1]) return fail(e, BPE_E_INTERNAL, "encode rounds did not converge");
+    run_old = hf[0] != 0;
+  }
+  if (n_docs > 0 && run_old) {
+    // per-document kernel: documents longer than a lane batch (marked EL_LONG), or everything when forced
+    TRY(ensure_merge_table(e));
+    if (max_doc_len > ENC_WARP_MAX) {
+      CK(sc.g_tok.reserve((size_t)n_ids));
+      CK(sc.g_nxt.reserve((size_t)n_ids));
+      CK(sc.g_prv.reserve((size_t)n_ids));
+      CK(sc.g_rk.reserve((size_t)n_ids));
+      CK(sc.g_sel.reserve((size_t)n_ids));
+    }
+    EncTables mt{MergeTable{e->d_mt.p, e->mt_cap - 1, (uint32_t)(32 - ilog2(e->mt_cap))}, e->d_minlr.p};
     int64_t blocks = std::min<int64_t>((n_docs + ENC_WARPS - 1) / ENC_WARPS, (int64_t)e->sm_count * 16);
-    k_encode<<<(int)blocks, ENC_THREADS, 0, e->stream>>>(dev_ids, dev_doc_off, n_docs, mt, sc.out_tmp.p, sc.out_len.p, sc.g_tok.p, sc.g_nxt.p, sc.g_prv.p, sc.g_rk.p, sc.g_sel.p);
+    k_encode<<<(int)blocks, ENC_THREADS, 0, e->stream>>>(dev_ids, dev_doc_off, n_docs, mt, sc.out_tmp.p, sc.out_len.p, sc.g_tok.p, sc.g_nxt.p, sc.g_prv.p,
+                                                         sc.g_rk.p, sc.g_sel.p, e->enc_force_old ? 0 : 1);
     CKL();
   }
   k_scan_counts<<<1, 1024, 0, e->stream>>>(sc.out_len.p, sc.out_off.p, (uint32_t)n_docs);
@@ -695,7 +832,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
         e->h_merges.push_back(r.c);
       }
       e->n_tokens += (int32_t)iters;
-      e->mt_dirty = true;
+      e->mt_dirty = e->lt_dirty = true;
       e->stats.merges_applied += iters;
     }
     uint32_t status = e->h_st->status;
@@ -852,6 +989,8 @@ int bpe_create(int device, bpe_engine** out) {
   }
   e->stream = e->own_stream;
   if (getenv("BPE_HOST_LOOP")) e->host_loop = 1;
+  if (getenv("BPE_ENC_OLD")) e->enc_force_old = 1;
+  if (const char* v = getenv("BPE_ENC_LMAX")) e->enc_lmax = (atoi(v) == 32) ? 32 : 48;
   *out = e;
   return BPE_OK;
 }
@@ -916,7 +1055,7 @@ int bpe_set_tokens(bpe_engine* e, const int32_t* utf16_len, int32_t n_tokens) {
   CK(cudaSetDevice(e->device));
   e->h_len16.assign(utf16_len, utf16_len + n_tokens);
   e->n_tokens = n_tokens;
-  e->mt_dirty = true;
+  e->mt_dirty = e->lt_dirty = true;
   TRY(sync_len16(e));
   e->hot_valid = false;
   return BPE_OK;
@@ -933,7 +1072,7 @@ int bpe_load_merges(bpe_engine* e, const int32_t* abc, int64_t n_merges) {
   for (int64_t i = 0; i < 3 * n_merges; i++)
     if (abc[i] < 0 || abc[i] >= BPE_MAX_TOKENS) return fail(e, BPE_E_INVALID, "merge %lld holds index %d", (long long)(i / 3), abc[i]);
   e->h_merges.assign(abc, abc + 3 * n_merges);
-  e->mt_dirty = true;
+  e->mt_dirty = e->lt_dirty = true;
   return BPE_OK;
 }
 
@@ -1064,7 +1203,7 @@ int bpe_apply_merge(bpe_engine* e, int32_t a, int32_t b, int32_t c, int64_t* n_r
     e->h_merges.push_back(a);
     e->h_merges.push_back(b);
     e->h_merges.push_back(c);
-    e->mt_dirty = true;
+    e->mt_dirty = e->lt_dirty = true;
     e->n_tokens++;
     e->index_valid = false;
     return BPE_OK;

@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode(const int32_t* __restric
                                                          EncTables T, int32_t* __restrict__ out_tmp,
                                                          uint32_t* __restrict__ out_len, uint32_t* __restrict__ g_tok,
                                                          uint32_t* __restrict__ g_sl, uint32_t* __restrict__ g_sr,
-                                                         uint32_t* __restrict__ g_rk, uint32_t* __restrict__ g_take) {
+                                                         uint32_t* __restrict__ g_rk, uint32_t* __restrict__ g_take,
+                                                         int only_marked) {
   __shared__ uint16_t s_tok[ENC_WARPS][ENC_WARP_MAX];
   __shared__ uint16_t s_sl[ENC_WARPS][ENC_WARP_MAX];
   __shared__ uint16_t s_sr[ENC_WARPS][ENC_WARP_MAX];
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode(const int32_t* __restric
   int64_t nw = (int64_t)gridDim.x * ENC_WARPS;
   int64_t base0 = doc_off[0];
   for (int64_t d = wid; d < n_docs; d += nw) {
+    if (only_marked && out_len[d] != 0xFFFFFFFFu) continue;  // the lane path (encode_lanes.cuh) left this one
     int64_t s = doc_off[d], e = doc_off[d + 1];
     uint32_t n = (uint32_t)(e - s);
     const int32_t* src = ids + s;

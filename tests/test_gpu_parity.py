@@ -314,3 +314,50 @@ def test_add_to_corpus_after_merges_appends_raw_ids():
         x.mergeUntil({})
     assert t.toJSON() == lit.toJSON()
     assert t.corpus_in_code == lit.corpus_in_code
+
+
+@pytest.mark.parametrize("lmax", ["48", "32"])
+@pytest.mark.parametrize("seed", range(6))
+def test_encode_batch_lane_path_fuzz(seed, lmax, monkeypatch):
+    """K4 lane path (encode_lanes.cuh): batches of ragged documents -- empty, single-token, runs, documents longer than
+    one lane batch (per-document fallback) -- against the sequential replaceAll of core.ts:404-406."""
+    monkeypatch.setenv("BPE_ENC_LMAX", lmax)
+    rng = random.Random(7000 + seed)
+    alphabet = ["ab", "abc", "abcdef ", "ab", "abcdefghijklmnopqrstuvwxyz ", "xy "][seed]
+    train = _random_docs(rng, alphabet, rng.randint(2, 10), rng.choice([50, 300, 2000]))
+    lit, gpu = LiteralTokenizer(), make()
+    for d in train:
+        lit.addToCorpus(d)
+        gpu.addToCorpus(d)
+    opts = {"max_length": rng.choice([None, 6]), "max_iterations": rng.choice([None, 3, 40])}
+    lit.mergeUntil(opts)
+    gpu.mergeUntil(opts)
+    assert gpu.toJSON() == lit.toJSON()
+    known = [ch for ch in alphabet if ch in lit.char_to_token]
+    docs = []
+    for _ in range(rng.randint(40, 400)):
+        kind = rng.random()
+        if kind < 0.08:
+            docs.append("")
+        elif kind < 0.16:
+            docs.append(rng.choice(known) * rng.randint(1, 130))
+        elif kind < 0.20:
+            docs.append("".join(rng.choice(known) for _ in range(rng.randint(1400, 4000))))
+        elif kind < 0.5:
+            docs.append("".join(rng.choice(known) for _ in range(rng.randint(1, 12))))
+        else:
+            docs.append("".join(rng.choice(known) for _ in range(rng.randint(1, 700))))
+    ids = np.array([lit.char_to_token[ch].index for d in docs for ch in d], dtype=np.int32)
+    off = np.zeros(len(docs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(d) for d in docs])
+    raw, roff, _ = gpu.encodeBatch(ids, off, vector=False)
+    assert roff[0] == 0 and roff[-1] == raw.size
+    for d, text in enumerate(docs):
+        want = [ord(ch) - 1 for ch in lit.encodeToCode(text)]
+        assert raw[roff[d]:roff[d + 1]].tolist() == want, (d, len(text))
+    # the per-document kernel must agree with the lane path on every document
+    monkeypatch.setenv("BPE_ENC_OLD", "1")
+    old = make()
+    old.fromJSON(gpu.toJSON())
+    raw2, roff2, _ = old.encodeBatch(ids, off, vector=False)
+    assert np.array_equal(raw, raw2) and np.array_equal(roff, roff2)
