@@ -117,6 +117,7 @@ struct bpe_engine {
   DevBuf<uint2> d_lt_dense;
   DevBuf<uint16_t> d_rule_c;
   uint32_t lt_cap = 0;
+  int32_t lt_c_affine = -1;
   int enc_lmax = 48;     // rows per lane of the lane path (32 or 48); BPE_ENC_LMAX overrides
   int enc_force_old = 0; // debug: BPE_ENC_OLD=1 routes every document through the per-document kernel
 
@@ -573,6 +574,9 @@ int ensure_lane_tables(bpe_engine* e) {
   CK(cudaMemcpyAsync(e->d_rule_c.p, rule_c.data(), rule_c.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   e->lt_cap = cap;
+  e->lt_c_affine = m ? (int32_t)rule_c[0] : 0;
+  for (size_t r = 0; r < m; r++)
+    if ((int64_t)rule_c[r] != (int64_t)rule_c[0] + (int64_t)r) e->lt_c_affine = -1;
   e->lt_dirty = false;
   return BPE_OK;
 }
@@ -636,7 +640,7 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
     k_range_starts<<<(int)std::min<uint32_t>((n_ranges + 256) / 256, (uint32_t)e->sm_count * 8), 256, 0, e->stream>>>(dev_doc_off, n_docs, stride, n_ranges,
                                                                                                              sc.range_first.p);
     CKL();
-    LaneTables lt{e->d_lt.p, e->lt_cap - 1, (uint32_t)(32 - ilog2(e->lt_cap)), e->d_lt_dense.p, e->d_rule_c.p};
+    LaneTables lt{e->d_lt.p, e->lt_cap - 1, (uint32_t)(32 - ilog2(e->lt_cap)), e->d_lt_dense.p, e->d_rule_c.p, e->lt_c_affine};
     if (lmax == 32)
       TRY((launch_encode_lanes<32, 10>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1)));
     else

@@ -35,6 +35,7 @@ struct LaneTables {
   uint32_t mask, shift;
   const uint2* dense;      // [EL_DENSE * EL_DENSE]: x = rk | c << 16, y = rs | ls << 16
   const uint16_t* rule_c;  // [n_merges] token produced by the rule of each rank
+  int32_t c_affine;        // >= 0: rule_c[r] == c_affine + r for every rank (the usual case: no load needed)
 };
 
 // (rk | c << 16, rs | ls << 16) of the pair (a, b)
@@ -150,29 +151,32 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
       }
       __syncwarp();
 
+      // ---- initial ranks: every record but the document ends is DIRTY; each lane resolves its own ----
+      uint32_t nonempty = __ballot_sync(FULL, cnt > 0);
+      int nlane = (nonempty >> lane) >> 1 ? (int)lane + __ffs((nonempty >> lane) >> 1) : -1;
+      uint32_t firstA = cnt ? sA[lane] : 0u;
+      uint32_t nf_tok = __shfl_sync(FULL, firstA, nlane < 0 ? (int)lane : nlane) & 0xFFFFu;
+      for (uint32_t j = 0; j < cnt; j++) {
+        uint32_t idx = j * 32 + lane;
+        uint32_t a = sA[idx];
+        if ((a >> 16) == EL_DIRTY) {
+          uint32_t nt = (j + 1 < cnt) ? (sA[idx + 32] & 0xFFFFu) : nf_tok;
+          uint2 r2 = el_lookup(T, s_dense, a & 0xFFFFu, nt);
+          sA[idx] = (a & 0xFFFFu) | ((r2.x & 0xFFFFu) << 16);
+          sB[idx] = r2.y;
+        }
+      }
+      unsigned long long dm = 0;  // rows of this lane whose record is DIRTY (set by pass 3, cleared by the probe phase)
+
       // ---- rounds ----
       for (uint32_t round = 0;; round++) {
-        uint32_t nonempty = __ballot_sync(FULL, cnt > 0);
-        int nlane = (nonempty >> lane) >> 1 ? (int)lane + __ffs((nonempty >> lane) >> 1) : -1;
-        int plane = (nonempty & lt_mask) ? 31 - __clz(nonempty & lt_mask) : -1;
-        uint32_t firstA = cnt ? sA[head * 32 + lane] : 0u;
-        uint32_t nf_tok = __shfl_sync(FULL, firstA, nlane < 0 ? (int)lane : nlane) & 0xFFFFu;
-        // probe loop: resolve DIRTY records; composites F (all records but the last) and G (all records)
+        // composites F (all records but the last) and G (all records) of this lane's segment
         uint32_t F = CL_IDENT, G = CL_IDENT;
         bool anyvalid = false;
         for (uint32_t j = 0; j < cnt; j++) {
           uint32_t idx = (head + j) * 32 + lane;
           uint32_t a = sA[idx], b = sB[idx];
           uint32_t rk = a >> 16;
-          if (rk == EL_DIRTY) {
-            uint32_t nt = (j + 1 < cnt) ? (sA[idx + 32] & 0xFFFFu) : nf_tok;
-            uint2 r2 = el_lookup(T, s_dense, a & 0xFFFFu, nt);
-            rk = r2.x & 0xFFFFu;
-            a = (a & 0xFFFFu) | (rk << 16);
-            b = r2.y;
-            sA[idx] = a;
-            sB[idx] = b;
-          }
           anyvalid |= rk < EL_DIRTY;
           G = cl_compose(G, cl_make(b >> 16, rk));
           if (j + 1 < cnt) F = cl_compose(cl_make(b & 0xFFFFu, rk), F);
@@ -183,6 +187,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
           break;
         }
         // neighbour records (pre-round state)
+        int plane = (nonempty & lt_mask) ? 31 - __clz(nonempty & lt_mask) : -1;
         uint32_t lastA = cnt ? sA[(head + cnt - 1) * 32 + lane] : 0u;
         uint32_t lastB = cnt ? sB[(head + cnt - 1) * 32 + lane] : 0u;
         firstA = cnt ? sA[head * 32 + lane] : 0u;
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
             sS[idx] = (uint16_t)y;
           }
         }
-        // pass 3: decide + compact, left to right
+        // pass 3: decide + compact, left to right (straight-line, predicated)
         uint32_t sl, g, prk;
         if (plane < 0) {
           sl = EL_INF;
@@ -241,43 +246,29 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
           uint32_t an = last ? nA : sA[idx + 32];
           uint32_t srn = last ? y_in : (uint32_t)sS[idx + 32];
           uint32_t r = a >> 16, rs = b & 0xFFFFu;
-          bool take = false;
-          if (r < EL_DIRTY) {
-            if (r == prk) {
-              par ^= 1u;
-              if (j == 0) run_ok = false;  // run carried in from the previous lane: parity unknown here
-              take = par == 0 && run_ok && r <= srn;
-            } else {
-              par = 0;
-              bool isxx = ((a ^ an) & 0xFFFFu) == 0;
-              run_ok = isxx ? (r <= g) : true;
-              take = r <= (isxx ? g : sl) && r <= srn;
-            }
-            if (consumed) take = false;
+          bool valid = r < EL_DIRTY;
+          bool cont = valid && r == prk;          // same rule as the pair to the left: inside a run x x x
+          bool isxx = ((a ^ an) & 0xFFFFu) == 0;
+          bool ok_new = r <= (isxx ? g : sl);     // a run start also needs T[j-1] >= r (the run must not grow leftwards)
+          par = cont ? (par ^ 1u) : 0u;
+          run_ok = cont ? (run_ok && j != 0) : ok_new;  // j == 0: run carried in from the previous lane, parity unknown
+          bool take = valid && !consumed && r <= srn && (cont ? (par == 0 && run_ok) : ok_new);
+          bool emit = !consumed;
+          if (take && have_pend && (pendA >> 16) != EL_BOUNDARY) pendA = (pendA & 0xFFFFu) | (EL_DIRTY << 16);
+          first_is_new |= take && !have_pend;
+          if (emit && have_pend) {
+            sA[w * 32 + lane] = pendA;
+            sB[w * 32 + lane] = pendB;
+            if ((pendA >> 16) == EL_DIRTY) dm |= 1ull << w;
+            w++;
           }
-          if (!consumed) {
-            if (take) {
-              if (have_pend) {
-                if ((pendA >> 16) != EL_BOUNDARY) pendA = (pendA & 0xFFFFu) | (EL_DIRTY << 16);
-              } else {
-                first_is_new = true;
-              }
-            }
-            if (have_pend) {
-              sA[w * 32 + lane] = pendA;
-              sB[w * 32 + lane] = pendB;
-              w++;
-            }
+          if (emit) {
             have_pend = true;
-            if (take) {
-              bool bnd = (an >> 16) == EL_BOUNDARY;
-              pendA = (uint32_t)__ldg(T.rule_c + r) | ((bnd ? EL_BOUNDARY : EL_DIRTY) << 16);
-              pendB = 0xFFFFFFFFu;
-              took_straddle = last;
-            } else {
-              pendA = a;
-              pendB = b;
-            }
+            uint32_t c = (T.c_affine >= 0) ? (uint32_t)T.c_affine + r : (take ? (uint32_t)__ldg(T.rule_c + r) : 0u);
+            uint32_t nrk = ((an >> 16) == EL_BOUNDARY) ? EL_BOUNDARY : EL_DIRTY;
+            pendA = take ? (c | (nrk << 16)) : a;
+            pendB = take ? 0xFFFFFFFFu : b;
+            took_straddle = take && last;
           }
           consumed = take;
           g = (r == EL_BOUNDARY) ? EL_INF : min(r, sl);
@@ -288,20 +279,60 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
         if (have_pend) {
           sA[w * 32 + lane] = pendA;
           sB[w * 32 + lane] = pendB;
+          if ((pendA >> 16) == EL_DIRTY) dm |= 1ull << w;
           w++;
         }
         // post: first tokens consumed by the lane to the left; ranks next to new tokens across lanes
         bool eaten = __shfl_sync(FULL, took_straddle, plane < 0 ? (int)lane : plane) && plane >= 0 && cnt > 0;
         head = eaten ? 1u : 0u;
         cnt = eaten ? w - 1u : w;
-        uint32_t nonempty2 = __ballot_sync(FULL, cnt > 0);
-        int nlane2 = (nonempty2 >> lane) >> 1 ? (int)lane + __ffs((nonempty2 >> lane) >> 1) : -1;
-        bool fin = __shfl_sync(FULL, first_is_new, nlane2 < 0 ? (int)lane : nlane2) && nlane2 >= 0;
+        if (eaten) dm &= ~1ull;
+        nonempty = __ballot_sync(FULL, cnt > 0);
+        nlane = (nonempty >> lane) >> 1 ? (int)lane + __ffs((nonempty >> lane) >> 1) : -1;
+        bool fin = __shfl_sync(FULL, first_is_new, nlane < 0 ? (int)lane : nlane) && nlane >= 0;
+        uint32_t lastrow = head + cnt - 1u;
         if (fin && cnt) {
-          uint32_t idx = (head + cnt - 1) * 32 + lane;
+          uint32_t idx = lastrow * 32 + lane;
           uint32_t v = sA[idx];
-          if ((v >> 16) != EL_BOUNDARY) sA[idx] = (v & 0xFFFFu) | (EL_DIRTY << 16);
+          if ((v >> 16) != EL_BOUNDARY) {
+            sA[idx] = (v & 0xFFFFu) | (EL_DIRTY << 16);
+            dm |= 1ull << lastrow;
+          }
         }
+        // ---- probe phase: the warp resolves all DIRTY records together (32 independent table loads in flight) ----
+        firstA = cnt ? sA[head * 32 + lane] : 0u;
+        nf_tok = __shfl_sync(FULL, firstA, nlane < 0 ? (int)lane : nlane) & 0xFFFFu;
+        uint32_t nd = (uint32_t)__popcll(dm), qpos = nd;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t other = __shfl_up_sync(FULL, qpos, o);
+          if ((int)lane >= o) qpos += other;
+        }
+        uint32_t Q = __shfl_sync(FULL, qpos, 31);
+        qpos -= nd;
+        __syncwarp();
+        while (dm) {
+          uint32_t row = (uint32_t)__ffsll((long long)dm) - 1u;
+          dm &= dm - 1ull;
+          sS[qpos++] = (uint16_t)(row * 32 + lane);
+        }
+        __syncwarp();
+        for (uint32_t q0 = 0; q0 < Q; q0 += 32) {
+          uint32_t q = q0 + lane;
+          bool act = q < Q;
+          uint32_t cell = act ? (uint32_t)sS[q] : lane;
+          uint32_t owner = cell & 31u;
+          uint32_t o_last = __shfl_sync(FULL, lastrow, owner);
+          uint32_t o_nf = __shfl_sync(FULL, nf_tok, owner);
+          if (act) {
+            uint32_t av = sA[cell];
+            uint32_t nt = ((cell >> 5) == o_last) ? o_nf : (sA[cell + 32] & 0xFFFFu);
+            uint2 r2 = el_lookup(T, s_dense, av & 0xFFFFu, nt);
+            sA[cell] = (av & 0xFFFFu) | ((r2.x & 0xFFFFu) << 16);
+            sB[cell] = r2.y;
+          }
+        }
+        __syncwarp();
       }
 
       // ---- output: token k of document dd -> out_tmp[doc_off[dd] + k], out_len[dd] ----
