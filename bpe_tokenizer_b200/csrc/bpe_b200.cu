@@ -118,7 +118,7 @@ struct bpe_engine {
   DevBuf<uint16_t> d_rule_c;
   uint32_t lt_cap = 0;
   int32_t lt_c_affine = -1;
-  int enc_lmax = 48;     // rows per lane of the lane path (32 or 48); BPE_ENC_LMAX overrides
+  int enc_lmax = 32;     // rows per lane of the lane path (32 or 48); BPE_ENC_LMAX overrides
   int enc_force_old = 0; // debug: BPE_ENC_OLD=1 routes every document through the per-document kernel
 
   // pair index
@@ -583,7 +583,8 @@ int ensure_lane_tables(bpe_engine* e) {
 
 template <int LMAX, int WARPS>
 int launch_encode_lanes(bpe_engine* e, const int32_t* dev_ids, const int64_t* dev_doc_off, int64_t n_docs, const uint32_t* range_first,
-                        uint32_t n_ranges, const LaneTables& lt, int32_t* out_tmp, uint32_t* out_len, uint32_t* n_long, uint32_t* err) {
+                        uint32_t n_ranges, const LaneTables& lt, int32_t* out_tmp, uint32_t* out_len, uint32_t* n_long, uint32_t* err,
+                        uint32_t* next_range) {
   size_t smem = (size_t)2 * EL_DENSE * EL_DENSE * 4 + (size_t)WARPS * (LMAX * 32 * 2 + LMAX * 16) * 4;
   auto kern = k_encode_lanes<LMAX, WARPS>;
   static bool attr_set = false;
@@ -596,7 +597,7 @@ int launch_encode_lanes(bpe_engine* e, const int32_t* dev_ids, const int64_t* de
   per_sm = std::max(per_sm, 1);
   int64_t blocks = std::min<int64_t>(((int64_t)n_ranges + WARPS - 1) / WARPS, (int64_t)e->sm_count * per_sm);
   kern<<<(int)std::max<int64_t>(blocks, 1), WARPS * 32, smem, e->stream>>>(dev_ids, dev_doc_off, n_docs, range_first, n_ranges, lt, out_tmp,
-                                                                       out_len, n_long, err);
+                                                                       out_len, n_long, err, next_range);
   CKL();
   return BPE_OK;
 }
@@ -606,8 +607,9 @@ struct EncodeScratch {
   DevBuf<uint32_t> out_len;
   DevBuf<uint64_t> out_off;
   DevBuf<uint32_t> g_tok, g_nxt, g_prv, g_rk, g_sel;
-  DevBuf<uint32_t> range_first;
-  DevBuf<uint32_t> flags;  // [0] long documents left for the per-document kernel, [1] error
+  DevBuf<uint32_t> range_first, tile_sums;
+  DevBuf<uint64_t> tile_off;
+  DevBuf<uint32_t> flags;  // [0] long documents left for the per-document kernel, [1] error, [2] next range to claim
 };
 
 // device-resident encode; leaves compacted output in dev_out / dev_out_offsets
@@ -619,7 +621,7 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
   CK(sc.out_tmp.reserve((size_t)std::max<int64_t>(n_ids, 1)));
   CK(sc.out_len.reserve((size_t)n_docs + 1));
   CK(sc.out_off.reserve((size_t)n_docs + 2));
-  CK(sc.flags.reserve(2));
+  CK(sc.flags.reserve(4));
   if (!e->ev0) {
     CK(cudaEventCreate(&e->ev0));
     CK(cudaEventCreate(&e->ev1));
@@ -629,22 +631,23 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
   if (n_docs > 0 && !run_old) {
     // lane path: one warp per batch of whole documents; position ranges of `stride` ids name the batches
     const int lmax = e->enc_lmax;
-    const uint32_t cap = 32u * (uint32_t)((lmax & 1) ? lmax : lmax - 1);
-    uint32_t stride = cap - (uint32_t)std::min<int64_t>(std::max<int64_t>(max_doc_len, 1), cap / 2);
+    const uint32_t cap = 32u * (uint32_t)lmax;
+    (void)max_doc_len;
+    uint32_t stride = 4u * cap;  // a range = the documents starting in `stride` consecutive positions, packed greedily into batches
     uint64_t nr64 = ((uint64_t)n_ids + stride - 1) / stride;
     if (nr64 == 0) nr64 = 1;
     if (nr64 > 0x7FFFFFF0ull || n_docs > 0x7FFFFFF0ll) return fail(e, BPE_E_DOMAIN, "batch too large for one encode call");
     uint32_t n_ranges = (uint32_t)nr64;
     CK(sc.range_first.reserve((size_t)n_ranges + 1));
-    CK(cudaMemsetAsync(sc.flags.p, 0, 2 * sizeof(uint32_t), e->stream));
+    CK(cudaMemsetAsync(sc.flags.p, 0, 4 * sizeof(uint32_t), e->stream));
     k_range_starts<<<(int)std::min<uint32_t>((n_ranges + 256) / 256, (uint32_t)e->sm_count * 8), 256, 0, e->stream>>>(dev_doc_off, n_docs, stride, n_ranges,
                                                                                                              sc.range_first.p);
     CKL();
     LaneTables lt{e->d_lt.p, e->lt_cap - 1, (uint32_t)(32 - ilog2(e->lt_cap)), e->d_lt_dense.p, e->d_rule_c.p, e->lt_c_affine};
     if (lmax == 32)
-      TRY((launch_encode_lanes<32, 10>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1)));
+      TRY((launch_encode_lanes<32, 10>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
     else
-      TRY((launch_encode_lanes<48, 6>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1)));
+      TRY((launch_encode_lanes<48, 6>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
     uint32_t hf[2] = {0, 0};
     CK(cudaMemcpyAsync(hf, sc.flags.p, sizeof hf, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
@@ -667,8 +670,20 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
                                                          sc.g_rk.p, sc.g_sel.p, e->enc_force_old ? 0 : 1);
     CKL();
   }
-  k_scan_counts<<<1, 1024, 0, e->stream>>>(sc.out_len.p, sc.out_off.p, (uint32_t)n_docs);
-  CKL();
+  if (n_docs <= 65536) {
+    k_scan_counts<<<1, 1024, 0, e->stream>>>(sc.out_len.p, sc.out_off.p, (uint32_t)n_docs);
+    CKL();
+  } else {
+    uint32_t n_tiles = (uint32_t)((n_docs + SC_TILE - 1) / SC_TILE);
+    CK(sc.tile_sums.reserve(n_tiles));
+    CK(sc.tile_off.reserve((size_t)n_tiles + 1));
+    k_sum_tiles<<<n_tiles, SC_THREADS, 0, e->stream>>>(sc.out_len.p, (uint32_t)n_docs, sc.tile_sums.p);
+    CKL();
+    k_scan_counts<<<1, 1024, 0, e->stream>>>(sc.tile_sums.p, sc.tile_off.p, n_tiles);
+    CKL();
+    k_scan_tiles<<<n_tiles, SC_THREADS, 0, e->stream>>>(sc.out_len.p, (uint32_t)n_docs, sc.tile_off.p, n_tiles, sc.out_off.p);
+    CKL();
+  }
   {
     int64_t warps = n_docs + 1;
     int64_t blocks = std::min<int64_t>((warps + 3) / 4, (int64_t)e->sm_count * 16);
@@ -994,7 +1009,7 @@ int bpe_create(int device, bpe_engine** out) {
   e->stream = e->own_stream;
   if (getenv("BPE_HOST_LOOP")) e->host_loop = 1;
   if (getenv("BPE_ENC_OLD")) e->enc_force_old = 1;
-  if (const char* v = getenv("BPE_ENC_LMAX")) e->enc_lmax = (atoi(v) == 32) ? 32 : 48;
+  if (const char* v = getenv("BPE_ENC_LMAX")) e->enc_lmax = (atoi(v) == 48) ? 48 : 32;
   *out = e;
   return BPE_OK;
 }

@@ -252,4 +252,57 @@ __global__ void __launch_bounds__(128) k_gather_map(const int32_t* __restrict__ 
   }
 }
 
+// ---- exclusive scan of the per-document token counts (u32 -> u64 offsets), three launches: tile sums, scan of the
+// tile sums (k_scan_counts, one block), tile-local scan + tile offset ----
+constexpr int SC_THREADS = 256, SC_ITEMS = 16, SC_TILE = SC_THREADS * SC_ITEMS;
+
+__global__ void __launch_bounds__(SC_THREADS) k_sum_tiles(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t s_w[SC_THREADS / 32];
+  uint32_t base = blockIdx.x * SC_TILE, s = 0;
+#pragma unroll
+  for (int j = 0; j < SC_ITEMS; j++) {
+    uint32_t i = base + j * SC_THREADS + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int i = 0; i < SC_THREADS / 32; i++) t += s_w[i];
+    tile_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan_tiles(const uint32_t* __restrict__ in, uint32_t n, const uint64_t* __restrict__ tile_off,
+                                                            uint32_t n_tiles, uint64_t* __restrict__ out) {
+  __shared__ uint32_t s_w[SC_THREADS / 32];
+  uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t first = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;  // SC_ITEMS consecutive elements per thread
+  uint32_t v[SC_ITEMS], s = 0;
+#pragma unroll
+  for (int j = 0; j < SC_ITEMS; j++) {
+    v[j] = (first + j < n) ? in[first + j] : 0u;
+    s += v[j];
+  }
+  uint32_t inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if ((int)lane >= o) inc += t;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (uint32_t i = 0; i < warp; i++) wbase += s_w[i];
+  uint64_t acc = tile_off[blockIdx.x] + wbase + (inc - s);
+#pragma unroll
+  for (int j = 0; j < SC_ITEMS; j++) {
+    if (first + j < n) out[first + j] = acc;
+    acc += v[j];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = tile_off[n_tiles];
+}
+
 }  // namespace bpe

@@ -80,15 +80,27 @@ __global__ void k_range_starts(const int64_t* __restrict__ doc_off, int64_t n_do
   }
 }
 
+template <int LMAX>
+struct DirtyMask {
+  typedef unsigned long long type;
+  static __device__ __forceinline__ int popc(type m) { return __popcll(m); }
+  static __device__ __forceinline__ int ffs(type m) { return __ffsll((long long)m); }
+};
+template <>
+struct DirtyMask<32> {
+  typedef uint32_t type;
+  static __device__ __forceinline__ int popc(type m) { return __popc(m); }
+  static __device__ __forceinline__ int ffs(type m) { return __ffs((int)m); }
+};
+
 template <int LMAX, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __restrict__ ids,
                                                               const int64_t* __restrict__ doc_off, int64_t n_docs,
                                                               const uint32_t* __restrict__ range_first, uint32_t n_ranges,
                                                               LaneTables T, int32_t* __restrict__ out_tmp,
                                                               uint32_t* __restrict__ out_len, uint32_t* __restrict__ n_long,
-                                                              uint32_t* __restrict__ err) {
-  constexpr int LODD = (LMAX & 1) ? LMAX : LMAX - 1;  // rows per lane are kept odd (conflict-free staging reads)
-  constexpr uint32_t CAP = 32u * LODD;
+                                                              uint32_t* __restrict__ err, uint32_t* __restrict__ next_range) {
+  constexpr uint32_t CAP = 32u * LMAX;
   extern __shared__ uint32_t el_smem[];
   uint2* s_dense = reinterpret_cast<uint2*>(el_smem);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -101,7 +113,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
   const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t gwarp = blockIdx.x * WARPS + warp, nwarps = gridDim.x * WARPS;
 
-  for (uint32_t k = gwarp; k < n_ranges; k += nwarps) {
+  // ranges (spans of consecutive documents, several batches each) are claimed dynamically: the first nwarps statically
+  for (uint32_t k = gwarp;;) {
+    if (k >= n_ranges) break;
     int64_t d = range_first[k];
     const int64_t d1 = range_first[k + 1];
     while (d < d1) {
@@ -134,8 +148,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
         continue;
       }
       // ---- load: coalesced ids -> u16 staging -> lane segments ----
-      uint32_t L = (n + 31u) >> 5;
-      L |= 1u;
+      const uint32_t L = (n + 31u) >> 5;
       __syncwarp();
       for (uint32_t p = lane; p < n; p += 32) sS[p] = (uint16_t)__ldg(ids + base + p);
       __syncwarp();
@@ -166,7 +179,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
           sB[idx] = r2.y;
         }
       }
-      unsigned long long dm = 0;  // rows of this lane whose record is DIRTY (set by pass 3, cleared by the probe phase)
+      typedef typename DirtyMask<(LMAX <= 32 ? 32 : 64)>::type mask_t;
+      typedef DirtyMask<(LMAX <= 32 ? 32 : 64)> DM;
+      mask_t dm = 0;  // rows of this lane whose record is DIRTY (set by pass 3, cleared by the probe phase)
 
       // ---- rounds ----
       for (uint32_t round = 0;; round++) {
@@ -259,7 +274,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
           if (emit && have_pend) {
             sA[w * 32 + lane] = pendA;
             sB[w * 32 + lane] = pendB;
-            if ((pendA >> 16) == EL_DIRTY) dm |= 1ull << w;
+            if ((pendA >> 16) == EL_DIRTY) dm |= (mask_t)1 << w;
             w++;
           }
           if (emit) {
@@ -279,14 +294,14 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
         if (have_pend) {
           sA[w * 32 + lane] = pendA;
           sB[w * 32 + lane] = pendB;
-          if ((pendA >> 16) == EL_DIRTY) dm |= 1ull << w;
+          if ((pendA >> 16) == EL_DIRTY) dm |= (mask_t)1 << w;
           w++;
         }
         // post: first tokens consumed by the lane to the left; ranks next to new tokens across lanes
         bool eaten = __shfl_sync(FULL, took_straddle, plane < 0 ? (int)lane : plane) && plane >= 0 && cnt > 0;
         head = eaten ? 1u : 0u;
         cnt = eaten ? w - 1u : w;
-        if (eaten) dm &= ~1ull;
+        if (eaten) dm &= ~(mask_t)1;
         nonempty = __ballot_sync(FULL, cnt > 0);
         nlane = (nonempty >> lane) >> 1 ? (int)lane + __ffs((nonempty >> lane) >> 1) : -1;
         bool fin = __shfl_sync(FULL, first_is_new, nlane < 0 ? (int)lane : nlane) && nlane >= 0;
@@ -296,13 +311,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
           uint32_t v = sA[idx];
           if ((v >> 16) != EL_BOUNDARY) {
             sA[idx] = (v & 0xFFFFu) | (EL_DIRTY << 16);
-            dm |= 1ull << lastrow;
+            dm |= (mask_t)1 << lastrow;
           }
         }
         // ---- probe phase: the warp resolves all DIRTY records together (32 independent table loads in flight) ----
         firstA = cnt ? sA[head * 32 + lane] : 0u;
         nf_tok = __shfl_sync(FULL, firstA, nlane < 0 ? (int)lane : nlane) & 0xFFFFu;
-        uint32_t nd = (uint32_t)__popcll(dm), qpos = nd;
+        uint32_t nd = (uint32_t)DM::popc(dm), qpos = nd;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           uint32_t other = __shfl_up_sync(FULL, qpos, o);
@@ -312,8 +327,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
         qpos -= nd;
         __syncwarp();
         while (dm) {
-          uint32_t row = (uint32_t)__ffsll((long long)dm) - 1u;
-          dm &= dm - 1ull;
+          uint32_t row = (uint32_t)DM::ffs(dm) - 1u;
+          dm &= dm - (mask_t)1;
           sS[qpos++] = (uint16_t)(row * 32 + lane);
         }
         __syncwarp();
@@ -382,6 +397,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
       __syncwarp();
       d = de;
     }
+    if (lane == 0) k = nwarps + atomicAdd(next_range, 1u);
+    k = __shfl_sync(FULL, k, 0);
   }
 }
 
