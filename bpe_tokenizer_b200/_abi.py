@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libbpe_b200.so")
 
 BPE_OK, BPE_E_INVALID, BPE_E_CUDA, BPE_E_CAPACITY, BPE_E_DOMAIN, BPE_E_NOMEM, BPE_E_INTERNAL = 0, -1, -2, -3, -4, -5, -6
 BPE_MAX_TOKENS = 56319
+MG_MAX_WORLD = 8
 _CODE_NAMES = {-1: "BPE_E_INVALID", -2: "BPE_E_CUDA", -3: "BPE_E_CAPACITY", -4: "BPE_E_DOMAIN", -5: "BPE_E_NOMEM", -6: "BPE_E_INTERNAL"}
 
 
@@ -62,6 +63,11 @@ SYMBOLS = {
     "bpe_pair_counts": (C.c_int, [vp, i32p, i32p, i64p, C.c_int64, i64p]),
     "bpe_encode_batch": (C.c_int, [vp, i32p, i64p, C.c_int64, i32p, C.c_int32, i32p, C.c_int64, i64p, i64p, i64p]),
     "bpe_encode_batch_dev": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int32, vp, vp, vp, i64p]),
+    "bpe_mg_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "bpe_mg_connect": (C.c_int, [vp, C.c_char_p]),
+    "bpe_mg_state": (C.c_int, [vp, C.POINTER(C.c_int)]),
+    "bpe_mg_export_counts": (C.c_int, [vp, vp, vp, C.c_int64, i64p]),
+    "bpe_mg_import_counts": (C.c_int, [vp, vp, vp, C.c_int64, C.c_int]),
     "bpe_synth_corpus": (C.c_int, [C.c_int64, C.c_uint64, C.c_int32, C.c_uint64, u8p, C.c_int64, i64p, C.c_int64, i64p, i64p]),
 }
 

@@ -15,6 +15,7 @@
 #include "encode_kernels.cuh"
 #include "encode_lanes.cuh"
 #include "train_kernels.cuh"
+#include "mg_kernels.cuh"
 
 using namespace bpe;
 
@@ -144,6 +145,19 @@ struct bpe_engine {
   int host_loop = 0;     // debug: drive mergeUntil from the host, one launch per phase
   int scan_mode = 0;     // debug: walk all slots instead of occurrence lists
 
+  // sharded training (mg_kernels.cuh): this rank's mailbox + the peers' mailboxes mapped through cudaIpc
+  int mg_rank = 0, mg_world = 1;
+  void* mg_mailbox = nullptr;            // cudaMalloc'ed, exported with cudaIpcGetMemHandle
+  size_t mg_mailbox_bytes = 0;
+  void* mg_peer[MG_MAX_WORLD] = {};      // [rank] == mg_mailbox
+  bool mg_connected = false;
+  bool mg_counts_global = false;         // the table's counts are the sum over all ranks (import done for this index)
+  uint32_t mg_inbox_stride = 0, mg_tie_cap = 0;
+  DevBuf<int32_t> mg_dlt;
+  DevBuf<uint32_t> mg_mark, mg_touched, mg_tie_sorted, mg_export_n;
+  int mg_loop_blocks = 0;
+  unsigned long long mg_epoch = 0, mg_tie_epoch = 0;
+
   // scratch
   DevBuf<int32_t> stage_ids;
   DevBuf<int64_t> stage_off;
@@ -236,6 +250,12 @@ int alloc_table(bpe_engine* e, uint32_t cap) {
   CK(cudaMemsetAsync(e->t_start.p, 0, (size_t)cap * 4, e->stream));
   CK(cudaMemsetAsync(e->t_len.p, 0, (size_t)cap * 4, e->stream));
   CK(cudaMemsetAsync(e->t_fill.p, 0, (size_t)cap * 4, e->stream));
+  if (e->mg_world > 1) {  // per-slot side arrays of the sharded loop follow the table (all zero between merges)
+    CK(e->mg_dlt.reserve(cap));
+    CK(e->mg_mark.reserve(cap));
+    CK(cudaMemsetAsync(e->mg_dlt.p, 0, (size_t)cap * 4, e->stream));
+    CK(cudaMemsetAsync(e->mg_mark.p, 0, (size_t)cap * 4, e->stream));
+  }
   return BPE_OK;
 }
 
@@ -299,6 +319,8 @@ int build_index(bpe_engine* e) {
     DevState init{};
     init.live_tokens = e->live_tokens;
     init.tie_pos = ~0ull;
+    init.mg_epoch = e->mg_epoch;  // the peers' flags keep counting across index rebuilds
+    init.mg_tie_epoch = e->mg_tie_epoch;
     CK(cudaMemcpyAsync(e->d_st.p, &init, sizeof init, cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     if (n) {
@@ -332,6 +354,7 @@ int build_index(bpe_engine* e) {
   e->stats.ms_index_build += ms;
   e->stats.index_builds++;
   e->index_valid = true;
+  e->mg_counts_global = false;
   return BPE_OK;
 }
 
@@ -419,6 +442,9 @@ ApplyArgs apply_args(bpe_engine* e) {
   A.new_cap = (uint32_t)std::min<size_t>(e->newslots.cap, 0xFFFFFFFFu);
   A.len16 = e->d_len16.p;
   A.scan_mode = e->scan_mode;
+  A.dlt = nullptr;
+  A.touched = nullptr;
+  A.touched_cap = 0;
   return A;
 }
 
@@ -917,6 +943,216 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
   return rc;
 }
 
+
+// ---- mergeUntil on a sharded corpus: k_merge_loop_mg, same host protocol as merge_until_device ---------------------
+MgArgs mg_args(bpe_engine* e) {
+  MgArgs M{};
+  M.rank = e->mg_rank;
+  M.world = e->mg_world;
+  M.inbox_stride = e->mg_inbox_stride;
+  M.tie_cap = e->mg_tie_cap;
+  const size_t flags_bytes = (size_t)MG_MAX_WORLD * 128;
+  const size_t inbox_bytes = (size_t)2 * e->mg_world * e->mg_inbox_stride * 8;
+  for (int q = 0; q < e->mg_world; q++) {
+    char* base = static_cast<char*>(e->mg_peer[q]);
+    M.flag_data[q] = reinterpret_cast<unsigned long long*>(base);
+    M.flag_tie[q] = reinterpret_cast<unsigned long long*>(base + flags_bytes);
+    M.inbox[q] = reinterpret_cast<unsigned long long*>(base + 2 * flags_bytes);
+    M.tiebox[q] = reinterpret_cast<uint32_t*>(base + 2 * flags_bytes + inbox_bytes);
+  }
+  M.mark = e->mg_mark.p;
+  M.tie_sorted = e->mg_tie_sorted.p;
+  return M;
+}
+
+int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations, bpe_merge* log, int64_t log_cap,
+                   int64_t* n_done) {
+  *n_done = 0;
+  CK(cudaSetDevice(e->device));
+  if (!e->mg_connected) return fail(e, BPE_E_INVALID, "sharded engine: call bpe_mg_connect first");
+  TRY(ensure_index(e));
+  if (!e->mg_counts_global) return fail(e, BPE_E_INVALID, "sharded engine: exchange the pair counts first (bpe_mg_export_counts / bpe_mg_import_counts)");
+  uint32_t ml = max_length > 0 ? (uint32_t)max_length : 0;
+  int64_t mw = min_weight > 0 ? min_weight : 2;
+  if (!e->mg_loop_blocks) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop_mg, ML_THREADS, 0));
+    if (per_sm < 1) return fail(e, BPE_E_CUDA, "k_merge_loop_mg does not fit on an SM");
+    e->mg_loop_blocks = e->sm_count * std::min(per_sm, 2);
+  }
+  CK(e->partials.reserve((size_t)std::max(e->mg_loop_blocks, e->grid(8))));
+  CK(e->sites.reserve(1u << 16, 0, e->stream, 1.0));
+  CK(e->newslots.reserve(1u << 17, 0, e->stream, 1.0));
+  CK(e->cands.reserve(4096, 0, e->stream, 1.0));
+  CK(e->barrier.reserve(64));
+  CK(e->mg_touched.reserve((size_t)4 * BPE_MAX_TOKENS + 64));
+  CK(e->mg_tie_sorted.reserve(e->mg_tie_cap));
+  cudaEvent_t t0, t1;
+  CK(cudaEventCreate(&t0));
+  CK(cudaEventCreate(&t1));
+  CK(cudaEventRecord(t0, e->stream));
+  int rc = BPE_OK;
+  int64_t done = 0;
+  std::vector<MergeRec> tmp;
+  for (;;) {
+    int64_t remaining = log_cap - done;
+    if (max_iterations > 0) remaining = std::min(remaining, max_iterations - done);  // core.ts:374-377
+    if (remaining <= 0) break;
+    if (!e->hot_valid || e->hot_max_length != ml) {
+      bool any = false;
+      if ((rc = rebuild_hot(e, ml, &any)) != BPE_OK) break;
+      if (!any) break;  // nothing countable left on ANY rank: the counts are global (core.ts:312)
+    }
+    uint32_t chunk = (uint32_t)std::min<int64_t>(remaining, 1 << 16);
+    if (e->n_tokens + (int64_t)chunk > BPE_MAX_TOKENS) chunk = (uint32_t)std::max<int64_t>(0, BPE_MAX_TOKENS - e->n_tokens);
+    if (chunk == 0) {
+      rc = fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
+      break;
+    }
+    cudaError_t ce;
+    if ((ce = e->dev_log.reserve(chunk)) != cudaSuccess ||
+        (ce = e->d_len16.reserve((size_t)e->n_tokens + chunk + 1, (size_t)e->n_tokens, e->stream, 1.5)) != cudaSuccess) {
+      rc = fail(e, BPE_E_NOMEM, "%s", cudaGetErrorString(ce));
+      break;
+    }
+    LoopArgsMg P;
+    LoopArgs& L = P.L;
+    L.A = apply_args(e);
+    L.A.dlt = e->mg_dlt.p;
+    L.A.touched = e->mg_touched.p;
+    L.A.touched_cap = (uint32_t)e->mg_touched.cap;
+    L.pool_cap = (uint32_t)std::min<size_t>(e->pool.cap, 0xFFFFFFF0u);
+    L.len16_cap = (uint32_t)std::min<size_t>(e->d_len16.cap, 0xFFFFFFF0u);
+    L.hot = e->hot.p;
+    L.hot_cap = (uint32_t)std::min<size_t>(e->hot.cap, 0xFFFFFFF0u);
+    L.hot_limit = e->hot_limit;
+    L.cands = e->cands.p;
+    L.cand_cap = (uint32_t)std::min<size_t>(e->cands.cap, 0xFFFFFFF0u);
+    L.partials = e->partials.p;
+    L.barrier = e->barrier.p;
+    L.log = e->dev_log.p;
+    L.log_cap = chunk;
+    L.max_length = ml;
+    L.min_weight = (uint32_t)std::min<int64_t>(mw, 0xFFFFFFFFll);
+    L.max_tokens = BPE_MAX_TOKENS;
+    L.tbl_cap = e->tbl_cap;
+    P.M = mg_args(e);
+    static const bool trace = getenv("BPE_TRACE") != nullptr;
+    auto tw0 = std::chrono::steady_clock::now();
+    k_loop_prepare<<<1, 32, 0, e->stream>>>(e->d_st.p, (uint32_t)e->n_tokens, e->barrier.p);
+    e->stats.kernel_launches++;
+    void* args[] = {&P};
+    ce = cudaLaunchCooperativeKernel((void*)k_merge_loop_mg, dim3(e->mg_loop_blocks), dim3(ML_THREADS), args, 0, e->stream);
+    if (ce != cudaSuccess) {
+      rc = fail(e, BPE_E_CUDA, "cooperative launch of k_merge_loop_mg: %s", cudaGetErrorString(ce));
+      break;
+    }
+    e->stats.kernel_launches++;
+    if ((rc = fetch_state(e)) != BPE_OK) break;
+    e->mg_epoch = e->h_st->mg_epoch;
+    e->mg_tie_epoch = e->h_st->mg_tie_epoch;
+    uint32_t iters = e->h_st->iters_done;
+    if (trace) {
+      double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
+      fprintf(stderr, "[bpe r%d] k_merge_loop_mg: %u merges in %.2f ms, status %u, best_cnt %u, hot_n %u thresh %u, keys %u/%u err 0x%x gerr 0x%x\n",
+              e->mg_rank, iters, ms, e->h_st->status, e->h_st->best_cnt, e->h_st->hot_n, e->h_st->hot_thresh, e->h_st->n_keys, e->tbl_cap,
+              e->h_st->err, e->h_st->g_err);
+    }
+    if (iters) {
+      tmp.resize(iters);
+      ce = cudaMemcpyAsync(tmp.data(), e->dev_log.p, (size_t)iters * sizeof(MergeRec), cudaMemcpyDeviceToHost, e->stream);
+      if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+      if (ce != cudaSuccess) {
+        rc = fail(e, BPE_E_CUDA, "merge log read-back: %s", cudaGetErrorString(ce));
+        break;
+      }
+      for (uint32_t i = 0; i < iters; i++) {
+        const MergeRec& r = tmp[i];
+        log[done].a = r.a;
+        log[done].b = r.b;
+        log[done].c = r.c;
+        log[done].reserved = 0;
+        log[done].weight = r.weight;
+        done++;
+        e->h_len16.push_back(e->h_len16[r.a] + e->h_len16[r.b]);
+        e->h_merges.push_back(r.a);
+        e->h_merges.push_back(r.b);
+        e->h_merges.push_back(r.c);
+      }
+      e->n_tokens += (int32_t)iters;
+      e->mt_dirty = e->lt_dirty = true;
+      e->stats.merges_applied += iters;
+    }
+    uint32_t status = e->h_st->status;
+    if (status == LOOP_DONE || status == LOOP_EMPTY) break;
+    if (status == LOOP_LIMIT) continue;
+    if (status == LOOP_NEED_REBUILD) {
+      e->hot_valid = false;
+      continue;
+    }
+    if (status == LOOP_ERROR) {
+      uint32_t f = e->h_st->err | e->h_st->g_err;
+      if (f & ERR_PEER_TIMEOUT) rc = fail(e, BPE_E_INTERNAL, "a peer GPU did not answer within %.0f s (flags 0x%x)", MG_TIMEOUT_NS / 1e9, f);
+      else {
+        rc = check_dev_err(e);
+        if (rc == BPE_OK) rc = fail(e, BPE_E_INTERNAL, "sharded merge loop stopped: local flags 0x%x, all ranks 0x%x", e->h_st->err, e->h_st->g_err);
+      }
+      break;
+    }
+    if (status == LOOP_NEED_HOST) {  // every rank is here with the same winner: each one grows what IT lacks
+      if (e->n_tokens >= BPE_MAX_TOKENS) {
+        rc = fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
+        break;
+      }
+      uint64_t w = e->h_st->best_cnt;
+      uint64_t new_keys = std::min<uint64_t>(2 * w + 2, 2 * ((uint64_t)e->n_tokens + 1) + 2);
+      uint64_t keys_after = (uint64_t)e->h_st->n_keys + new_keys;
+      if (keys_after * 2 > e->tbl_cap) {
+        uint64_t want = std::min<uint64_t>(keys_after * 5 / 2, 0x80000000ull);
+        if (keys_after * 2 > pow2_at_least(want)) {
+          rc = fail(e, BPE_E_NOMEM, "pair table cannot grow further");
+          break;
+        }
+        if ((rc = grow_table(e, pow2_at_least(want))) != BPE_OK) break;
+      }
+      uint64_t pool_after = (uint64_t)e->h_st->pool_cursor + 4 * w;  // the in-kernel test is one merge conservative
+      if (pool_after > 0xFFFFFFF0ull) {
+        rc = fail(e, BPE_E_DOMAIN, "occurrence pool exceeds 2^32 cells");
+        break;
+      }
+      if ((ce = e->pool.reserve((size_t)pool_after, e->h_st->pool_cursor, e->stream, 1.5)) != cudaSuccess ||
+          (ce = e->sites.reserve((size_t)w, 0, e->stream, 1.25)) != cudaSuccess ||
+          (ce = e->newslots.reserve((size_t)new_keys, 0, e->stream, 1.25)) != cudaSuccess ||
+          (ce = e->hot.reserve((size_t)e->h_st->hot_n + 2 * new_keys, e->h_st->hot_n, e->stream, 1.5)) != cudaSuccess ||
+          (ce = e->cands.reserve((size_t)e->h_st->best_mult, 0, e->stream, 1.5)) != cudaSuccess) {
+        rc = fail(e, BPE_E_NOMEM, "growing merge buffers: %s", cudaGetErrorString(ce));
+        break;
+      }
+      if (e->h_st->best_mult > e->mg_tie_cap) {
+        rc = fail(e, BPE_E_DOMAIN, "%u pairs tie on (weight, index sum): more than the tie mailbox holds (%u)", e->h_st->best_mult, e->mg_tie_cap);
+        break;
+      }
+      continue;
+    }
+    rc = fail(e, BPE_E_INTERNAL, "merge loop returned status %u", status);
+    break;
+  }
+  *n_done = done;
+  if (rc == BPE_OK) {
+    CK(cudaEventRecord(t1, e->stream));
+    TRY(fetch_state(e));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, t0, t1));
+    e->stats.ms_last_merge_until = ms;
+    e->live_tokens = e->h_st->live_tokens;
+    e->stats.sites_merged = (int64_t)e->h_st->sites_total;
+    e->stats.tie_breaks = e->h_st->tie_breaks;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  return rc;
+}
+
 int merge_until_host(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations, bpe_merge* log,
                             int64_t log_cap, int64_t* n_done) {
   if (!e || !n_done || (log_cap > 0 && !log) || log_cap < 0) return BPE_E_INVALID;
@@ -1015,6 +1251,13 @@ int bpe_create(int device, bpe_engine** out) {
 }
 
 void bpe_destroy(bpe_engine* e) {
+  if (e && e->mg_mailbox) {
+    cudaSetDevice(e->device);
+    for (int q = 0; q < e->mg_world; q++)
+      if (q != e->mg_rank && e->mg_peer[q]) cudaIpcCloseMemHandle(e->mg_peer[q]);
+    cudaFree(e->mg_mailbox);
+    e->mg_mailbox = nullptr;
+  }
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
@@ -1242,8 +1485,94 @@ int bpe_apply_merge(bpe_engine* e, int32_t a, int32_t b, int32_t c, int64_t* n_r
 int bpe_merge_until(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations, bpe_merge* log,
                     int64_t log_cap, int64_t* n_done) {
   if (!e || !n_done || (log_cap > 0 && !log) || log_cap < 0) return BPE_E_INVALID;
+  if (e->mg_world > 1) return merge_until_mg(e, min_weight, max_length, max_iterations, log, log_cap, n_done);
   if (e->host_loop) return merge_until_host(e, min_weight, max_length, max_iterations, log, log_cap, n_done);
   return merge_until_device(e, min_weight, max_length, max_iterations, log, log_cap, n_done);
+}
+
+
+// ---- sharded training: mailbox set-up and the initial pair-count exchange ------------------------------------------
+int bpe_mg_init(bpe_engine* e, int rank, int world, void* handle_out64) {
+  if (!e || !handle_out64 || world < 1 || world > MG_MAX_WORLD || rank < 0 || rank >= world) return fail(e, BPE_E_INVALID, "bad rank/world");
+  CK(cudaSetDevice(e->device));
+  if (e->mg_mailbox) return fail(e, BPE_E_INVALID, "bpe_mg_init called twice");
+  e->mg_rank = rank;
+  e->mg_world = world;
+  e->mg_inbox_stride = MG_HDR + 4u * BPE_MAX_TOKENS + 64u;
+  e->mg_tie_cap = 4096;
+  size_t bytes = (size_t)2 * MG_MAX_WORLD * 128 + (size_t)2 * world * e->mg_inbox_stride * 8 + (size_t)2 * world * e->mg_tie_cap * 4;
+  CK(cudaMalloc(&e->mg_mailbox, bytes));
+  CK(cudaMemset(e->mg_mailbox, 0, bytes));
+  e->mg_mailbox_bytes = bytes;
+  e->mg_peer[rank] = e->mg_mailbox;
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CK(cudaIpcGetMemHandle(&h, e->mg_mailbox));
+  memcpy(handle_out64, &h, sizeof h);
+  e->index_valid = false;  // per-slot side arrays are allocated with the table
+  e->mg_connected = (world == 1);
+  return BPE_OK;
+}
+
+int bpe_mg_connect(bpe_engine* e, const char* handles /* world x 64 bytes, by rank */) {
+  if (!e || !handles || !e->mg_mailbox) return fail(e, BPE_E_INVALID, "call bpe_mg_init first");
+  CK(cudaSetDevice(e->device));
+  for (int q = 0; q < e->mg_world; q++) {
+    if (q == e->mg_rank || e->mg_peer[q]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)q * 64, sizeof h);
+    CK(cudaIpcOpenMemHandle(&e->mg_peer[q], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  e->mg_connected = true;
+  return BPE_OK;
+}
+
+int bpe_mg_state(bpe_engine* e, int* counts_global) {
+  if (!e || !counts_global) return BPE_E_INVALID;
+  *counts_global = (e->index_valid && e->mg_counts_global) ? 1 : 0;
+  return BPE_OK;
+}
+
+int bpe_mg_export_counts(bpe_engine* e, uint32_t* dev_keys, uint32_t* dev_counts, int64_t cap, int64_t* n) {
+  if (!e || !n || cap < 0 || (cap > 0 && (!dev_keys || !dev_counts))) return fail(e, BPE_E_INVALID, "bad export arguments");
+  CK(cudaSetDevice(e->device));
+  TRY(ensure_index(e));
+  if (e->mg_counts_global) return fail(e, BPE_E_INVALID, "pair counts of this index were already exchanged");
+  TRY(fetch_state(e));
+  *n = e->h_st->n_keys;
+  if (cap == 0) return BPE_OK;  // size query
+  CK(e->mg_export_n.reserve(1));
+  CK(cudaMemsetAsync(e->mg_export_n.p, 0, 4, e->stream));
+  k_mg_export_counts<<<e->grid(4), 256, 0, e->stream>>>(e->table(), dev_keys, dev_counts, (uint32_t)std::min<int64_t>(cap, 0xFFFFFFFFll), e->mg_export_n.p);
+  CKL();
+  uint32_t got = 0;
+  CK(cudaMemcpyAsync(&got, e->mg_export_n.p, 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  *n = got;
+  if ((int64_t)got > cap) return fail(e, BPE_E_CAPACITY, "export buffers hold %lld pairs, need %u", (long long)cap, got);
+  return BPE_OK;
+}
+
+int bpe_mg_import_counts(bpe_engine* e, const uint32_t* dev_keys, const uint32_t* dev_counts, int64_t n, int last) {
+  if (!e || n < 0 || (n > 0 && (!dev_keys || !dev_counts))) return fail(e, BPE_E_INVALID, "bad import arguments");
+  CK(cudaSetDevice(e->device));
+  if (!e->index_valid) return fail(e, BPE_E_INVALID, "no pair index to import into");
+  TRY(fetch_state(e));
+  uint64_t keys_after = (uint64_t)e->h_st->n_keys + (uint64_t)n;
+  if (keys_after * 2 > e->tbl_cap) {
+    uint64_t want = std::min<uint64_t>(keys_after * 5 / 2, 0x80000000ull);
+    if (keys_after * 2 > pow2_at_least(want)) return fail(e, BPE_E_NOMEM, "pair table cannot grow further");
+    TRY(grow_table(e, pow2_at_least(want)));
+  }
+  if (n) {
+    k_mg_import_counts<<<e->grid(4), 256, 0, e->stream>>>(e->table(), dev_keys, dev_counts, (uint32_t)n, e->d_st.p);
+    CKL();
+  }
+  TRY(fetch_state(e));
+  TRY(check_dev_err(e));
+  e->hot_valid = false;
+  if (last) e->mg_counts_global = true;
+  return BPE_OK;
 }
 
 int bpe_pair_counts(bpe_engine* e, int32_t* a, int32_t* b, int64_t* count, int64_t cap, int64_t* n) {

@@ -1,0 +1,417 @@
+// mg_kernels.cuh -- mergeUntil on a corpus sharded by document over several GPUs (one process per GPU).
+//
+// Reference semantics: the corpus is one list of documents (core.ts:106); findNextMerge counts pairs over ALL of them
+// (core.ts:265-310) and applyMerge rewrites ALL of them (core.ts:356-359).  Documents never interact except through
+// the global pair counts and the arg-max, so the corpus shards by document:
+//   * rank r owns a contiguous range of documents (global scan order = (rank, local position), which is what the
+//     reference's position tie-break needs, core.ts:294-305), its slots, occurrence lists and pool;
+//   * the pair table's COUNTS are global and replicated: every merge, each rank stages its local count deltas
+//     (cnt_delta), aggregates them per pair, and stores the (pair, delta) records straight into every peer's inbox
+//     over NVLink (peer-mapped memory, cudaIpc); one flag store per peer publishes them.  Every rank then applies all
+//     G record lists, so all tables hold the same counts and the arg-max needs NO collective: it is computed
+//     redundantly and identically everywhere;
+//   * only when several pairs tie on (weight, a.index + b.index) a second small exchange carries each rank's last
+//     counted position per candidate (candidates in canonical key order); the highest rank holding a candidate owns its
+//     last occurrence.
+// Everything runs inside ONE persistent cooperative kernel per GPU (k_merge_loop_mg): compute and the exchange are
+// fused, there is no host round trip and no NCCL call per merge.  Every decision that ends or interrupts the loop is
+// taken from replicated values (or minima over ranks carried in the message headers), so all ranks leave the kernel
+// at the same merge with the same status.  Waits on peers are bounded (MG_TIMEOUT_NS) and abort the loop.
+#pragma once
+#include "train_kernels.cuh"
+
+namespace bpe {
+
+constexpr int MG_MAX_WORLD = 8;
+constexpr uint32_t MG_HDR = 16;  // u64 words of header in front of the records of one message
+enum { H_N = 0, H_ERR, H_POOL_FREE, H_SITES_CAP, H_NEW_CAP, H_HOT_CAP, H_LEN16_CAP, H_TBL_CAP, H_CAND_CAP, H_STATUS };
+constexpr unsigned long long MG_TIMEOUT_NS = 8000000000ull;
+
+struct MgArgs {
+  int rank, world;
+  uint32_t inbox_stride;  // u64 words per (parity, sender) message area, header included
+  uint32_t tie_cap;       // candidates per tie message
+  // mailboxes, indexed by rank; [rank] is this GPU's own (peers store into it), the others are peer-mapped
+  unsigned long long* flag_data[MG_MAX_WORLD];  // [world] one 128-byte line per sender
+  unsigned long long* flag_tie[MG_MAX_WORLD];
+  unsigned long long* inbox[MG_MAX_WORLD];      // [2][world][inbox_stride]
+  uint32_t* tiebox[MG_MAX_WORLD];               // [2][world][tie_cap]
+  // local scratch
+  uint32_t* mark;          // per table slot: last merge (c + 1) that put the pair on the hot list
+  uint32_t* tie_sorted;    // candidates (table slots) in canonical key order
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// thread 0 of block 0: publish `epoch` to every peer and wait until every peer has published it to us
+__device__ __forceinline__ void mg_signal_and_wait(const MgArgs& M, unsigned long long* const* flags, unsigned long long epoch,
+                                                   DevState* st) {
+  for (int q = 0; q < M.world; q++)
+    if (q != M.rank) st_release_sys(flags[q] + 16 * M.rank, epoch);
+  unsigned long long t0 = now_ns();
+  for (int q = 0; q < M.world; q++) {
+    if (q == M.rank) continue;
+    const unsigned long long* f = flags[M.rank] + 16 * q;
+    uint32_t ns = 32;
+    while (ld_acquire_sys(f) < epoch) {
+      __nanosleep(ns);
+      if (ns < 1024) ns <<= 1;
+      if (now_ns() - t0 > MG_TIMEOUT_NS) {
+        atomicOr(&st->err, ERR_PEER_TIMEOUT);
+        st->mg_abort = 1;
+        return;
+      }
+    }
+  }
+}
+
+struct LoopArgsMg {
+  LoopArgs L;
+  MgArgs M;
+};
+
+// ---- initial histogram exchange (host-driven, once per index build) ----------------------------------------------
+__global__ void k_mg_export_counts(PairTable t, uint32_t* __restrict__ keys, uint32_t* __restrict__ cnts, uint32_t cap,
+                                   uint32_t* __restrict__ n_out) {
+  uint32_t tcap = t.mask + 1;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < tcap; i += gridDim.x * blockDim.x) {
+    uint32_t key = t.keys[i];
+    if (key == EMPTY_KEY) continue;
+    uint32_t c = t.cnt[i];
+    if (c == 0) continue;
+    uint32_t k = atomicAdd(n_out, 1u);
+    if (k < cap) {
+      keys[k] = key;
+      cnts[k] = c;
+    }
+  }
+}
+
+__global__ void k_mg_import_counts(PairTable t, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ cnts, uint32_t n,
+                                   DevState* st) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t s = tbl_find_or_insert(t, keys[i], &st->n_keys);
+    if (s == NOSLOT) atomicOr(&st->err, ERR_TABLE_FULL);
+    else atomicAdd(t.cnt + s, cnts[i]);
+  }
+}
+
+// ---- the loop ----------------------------------------------------------------------------------------------------
+// message of this rank for exchange `epoch`: header + n records (pair_key << 32 | (u32)delta) in every inbox
+__device__ __forceinline__ unsigned long long* mg_area(const MgArgs& M, int dst, uint32_t par, int sender) {
+  return M.inbox[dst] + ((size_t)par * M.world + sender) * M.inbox_stride;
+}
+
+__device__ __forceinline__ void mg_write_header(const LoopArgsMg& P, DevState* st, uint32_t par, uint32_t n_rec, uint32_t status) {
+  const MgArgs& M = P.M;
+  const LoopArgs& L = P.L;
+  unsigned long long h[MG_HDR];
+  for (uint32_t i = 0; i < MG_HDR; i++) h[i] = 0;
+  h[H_N] = n_rec;
+  h[H_ERR] = st->err;
+  uint32_t cur = st->pool_cursor;
+  h[H_POOL_FREE] = L.pool_cap > cur ? L.pool_cap - cur : 0;
+  h[H_SITES_CAP] = L.A.sites_cap;
+  h[H_NEW_CAP] = L.A.new_cap;
+  h[H_HOT_CAP] = min(L.hot_cap, L.hot_limit);
+  h[H_LEN16_CAP] = L.len16_cap;
+  h[H_TBL_CAP] = L.tbl_cap;
+  h[H_CAND_CAP] = min(L.cand_cap, M.tie_cap);
+  h[H_STATUS] = status;
+  for (int q = 0; q < M.world; q++) {
+    unsigned long long* dst = mg_area(M, q, par, M.rank);
+    for (uint32_t i = 0; i < MG_HDR; i++) dst[i] = h[i];
+  }
+  __threadfence_system();
+}
+
+// block 0, thread 0, after the exchange: minima / OR over the G headers
+__device__ __forceinline__ void mg_fold_headers(const MgArgs& M, DevState* st, uint32_t par) {
+  uint32_t err = 0;
+  unsigned long long mins[H_CAND_CAP + 1];
+  for (int i = 0; i <= H_CAND_CAP; i++) mins[i] = ~0ull;
+  for (int q = 0; q < M.world; q++) {
+    const unsigned long long* h = mg_area(M, M.rank, par, q);
+    err |= (uint32_t)ld_cg(h + H_ERR);
+    for (int i = H_POOL_FREE; i <= H_CAND_CAP; i++) mins[i] = min(mins[i], ld_cg(h + i));
+  }
+  st->g_err = err;
+  st->g_pool_free = (uint32_t)min(mins[H_POOL_FREE], 0xFFFFFFFFull);
+  st->g_sites_cap = (uint32_t)min(mins[H_SITES_CAP], 0xFFFFFFFFull);
+  st->g_new_cap = (uint32_t)min(mins[H_NEW_CAP], 0xFFFFFFFFull);
+  st->g_hot_cap = (uint32_t)min(mins[H_HOT_CAP], 0xFFFFFFFFull);
+  st->g_len16_cap = (uint32_t)min(mins[H_LEN16_CAP], 0xFFFFFFFFull);
+  st->g_tbl_cap = (uint32_t)min(mins[H_TBL_CAP], 0xFFFFFFFFull);
+  st->g_cand_cap = (uint32_t)min(mins[H_CAND_CAP], 0xFFFFFFFFull);
+}
+
+__global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
+  __shared__ Best s_best[ML_THREADS / 32];
+  __shared__ uint32_t s_max[32];
+  const LoopArgs& L = P.L;
+  const MgArgs& M = P.M;
+  const ApplyArgs& A = L.A;
+  DevState* st = A.st;
+  const PairTable& t = A.t;
+  const uint32_t bid = blockIdx.x, nblk = gridDim.x;
+  const uint32_t gtid = bid * blockDim.x + threadIdx.x, gthreads = nblk * blockDim.x;
+  const bool lead = (bid == 0 && threadIdx.x == 0);
+  unsigned long long bar = 0;
+  const uint32_t n_tokens0 = ld_cg(&st->n_tokens);
+  const uint32_t thresh = ld_cg(&st->hot_thresh);
+  unsigned long long epoch = ld_cg(&st->mg_epoch);
+  unsigned long long tie_epoch = ld_cg(&st->mg_tie_epoch);
+#define GRID_BARRIER() grid_barrier(L.barrier, ++bar * nblk)
+
+  // ---- hello exchange: headers only (capacities, errors), so that the first decision is taken on global minima ----
+  if (lead) {
+    st->snap_n_keys = st->n_keys;
+    st->snap_hot_n = st->hot_n;
+    st->mg_abort = 0;
+    mg_write_header(P, st, (uint32_t)((epoch + 1) & 1u), 0, LOOP_RUNNING);
+    mg_signal_and_wait(M, M.flag_data, epoch + 1, st);
+    mg_fold_headers(M, st, (uint32_t)((epoch + 1) & 1u));
+  }
+  epoch++;
+  {
+    Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
+    if (threadIdx.x == 0) L.partials[bid] = v;
+  }
+  GRID_BARRIER();
+  uint32_t wcnt_prev = 0;
+  unsigned long long newk_prev = 0;  // upper bound of the hot-list entries appended by the previous merge's P3
+
+  for (uint32_t it = 0;; it++) {
+    const uint32_t par = it & 1u;
+    // ---- every block (on every rank) folds the partials and takes the same decision ----
+    Best w{0ull, NOSLOT, 0};
+    for (uint32_t i = threadIdx.x; i < nblk; i += blockDim.x) {
+      Best pb;
+      pb.primary = ld_cg(&L.partials[i].primary);
+      pb.slot = ld_cg(&L.partials[i].slot);
+      pb.mult = ld_cg(&L.partials[i].mult);
+      w = best_merge(w, pb);
+    }
+    w = best_block_reduce(w, s_best);
+    uint32_t status = LOOP_RUNNING;
+    uint32_t wa = 0, wb = 0, wcnt = 0;
+    if (w.primary) {
+      uint32_t key = t.keys[w.slot];
+      wa = key >> 16;
+      wb = key & 0xFFFFu;
+      wcnt = (uint32_t)(w.primary >> 20);
+    }
+    const uint32_t c = n_tokens0 + it;
+    if (ld_cg(&st->mg_abort) || ld_cg(&st->g_err)) status = LOOP_ERROR;
+    else if (!w.primary) status = (thresh <= 1) ? LOOP_EMPTY : LOOP_NEED_REBUILD;
+    else if (wcnt < thresh) status = LOOP_NEED_REBUILD;
+    else if (wcnt < L.min_weight) status = LOOP_DONE;  // core.ts:313
+    else if (it >= L.log_cap) status = LOOP_LIMIT;
+    else if (c >= L.max_tokens) status = LOOP_NEED_HOST;
+    if (status == LOOP_RUNNING) {
+      unsigned long long new_keys = min(2ull * wcnt + 2ull, 2ull * (c + 1ull) + 2ull);
+      unsigned long long pool_free = ld_cg(&st->g_pool_free);
+      pool_free = pool_free > 2ull * wcnt_prev ? pool_free - 2ull * wcnt_prev : 0;  // headers are one merge old
+      if ((unsigned long long)ld_cg(&st->snap_n_keys) + new_keys > (unsigned long long)(ld_cg(&st->g_tbl_cap) >> 1)) status = LOOP_NEED_HOST;
+      else if (2ull * wcnt > pool_free) status = LOOP_NEED_HOST;
+      else if (wcnt > ld_cg(&st->g_sites_cap) || new_keys > ld_cg(&st->g_new_cap)) status = LOOP_NEED_HOST;
+      else if ((unsigned long long)ld_cg(&st->snap_hot_n) + newk_prev + new_keys > ld_cg(&st->g_hot_cap)) status = LOOP_NEED_REBUILD;
+      else if (c + 1 > ld_cg(&st->g_len16_cap)) status = LOOP_NEED_HOST;
+      else if (w.mult > 1 && w.mult > ld_cg(&st->g_cand_cap)) status = LOOP_NEED_HOST;
+    }
+    if (status == LOOP_RUNNING && w.mult > 1) {
+      // ---- tie on (weight, a.index+b.index): last counted occurrence in GLOBAL scan order decides (core.ts:294-305) ----
+      const uint32_t tpar = (uint32_t)((tie_epoch + 1) & 1u);
+      phase_collect(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), w.primary, L.cands, L.cand_cap, st, bid, nblk);
+      GRID_BARRIER();
+      const uint32_t nc = ld_cg(&st->n_cand);  // == w.mult on every rank
+      for (uint32_t i = gtid; i < nc; i += gthreads) {  // canonical order: by pair key
+        uint32_t si = ld_cg(&L.cands[i]);
+        uint32_t ki = t.keys[si], r = 0;
+        for (uint32_t j = 0; j < nc; j++) r += t.keys[ld_cg(&L.cands[j])] < ki;
+        M.tie_sorted[r] = si;
+      }
+      GRID_BARRIER();
+      for (uint32_t cnd = bid; cnd < nc; cnd += nblk) {  // one block per candidate: its last counted local occurrence
+        uint32_t s = ld_cg(&M.tie_sorted[cnd]);
+        uint32_t key = t.keys[s];
+        uint32_t a = key >> 16, b = key & 0xFFFFu;
+        uint32_t start = t.occ_start[s], len = t.occ_len[s];
+        uint32_t v = 0;
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+          uint32_t p = A.pool[start + i];
+          if (counted_occurrence(A.slots, A.n, p, a, b)) v = max(v, p + 1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+        __syncthreads();
+        if (lane_id() == 0) s_max[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          uint32_t m = 0;
+          for (uint32_t i = 0; i < (blockDim.x >> 5); i++) m = max(m, s_max[i]);
+          for (int q = 0; q < M.world; q++) M.tiebox[q][((size_t)tpar * M.world + M.rank) * M.tie_cap + cnd] = m;
+          __threadfence_system();
+        }
+      }
+      GRID_BARRIER();
+      if (lead) {
+        st->tie_pos = ~0ull;
+        mg_signal_and_wait(M, M.flag_tie, tie_epoch + 1, st);
+      }
+      tie_epoch++;
+      GRID_BARRIER();
+      if (bid == 0) {
+        const uint32_t* box = M.tiebox[M.rank] + (size_t)tpar * M.world * M.tie_cap;
+        for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
+          for (int q = M.world - 1; q >= 0; q--) {  // the highest rank holding the pair owns its last occurrence
+            uint32_t v = ld_cg(box + (size_t)q * M.tie_cap + i);
+            if (v) {
+              atomicMin(&st->tie_pos, ((((unsigned long long)q << 32) | (v - 1)) << 16) | i);
+              break;
+            }
+          }
+        }
+      }
+      GRID_BARRIER();
+      unsigned long long tp = ld_cg(&st->tie_pos);
+      if (ld_cg(&st->mg_abort) || tp == ~0ull) status = LOOP_ERROR;
+      else {
+        uint32_t s = ld_cg(&M.tie_sorted[(uint32_t)(tp & 0xFFFFu)]);
+        uint32_t key = t.keys[s];
+        w.slot = s;
+        wa = key >> 16;
+        wb = key & 0xFFFFu;
+      }
+    }
+    if (status != LOOP_RUNNING) {
+      if (lead) {
+        st->status = status;
+        st->iters_done = it;
+        st->n_tokens = n_tokens0 + it;
+        publish_best(t, st, w);
+        st->n_cand = 0;
+        st->tie_pos = ~0ull;
+        st->mg_epoch = epoch;
+        st->mg_tie_epoch = tie_epoch;
+      }
+      return;
+    }
+    // ---- P1: local sites, staged count deltas ----
+    if (lead) {
+      A.len16[c] = A.len16[wa] + A.len16[wb];  // chars = a.chars + b.chars (:318)
+      MergeRec r;
+      r.a = (int32_t)wa;
+      r.b = (int32_t)wb;
+      r.c = (int32_t)c;
+      r.reserved = 0;
+      r.weight = (long long)wcnt;
+      L.log[it] = r;
+      st->n_sites[par ^ 1u] = 0;
+      st->n_new[par ^ 1u] = 0;
+      st->n_touched[par ^ 1u] = 0;
+      st->n_out = 0;
+      if (w.mult > 1) st->tie_breaks++;
+    }
+    phase_sites(A, wa, wb, c, par, w.slot, bid, nblk);
+    GRID_BARRIER();
+    // ---- M1: one (pair, delta) record per touched pair, stored straight into every rank's inbox (NVLink) ----
+    const uint32_t epar = (uint32_t)((epoch + 1) & 1u);
+    {
+      const uint32_t nt = min(ld_cg(&st->n_touched[par]), A.touched_cap);
+      for (uint32_t i = gtid; i < nt; i += gthreads) {
+        uint32_t s = ld_cg(&A.touched[i]);
+        int32_t d = atomicExch(A.dlt + s, 0);
+        if (d == 0) continue;
+        uint32_t k = atomicAdd(&st->n_out, 1u);
+        if (MG_HDR + k >= M.inbox_stride) {
+          atomicOr(&st->err, ERR_INBOX_OVERFLOW);
+          continue;
+        }
+        unsigned long long rec = ((unsigned long long)t.keys[s] << 32) | (uint32_t)d;
+        for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MG_HDR + k] = rec;
+      }
+      __threadfence_system();
+    }
+    GRID_BARRIER();
+    if (lead) {
+      mg_write_header(P, st, epar, min(ld_cg(&st->n_out), M.inbox_stride - MG_HDR), LOOP_RUNNING);
+      mg_signal_and_wait(M, M.flag_data, epoch + 1, st);
+      mg_fold_headers(M, st, epar);
+      st->n_cand = 0;
+      st->tie_pos = ~0ull;
+      t.cnt[w.slot] = 0;  // every counted occurrence of the winner, on every rank, is being replaced
+      st->snap_hot_n = st->hot_n;  // stable: the appends of the previous merge are complete, the next ones come in P3
+    }
+    epoch++;
+    GRID_BARRIER();
+    if (ld_cg(&st->mg_abort)) {
+      if (lead) {
+        st->status = LOOP_ERROR;
+        st->iters_done = it;  // the merge was not applied
+        st->n_tokens = n_tokens0 + it;
+        st->mg_epoch = epoch;
+        st->mg_tie_epoch = tie_epoch;
+      }
+      return;
+    }
+    // ---- P2: apply the deltas of all ranks to the replicated counts; lists of the locally new pairs ----
+    for (int q = 0; q < M.world; q++) {
+      const unsigned long long* area = mg_area(M, M.rank, epar, q);
+      const uint32_t nrec = (uint32_t)ld_cg(area + H_N);
+      for (uint32_t i = gtid; i < nrec; i += gthreads) {
+        unsigned long long rec = ld_cg(area + MG_HDR + i);
+        uint32_t s = tbl_find_or_insert(t, (uint32_t)(rec >> 32), &st->n_keys);
+        if (s == NOSLOT) atomicOr(&st->err, ERR_TABLE_FULL);
+        else atomicAdd(t.cnt + s, (uint32_t)rec);
+      }
+    }
+    phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);
+    GRID_BARRIER();
+    // ---- P3: rewrite the local shard; pairs born in this merge join the hot list; next arg-max partials ----
+    if (lead) {
+      st->snap_n_keys = st->n_keys;
+      st->snap_pool_cursor = st->pool_cursor;
+      st->snap_err = st->err;
+    }
+    const uint32_t hot_n0 = ld_cg(&st->snap_hot_n);
+    phase_apply(A, wa, wb, c, ld_cg(&st->n_sites[par]), false, bid, nblk);
+    Best mine{0ull, NOSLOT, 0};
+    for (int q = 0; q < M.world; q++) {
+      const unsigned long long* area = mg_area(M, M.rank, epar, q);
+      const uint32_t nrec = (uint32_t)ld_cg(area + H_N);
+      for (uint32_t i = gtid; i < nrec; i += gthreads) {
+        uint32_t key = (uint32_t)(ld_cg(area + MG_HDR + i) >> 32);
+        if ((key >> 16) != c && (key & 0xFFFFu) != c) continue;
+        uint32_t s = tbl_find(t, key);
+        if (s == NOSLOT) continue;
+        if (atomicMax(M.mark + s, c + 1u) >= c + 1u) continue;  // another rank's record already handled this pair
+        unsigned long long pr = slot_primary(t, A.len16, s, L.max_length);
+        if (pr && (uint32_t)(pr >> 20) >= thresh) {
+          uint32_t k = atomicAdd(&st->hot_n, 1u);
+          if (k < L.hot_cap) L.hot[k] = s;
+          else atomicOr(&st->err, ERR_HOT_OVERFLOW);
+          mine = best_merge(mine, Best{pr, s, 1});
+        }
+      }
+    }
+    {
+      Best stripe = argmax_stripe(t, A.len16, L.max_length, 1, L.hot, hot_n0, bid, nblk);
+      Best v = best_block_reduce(best_merge(mine, stripe), s_best);
+      if (threadIdx.x == 0) L.partials[bid] = v;
+    }
+    GRID_BARRIER();
+    wcnt_prev = wcnt;
+    newk_prev = min(2ull * wcnt + 2ull, 2ull * (c + 1ull) + 2ull);
+  }
+#undef GRID_BARRIER
+}
+
+}  // namespace bpe

@@ -54,6 +54,14 @@ struct DevState {
   uint32_t snap_n_keys, snap_pool_cursor, snap_hot_n, snap_err;
   unsigned long long prof_ns[8];  // block 0's view: decide, P1 work, P1 wait, P2 work, P2 wait, P3 work, P3 wait, tie path
   uint32_t bins[36];  // histogram of bit lengths of counts (hot-list threshold selection)
+  // ---- sharded (multi-GPU) training, mg_kernels.cuh ----
+  unsigned long long mg_epoch;      // count-delta exchanges completed (monotone across launches)
+  unsigned long long mg_tie_epoch;  // tie exchanges completed
+  uint32_t n_touched[2];            // pairs whose count changed on this rank in the current merge (by iteration parity)
+  uint32_t n_out;                   // records in the outgoing delta message
+  uint32_t mg_abort;                // a peer did not answer in time / a rank reported an error: every block leaves
+  uint32_t g_err;                   // OR of all ranks' error flags
+  uint32_t g_pool_free, g_sites_cap, g_new_cap, g_hot_cap, g_len16_cap, g_tbl_cap, g_cand_cap;  // minima over ranks
 };
 
 constexpr uint32_t LOOP_RUNNING = 0, LOOP_DONE = 1, LOOP_NEED_REBUILD = 2, LOOP_NEED_HOST = 3, LOOP_EMPTY = 4,
@@ -581,23 +589,47 @@ struct ApplyArgs {
   uint32_t new_cap;
   uint32_t* len16;
   int scan_mode;
+  // sharded training: count deltas are staged per pair (dlt) and listed (touched) instead of applied, see mg_kernels.cuh
+  int32_t* dlt;
+  uint32_t* touched;
+  uint32_t touched_cap;
 };
 
+constexpr uint32_t ERR_TOUCH_OVERFLOW = 128u, ERR_PEER_TIMEOUT = 256u, ERR_INBOX_OVERFLOW = 512u, ERR_PEER = 1024u;
+
+// one count delta of pair slot s: applied to the table (single GPU) or staged for the exchange (sharded)
+__device__ __forceinline__ void cnt_delta(const ApplyArgs& A, uint32_t s, int32_t d, uint32_t par) {
+  if (A.dlt) {
+    if (atomicAdd(A.dlt + s, d) == 0) {  // first delta of this pair in this merge (deltas of one pair share a sign)
+      uint32_t i = atomicAdd(&A.st->n_touched[par], 1u);
+      if (i < A.touched_cap) A.touched[i] = s;
+      else atomicOr(&A.st->err, ERR_TOUCH_OVERFLOW);
+    }
+  } else {
+    atomicAdd(A.t.cnt + s, (uint32_t)d);
+  }
+}
+
 // all 32 lanes call; lanes with has == false pass any key
-__device__ __forceinline__ void agg_dec(const PairTable& t, DevState* st, uint32_t key, bool has) {
+__device__ __forceinline__ void agg_dec(const ApplyArgs& A, uint32_t key, bool has, uint32_t par) {
+  const PairTable& t = A.t;
+  DevState* st = A.st;
   uint32_t lane = lane_id();
   uint32_t k = has ? key : (EMPTY_KEY - 1 - lane);
   uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
   if (has && lane == (uint32_t)(__ffs(peers) - 1)) {
     uint32_t s = tbl_find(t, key);
     if (s == NOSLOT) atomicOr(&st->err, ERR_MISSING_KEY);
-    else atomicSub(t.cnt + s, (uint32_t)__popc(peers));
+    else cnt_delta(A, s, -(int32_t)__popc(peers), par);
   }
 }
 
 // returns the table slot of `key` to every lane with has == true
-__device__ __forceinline__ uint32_t agg_new(const PairTable& t, DevState* st, uint32_t key, bool has, bool counted,
-                                            uint32_t* newslots, uint32_t new_cap, uint32_t par) {
+__device__ __forceinline__ uint32_t agg_new(const ApplyArgs& A, uint32_t key, bool has, bool counted, uint32_t par) {
+  const PairTable& t = A.t;
+  DevState* st = A.st;
+  uint32_t* newslots = A.newslots;
+  const uint32_t new_cap = A.new_cap;
   uint32_t lane = lane_id();
   uint32_t k = has ? key : (EMPTY_KEY - 1 - lane);
   uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
@@ -610,7 +642,7 @@ __device__ __forceinline__ uint32_t agg_new(const PairTable& t, DevState* st, ui
       atomicOr(&st->err, ERR_TABLE_FULL);
     } else {
       uint32_t nc = __popc(peers & cmask);
-      if (nc) atomicAdd(t.cnt + s, nc);
+      if (nc) cnt_delta(A, s, (int32_t)nc, par);
       if (atomicAdd(t.occ_len + s, (uint32_t)__popc(peers)) == 0) {  // first adjacency of a pair born in this iteration
         uint32_t i = atomicAdd(&st->n_new[par], 1u);
         if (i < new_cap) newslots[i] = s;
@@ -702,8 +734,8 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
         }
       }
     }
-    agg_dec(t, st, dec1_key, dec1);
-    rec.lslot = agg_new(t, st, new1_key, new1, new1_counted, A.newslots, A.new_cap, par);
+    agg_dec(A, dec1_key, dec1, par);
+    rec.lslot = agg_new(A, new1_key, new1, new1_counted, par);
 
     // ---- adjacency on the right of the new token (left to the next site when that one is chained) ----
     uint32_t dec2_key = 0, new2_key = 0;
@@ -731,8 +763,8 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
         }
       }
     }
-    agg_dec(t, st, dec2_key, dec2);
-    rec.rslot = agg_new(t, st, new2_key, new2, true, A.newslots, A.new_cap, par);
+    agg_dec(A, dec2_key, dec2, par);
+    rec.rslot = agg_new(A, new2_key, new2, true, par);
 
     // ---- record the site (one counter atomic per warp) ----
     uint32_t smask = __ballot_sync(0xFFFFFFFFu, site);
@@ -906,6 +938,9 @@ __global__ void k_loop_prepare(DevState* st, uint32_t n_tokens, unsigned long lo
     st->n_cand = 0;
     st->blocks_done = 0;
     st->tie_pos = ~0ull;
+    st->n_touched[0] = st->n_touched[1] = 0;
+    st->n_out = 0;
+    st->mg_abort = 0;
   }
 }
 

@@ -137,6 +137,31 @@ int bpe_merge_until(bpe_engine* e, int64_t min_weight, int32_t max_length, int64
 /* Debug / parity: dump the pair histogram (pairs with count > 0, unspecified order). */
 int bpe_pair_counts(bpe_engine* e, int32_t* a, int32_t* b, int64_t* count, int64_t cap, int64_t* n);
 
+/* ---- sharded training: one engine (process) per GPU of an NVLink domain --------------------------
+ * The reference has ONE corpus in one process (core.ts:106; findNextMerge counts over all documents,
+ * core.ts:265-310, applyMerge rewrites all of them, core.ts:356-359) and no device boundary.  A sharded
+ * deployment keeps that contract: rank r adds a contiguous range of the documents (ranks in document
+ * order), pair counts are global, and bpe_merge_until returns the same merge log on every rank as a
+ * single engine holding the whole corpus would (csrc/mg_kernels.cuh).  Call order on every rank:
+ *   bpe_create -> bpe_mg_init -> (exchange the 64-byte handles, e.g. torch.distributed all_gather)
+ *   -> bpe_mg_connect -> bpe_set_tokens / bpe_add_documents* (this rank's shard)
+ *   -> bpe_mg_export_counts -> (all-gather the (pair,count) lists) -> bpe_mg_import_counts per peer
+ *   -> bpe_merge_until (collective: all ranks, same arguments).
+ * Single-step bpe_find_next_merge / bpe_apply_merge stay local to the shard. */
+#define BPE_MG_MAX_WORLD 8
+/* Allocates this rank's mailbox (peers store count deltas into it over NVLink) and writes its
+ * cudaIpcMemHandle_t (64 bytes) to handle_out. */
+int bpe_mg_init(bpe_engine* e, int rank, int world, void* handle_out);
+/* handles: world x 64 bytes, ordered by rank (the entry of this rank is ignored). */
+int bpe_mg_connect(bpe_engine* e, const char* handles);
+/* *counts_global = 1 when the pair index holds counts summed over all ranks. */
+int bpe_mg_state(bpe_engine* e, int* counts_global);
+/* This shard's pair histogram as device arrays: dev_keys[i] = (a << 16) | b, dev_counts[i].
+ * cap = 0 only reports an upper bound of the number of pairs in *n. */
+int bpe_mg_export_counts(bpe_engine* e, uint32_t* dev_keys, uint32_t* dev_counts, int64_t cap, int64_t* n);
+/* Adds a peer's histogram (device arrays) to this engine's counts; last != 0 on the final peer. */
+int bpe_mg_import_counts(bpe_engine* e, const uint32_t* dev_keys, const uint32_t* dev_counts, int64_t n, int last);
+
 /* ---- encode / decode ---------------------------------------------------------------------- */
 /* encodeToCode + encodeToVector (core.ts:392-409, :424-445) for a batch of documents.
  *   ids/doc_offsets      single-character token indices per document (as bpe_add_documents)
