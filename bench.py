@@ -145,16 +145,26 @@ def run_b200(args):
         merges = args.merges
     peak, peak_src = measured_peak()
 
-    # ---- synthetic inputs: every rank owns its own shard of documents (weak scaling) ----------------
-    # rank r trains/encodes the text with seed (seed + 1000*r): independent document sets per GPU.
+    # ---- synthetic inputs: ONE corpus (BASELINE.json config), sharded by document over the ranks (strong scaling) ----
+    # every rank generates the same seeded text and keeps a contiguous, token-balanced range of its documents
+    # (ranks in document order: global scan order = (rank, local position), see bpe_tokenizer_b200/sharded.py).
+    from bpe_tokenizer_b200.sharded import exchange_pair_counts, shard_bounds
+
     t0 = time.time()
-    text, off = synth(lib, train_bytes, TRAIN_SEED + 1000 * rank)
+    text, off = synth(lib, train_bytes, TRAIN_SEED)
     lut, alphabet = alphabet_lut(text)
-    ids_host = torch.from_numpy(lut[text]).pin_memory()
-    off_host = np.ascontiguousarray(off)
+    n0_total, n_docs_total = int(text.size), len(off) - 1
+    b = shard_bounds(np.diff(off), world)
+    lo, hi = b[rank], b[rank + 1]
+    ids_host = torch.from_numpy(lut[text[off[lo]:off[hi]]]).pin_memory()
+    off_host = np.ascontiguousarray(off[lo:hi + 1] - off[lo])
     del text
-    text2, off2 = synth(lib, encode_bytes, ENCODE_SEED + 1000 * rank)
-    ids2_host = torch.from_numpy(lut[text2]).pin_memory()
+    text2, off2 = synth(lib, encode_bytes, ENCODE_SEED)
+    c2_total = int(text2.size)
+    b2 = shard_bounds(np.diff(off2), world)
+    lo2, hi2 = b2[rank], b2[rank + 1]
+    ids2_host = torch.from_numpy(lut[text2[off2[lo2]:off2[hi2]]]).pin_memory()
+    off2 = np.ascontiguousarray(off2[lo2:hi2 + 1] - off2[lo2])
     del text2
     n0, n_docs = ids_host.numel(), len(off_host) - 1
     c2, n_docs2 = ids2_host.numel(), len(off2) - 1
@@ -169,6 +179,14 @@ def run_b200(args):
     assert lib.bpe_create(local, C.byref(h)) == 0, "bpe_create failed"
     stream = torch.cuda.current_stream()
     assert lib.bpe_set_stream(h, C.c_void_p(stream.cuda_stream)) == 0
+    dev = torch.device("cuda", local)
+    if world > 1:  # mailboxes of the sharded merge loop: exchange the cudaIpc handles once
+        handle = C.create_string_buffer(64)
+        assert lib.bpe_mg_init(h, rank, world, handle) == 0, lib.bpe_last_error(h)
+        handles = [b""] * world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        assert lib.bpe_mg_connect(h, b"".join(handles)) == 0, lib.bpe_last_error(h)
+        dist.barrier()
     len16 = np.ones(len(alphabet), dtype=np.int32)
     log = np.zeros(merges, dtype=MERGE_DTYPE)
     n_done = C.c_int64()
@@ -188,6 +206,7 @@ def run_b200(args):
             check(lib.bpe_add_documents(h, C.cast(ids_host.data_ptr(), _abi.i32p), p64(off_host), n_docs))
         else:
             check(lib.bpe_add_documents_dev(h, C.c_void_p(ids_dev.data_ptr()), p64(off_host), n_docs))
+        exchange_pair_counts(lib, h, rank, world, dev)  # world > 1: K1 histograms of all shards summed (NCCL all-gather)
         check(lib.bpe_merge_until(h, 2, 0, merges, log.ctypes.data_as(C.c_void_p), merges, C.byref(n_done)))
         return n_done.value
 
@@ -232,8 +251,15 @@ def run_b200(args):
     reset()
     check(lib.bpe_add_documents_dev(h, C.c_void_p(ids_dev.data_ptr()), p64(off_host), n_docs))
     m, found = _abi.bpe_merge(), C.c_int()
-    check(lib.bpe_find_next_merge(h, 2, 0, C.byref(m), C.byref(found)))
+    check(lib.bpe_find_next_merge(h, 2, 0, C.byref(m), C.byref(found)))  # builds this shard's index (local counts)
     k1_ms = stats().ms_index_build - s_before.ms_index_build
+    if world > 1:  # every rank must hold the same merge log
+        import hashlib
+
+        digest = hashlib.sha1(log[:done].tobytes()).hexdigest()
+        digests = [None] * world
+        dist.all_gather_object(digests, digest)
+        assert all(d == digest for d in digests), "ranks disagree on the merge log: %r" % (digests,)
     # ---- train: end to end from host buffers ----------------------------------------------------------
     e2e_steps = max(1, min(args.steps, 2))
     train_step(True)
@@ -277,19 +303,26 @@ def run_b200(args):
         dist.all_reduce(t)
         return float(t.item())
 
-    total_merges = allsum(done * args.steps)
+    import hashlib
+
+    log_sha1 = hashlib.sha1(log[:done].tobytes()).hexdigest()
     step_s = ms_train / 1e3 / args.steps
-    value = total_merges / (ms_train / 1e3)
-    e2e_value = allsum(done * e2e_steps) / (ms_train_e2e / 1e3)
-    scan_bytes = scan_equivalent_bytes(n0, weights)
-    achieved = allsum(scan_bytes) / step_s / 1e9 / world  # per GPU
+    value = done * args.steps / (ms_train / 1e3)  # ONE merge sequence for the whole (sharded) corpus
+    e2e_value = done * e2e_steps / (ms_train_e2e / 1e3)
+    scan_bytes = scan_equivalent_bytes(n0_total, weights)
+    achieved = scan_bytes / step_s / 1e9 / world  # per GPU
     enc_gbs = allsum(c2 * args.steps) / (ms_enc / 1e3) / 1e9
     enc_e2e_gbs = allsum(c2 * e2e_steps) / (ms_enc_e2e / 1e3) / 1e9
-    enc_alg_bytes = 4 * c2 + 4 * k_out
+    enc_alg_bytes = 4 * c2 + 4 * k_out  # this rank's shard, against this rank's kernel time
     enc_achieved = enc_alg_bytes / (enc_kernel_ms / 1e3) / 1e9
+    h2d_total = int(allsum(n0 * 4 + off_host.nbytes))
+    k_out_total = int(allsum(k_out))
+    n_docs2_total = int(allsum(n_docs2))
+    enc_h2d_total = int(allsum(c2 * 4 + off2.nbytes + tvi.nbytes))
+    enc_d2h_total = int(allsum(k_out * 4 + off2.nbytes))
 
     if rank == 0:
-        cpu = cpu_baseline(args, merges_sample=8)
+        cpu = cpu_baseline(args, merges_sample=8) if world == 1 else None  # timed on rank 0 at N=1 only
         line = {
             "metric": "mergeUntil merges/sec",
             "value": value,
@@ -299,18 +332,20 @@ def run_b200(args):
             "warmup": args.warmup,
             "ms_per_step": ms_train / args.steps,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong",
             "vs_baseline": None,
             "dtype": "u32",
             "data": "synthetic",
             "config": {
-                "workload": "%s: %d B Zipf-word corpus per GPU (seed %d+1000*rank, %d docs), addToCorpus + mergeUntil to %d merges"
-                            % (args.workload, train_bytes, TRAIN_SEED, n_docs, merges),
+                "workload": "%s: %d B Zipf-word corpus (seed %d, %d docs), addToCorpus + mergeUntil to %d merges"
+                            % (args.workload, n0_total, TRAIN_SEED, n_docs_total, merges),
                 "merges_done": done,
-                "sharding": "documents per GPU, independent shards" if world > 1 else "single GPU",
+                "merge_log_sha1": log_sha1,
+                "sharding": ("corpus sharded by document over %d GPUs (contiguous, token-balanced); global pair counts replicated, "
+                             "per-merge count deltas exchanged GPU-to-GPU over NVLink inside the persistent kernel" % world) if world > 1 else "single GPU",
                 "l2": "corpus (4 B/char) and occurrence pool are larger than the 126 MB L2" if n0 * 4 > 126e6 else "inputs smaller than L2; every step re-ingests and rebuilds the index (cold tables)",
             },
-            "e2e": {"value": e2e_value, "unit": "merges/s", "h2d_bytes_per_step": int(n0 * 4 + off_host.nbytes), "d2h_bytes_per_step": int(done * MERGE_DTYPE.itemsize),
+            "e2e": {"value": e2e_value, "unit": "merges/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": int(done * MERGE_DTYPE.itemsize * world),
                     "ms_per_step": ms_train_e2e / e2e_steps},
             "gpu_launches": int(l1 - l0),
             "clocks": clocks,
@@ -324,14 +359,15 @@ def run_b200(args):
                             "frac": 4 * n0 / (k1_ms / 1e3) / 1e9 / peak, "ms": k1_ms, "kernel": "k_hist + k_alloc_lists + k_scatter"},
             "encode": {
                 "metric": "encodeToVector GB/s of input text", "value": enc_gbs, "unit": "GB/s", "ms_per_step": ms_enc / args.steps,
-                "chars": c2, "tokens_out": k_out, "docs": n_docs2, "gpu_launches": int(le1 - le0),
-                "e2e": {"value": enc_e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": int(c2 * 4 + off2.nbytes + tvi.nbytes), "d2h_bytes_per_step": int(k_out * 4 + off2.nbytes)},
+                "chars": c2_total, "tokens_out": k_out_total, "docs": n_docs2_total, "gpu_launches": int(le1 - le0),
+                "e2e": {"value": enc_e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": enc_h2d_total, "d2h_bytes_per_step": enc_d2h_total},
                 "roofline": {"bound": "hbm", "achieved": enc_achieved, "peak": peak, "unit": "GB/s", "frac": enc_achieved / peak, "traffic": None,
-                             "kernel": "k_encode + k_scan_counts + k_gather_map", "alg_bytes": enc_alg_bytes},
+                             "kernel": "k_range_starts + k_encode_lanes + scan + k_gather_map (ms_encode of the engine, rank 0 shard)", "alg_bytes": enc_alg_bytes},
             },
-            "cpu_baseline": cpu,
             "setup": {"synth_s": gen_s},
         }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         print(json.dumps(line))
     lib.bpe_destroy(h)
     if world > 1:

@@ -186,6 +186,13 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
   }
   GRID_BARRIER();
   uint32_t wcnt_prev = 0;
+  unsigned long long tp0 = lead ? now_ns() : 0, tp1;
+#define MGPROF(i)                    \
+  if (lead) {                        \
+    tp1 = now_ns();                  \
+    st->mg_prof_ns[i] += tp1 - tp0;  \
+    tp0 = tp1;                       \
+  }
   unsigned long long newk_prev = 0;  // upper bound of the hot-list entries appended by the previous merge's P3
 
   for (uint32_t it = 0;; it++) {
@@ -226,6 +233,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
       else if (c + 1 > ld_cg(&st->g_len16_cap)) status = LOOP_NEED_HOST;
       else if (w.mult > 1 && w.mult > ld_cg(&st->g_cand_cap)) status = LOOP_NEED_HOST;
     }
+    MGPROF(0)
     if (status == LOOP_RUNNING && w.mult > 1) {
       // ---- tie on (weight, a.index+b.index): last counted occurrence in GLOBAL scan order decides (core.ts:294-305) ----
       const uint32_t tpar = (uint32_t)((tie_epoch + 1) & 1u);
@@ -291,6 +299,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
         wb = key & 0xFFFFu;
       }
     }
+    MGPROF(11)
     if (status != LOOP_RUNNING) {
       if (lead) {
         st->status = status;
@@ -321,7 +330,9 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
       if (w.mult > 1) st->tie_breaks++;
     }
     phase_sites(A, wa, wb, c, par, w.slot, bid, nblk);
+    MGPROF(1)
     GRID_BARRIER();
+    MGPROF(2)
     // ---- M1: one (pair, delta) record per touched pair, stored straight into every rank's inbox (NVLink) ----
     const uint32_t epar = (uint32_t)((epoch + 1) & 1u);
     {
@@ -340,7 +351,9 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
       }
       __threadfence_system();
     }
+    MGPROF(3)
     GRID_BARRIER();
+    MGPROF(4)
     if (lead) {
       mg_write_header(P, st, epar, min(ld_cg(&st->n_out), M.inbox_stride - MG_HDR), LOOP_RUNNING);
       mg_signal_and_wait(M, M.flag_data, epoch + 1, st);
@@ -351,7 +364,9 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
       st->snap_hot_n = st->hot_n;  // stable: the appends of the previous merge are complete, the next ones come in P3
     }
     epoch++;
+    MGPROF(5)
     GRID_BARRIER();
+    MGPROF(6)
     if (ld_cg(&st->mg_abort)) {
       if (lead) {
         st->status = LOOP_ERROR;
@@ -374,7 +389,9 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
       }
     }
     phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);
+    MGPROF(7)
     GRID_BARRIER();
+    MGPROF(8)
     // ---- P3: rewrite the local shard; pairs born in this merge join the hot list; next arg-max partials ----
     if (lead) {
       st->snap_n_keys = st->n_keys;
@@ -407,11 +424,14 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
       Best v = best_block_reduce(best_merge(mine, stripe), s_best);
       if (threadIdx.x == 0) L.partials[bid] = v;
     }
+    MGPROF(9)
     GRID_BARRIER();
+    MGPROF(10)
     wcnt_prev = wcnt;
     newk_prev = min(2ull * wcnt + 2ull, 2ull * (c + 1ull) + 2ull);
   }
 #undef GRID_BARRIER
+#undef MGPROF
 }
 
 }  // namespace bpe

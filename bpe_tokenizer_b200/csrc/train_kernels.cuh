@@ -61,6 +61,7 @@ struct DevState {
   uint32_t n_out;                   // records in the outgoing delta message
   uint32_t mg_abort;                // a peer did not answer in time / a rank reported an error: every block leaves
   uint32_t g_err;                   // OR of all ranks' error flags
+  unsigned long long mg_prof_ns[12];  // block 0: decide, P1, wait, M1, wait, exchange, wait, P2, wait, P3, wait, tie path
   uint32_t g_pool_free, g_sites_cap, g_new_cap, g_hot_cap, g_len16_cap, g_tbl_cap, g_cand_cap;  // minima over ranks
 };
 
