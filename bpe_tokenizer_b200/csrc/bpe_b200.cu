@@ -445,6 +445,9 @@ ApplyArgs apply_args(bpe_engine* e) {
   A.dlt = nullptr;
   A.touched = nullptr;
   A.touched_cap = 0;
+  for (int q = 0; q < 8; q++) A.push[q] = nullptr;
+  A.push_world = 0;
+  A.push_cap = 0;
   return A;
 }
 
@@ -994,13 +997,19 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
   int rc = BPE_OK;
   int64_t done = 0;
   std::vector<MergeRec> tmp;
+  double host_ms[4] = {0, 0, 0, 0};  // hot rebuilds, growth (NEED_HOST), launch+state fetch, log read-back
+  auto clk = [] { return std::chrono::steady_clock::now(); };
+  auto since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
   for (;;) {
     int64_t remaining = log_cap - done;
     if (max_iterations > 0) remaining = std::min(remaining, max_iterations - done);  // core.ts:374-377
     if (remaining <= 0) break;
     if (!e->hot_valid || e->hot_max_length != ml) {
       bool any = false;
-      if ((rc = rebuild_hot(e, ml, &any)) != BPE_OK) break;
+      auto th = clk();
+      rc = rebuild_hot(e, ml, &any);
+      host_ms[0] += since(th);
+      if (rc != BPE_OK) break;
       if (!any) break;  // nothing countable left on ANY rank: the counts are global (core.ts:312)
     }
     uint32_t chunk = (uint32_t)std::min<int64_t>(remaining, 1 << 16);
@@ -1049,6 +1058,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
     }
     e->stats.kernel_launches++;
     if ((rc = fetch_state(e)) != BPE_OK) break;
+    host_ms[2] += since(tw0);
     e->mg_epoch = e->h_st->mg_epoch;
     e->mg_tie_epoch = e->h_st->mg_tie_epoch;
     uint32_t iters = e->h_st->iters_done;
@@ -1056,8 +1066,9 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
       double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
       fprintf(stderr, "[bpe r%d] k_merge_loop_mg: %u merges in %.2f ms, status %u, best_cnt %u, hot_n %u thresh %u, keys %u/%u err 0x%x gerr 0x%x\n",
               e->mg_rank, iters, ms, e->h_st->status, e->h_st->best_cnt, e->h_st->hot_n, e->h_st->hot_thresh, e->h_st->n_keys, e->tbl_cap,
-              e->h_st->err, e->h_st->g_err);
+              e->h_st->err, e->h_st->g_vals[0]);
     }
+    auto tl = clk();
     if (iters) {
       tmp.resize(iters);
       ce = cudaMemcpyAsync(tmp.data(), e->dev_log.p, (size_t)iters * sizeof(MergeRec), cudaMemcpyDeviceToHost, e->stream);
@@ -1083,6 +1094,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
       e->mt_dirty = e->lt_dirty = true;
       e->stats.merges_applied += iters;
     }
+    host_ms[3] += since(tl);
     uint32_t status = e->h_st->status;
     if (status == LOOP_DONE || status == LOOP_EMPTY) break;
     if (status == LOOP_LIMIT) continue;
@@ -1091,15 +1103,16 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
       continue;
     }
     if (status == LOOP_ERROR) {
-      uint32_t f = e->h_st->err | e->h_st->g_err;
+      uint32_t f = e->h_st->err | e->h_st->g_vals[0];
       if (f & ERR_PEER_TIMEOUT) rc = fail(e, BPE_E_INTERNAL, "a peer GPU did not answer within %.0f s (flags 0x%x)", MG_TIMEOUT_NS / 1e9, f);
       else {
         rc = check_dev_err(e);
-        if (rc == BPE_OK) rc = fail(e, BPE_E_INTERNAL, "sharded merge loop stopped: local flags 0x%x, all ranks 0x%x", e->h_st->err, e->h_st->g_err);
+        if (rc == BPE_OK) rc = fail(e, BPE_E_INTERNAL, "sharded merge loop stopped: local flags 0x%x, all ranks 0x%x", e->h_st->err, e->h_st->g_vals[0]);
       }
       break;
     }
     if (status == LOOP_NEED_HOST) {  // every rank is here with the same winner: each one grows what IT lacks
+      auto tg = clk();
       if (e->n_tokens >= BPE_MAX_TOKENS) {
         rc = fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
         break;
@@ -1132,6 +1145,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
         rc = fail(e, BPE_E_DOMAIN, "%u pairs tie on (weight, index sum): more than the tie mailbox holds (%u)", e->h_st->best_mult, e->mg_tie_cap);
         break;
       }
+      host_ms[1] += since(tg);
       continue;
     }
     rc = fail(e, BPE_E_INTERNAL, "merge loop returned status %u", status);
@@ -1150,7 +1164,8 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
     if (getenv("BPE_TRACE") && e->mg_rank == 0) {
       fprintf(stderr, "[bpe r0] mg phases ms (decide, P1, wait, M1, wait, exchange, wait, P2, wait, P3, wait, tie):");
       for (int i = 0; i < 12; i++) fprintf(stderr, " %.1f", (double)e->h_st->mg_prof_ns[i] * 1e-6);
-      fprintf(stderr, "  total %.1f ms, %lld merges\n", ms, (long long)done);
+      fprintf(stderr, "  total %.1f ms, %lld merges; host ms: hot rebuild %.1f, growth %.1f, launch..fetch %.1f, log %.1f\n", ms, (long long)done,
+              host_ms[0], host_ms[1], host_ms[2], host_ms[3]);
     }
   }
   cudaEventDestroy(t0);

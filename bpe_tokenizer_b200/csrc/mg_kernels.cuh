@@ -26,6 +26,7 @@ constexpr int MG_MAX_WORLD = 8;
 constexpr uint32_t MG_HDR = 16;  // u64 words of header in front of the records of one message
 enum { H_N = 0, H_ERR, H_POOL_FREE, H_SITES_CAP, H_NEW_CAP, H_HOT_CAP, H_LEN16_CAP, H_TBL_CAP, H_CAND_CAP, H_STATUS };
 constexpr unsigned long long MG_TIMEOUT_NS = 8000000000ull;
+constexpr uint32_t MG_DIRECT_MAX = 8192;  // merges with at most this many (global) occurrences push their deltas unstaged
 
 struct MgArgs {
   int rank, world;
@@ -109,11 +110,13 @@ __device__ __forceinline__ unsigned long long* mg_area(const MgArgs& M, int dst,
   return M.inbox[dst] + ((size_t)par * M.world + sender) * M.inbox_stride;
 }
 
+// header of a message: 16 u32 (H_* indices) in the first 64 bytes of the area, moved with 128-bit accesses
 __device__ __forceinline__ void mg_write_header(const LoopArgsMg& P, DevState* st, uint32_t par, uint32_t n_rec, uint32_t status) {
   const MgArgs& M = P.M;
   const LoopArgs& L = P.L;
-  unsigned long long h[MG_HDR];
-  for (uint32_t i = 0; i < MG_HDR; i++) h[i] = 0;
+  uint32_t h[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) h[i] = 0;
   h[H_N] = n_rec;
   h[H_ERR] = st->err;
   uint32_t cur = st->pool_cursor;
@@ -126,30 +129,34 @@ __device__ __forceinline__ void mg_write_header(const LoopArgsMg& P, DevState* s
   h[H_CAND_CAP] = min(L.cand_cap, M.tie_cap);
   h[H_STATUS] = status;
   for (int q = 0; q < M.world; q++) {
-    unsigned long long* dst = mg_area(M, q, par, M.rank);
-    for (uint32_t i = 0; i < MG_HDR; i++) dst[i] = h[i];
+    uint4* dst = reinterpret_cast<uint4*>(mg_area(M, q, par, M.rank));
+#pragma unroll
+    for (int i = 0; i < 4; i++) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
   }
   __threadfence_system();
 }
 
-// block 0, thread 0, after the exchange: minima / OR over the G headers
+// block 0, thread 0, after the exchange: minima / OR over the G headers -> one 32-byte block every thread reads at once
+struct MgGlobals {
+  uint32_t err, pool_free, sites_cap, new_cap, hot_cap, len16_cap, tbl_cap, cand_cap;
+};
+
 __device__ __forceinline__ void mg_fold_headers(const MgArgs& M, DevState* st, uint32_t par) {
   uint32_t err = 0;
-  unsigned long long mins[H_CAND_CAP + 1];
-  for (int i = 0; i <= H_CAND_CAP; i++) mins[i] = ~0ull;
+  uint32_t mins[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) mins[i] = 0xFFFFFFFFu;
   for (int q = 0; q < M.world; q++) {
-    const unsigned long long* h = mg_area(M, M.rank, par, q);
-    err |= (uint32_t)ld_cg(h + H_ERR);
-    for (int i = H_POOL_FREE; i <= H_CAND_CAP; i++) mins[i] = min(mins[i], ld_cg(h + i));
+    const uint4* h = reinterpret_cast<const uint4*>(mg_area(M, M.rank, par, q));
+    uint4 v0 = ld_cg4(h), v1 = ld_cg4(h + 1), v2 = ld_cg4(h + 2);
+    uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+    err |= w[H_ERR];
+#pragma unroll
+    for (int i = H_POOL_FREE; i <= H_CAND_CAP; i++) mins[i] = min(mins[i], w[i]);
   }
-  st->g_err = err;
-  st->g_pool_free = (uint32_t)min(mins[H_POOL_FREE], 0xFFFFFFFFull);
-  st->g_sites_cap = (uint32_t)min(mins[H_SITES_CAP], 0xFFFFFFFFull);
-  st->g_new_cap = (uint32_t)min(mins[H_NEW_CAP], 0xFFFFFFFFull);
-  st->g_hot_cap = (uint32_t)min(mins[H_HOT_CAP], 0xFFFFFFFFull);
-  st->g_len16_cap = (uint32_t)min(mins[H_LEN16_CAP], 0xFFFFFFFFull);
-  st->g_tbl_cap = (uint32_t)min(mins[H_TBL_CAP], 0xFFFFFFFFull);
-  st->g_cand_cap = (uint32_t)min(mins[H_CAND_CAP], 0xFFFFFFFFull);
+  uint4* g = reinterpret_cast<uint4*>(st->g_vals);
+  g[0] = make_uint4(err, mins[H_POOL_FREE], mins[H_SITES_CAP], mins[H_NEW_CAP]);
+  g[1] = make_uint4(mins[H_HOT_CAP], mins[H_LEN16_CAP], mins[H_TBL_CAP], mins[H_CAND_CAP]);
 }
 
 __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
@@ -216,7 +223,11 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
       wcnt = (uint32_t)(w.primary >> 20);
     }
     const uint32_t c = n_tokens0 + it;
-    if (ld_cg(&st->mg_abort) || ld_cg(&st->g_err)) status = LOOP_ERROR;
+    const uint4 g0 = ld_cg4(reinterpret_cast<const uint4*>(st->g_vals)), g1 = ld_cg4(reinterpret_cast<const uint4*>(st->g_vals) + 1);
+    const uint32_t g_err = g0.x, g_pool_free = g0.y, g_sites_cap = g0.z, g_new_cap = g0.w, g_hot_cap = g1.x, g_len16_cap = g1.y,
+                   g_tbl_cap = g1.z, g_cand_cap = g1.w;
+    const uint32_t snap_n_keys = ld_cg(&st->snap_n_keys), snap_hot_n = ld_cg(&st->snap_hot_n), aborted = ld_cg(&st->mg_abort);
+    if (aborted || g_err) status = LOOP_ERROR;
     else if (!w.primary) status = (thresh <= 1) ? LOOP_EMPTY : LOOP_NEED_REBUILD;
     else if (wcnt < thresh) status = LOOP_NEED_REBUILD;
     else if (wcnt < L.min_weight) status = LOOP_DONE;  // core.ts:313
@@ -224,14 +235,14 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
     else if (c >= L.max_tokens) status = LOOP_NEED_HOST;
     if (status == LOOP_RUNNING) {
       unsigned long long new_keys = min(2ull * wcnt + 2ull, 2ull * (c + 1ull) + 2ull);
-      unsigned long long pool_free = ld_cg(&st->g_pool_free);
+      unsigned long long pool_free = g_pool_free;
       pool_free = pool_free > 2ull * wcnt_prev ? pool_free - 2ull * wcnt_prev : 0;  // headers are one merge old
-      if ((unsigned long long)ld_cg(&st->snap_n_keys) + new_keys > (unsigned long long)(ld_cg(&st->g_tbl_cap) >> 1)) status = LOOP_NEED_HOST;
+      if ((unsigned long long)snap_n_keys + new_keys > (unsigned long long)(g_tbl_cap >> 1)) status = LOOP_NEED_HOST;
       else if (2ull * wcnt > pool_free) status = LOOP_NEED_HOST;
-      else if (wcnt > ld_cg(&st->g_sites_cap) || new_keys > ld_cg(&st->g_new_cap)) status = LOOP_NEED_HOST;
-      else if ((unsigned long long)ld_cg(&st->snap_hot_n) + newk_prev + new_keys > ld_cg(&st->g_hot_cap)) status = LOOP_NEED_REBUILD;
-      else if (c + 1 > ld_cg(&st->g_len16_cap)) status = LOOP_NEED_HOST;
-      else if (w.mult > 1 && w.mult > ld_cg(&st->g_cand_cap)) status = LOOP_NEED_HOST;
+      else if (wcnt > g_sites_cap || new_keys > g_new_cap) status = LOOP_NEED_HOST;
+      else if ((unsigned long long)snap_hot_n + newk_prev + new_keys > g_hot_cap) status = LOOP_NEED_REBUILD;
+      else if (c + 1 > g_len16_cap) status = LOOP_NEED_HOST;
+      else if (w.mult > 1 && w.mult > g_cand_cap) status = LOOP_NEED_HOST;
     }
     MGPROF(0)
     if (status == LOOP_RUNNING && w.mult > 1) {
@@ -326,16 +337,27 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
       st->n_sites[par ^ 1u] = 0;
       st->n_new[par ^ 1u] = 0;
       st->n_touched[par ^ 1u] = 0;
-      st->n_out = 0;
       if (w.mult > 1) st->tie_breaks++;
     }
-    phase_sites(A, wa, wb, c, par, w.slot, bid, nblk);
+    const uint32_t epar = (uint32_t)((epoch + 1) & 1u);
+    // small merges: every warp-aggregated delta goes straight into all inboxes (no staging pass, one barrier less);
+    // big merges stage per pair first (a handful of pairs get millions of deltas)
+    const bool direct = wcnt <= MG_DIRECT_MAX;
+    {
+      ApplyArgs Ad = A;
+      if (direct) {
+        for (int q = 0; q < M.world; q++) Ad.push[q] = mg_area(M, q, epar, M.rank) + MG_HDR;
+        Ad.push_world = M.world;
+        Ad.push_cap = M.inbox_stride - MG_HDR;
+      }
+      phase_sites(Ad, wa, wb, c, par, w.slot, bid, nblk);
+      if (direct) __threadfence_system();
+    }
     MGPROF(1)
     GRID_BARRIER();
     MGPROF(2)
-    // ---- M1: one (pair, delta) record per touched pair, stored straight into every rank's inbox (NVLink) ----
-    const uint32_t epar = (uint32_t)((epoch + 1) & 1u);
-    {
+    // ---- M1 (staged mode): one (pair, delta) record per touched pair, stored into every rank's inbox (NVLink) ----
+    if (!direct) {
       const uint32_t nt = min(ld_cg(&st->n_touched[par]), A.touched_cap);
       for (uint32_t i = gtid; i < nt; i += gthreads) {
         uint32_t s = ld_cg(&A.touched[i]);
@@ -350,12 +372,13 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
         for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MG_HDR + k] = rec;
       }
       __threadfence_system();
+      MGPROF(3)
+      GRID_BARRIER();
+      MGPROF(4)
     }
-    MGPROF(3)
-    GRID_BARRIER();
-    MGPROF(4)
     if (lead) {
       mg_write_header(P, st, epar, min(ld_cg(&st->n_out), M.inbox_stride - MG_HDR), LOOP_RUNNING);
+      st->n_out = 0;  // nobody appends before the next merge's P1
       mg_signal_and_wait(M, M.flag_data, epoch + 1, st);
       mg_fold_headers(M, st, epar);
       st->n_cand = 0;
@@ -380,7 +403,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
     // ---- P2: apply the deltas of all ranks to the replicated counts; lists of the locally new pairs ----
     for (int q = 0; q < M.world; q++) {
       const unsigned long long* area = mg_area(M, M.rank, epar, q);
-      const uint32_t nrec = (uint32_t)ld_cg(area + H_N);
+      const uint32_t nrec = ld_cg(reinterpret_cast<const uint32_t*>(area) + H_N);
       for (uint32_t i = gtid; i < nrec; i += gthreads) {
         unsigned long long rec = ld_cg(area + MG_HDR + i);
         uint32_t s = tbl_find_or_insert(t, (uint32_t)(rec >> 32), &st->n_keys);
@@ -403,7 +426,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
     Best mine{0ull, NOSLOT, 0};
     for (int q = 0; q < M.world; q++) {
       const unsigned long long* area = mg_area(M, M.rank, epar, q);
-      const uint32_t nrec = (uint32_t)ld_cg(area + H_N);
+      const uint32_t nrec = ld_cg(reinterpret_cast<const uint32_t*>(area) + H_N);
       for (uint32_t i = gtid; i < nrec; i += gthreads) {
         uint32_t key = (uint32_t)(ld_cg(area + MG_HDR + i) >> 32);
         if ((key >> 16) != c && (key & 0xFFFFu) != c) continue;

@@ -60,9 +60,10 @@ struct DevState {
   uint32_t n_touched[2];            // pairs whose count changed on this rank in the current merge (by iteration parity)
   uint32_t n_out;                   // records in the outgoing delta message
   uint32_t mg_abort;                // a peer did not answer in time / a rank reported an error: every block leaves
-  uint32_t g_err;                   // OR of all ranks' error flags
   unsigned long long mg_prof_ns[12];  // block 0: decide, P1, wait, M1, wait, exchange, wait, P2, wait, P3, wait, tie path
-  uint32_t g_pool_free, g_sites_cap, g_new_cap, g_hot_cap, g_len16_cap, g_tbl_cap, g_cand_cap;  // minima over ranks
+  // folded message headers, read by every thread with two 128-bit loads: [0] OR of all ranks' error flags, then the
+  // minima over ranks of pool_free, sites_cap, new_cap, hot_cap, len16_cap, tbl_cap, cand_cap
+  alignas(16) uint32_t g_vals[8];
 };
 
 constexpr uint32_t LOOP_RUNNING = 0, LOOP_DONE = 1, LOOP_NEED_REBUILD = 2, LOOP_NEED_HOST = 3, LOOP_EMPTY = 4,
@@ -594,13 +595,25 @@ struct ApplyArgs {
   int32_t* dlt;
   uint32_t* touched;
   uint32_t touched_cap;
+  // sharded training, small merges: every (pair, delta) goes straight into the record area of each rank's inbox
+  unsigned long long* push[8];
+  int push_world;  // 0: staged mode (or single GPU)
+  uint32_t push_cap;
 };
 
 constexpr uint32_t ERR_TOUCH_OVERFLOW = 128u, ERR_PEER_TIMEOUT = 256u, ERR_INBOX_OVERFLOW = 512u, ERR_PEER = 1024u;
 
 // one count delta of pair slot s: applied to the table (single GPU) or staged for the exchange (sharded)
-__device__ __forceinline__ void cnt_delta(const ApplyArgs& A, uint32_t s, int32_t d, uint32_t par) {
-  if (A.dlt) {
+__device__ __forceinline__ void cnt_delta(const ApplyArgs& A, uint32_t s, uint32_t key, int32_t d, uint32_t par) {
+  if (A.push_world) {
+    uint32_t k = atomicAdd(&A.st->n_out, 1u);
+    if (k < A.push_cap) {
+      unsigned long long rec = ((unsigned long long)key << 32) | (uint32_t)d;
+      for (int q = 0; q < A.push_world; q++) A.push[q][k] = rec;
+    } else {
+      atomicOr(&A.st->err, ERR_INBOX_OVERFLOW);
+    }
+  } else if (A.dlt) {
     if (atomicAdd(A.dlt + s, d) == 0) {  // first delta of this pair in this merge (deltas of one pair share a sign)
       uint32_t i = atomicAdd(&A.st->n_touched[par], 1u);
       if (i < A.touched_cap) A.touched[i] = s;
@@ -621,7 +634,7 @@ __device__ __forceinline__ void agg_dec(const ApplyArgs& A, uint32_t key, bool h
   if (has && lane == (uint32_t)(__ffs(peers) - 1)) {
     uint32_t s = tbl_find(t, key);
     if (s == NOSLOT) atomicOr(&st->err, ERR_MISSING_KEY);
-    else cnt_delta(A, s, -(int32_t)__popc(peers), par);
+    else cnt_delta(A, s, key, -(int32_t)__popc(peers), par);
   }
 }
 
@@ -643,7 +656,7 @@ __device__ __forceinline__ uint32_t agg_new(const ApplyArgs& A, uint32_t key, bo
       atomicOr(&st->err, ERR_TABLE_FULL);
     } else {
       uint32_t nc = __popc(peers & cmask);
-      if (nc) cnt_delta(A, s, (int32_t)nc, par);
+      if (nc) cnt_delta(A, s, key, (int32_t)nc, par);
       if (atomicAdd(t.occ_len + s, (uint32_t)__popc(peers)) == 0) {  // first adjacency of a pair born in this iteration
         uint32_t i = atomicAdd(&st->n_new[par], 1u);
         if (i < new_cap) newslots[i] = s;
