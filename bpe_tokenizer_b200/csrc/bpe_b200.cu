@@ -87,6 +87,16 @@ int ilog2(uint32_t p) {
 
 }  // namespace
 
+struct EncodeScratch {
+  DevBuf<int32_t> out_tmp;
+  DevBuf<uint32_t> out_len;
+  DevBuf<uint64_t> out_off;
+  DevBuf<uint32_t> g_tok, g_nxt, g_prv, g_rk, g_sel;
+  DevBuf<uint32_t> range_first, tile_sums;
+  DevBuf<uint64_t> tile_off;
+  DevBuf<uint32_t> flags;  // [0] long documents left for the per-document kernel, [1] error, [2] next range to claim
+};
+
 struct bpe_engine {
   int device = 0;
   int sm_count = 148;
@@ -157,6 +167,13 @@ struct bpe_engine {
   DevBuf<uint32_t> mg_mark, mg_touched, mg_tie_sorted, mg_export_n;
   int mg_loop_blocks = 0;
   unsigned long long mg_epoch = 0, mg_tie_epoch = 0;
+
+  // staging of the host-buffer encode / restore calls (grow-only, reused across calls)
+  DevBuf<int32_t> x_ids, x_out, x_tvi;
+  DevBuf<int64_t> x_off, x_ooff, x_bad;
+  DevBuf<unsigned long long> x_flag;
+  std::vector<int64_t> h_rel;
+  EncodeScratch x_scratch;
 
   // scratch
   DevBuf<int32_t> stage_ids;
@@ -631,15 +648,6 @@ int launch_encode_lanes(bpe_engine* e, const int32_t* dev_ids, const int64_t* de
   return BPE_OK;
 }
 
-struct EncodeScratch {
-  DevBuf<int32_t> out_tmp;
-  DevBuf<uint32_t> out_len;
-  DevBuf<uint64_t> out_off;
-  DevBuf<uint32_t> g_tok, g_nxt, g_prv, g_rk, g_sel;
-  DevBuf<uint32_t> range_first, tile_sums;
-  DevBuf<uint64_t> tile_off;
-  DevBuf<uint32_t> flags;  // [0] long documents left for the per-document kernel, [1] error, [2] next range to claim
-};
 
 // device-resident encode; leaves compacted output in dev_out / dev_out_offsets
 int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const int64_t* dev_doc_off, int64_t n_docs,
@@ -1637,45 +1645,64 @@ int bpe_encode_batch_dev(bpe_engine* e, const int32_t* dev_ids, const int64_t* d
                     dev_out_offsets, dev_first_bad, n_out);
 }
 
+// host buffers in, host buffers out: stage through grow-only device buffers owned by the engine
+int stage_encode_inputs(bpe_engine* e, const int32_t* ids, const int64_t* doc_offsets, int64_t n_docs, int64_t* total_out, int64_t* max_len_out) {
+  int64_t base = n_docs ? doc_offsets[0] : 0, total = n_docs ? doc_offsets[n_docs] - base : 0;
+  if (total > 0 && !ids) return fail(e, BPE_E_INVALID, "null ids");
+  int64_t max_len = 0;
+  e->h_rel.resize((size_t)n_docs + 1);
+  e->h_rel[0] = 0;
+  for (int64_t d = 0; d < n_docs; d++) {
+    e->h_rel[d + 1] = doc_offsets[d + 1] - base;
+    max_len = std::max(max_len, doc_offsets[d + 1] - doc_offsets[d]);
+  }
+  CK(e->x_ids.reserve((size_t)std::max<int64_t>(total, 1)));
+  CK(e->x_out.reserve((size_t)std::max<int64_t>(total, 1)));
+  CK(e->x_off.reserve((size_t)n_docs + 1));
+  CK(e->x_ooff.reserve((size_t)n_docs + 1));
+  CK(e->x_flag.reserve(1));
+  if (total) CK(cudaMemcpyAsync(e->x_ids.p, ids + base, (size_t)total * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->x_off.p, e->h_rel.data(), (size_t)(n_docs + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  if (total) {  // ids must name existing tokens; report the first offender like the reference's left-to-right scan would
+    CK(cudaMemsetAsync(e->x_flag.p, 0xFF, 8, e->stream));
+    k_first_bad_id<<<e->grid(8), 256, 0, e->stream>>>(e->x_ids.p, (uint64_t)total, (uint32_t)e->n_tokens, e->x_flag.p);
+    CKL();
+    unsigned long long fb = ~0ull;
+    CK(cudaMemcpyAsync(&fb, e->x_flag.p, 8, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (fb != ~0ull) return fail(e, BPE_E_INVALID, "id %d at %lld outside the token table", ids[base + (int64_t)fb], (long long)fb);
+  }
+  *total_out = total;
+  *max_len_out = max_len;
+  return BPE_OK;
+}
+
 int bpe_encode_batch(bpe_engine* e, const int32_t* ids, const int64_t* doc_offsets, int64_t n_docs, const int32_t* to_vector_index,
                      int32_t n_tvi, int32_t* out, int64_t out_cap, int64_t* out_offsets, int64_t* first_bad, int64_t* n_out) {
   if (!e || !n_out || !out_offsets) return fail(e, BPE_E_INVALID, "bad encode arguments");
   TRY(check_offsets(e, doc_offsets, n_docs));
   CK(cudaSetDevice(e->device));
-  int64_t base = n_docs ? doc_offsets[0] : 0, total = n_docs ? doc_offsets[n_docs] - base : 0;
-  if (total > 0 && !ids) return fail(e, BPE_E_INVALID, "null ids");
-  int64_t max_len = 0;
-  std::vector<int64_t> rel((size_t)n_docs + 1, 0);
-  for (int64_t d = 0; d < n_docs; d++) {
-    rel[d + 1] = doc_offsets[d + 1] - base;
-    max_len = std::max(max_len, doc_offsets[d + 1] - doc_offsets[d]);
-  }
-  for (int64_t i = 0; i < total; i++)
-    if (ids[base + i] < 0 || ids[base + i] >= e->n_tokens) return fail(e, BPE_E_INVALID, "id %d at %lld outside the token table", ids[base + i], (long long)i);
-  DevBuf<int32_t> d_ids, d_out, d_tvi;
-  DevBuf<int64_t> d_off, d_ooff, d_bad;
-  CK(d_ids.reserve((size_t)std::max<int64_t>(total, 1)));
-  CK(d_out.reserve((size_t)std::max<int64_t>(total, 1)));
-  CK(d_off.reserve((size_t)n_docs + 1));
-  CK(d_ooff.reserve((size_t)n_docs + 1));
-  if (first_bad) CK(d_bad.reserve((size_t)std::max<int64_t>(n_docs, 1)));
+  int64_t total = 0, max_len = 0;
+  TRY(stage_encode_inputs(e, ids, doc_offsets, n_docs, &total, &max_len));
+  if (first_bad) CK(e->x_bad.reserve((size_t)std::max<int64_t>(n_docs, 1)));
   if (to_vector_index && n_tvi > 0) {
-    CK(d_tvi.reserve((size_t)n_tvi));
-    CK(cudaMemcpyAsync(d_tvi.p, to_vector_index, (size_t)n_tvi * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(e->x_tvi.reserve((size_t)n_tvi));
+    CK(cudaMemcpyAsync(e->x_tvi.p, to_vector_index, (size_t)n_tvi * 4, cudaMemcpyHostToDevice, e->stream));
   }
-  if (total) CK(cudaMemcpyAsync(d_ids.p, ids + base, (size_t)total * 4, cudaMemcpyHostToDevice, e->stream));
-  CK(cudaMemcpyAsync(d_off.p, rel.data(), (size_t)(n_docs + 1) * 8, cudaMemcpyHostToDevice, e->stream));
-  EncodeScratch sc;
-  TRY(encode_dev(e, sc, d_ids.p, d_off.p, n_docs, total, max_len, to_vector_index ? d_tvi.p : nullptr, n_tvi, d_out.p, d_ooff.p,
-                 first_bad ? d_bad.p : nullptr, n_out));
-  CK(cudaMemcpyAsync(out_offsets, d_ooff.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
-  if (first_bad && n_docs) CK(cudaMemcpyAsync(first_bad, d_bad.p, (size_t)n_docs * 8, cudaMemcpyDeviceToHost, e->stream));
+  TRY(encode_dev(e, e->x_scratch, e->x_ids.p, e->x_off.p, n_docs, total, max_len, to_vector_index ? e->x_tvi.p : nullptr, n_tvi, e->x_out.p,
+                 e->x_ooff.p, first_bad ? e->x_bad.p : nullptr, n_out));
+  CK(cudaMemcpyAsync(out_offsets, e->x_ooff.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (first_bad && n_docs) CK(cudaMemcpyAsync(first_bad, e->x_bad.p, (size_t)n_docs * 8, cudaMemcpyDeviceToHost, e->stream));
   if (*n_out > out_cap || (*n_out && !out)) {
     CK(cudaStreamSynchronize(e->stream));
     return fail(e, BPE_E_CAPACITY, "output buffer holds %lld values, need %lld", (long long)out_cap, (long long)*n_out);
   }
-  if (*n_out) CK(cudaMemcpyAsync(out, d_out.p, (size_t)*n_out * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (*n_out) CK(cudaMemcpyAsync(out, e->x_out.p, (size_t)*n_out * 4, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  if (total > (256ll << 20)) {  // do not sit on GBs of staging after a bulk call
+    e->x_ids.release();
+    e->x_out.release();
+  }
   return BPE_OK;
 }
 
@@ -1684,31 +1711,14 @@ int bpe_restore_documents(bpe_engine* e, const int32_t* ids, const int64_t* doc_
   TRY(check_offsets(e, doc_offsets, n_docs));
   if (n_docs == 0) return BPE_OK;
   CK(cudaSetDevice(e->device));
-  int64_t base = doc_offsets[0], total = doc_offsets[n_docs] - base;
-  if (total > 0 && !ids) return fail(e, BPE_E_INVALID, "null ids");
-  int64_t max_len = 0;
-  std::vector<int64_t> rel((size_t)n_docs + 1, 0);
-  for (int64_t d = 0; d < n_docs; d++) {
-    rel[d + 1] = doc_offsets[d + 1] - base;
-    max_len = std::max(max_len, doc_offsets[d + 1] - doc_offsets[d]);
-  }
-  for (int64_t i = 0; i < total; i++)
-    if (ids[base + i] < 0 || ids[base + i] >= e->n_tokens) return fail(e, BPE_E_INVALID, "id %d at %lld outside the token table", ids[base + i], (long long)i);
-  DevBuf<int32_t> d_ids, d_out;
-  DevBuf<int64_t> d_off, d_ooff;
-  CK(d_ids.reserve((size_t)std::max<int64_t>(total, 1)));
-  CK(d_out.reserve((size_t)std::max<int64_t>(total, 1)));
-  CK(d_off.reserve((size_t)n_docs + 1));
-  CK(d_ooff.reserve((size_t)n_docs + 1));
-  if (total) CK(cudaMemcpyAsync(d_ids.p, ids + base, (size_t)total * 4, cudaMemcpyHostToDevice, e->stream));
-  CK(cudaMemcpyAsync(d_off.p, rel.data(), (size_t)(n_docs + 1) * 8, cudaMemcpyHostToDevice, e->stream));
-  EncodeScratch sc;
+  int64_t total = 0, max_len = 0;
+  TRY(stage_encode_inputs(e, ids, doc_offsets, n_docs, &total, &max_len));
   int64_t n_out = 0;
-  TRY(encode_dev(e, sc, d_ids.p, d_off.p, n_docs, total, max_len, nullptr, 0, d_out.p, d_ooff.p, nullptr, &n_out));
+  TRY(encode_dev(e, e->x_scratch, e->x_ids.p, e->x_off.p, n_docs, total, max_len, nullptr, 0, e->x_out.p, e->x_ooff.p, nullptr, &n_out));
   std::vector<int64_t> ooff((size_t)n_docs + 1);
-  CK(cudaMemcpyAsync(ooff.data(), d_ooff.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(ooff.data(), e->x_ooff.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  return append_docs_dev(e, d_out.p, ooff.data(), n_docs);
+  return append_docs_dev(e, e->x_out.p, ooff.data(), n_docs);
 }
 
 }  // extern "C"

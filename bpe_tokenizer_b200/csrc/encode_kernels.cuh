@@ -305,4 +305,15 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_tiles(const uint32_t* __res
   if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = tile_off[n_tiles];
 }
 
+// first position whose id lies outside [0, n_tokens): the reference throws at the FIRST offending character (core.ts:396-402)
+__global__ void k_first_bad_id(const int32_t* __restrict__ ids, uint64_t n, uint32_t n_tokens, unsigned long long* __restrict__ first_bad) {
+  unsigned long long best = ~0ull;
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if ((uint32_t)__ldg(ids + i) >= n_tokens && i < best) best = i;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
+  if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(first_bad, best);
+}
+
 }  // namespace bpe

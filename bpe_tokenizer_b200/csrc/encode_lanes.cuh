@@ -51,13 +51,15 @@ __device__ __forceinline__ uint2 el_lookup(const LaneTables& T, const uint2* s_d
   }
 }
 
-// clamp functions packed as lo | hi << 16
+// clamp functions packed as lo | hi << 16, evaluated on both halves at once with the packed u16x2 min/max of sm_100
+// (VIMNMX.U16x2): outer o inner = (outer(inner.lo), outer(inner.hi))
 __device__ __forceinline__ uint32_t cl_apply(uint32_t f, uint32_t x) { return max(f & 0xFFFFu, min(f >> 16, x)); }
-// outer o inner
 __device__ __forceinline__ uint32_t cl_compose(uint32_t outer, uint32_t inner) {
-  return cl_apply(outer, inner & 0xFFFFu) | (cl_apply(outer, inner >> 16) << 16);
+  return __vmaxu2(__byte_perm(outer, 0, 0x1010), __vminu2(__byte_perm(outer, 0, 0x3232), inner));
 }
 constexpr uint32_t CL_IDENT = 0xFFFF0000u;
+// step of one record: lo | max(rk, lo) << 16, with a = tok | rk << 16
+__device__ __forceinline__ uint32_t cl_make2(uint32_t lo2 /* lo | lo << 16 */, uint32_t a) { return __vmaxu2(lo2, a & 0xFFFF0000u); }
 __device__ __forceinline__ uint32_t cl_make(uint32_t lo, uint32_t rk) { return lo | (max(rk, lo) << 16); }
 
 // index of the range's first document: lower bound of base0 + k*stride in doc_off[0..n_docs]
@@ -193,8 +195,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_lanes(const int32_t* __re
           uint32_t a = sA[idx], b = sB[idx];
           uint32_t rk = a >> 16;
           anyvalid |= rk < EL_DIRTY;
-          G = cl_compose(G, cl_make(b >> 16, rk));
-          if (j + 1 < cnt) F = cl_compose(cl_make(b & 0xFFFFu, rk), F);
+          G = cl_compose(G, cl_make2(__byte_perm(b, 0, 0x3232), a));
+          if (j + 1 < cnt) F = cl_compose(cl_make2(__byte_perm(b, 0, 0x1010), a), F);
         }
         if (!__any_sync(FULL, anyvalid)) break;
         if (round > n + 8u) {  // every round merges at least one pair
