@@ -135,8 +135,8 @@ struct bpe_engine {
   // pair index
   bool index_valid = false;
   uint32_t tbl_cap = 0;
-  DevBuf<uint32_t> t_keys, t_cnt, t_start, t_len, t_fill;
-  DevBuf<uint32_t> u_keys, u_cnt, u_start, u_len, u_fill;  // second set, target of the next rehash (kept at high water)
+  DevBuf<uint32_t> t_ent;  // 5 fields x capacity words (field-major when TBL_STRIDE == 1, common.cuh)
+  DevBuf<uint32_t> u_ent;  // second buffer, target of the next rehash (kept at high water)
   DevBuf<uint32_t> pool;
   DevBuf<DevState> d_st;
   DevState* h_st = nullptr;  // pinned
@@ -183,11 +183,12 @@ struct bpe_engine {
 
   PairTable table() const {
     PairTable t;
-    t.keys = t_keys.p;
-    t.cnt = t_cnt.p;
-    t.occ_start = t_start.p;
-    t.occ_len = t_len.p;
-    t.occ_fill = t_fill.p;
+    const size_t fs = (TBL_STRIDE == 1) ? (size_t)tbl_cap : 1;  // distance between fields
+    t.keys.p = t_ent.p;
+    t.cnt.p = t_ent.p + fs;
+    t.occ_start.p = t_ent.p + 2 * fs;
+    t.occ_len.p = t_ent.p + 3 * fs;
+    t.occ_fill.p = t_ent.p + 4 * fs;
     t.mask = tbl_cap - 1;
     t.shift = 32 - ilog2(tbl_cap);
     return t;
@@ -254,19 +255,25 @@ int sync_len16(bpe_engine* e) {
 }
 
 // ---- pair table allocation / growth -------------------------------------------------------------
+__global__ void k_init_table(uint4* __restrict__ ent, uint64_t cap) {  // key = EMPTY_KEY, every other field 0
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
+    ent[2 * i] = make_uint4(EMPTY_KEY, 0u, 0u, 0u);
+    ent[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 int alloc_table(bpe_engine* e, uint32_t cap) {
   // buffers only ever grow (cudaFree / cudaMalloc of GBs costs up to seconds); the logical capacity is `cap`
-  CK(e->t_keys.reserve(cap));
-  CK(e->t_cnt.reserve(cap));
-  CK(e->t_start.reserve(cap));
-  CK(e->t_len.reserve(cap));
-  CK(e->t_fill.reserve(cap));
+  CK(e->t_ent.reserve((size_t)cap * (TBL_STRIDE == 1 ? 5 : TBL_STRIDE)));
   e->tbl_cap = cap;
-  CK(cudaMemsetAsync(e->t_keys.p, 0xFF, (size_t)cap * 4, e->stream));
-  CK(cudaMemsetAsync(e->t_cnt.p, 0, (size_t)cap * 4, e->stream));
-  CK(cudaMemsetAsync(e->t_start.p, 0, (size_t)cap * 4, e->stream));
-  CK(cudaMemsetAsync(e->t_len.p, 0, (size_t)cap * 4, e->stream));
-  CK(cudaMemsetAsync(e->t_fill.p, 0, (size_t)cap * 4, e->stream));
+  if (TBL_STRIDE == 1) {
+    CK(cudaMemsetAsync(e->t_ent.p, 0xFF, (size_t)cap * 4, e->stream));
+    CK(cudaMemsetAsync(e->t_ent.p + cap, 0, (size_t)cap * 16, e->stream));
+  } else {
+    k_init_table<<<e->grid(8), 256, 0, e->stream>>>(reinterpret_cast<uint4*>(e->t_ent.p), (uint64_t)cap);
+    CKL();
+  }
   if (e->mg_world > 1) {  // per-slot side arrays of the sharded loop follow the table (all zero between merges)
     CK(e->mg_dlt.reserve(cap));
     CK(e->mg_mark.reserve(cap));
@@ -296,11 +303,7 @@ __global__ void k_rehash(PairTable src, PairTable dst, DevState* st) {
 
 int grow_table(bpe_engine* e, uint32_t new_cap) {
   PairTable old = e->table();
-  std::swap(e->t_keys, e->u_keys);
-  std::swap(e->t_cnt, e->u_cnt);
-  std::swap(e->t_start, e->u_start);
-  std::swap(e->t_len, e->u_len);
-  std::swap(e->t_fill, e->u_fill);
+  std::swap(e->t_ent, e->u_ent);
   TRY(alloc_table(e, new_cap));  // the (former) alternate set becomes the live table
   k_rehash<<<e->grid(), 256, 0, e->stream>>>(old, e->table(), e->d_st.p);
   CKL();
@@ -1329,6 +1332,16 @@ int bpe_get_stats(bpe_engine* e, bpe_stats* out) {
     e->live_tokens = e->h_st->live_tokens;
     e->stats.distinct_pairs = e->h_st->n_keys;
     for (int i = 0; i < 8; i++) e->stats.ms_loop_phase[i] = (double)e->h_st->prof_ns[i] * 1e-6;
+#ifdef BPE_FINE_PROF
+    fprintf(stderr, "[bpe] phase_sites sub-steps ms (pool, slot+right, left, dec1, new1, right, dec2, new2, record):");
+    for (int i = 0; i < 9; i++) fprintf(stderr, " %.1f", (double)e->h_st->fine_ns[i] * 1e-6);
+    fprintf(stderr, "\n[bpe] per log2(weight) bucket: merges, P1 us/merge, P2 us/merge, P3 us/merge, P1 ns/site\n");
+    for (int b = 0; b < 32; b++) {
+      double m = (double)e->h_st->bucket_ns[b][3];
+      if (m > 0) fprintf(stderr, "  2^%-2d %8.0f  %8.1f %8.1f %8.1f  %8.2f\n", b, m, e->h_st->bucket_ns[b][0] / m * 1e-3, e->h_st->bucket_ns[b][1] / m * 1e-3,
+                         e->h_st->bucket_ns[b][2] / m * 1e-3, e->h_st->bucket_ns[b][0] / m / (1.5 * (double)(1u << b)));
+    }
+#endif
     e->stats.pool_used = e->h_st->pool_cursor;
   }
   e->stats.corpus_positions = (int64_t)e->n_slots;

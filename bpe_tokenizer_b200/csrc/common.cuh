@@ -117,14 +117,24 @@ __device__ __forceinline__ uint32_t run_right(const uint32_t* slots, uint32_t n,
 // ---- pair table: open addressing, linear probing, keys never deleted --------------------------
 // (the reference rebuilds a Map<Token, Map<Token, number>> on every findNextMerge, core.ts:259;
 //  here the histogram persists and is updated by count deltas.)
+// One array per field (TBL_STRIDE = 1).  A 32-byte entry per slot (TBL_STRIDE = 8: key, count and list fields of a pair
+// in one DRAM sector) was measured on the 1 GB corpus and LOST 8 %: linear probing then pays one sector per probe
+// instead of one per eight, and the hot-list / threshold scans read four times the bytes.  TblField keeps the
+// `t.cnt[i]` / `t.cnt + i` notation either way.
+constexpr uint32_t TBL_STRIDE = 1;  // u32 words between consecutive slots of one field
+struct TblField {
+  uint32_t* p;
+  __host__ __device__ __forceinline__ uint32_t& operator[](uint32_t i) const { return p[(size_t)i * TBL_STRIDE]; }
+  __host__ __device__ __forceinline__ uint32_t* operator+(uint32_t i) const { return p + (size_t)i * TBL_STRIDE; }
+};
 struct PairTable {
-  uint32_t* keys;       // pair_key(a,b) or EMPTY_KEY
-  uint32_t* cnt;        // counted occurrences (run-parity rule of core.ts:285-290 applied)
-  uint32_t* occ_start;  // occurrence list = pool[occ_start .. occ_start+occ_len)
-  uint32_t* occ_len;    //   every adjacency (a,b) born in the iteration that created the pair
-  uint32_t* occ_fill;   //   scatter cursor
-  uint32_t mask;        // capacity - 1
-  uint32_t shift;       // 32 - log2(capacity)
+  TblField keys;       // pair_key(a,b) or EMPTY_KEY
+  TblField cnt;        // counted occurrences (run-parity rule of core.ts:285-290 applied)
+  TblField occ_start;  // occurrence list = pool[occ_start .. occ_start+occ_len)
+  TblField occ_len;    //   every adjacency (a,b) born in the iteration that created the pair
+  TblField occ_fill;   //   scatter cursor
+  uint32_t mask;       // capacity - 1
+  uint32_t shift;      // 32 - log2(capacity)
 };
 
 __device__ __forceinline__ uint32_t tbl_hash(const PairTable& t, uint32_t key) { return (key * 0x9E3779B1u) >> t.shift; }
@@ -149,6 +159,27 @@ __device__ __forceinline__ uint32_t tbl_find_or_insert(const PairTable& t, uint3
       uint32_t old = atomicCAS(t.keys + i, EMPTY_KEY, key);
       if (old == EMPTY_KEY) {
         atomicAdd(n_keys, 1u);
+        return i;
+      }
+      if (old == key) return i;
+    }
+    i = (i + 1) & t.mask;
+  }
+  return NOSLOT;  // table full
+}
+
+// Same as tbl_find_or_insert, but the caller accounts for the new key (one n_keys atomic per warp / block instead of
+// one per key: thousands of atomics on ONE address serialise in L2 and used to dominate a merge iteration).
+__device__ __forceinline__ uint32_t tbl_find_or_insert_ex(const PairTable& t, uint32_t key, bool* inserted) {
+  *inserted = false;
+  uint32_t i = tbl_hash(t, key);
+  for (uint32_t probes = 0; probes <= t.mask; probes++) {
+    uint32_t k = t.keys[i];
+    if (k == key) return i;
+    if (k == EMPTY_KEY) {
+      uint32_t old = atomicCAS(t.keys + i, EMPTY_KEY, key);
+      if (old == EMPTY_KEY) {
+        *inserted = true;
         return i;
       }
       if (old == key) return i;

@@ -404,11 +404,16 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
     for (int q = 0; q < M.world; q++) {
       const unsigned long long* area = mg_area(M, M.rank, epar, q);
       const uint32_t nrec = ld_cg(reinterpret_cast<const uint32_t*>(area) + H_N);
-      for (uint32_t i = gtid; i < nrec; i += gthreads) {
-        unsigned long long rec = ld_cg(area + MG_HDR + i);
-        uint32_t s = tbl_find_or_insert(t, (uint32_t)(rec >> 32), &st->n_keys);
-        if (s == NOSLOT) atomicOr(&st->err, ERR_TABLE_FULL);
-        else atomicAdd(t.cnt + s, (uint32_t)rec);
+      for (uint32_t i = gtid; i < ((nrec + 31u) & ~31u); i += gthreads) {  // warp-uniform: one n_keys atomic per warp
+        bool ins = false;
+        if (i < nrec) {
+          unsigned long long rec = ld_cg(area + MG_HDR + i);
+          uint32_t s = tbl_find_or_insert_ex(t, (uint32_t)(rec >> 32), &ins);
+          if (s == NOSLOT) atomicOr(&st->err, ERR_TABLE_FULL);
+          else atomicAdd(t.cnt + s, (uint32_t)rec);
+        }
+        uint32_t im = __ballot_sync(0xFFFFFFFFu, ins);
+        if (im && lane_id() == (uint32_t)(__ffs(im) - 1)) atomicAdd(&st->n_keys, (uint32_t)__popc(im));
       }
     }
     phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);

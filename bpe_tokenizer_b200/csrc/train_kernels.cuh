@@ -64,6 +64,8 @@ struct DevState {
   // folded message headers, read by every thread with two 128-bit loads: [0] OR of all ranks' error flags, then the
   // minima over ranks of pool_free, sites_cap, new_cap, hot_cap, len16_cap, tbl_cap, cand_cap
   alignas(16) uint32_t g_vals[8];
+  unsigned long long fine_ns[12];  // BPE_FINE_PROF builds: block 0 / thread 0 sub-steps of phase_sites
+  unsigned long long bucket_ns[32][4];  // BPE_FINE_PROF: per log2(weight) bucket: P1, P2, P3 work (block 0), merges
 };
 
 constexpr uint32_t LOOP_RUNNING = 0, LOOP_DONE = 1, LOOP_NEED_REBUILD = 2, LOOP_NEED_HOST = 3, LOOP_EMPTY = 4,
@@ -242,17 +244,23 @@ __global__ void __launch_bounds__(K1_THREADS) k_hist(const uint32_t* __restrict_
     }
   }
   __syncthreads();
+  uint32_t n_ins = 0;
   for (int i = threadIdx.x; i < K1_SMEM_SLOTS; i += K1_THREADS) {
     uint32_t key = sh.key[i];
     if (key == EMPTY_KEY) continue;
-    uint32_t gs = tbl_find_or_insert(t, key, &st->n_keys);
+    bool ins;
+    uint32_t gs = tbl_find_or_insert_ex(t, key, &ins);
     if (gs == NOSLOT) {
       atomicOr(&st->err, ERR_TABLE_FULL);
       continue;
     }
+    n_ins += ins ? 1u : 0u;
     if (sh.a[i] != sh.b[i]) atomicAdd(t.cnt + gs, sh.a[i] - sh.b[i]);
     if (sh.a[i]) atomicAdd(t.occ_len + gs, sh.a[i]);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_ins += __shfl_xor_sync(0xFFFFFFFFu, n_ins, o);
+  if ((threadIdx.x & 31) == 0 && n_ins) atomicAdd(&st->n_keys, n_ins);  // one n_keys atomic per warp
 }
 
 // carve every pair's occurrence list out of the pool
@@ -603,23 +611,53 @@ struct ApplyArgs {
 
 constexpr uint32_t ERR_TOUCH_OVERFLOW = 128u, ERR_PEER_TIMEOUT = 256u, ERR_INBOX_OVERFLOW = 512u, ERR_PEER = 1024u;
 
-// one count delta of pair slot s: applied to the table (single GPU) or staged for the exchange (sharded)
-__device__ __forceinline__ void cnt_delta(const ApplyArgs& A, uint32_t s, uint32_t key, int32_t d, uint32_t par) {
+__device__ __forceinline__ unsigned long long now_ns();
+// non-blocking hints: the per-site chain of dependent DRAM round trips is what bounds a merge iteration, so the
+// neighbourhood of a site and the table cells of its (up to four) pairs are requested before they are walked / updated
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_pair(const PairTable& t, uint32_t key) {
+  uint32_t h = tbl_hash(t, key);
+  prefetch_l1(t.keys + h);
+  prefetch_l2(t.cnt + h);
+  prefetch_l2(t.occ_len + h);
+}
+
+// Count deltas, warp-collective (all 32 lanes call; `has` lanes carry one delta of pair slot s): applied to the table
+// (single GPU), pushed into every rank's inbox (sharded, small merges) or staged per pair (sharded, big merges).
+// Counters shared by the whole grid (n_out, n_touched) get ONE atomic per warp.
+__device__ __forceinline__ void cnt_delta_warp(const ApplyArgs& A, bool has, uint32_t s, uint32_t key, int32_t d, uint32_t par) {
+  const uint32_t lane = lane_id();
   if (A.push_world) {
-    uint32_t k = atomicAdd(&A.st->n_out, 1u);
-    if (k < A.push_cap) {
-      unsigned long long rec = ((unsigned long long)key << 32) | (uint32_t)d;
-      for (int q = 0; q < A.push_world; q++) A.push[q][k] = rec;
-    } else {
-      atomicOr(&A.st->err, ERR_INBOX_OVERFLOW);
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
+    if (!m) return;
+    uint32_t base = 0;
+    int src = __ffs(m) - 1;
+    if ((int)lane == src) base = atomicAdd(&A.st->n_out, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, src);
+    if (has) {
+      uint32_t k = base + __popc(m & ((1u << lane) - 1u));
+      if (k < A.push_cap) {
+        unsigned long long rec = ((unsigned long long)key << 32) | (uint32_t)d;
+        for (int q = 0; q < A.push_world; q++) A.push[q][k] = rec;
+      } else {
+        atomicOr(&A.st->err, ERR_INBOX_OVERFLOW);
+      }
     }
   } else if (A.dlt) {
-    if (atomicAdd(A.dlt + s, d) == 0) {  // first delta of this pair in this merge (deltas of one pair share a sign)
-      uint32_t i = atomicAdd(&A.st->n_touched[par], 1u);
+    bool first = has && atomicAdd(A.dlt + s, d) == 0;  // first delta of this pair in this merge (deltas of a pair share a sign)
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, first);
+    if (!m) return;
+    uint32_t base = 0;
+    int src = __ffs(m) - 1;
+    if ((int)lane == src) base = atomicAdd(&A.st->n_touched[par], (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, src);
+    if (first) {
+      uint32_t i = base + __popc(m & ((1u << lane) - 1u));
       if (i < A.touched_cap) A.touched[i] = s;
       else atomicOr(&A.st->err, ERR_TOUCH_OVERFLOW);
     }
-  } else {
+  } else if (has) {
     atomicAdd(A.t.cnt + s, (uint32_t)d);
   }
 }
@@ -627,41 +665,52 @@ __device__ __forceinline__ void cnt_delta(const ApplyArgs& A, uint32_t s, uint32
 // all 32 lanes call; lanes with has == false pass any key
 __device__ __forceinline__ void agg_dec(const ApplyArgs& A, uint32_t key, bool has, uint32_t par) {
   const PairTable& t = A.t;
-  DevState* st = A.st;
   uint32_t lane = lane_id();
   uint32_t k = has ? key : (EMPTY_KEY - 1 - lane);
   uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
-  if (has && lane == (uint32_t)(__ffs(peers) - 1)) {
-    uint32_t s = tbl_find(t, key);
-    if (s == NOSLOT) atomicOr(&st->err, ERR_MISSING_KEY);
-    else cnt_delta(A, s, key, -(int32_t)__popc(peers), par);
+  bool leader = has && lane == (uint32_t)(__ffs(peers) - 1);
+  uint32_t s = NOSLOT;
+  if (leader) {
+    s = tbl_find(t, key);
+    if (s == NOSLOT) atomicOr(&A.st->err, ERR_MISSING_KEY);
   }
+  cnt_delta_warp(A, leader && s != NOSLOT, s, key, -(int32_t)__popc(peers), par);
 }
 
 // returns the table slot of `key` to every lane with has == true
 __device__ __forceinline__ uint32_t agg_new(const ApplyArgs& A, uint32_t key, bool has, bool counted, uint32_t par) {
   const PairTable& t = A.t;
   DevState* st = A.st;
-  uint32_t* newslots = A.newslots;
-  const uint32_t new_cap = A.new_cap;
   uint32_t lane = lane_id();
   uint32_t k = has ? key : (EMPTY_KEY - 1 - lane);
   uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
   uint32_t cmask = __ballot_sync(0xFFFFFFFFu, has && counted);
   uint32_t leader = __ffs(peers) - 1;
-  uint32_t s = NOSLOT;
+  uint32_t s = NOSLOT, nc = 0;
+  bool inserted = false, born = false;
   if (has && lane == leader) {
-    s = tbl_find_or_insert(t, key, &st->n_keys);
+    s = tbl_find_or_insert_ex(t, key, &inserted);
     if (s == NOSLOT) {
       atomicOr(&st->err, ERR_TABLE_FULL);
     } else {
-      uint32_t nc = __popc(peers & cmask);
-      if (nc) cnt_delta(A, s, key, (int32_t)nc, par);
-      if (atomicAdd(t.occ_len + s, (uint32_t)__popc(peers)) == 0) {  // first adjacency of a pair born in this iteration
-        uint32_t i = atomicAdd(&st->n_new[par], 1u);
-        if (i < new_cap) newslots[i] = s;
-        else atomicOr(&st->err, ERR_SITE_OVERFLOW);
-      }
+      nc = __popc(peers & cmask);
+      born = atomicAdd(t.occ_len + s, (uint32_t)__popc(peers)) == 0;  // first adjacency of a pair born in this iteration
+    }
+  }
+  cnt_delta_warp(A, nc != 0, s, key, (int32_t)nc, par);
+  // grid-wide counters: one atomic per warp
+  uint32_t im = __ballot_sync(0xFFFFFFFFu, inserted);
+  if (im && lane == (uint32_t)(__ffs(im) - 1)) atomicAdd(&st->n_keys, (uint32_t)__popc(im));
+  uint32_t bm = __ballot_sync(0xFFFFFFFFu, born);
+  if (bm) {
+    uint32_t base = 0;
+    int src = __ffs(bm) - 1;
+    if ((int)lane == src) base = atomicAdd(&st->n_new[par], (uint32_t)__popc(bm));
+    base = __shfl_sync(0xFFFFFFFFu, base, src);
+    if (born) {
+      uint32_t i = base + __popc(bm & ((1u << lane) - 1u));
+      if (i < A.new_cap) A.newslots[i] = s;
+      else atomicOr(&st->err, ERR_SITE_OVERFLOW);
     }
   }
   return __shfl_sync(0xFFFFFFFFu, s, leader);
@@ -681,11 +730,25 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
   }
   uint32_t lane = lane_id();
   uint32_t total_round = (total + 31u) & ~31u;
+#ifdef BPE_FINE_PROF
+  const bool fine = (bid == 0 && threadIdx.x == 0);
+  unsigned long long ft0 = fine ? now_ns() : 0, ft1;
+#define FINE(k, dep)                                   \
+  if (fine) {                                          \
+    if ((uint32_t)(dep) == 0xDEADBEEFu) ft0++;         \
+    ft1 = now_ns();                                    \
+    st->fine_ns[k] += ft1 - ft0;                       \
+    ft0 = ft1;                                         \
+  }
+#else
+#define FINE(k, dep)
+#endif
   for (uint32_t i = bid * blockDim.x + threadIdx.x; i < total_round; i += nblk * blockDim.x) {
     bool site = false;
     uint32_t p = 0, w = 0, q = 0, koff = 0;
     if (i < total) {
       p = A.scan_mode ? i : A.pool[list_start + i];
+      FINE(0, p)
       w = ld_slot(slots + p);
       if (slot_is_id(w) && slot_val(w) == a && right_token(slots, n, p, &q) == (int)b) {
         site = true;
@@ -695,6 +758,7 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
         }
       }
     }
+    FINE(1, w + q + koff)
     if (!__any_sync(0xFFFFFFFFu, site)) continue;
     SiteRec rec{p, NOPOS, NOSLOT, NOSLOT};
     // ---- adjacency on the left of the new token ----
@@ -748,8 +812,11 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
         }
       }
     }
+    FINE(2, (uint32_t)dec1_key + new1_key)
     agg_dec(A, dec1_key, dec1, par);
+    FINE(3, 0)
     rec.lslot = agg_new(A, new1_key, new1, new1_counted, par);
+    FINE(4, rec.lslot)
 
     // ---- adjacency on the right of the new token (left to the next site when that one is chained) ----
     uint32_t dec2_key = 0, new2_key = 0;
@@ -777,8 +844,11 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
         }
       }
     }
+    FINE(5, (uint32_t)dec2_key + new2_key)
     agg_dec(A, dec2_key, dec2, par);
+    FINE(6, 0)
     rec.rslot = agg_new(A, new2_key, new2, true, par);
+    FINE(7, rec.rslot)
 
     // ---- record the site (one counter atomic per warp) ----
     uint32_t smask = __ballot_sync(0xFFFFFFFFu, site);
@@ -790,7 +860,9 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
       if (k < A.sites_cap) reinterpret_cast<uint4*>(A.sites)[k] = make_uint4(rec.p, rec.lpos, rec.lslot, rec.rslot);
       else atomicOr(&st->err, ERR_SITE_OVERFLOW);
     }
+    FINE(8, base)
   }
+#undef FINE
 }
 
 // K3 phase 2: allocate the lists of the pairs born in this iteration; feed the hot list.
@@ -799,10 +871,25 @@ __device__ __forceinline__ void phase_alloc_new(const PairTable& t, const uint32
                                                 uint32_t hot_cap, uint32_t pool_cap, DevState* st, uint32_t bid,
                                                 uint32_t nblk) {
   uint32_t thresh = st->hot_thresh;
-  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n_new; i += nblk * blockDim.x) {
-    uint32_t s = newslots[i];
-    uint32_t len = t.occ_len[s];
-    uint32_t start = atomicAdd(&st->pool_cursor, len);
+  const uint32_t lane = lane_id();
+  const uint32_t n_round = (n_new + 31u) & ~31u;
+  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n_round; i += nblk * blockDim.x) {
+    const bool act = i < n_new;
+    uint32_t s = act ? newslots[i] : 0u;
+    uint32_t len = act ? t.occ_len[s] : 0u;
+    // one pool_cursor atomic per warp: inclusive scan of the list lengths
+    uint32_t inc = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if ((int)lane >= o) inc += v;
+    }
+    uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    uint32_t wbase = 0;
+    if (lane == 31 && total) wbase = atomicAdd(&st->pool_cursor, total);
+    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+    if (!act) continue;
+    uint32_t start = wbase + (inc - len);
     if (start > pool_cap || len > pool_cap - start) {
       atomicOr(&st->err, ERR_POOL_FULL);
       start = 0;
@@ -851,6 +938,11 @@ __device__ __forceinline__ void phase_apply(const ApplyArgs& A, uint32_t a, uint
     bool has = i < n_sites;
     uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(A.sites) + i) : make_uint4(0, NOPOS, NOSLOT, NOSLOT);
     uint32_t p = rv.x, lpos = rv.y, lslot = rv.z, rslot = rv.w;
+    if (has) {
+      if (p + 8 < n) prefetch_l1(slots + p + 8);
+      if (p + 16 < n) prefetch_l1(slots + p + 16);
+      prefetch_l1(slots + p);
+    }
     bool hl = has && lslot != NOSLOT && t.occ_len[lslot];
     bool hr = has && rslot != NOSLOT && t.occ_len[rslot];
     uint32_t il = agg_cursor(t, lslot, hl);
@@ -1074,6 +1166,13 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
       if (w.mult > 1) st->tie_breaks++;
     }
     phase_sites(A, wa, wb, c, par, w.slot, bid, nblk);
+#ifdef BPE_FINE_PROF
+    const int bkt = 31 - __clz(wcnt | 1u);
+    if (prof) {
+      st->bucket_ns[bkt][0] += now_ns() - tp0;
+      st->bucket_ns[bkt][3] += 1;
+    }
+#endif
     PROF(1)
     grid_barrier(L.barrier, ++epoch * nblk);
     PROF(2)
@@ -1085,6 +1184,9 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
                           // next arg-max partials are taken in P3 (no delta of P1 touches the winner's own pair)
     }
     phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, 1, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);
+#ifdef BPE_FINE_PROF
+    if (prof) st->bucket_ns[bkt][1] += now_ns() - tp0;
+#endif
     PROF(3)
     grid_barrier(L.barrier, ++epoch * nblk);
     PROF(4)
@@ -1100,6 +1202,9 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
       Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
       if (threadIdx.x == 0) L.partials[bid] = v;
     }
+#ifdef BPE_FINE_PROF
+    if (prof) st->bucket_ns[bkt][2] += now_ns() - tp0;
+#endif
     PROF(5)
     grid_barrier(L.barrier, ++epoch * nblk);
     PROF(6)
