@@ -788,7 +788,7 @@ int append_docs_dev(bpe_engine* e, const int32_t* dev_ids, const int64_t* host_o
 
 // ---- mergeUntil: persistent cooperative kernel, the host only grows buffers / rebuilds the hot list -----------
 int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations, bpe_merge* log,
-                       int64_t log_cap, int64_t* n_done) {
+                       int64_t log_cap, int64_t* n_done, const int32_t* dev_replay = nullptr) {
   *n_done = 0;
   CK(cudaSetDevice(e->device));
   if (e->n_slots == 0) return BPE_OK;
@@ -817,7 +817,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     int64_t remaining = log_cap - done;
     if (max_iterations > 0) remaining = std::min(remaining, max_iterations - done);  // core.ts:374-377
     if (remaining <= 0) break;
-    if (!e->hot_valid || e->hot_max_length != ml) {
+    if (!dev_replay && (!e->hot_valid || e->hot_max_length != ml)) {
       bool any = false;
       if ((rc = rebuild_hot(e, ml, &any)) != BPE_OK) break;
       if (!any) break;  // nothing countable left (core.ts:312)
@@ -851,6 +851,8 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     L.min_weight = (uint32_t)std::min<int64_t>(mw, 0xFFFFFFFFll);
     L.max_tokens = BPE_MAX_TOKENS;
     L.tbl_cap = e->tbl_cap;
+    L.replay = dev_replay ? dev_replay + 2 * done : nullptr;
+    if (dev_replay) e->hot_valid = false;  // replayed merges do not feed the hot list
     static const bool trace = getenv("BPE_TRACE") != nullptr;
     auto tw0 = std::chrono::steady_clock::now();
     k_loop_prepare<<<1, 32, 0, e->stream>>>(e->d_st.p, (uint32_t)e->n_tokens, e->barrier.p);
@@ -1056,6 +1058,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
     L.min_weight = (uint32_t)std::min<int64_t>(mw, 0xFFFFFFFFll);
     L.max_tokens = BPE_MAX_TOKENS;
     L.tbl_cap = e->tbl_cap;
+    L.replay = nullptr;
     P.M = mg_args(e);
     static const bool trace = getenv("BPE_TRACE") != nullptr;
     auto tw0 = std::chrono::steady_clock::now();
@@ -1523,6 +1526,43 @@ int bpe_apply_merge(bpe_engine* e, int32_t a, int32_t b, int32_t c, int64_t* n_r
   return BPE_OK;
 }
 
+
+// Batched restoreMerge (core.ts:477-494; example/import-merge-log-to-ram.ts:24-31 replays one line per call): applies
+// merges (a_i, b_i) -> n_tokens + i in order inside the persistent loop kernel, no arg-max, no host round trip per merge.
+int bpe_apply_merges(bpe_engine* e, const int32_t* ab, int64_t n, int64_t* n_replaced) {
+  if (!e || n < 0 || (n > 0 && !ab)) return fail(e, BPE_E_INVALID, "bad merge list");
+  if (n == 0) return BPE_OK;
+  CK(cudaSetDevice(e->device));
+  if (e->mg_world > 1) return fail(e, BPE_E_INVALID, "bpe_apply_merges is not available on a sharded engine");
+  if ((int64_t)e->n_tokens + n > BPE_MAX_TOKENS) return fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
+  for (int64_t i = 0; i < n; i++)
+    if (ab[2 * i] < 0 || ab[2 * i + 1] < 0 || ab[2 * i] >= e->n_tokens + i || ab[2 * i + 1] >= e->n_tokens + i)
+      return fail(e, BPE_E_INVALID, "merge %lld refers to a token that does not exist yet", (long long)i);
+  if (e->n_slots == 0) {  // no corpus: only the vocabulary / merge list grow (import-merge-log-to-ram.ts:22 empties the corpus first)
+    for (int64_t i = 0; i < n; i++) {
+      e->h_len16.push_back(e->h_len16[ab[2 * i]] + e->h_len16[ab[2 * i + 1]]);
+      e->h_merges.push_back(ab[2 * i]);
+      e->h_merges.push_back(ab[2 * i + 1]);
+      e->h_merges.push_back(e->n_tokens);
+      e->n_tokens++;
+      if (n_replaced) n_replaced[i] = 0;
+    }
+    e->mt_dirty = e->lt_dirty = true;
+    TRY(sync_len16(e));
+    return BPE_OK;
+  }
+  DevBuf<int32_t> d_ab;
+  CK(d_ab.reserve((size_t)2 * n));
+  CK(cudaMemcpyAsync(d_ab.p, ab, (size_t)2 * n * 4, cudaMemcpyHostToDevice, e->stream));
+  std::vector<bpe_merge> log((size_t)n);
+  int64_t done = 0;
+  TRY(merge_until_device(e, 1, 0, n, log.data(), n, &done, d_ab.p));
+  if (done != n) return fail(e, BPE_E_INTERNAL, "replayed %lld of %lld merges", (long long)done, (long long)n);
+  if (n_replaced)
+    for (int64_t i = 0; i < n; i++) n_replaced[i] = log[(size_t)i].weight;
+  return BPE_OK;
+}
+
 int bpe_merge_until(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations, bpe_merge* log,
                     int64_t log_cap, int64_t* n_done) {
   if (!e || !n_done || (log_cap > 0 && !log) || log_cap < 0) return BPE_E_INVALID;
@@ -1716,6 +1756,95 @@ int bpe_encode_batch(bpe_engine* e, const int32_t* ids, const int64_t* doc_offse
     e->x_ids.release();
     e->x_out.release();
   }
+  return BPE_OK;
+}
+
+
+// exclusive scan u32 -> u64 (n + 1 outputs) with the tiled kernels of encode_kernels.cuh
+int scan_u32(bpe_engine* e, EncodeScratch& sc, const uint32_t* in, uint64_t* out, uint32_t n) {
+  if (n <= 65536) {
+    k_scan_counts<<<1, 1024, 0, e->stream>>>(in, out, n);
+    CKL();
+    return BPE_OK;
+  }
+  uint32_t n_tiles = (n + SC_TILE - 1) / SC_TILE;
+  CK(sc.tile_sums.reserve(n_tiles));
+  CK(sc.tile_off.reserve((size_t)n_tiles + 1));
+  k_sum_tiles<<<n_tiles, SC_THREADS, 0, e->stream>>>(in, n, sc.tile_sums.p);
+  CKL();
+  k_scan_counts<<<1, 1024, 0, e->stream>>>(sc.tile_sums.p, sc.tile_off.p, n_tiles);
+  CKL();
+  k_scan_tiles<<<n_tiles, SC_THREADS, 0, e->stream>>>(in, n, sc.tile_off.p, n_tiles, out);
+  CKL();
+  return BPE_OK;
+}
+
+int bpe_decode_batch(bpe_engine* e, const int32_t* values, const int64_t* doc_offsets, int64_t n_docs, const int32_t* from_vector_index,
+                     int32_t n_fvi, const uint8_t* token_bytes, const int64_t* token_byte_offsets, int32_t n_tokens, uint8_t* out,
+                     int64_t out_cap, int64_t* out_offsets, int64_t* first_bad, int64_t* n_out) {
+  if (!e || !n_out || !out_offsets || n_tokens < 0 || (n_tokens > 0 && (!token_byte_offsets))) return fail(e, BPE_E_INVALID, "bad decode arguments");
+  TRY(check_offsets(e, doc_offsets, n_docs));
+  CK(cudaSetDevice(e->device));
+  int64_t base = n_docs ? doc_offsets[0] : 0, total = n_docs ? doc_offsets[n_docs] - base : 0;
+  if (total > 0 && !values) return fail(e, BPE_E_INVALID, "null values");
+  if ((uint64_t)total >= 0xFFFFFFF0ull) return fail(e, BPE_E_DOMAIN, "batch too large for one decode call");
+  const int64_t arena = n_tokens ? token_byte_offsets[n_tokens] : 0;
+  if (arena > 0 && !token_bytes) return fail(e, BPE_E_INVALID, "null token bytes");
+  e->h_rel.resize((size_t)n_docs + 1);
+  e->h_rel[0] = 0;
+  for (int64_t d = 0; d < n_docs; d++) e->h_rel[d + 1] = doc_offsets[d + 1] - base;
+  DevBuf<uint8_t> d_arena, d_out;
+  DevBuf<int64_t> d_tokoff;
+  DevBuf<uint32_t> d_lens;
+  DevBuf<uint64_t> d_boff;
+  DevBuf<unsigned long long> d_bad;
+  CK(e->x_ids.reserve((size_t)std::max<int64_t>(total, 1)));
+  CK(e->x_off.reserve((size_t)n_docs + 1));
+  CK(e->x_ooff.reserve((size_t)n_docs + 1));
+  CK(d_arena.reserve((size_t)std::max<int64_t>(arena, 1)));
+  CK(d_tokoff.reserve((size_t)n_tokens + 1));
+  CK(d_lens.reserve((size_t)std::max<int64_t>(total, 1)));
+  CK(d_boff.reserve((size_t)total + 1));
+  if (total) CK(cudaMemcpyAsync(e->x_ids.p, values + base, (size_t)total * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->x_off.p, e->h_rel.data(), (size_t)(n_docs + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  if (arena) CK(cudaMemcpyAsync(d_arena.p, token_bytes, (size_t)arena, cudaMemcpyHostToDevice, e->stream));
+  if (n_tokens) CK(cudaMemcpyAsync(d_tokoff.p, token_byte_offsets, (size_t)(n_tokens + 1) * 8, cudaMemcpyHostToDevice, e->stream));
+  else CK(cudaMemsetAsync(d_tokoff.p, 0, 8, e->stream));
+  if (from_vector_index && n_fvi > 0) {
+    CK(e->x_tvi.reserve((size_t)n_fvi));
+    CK(cudaMemcpyAsync(e->x_tvi.p, from_vector_index, (size_t)n_fvi * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  if (first_bad) {
+    CK(d_bad.reserve((size_t)std::max<int64_t>(n_docs, 1)));
+    CK(cudaMemsetAsync(d_bad.p, 0xFF, (size_t)std::max<int64_t>(n_docs, 1) * 8, e->stream));
+  }
+  const int32_t* fvi = from_vector_index ? e->x_tvi.p : nullptr;
+  int blocks = (int)std::min<int64_t>((total + 255) / 256 + 1, (int64_t)e->grid(8));
+  k_decode_lens<<<blocks, 256, 0, e->stream>>>(e->x_ids.p, (uint64_t)total, fvi, from_vector_index ? n_fvi : 0, d_tokoff.p, n_tokens, e->x_off.p, n_docs, d_lens.p,
+                                            first_bad ? d_bad.p : nullptr);
+  CKL();
+  TRY(scan_u32(e, e->x_scratch, d_lens.p, d_boff.p, (uint32_t)total));
+  uint64_t nbytes = 0;
+  CK(cudaMemcpyAsync(&nbytes, d_boff.p + total, 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  *n_out = (int64_t)nbytes;
+  k_decode_doc_offsets<<<(int)std::min<int64_t>((n_docs + 256) / 256, (int64_t)e->grid(8)), 256, 0, e->stream>>>(e->x_off.p, n_docs, d_boff.p, e->x_ooff.p);
+  CKL();
+  CK(cudaMemcpyAsync(out_offsets, e->x_ooff.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (first_bad && n_docs) {
+    CK(cudaMemcpyAsync(first_bad, d_bad.p, (size_t)n_docs * 8, cudaMemcpyDeviceToHost, e->stream));  // ~0 (== -1) = no offender
+  }
+  if ((int64_t)nbytes > out_cap || (nbytes && !out)) {
+    CK(cudaStreamSynchronize(e->stream));
+    return fail(e, BPE_E_CAPACITY, "output buffer holds %lld bytes, need %llu", (long long)out_cap, (unsigned long long)nbytes);
+  }
+  if (nbytes) {
+    CK(d_out.reserve((size_t)nbytes));
+    k_decode_gather<<<blocks, 256, 0, e->stream>>>(e->x_ids.p, (uint64_t)total, fvi, from_vector_index ? n_fvi : 0, d_arena.p, d_tokoff.p, n_tokens, d_boff.p, d_out.p);
+    CKL();
+    CK(cudaMemcpyAsync(out, d_out.p, (size_t)nbytes, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CK(cudaStreamSynchronize(e->stream));
   return BPE_OK;
 }
 

@@ -316,4 +316,52 @@ __global__ void k_first_bad_id(const int32_t* __restrict__ ids, uint64_t n, uint
   if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(first_bad, best);
 }
 
+// ---- decodeVector / decodeTokens (core.ts:447-471) on the device: vector index -> token -> its UTF-8 bytes ----
+// lens[i] = byte length of value i (0 for an unknown vector index); bad values are reported per document
+__global__ void k_decode_lens(const int32_t* __restrict__ values, uint64_t n, const int32_t* __restrict__ fvi, int32_t n_fvi,
+                              const int64_t* __restrict__ tok_off, int32_t n_tokens, const int64_t* __restrict__ doc_off, int64_t n_docs,
+                              uint32_t* __restrict__ lens, unsigned long long* __restrict__ first_bad) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int32_t v = __ldg(values + i);
+    int32_t tok = v;
+    if (fvi) tok = (v >= 0 && v < n_fvi) ? __ldg(fvi + v) : -1;  // `vector_index in from_vector_index` (core.ts:463)
+    uint32_t len = 0;
+    if (tok >= 0 && tok < n_tokens) {
+      len = (uint32_t)(tok_off[tok + 1] - tok_off[tok]);
+    } else if (first_bad) {  // first offender of its document (core.ts:466-468 throws there)
+      int64_t lo = 0, hi = n_docs;  // last d with doc_off[d] <= i (relative offsets, doc_off[0] == 0)
+      while (lo + 1 < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((uint64_t)doc_off[mid] <= i) lo = mid;
+        else hi = mid;
+      }
+      atomicMin(first_bad + lo, (unsigned long long)(i - (uint64_t)doc_off[lo]));
+    }
+    lens[i] = len;
+  }
+}
+
+__global__ void k_decode_gather(const int32_t* __restrict__ values, uint64_t n, const int32_t* __restrict__ fvi, int32_t n_fvi,
+                                const uint8_t* __restrict__ tok_bytes, const int64_t* __restrict__ tok_off, int32_t n_tokens,
+                                const uint64_t* __restrict__ byte_off, uint8_t* __restrict__ out) {
+  uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int32_t v = __ldg(values + i);
+    int32_t tok = v;
+    if (fvi) tok = (v >= 0 && v < n_fvi) ? __ldg(fvi + v) : -1;
+    if (tok < 0 || tok >= n_tokens) continue;
+    int64_t s = tok_off[tok], e = tok_off[tok + 1];
+    uint8_t* dst = out + byte_off[i];
+    for (int64_t k = s; k < e; k++) dst[k - s] = __ldg(tok_bytes + k);
+  }
+}
+
+// out_offsets[d] = byte offset of document d's first value (byte_off has n + 1 entries)
+__global__ void k_decode_doc_offsets(const int64_t* __restrict__ doc_off, int64_t n_docs, const uint64_t* __restrict__ byte_off,
+                                     int64_t* __restrict__ out_offsets) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d <= n_docs; d += stride) out_offsets[d] = (int64_t)byte_off[doc_off[d]];
+}
+
 }  // namespace bpe

@@ -1007,6 +1007,9 @@ struct LoopArgs {
   uint32_t min_weight;
   uint32_t max_tokens;
   uint32_t tbl_cap;
+  // replay mode (batched restoreMerge, core.ts:477-494): the winners are GIVEN -- (a,b) of merge i at replay[2i..2i+1]
+  // -- instead of found by the arg-max; the hot list is neither read nor fed
+  const int32_t* replay;
 };
 
 // Grid barrier for the co-resident (cooperative) launch.  The arrival counter lives in its own 128-byte line, away
@@ -1061,6 +1064,9 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
   const uint32_t n_tokens0 = ld_cg(&st->n_tokens);
   const uint32_t thresh = ld_cg(&st->hot_thresh);
 
+  const bool replay = L.replay != nullptr;
+  __shared__ uint32_t s_rslot;
+
   // first arg-max partials
   if (bid == 0 && threadIdx.x == 0) {
     st->snap_n_keys = st->n_keys;
@@ -1068,7 +1074,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
     st->snap_hot_n = st->hot_n;
     st->snap_err = st->err;
   }
-  {
+  if (!replay) {
     Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
     if (threadIdx.x == 0) L.partials[bid] = v;
   }
@@ -1086,24 +1092,40 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
     const uint32_t par = it & 1u;
     // ---- every block folds the partials and takes the same decision ----
     Best w{0ull, NOSLOT, 0};
-    for (uint32_t i = threadIdx.x; i < nblk; i += blockDim.x) {
-      Best pb;
-      pb.primary = ld_cg(&L.partials[i].primary);
-      pb.slot = ld_cg(&L.partials[i].slot);
-      pb.mult = ld_cg(&L.partials[i].mult);
-      w = best_merge(w, pb);
-    }
-    w = best_block_reduce(w, s_best);
     uint32_t status = LOOP_RUNNING;
     uint32_t wa = 0, wb = 0, wcnt = 0;
-    if (w.primary) {
-      uint32_t key = t.keys[w.slot];
-      wa = key >> 16;
-      wb = key & 0xFFFFu;
-      wcnt = (uint32_t)(w.primary >> 20);
-    }
     const uint32_t c = n_tokens0 + it;
+    if (replay) {
+      // the logged pair; it may not occur at all (a merge whose pair is absent still appends its token, core.ts:350-354)
+      if (it < L.log_cap) {
+        wa = (uint32_t)L.replay[2 * it];
+        wb = (uint32_t)L.replay[2 * it + 1];
+        __syncthreads();
+        if (threadIdx.x == 0) s_rslot = tbl_find(t, pair_key(wa, wb));
+        __syncthreads();
+        w.slot = s_rslot;
+        w.mult = 1;
+        w.primary = 1;
+        if (w.slot != NOSLOT) wcnt = max(t.cnt[w.slot], t.occ_len[w.slot]);  // bound on the sites (the list may hold stale entries)
+      }
+    } else {
+      for (uint32_t i = threadIdx.x; i < nblk; i += blockDim.x) {
+        Best pb;
+        pb.primary = ld_cg(&L.partials[i].primary);
+        pb.slot = ld_cg(&L.partials[i].slot);
+        pb.mult = ld_cg(&L.partials[i].mult);
+        w = best_merge(w, pb);
+      }
+      w = best_block_reduce(w, s_best);
+      if (w.primary) {
+        uint32_t key = t.keys[w.slot];
+        wa = key >> 16;
+        wb = key & 0xFFFFu;
+        wcnt = (uint32_t)(w.primary >> 20);
+      }
+    }
     if (ld_cg(&st->snap_err)) status = LOOP_ERROR;
+    else if (replay) status = (it >= L.log_cap) ? LOOP_LIMIT : (c >= L.max_tokens ? LOOP_NEED_HOST : LOOP_RUNNING);
     else if (!w.primary) status = (thresh <= 1) ? LOOP_EMPTY : LOOP_NEED_REBUILD;
     else if (wcnt < thresh) status = LOOP_NEED_REBUILD;
     else if (wcnt < L.min_weight) status = LOOP_DONE;  // core.ts:313
@@ -1137,7 +1159,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
       if ((unsigned long long)ld_cg(&st->snap_n_keys) + new_keys > (unsigned long long)(L.tbl_cap >> 1)) status = LOOP_NEED_HOST;
       else if ((unsigned long long)ld_cg(&st->snap_pool_cursor) + 2ull * wcnt > L.pool_cap) status = LOOP_NEED_HOST;
       else if (wcnt > A.sites_cap || new_keys > A.new_cap) status = LOOP_NEED_HOST;
-      else if ((unsigned long long)ld_cg(&st->snap_hot_n) + new_keys > min(L.hot_cap, L.hot_limit)) status = LOOP_NEED_REBUILD;
+      else if (!replay && (unsigned long long)ld_cg(&st->snap_hot_n) + new_keys > min(L.hot_cap, L.hot_limit)) status = LOOP_NEED_REBUILD;
       else if (c + 1 > L.len16_cap) status = LOOP_NEED_HOST;
     }
     if (status != LOOP_RUNNING) {
@@ -1145,7 +1167,13 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
         st->status = status;
         st->iters_done = it;
         st->n_tokens = n_tokens0 + it;
-        publish_best(t, st, w);
+        if (replay) {
+          st->best_primary = 0;
+          st->best_cnt = wcnt;  // what the host must make room for
+          st->best_mult = 1;
+        } else {
+          publish_best(t, st, w);
+        }
         st->n_cand = 0;
         st->tie_pos = ~0ull;
       }
@@ -1180,10 +1208,12 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
     if (bid == 0 && threadIdx.x == 0) {
       st->n_cand = 0;
       st->tie_pos = ~0ull;
-      t.cnt[w.slot] = 0;  // every counted occurrence of the winner is being replaced; must be visible before the
-                          // next arg-max partials are taken in P3 (no delta of P1 touches the winner's own pair)
+      if (w.slot != NOSLOT) t.cnt[w.slot] = 0;  // every counted occurrence of the winner is being replaced; must be visible
+                                                // before the next arg-max partials are taken in P3 (no delta of P1 touches
+                                                // the winner's own pair)
+      if (replay) L.log[it].weight = (long long)st->n_sites[par];  // replacements performed (bpe_apply_merge's n_replaced)
     }
-    phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, 1, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);
+    phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, replay ? 0 : 1, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);
 #ifdef BPE_FINE_PROF
     if (prof) st->bucket_ns[bkt][1] += now_ns() - tp0;
 #endif
@@ -1198,7 +1228,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
       st->snap_err = st->err;
     }
     phase_apply(A, wa, wb, c, ld_cg(&st->n_sites[par]), false, bid, nblk);
-    {
+    if (!replay) {
       Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
       if (threadIdx.x == 0) L.partials[bid] = v;
     }

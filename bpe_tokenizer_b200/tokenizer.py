@@ -405,6 +405,34 @@ class BPETokenizer:
         index = len(self.token_table)
         self.applyMerge((a, b, Token(a.chars + b.chars, c_weight, c_weight, chr(index + 1), index)))
 
+    def restoreMerges(self, compacts: Sequence) -> None:
+        """Replay a whole merge log -- lines ``[a_code, b_code, c_weight]`` as written by ``compactMerge``
+        (core.ts:500-503; example/scan-to-merge-log.ts:38-40) -- in ONE device call.  Equivalent to calling
+        ``restoreMerge`` per line (core.ts:477-494; example/import-merge-log-to-ram.ts:24-31), including its throws."""
+        self._flush()
+        base = len(self.token_table)
+        pending: List[Tuple[Token, Token, Token]] = []
+        code_to_new: Dict[str, Token] = {}
+        ab = np.empty((len(compacts), 2), dtype=np.int32)
+        for i, (a_code, b_code, c_weight) in enumerate(compacts):
+            a = self.code_to_token.get(a_code) or code_to_new.get(a_code)
+            if a is None:
+                raise ValueError("unknown token, a_code: " + _js_stringify(a_code))  # core.ts:481
+            b = self.code_to_token.get(b_code) or code_to_new.get(b_code)
+            if b is None:
+                raise ValueError("unknown token, b_code: " + _js_stringify(b_code))  # core.ts:483
+            index = base + i
+            c = Token(a.chars + b.chars, c_weight, c_weight, chr(index + 1), index)
+            code_to_new[c.code] = c
+            pending.append((a, b, c))
+            ab[i] = (a.index, b.index)
+        if not pending:
+            return
+        self._check(self._lib.bpe_apply_merges(self._h, p32(ab.reshape(-1)), len(pending), None))
+        for a, b, c in pending:
+            self._record_merge(a, b, c)
+        self._invalidateVectorIndex()
+
     # ---- encode / decode ------------------------------------------------------------------------
     def encodeBatch(self, ids: np.ndarray, doc_offsets: np.ndarray, vector: bool = True):
         """Encode many documents (single-character token indices) in one device call.
@@ -449,6 +477,37 @@ class BPETokenizer:
         if bad[0] >= 0:
             raise ValueError("unknown token index: %d" % (-int(out[bad[0]]) - 1))  # core.ts:440
         return out.tolist()
+
+    def decodeBatch(self, values: np.ndarray, doc_offsets: np.ndarray, vector: bool = True):
+        """decodeVector / decodeTokens (core.ts:447-471) for many documents in one device call.
+        -> (utf8 bytes, out_offsets int64[n_docs+1], first_bad int64[n_docs]); first_bad[d] >= 0 is the position of the
+        first value of document d the reference would throw `unknown vector index` on."""
+        self._flush()
+        values = np.ascontiguousarray(values, dtype=np.int32)
+        doc_offsets = np.ascontiguousarray(doc_offsets, dtype=np.int64)
+        n_docs = len(doc_offsets) - 1
+        fvi = None
+        if vector:
+            if self.from_vector_index is None:
+                self.compactVectorIndex()
+            n = (max(self.from_vector_index) + 1) if self.from_vector_index else 0
+            fvi = np.full(max(n, 1), -1, dtype=np.int32)
+            for k, v in self.from_vector_index.items():
+                fvi[k] = v
+        chunks = [t.chars.encode("utf-8", "surrogatepass") for t in self.token_table]
+        tok_off = np.zeros(len(chunks) + 1, dtype=np.int64)
+        np.cumsum([len(c) for c in chunks], out=tok_off[1:])
+        arena = np.frombuffer(b"".join(chunks) or b"\0", dtype=np.uint8)
+        total = int(doc_offsets[-1] - doc_offsets[0]) if n_docs else 0
+        longest = max((len(c) for c in chunks), default=0)
+        out = np.empty(max(total * longest, 1), dtype=np.uint8)
+        out_off = np.zeros(n_docs + 1, dtype=np.int64)
+        bad = np.full(max(n_docs, 1), -1, dtype=np.int64)
+        n = C.c_int64()
+        self._check(self._lib.bpe_decode_batch(self._h, p32(values), p64(doc_offsets), n_docs, p32(fvi) if fvi is not None else None,
+                                               len(fvi) if fvi is not None else 0, arena.ctypes.data_as(_abi.u8p), p64(tok_off), len(chunks),
+                                               out.ctypes.data_as(_abi.u8p), out.size, p64(out_off), p64(bad), C.byref(n)))
+        return out[: n.value].tobytes(), out_off, bad[:n_docs]
 
     def decodeTokens(self, tokens: Iterable[Token]) -> str:  # core.ts:447-453
         return "".join(t.chars for t in tokens)

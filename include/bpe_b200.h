@@ -134,6 +134,11 @@ int bpe_apply_merge(bpe_engine* e, int32_t a, int32_t b, int32_t c, int64_t* n_r
  * log[0..*n_done) receives the merges in order; stops early (BPE_OK) when log_cap is reached. */
 int bpe_merge_until(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations,
                     bpe_merge* log, int64_t log_cap, int64_t* n_done);
+/* Batched restoreMerge (core.ts:477-494): merge i rewrites (ab[2i], ab[2i+1]) -> token n_tokens + i, in order, inside
+ * the device-resident loop (the reference's resume script replays its merge log one call per line,
+ * example/import-merge-log-to-ram.ts:24-31).  A pair that does not occur still appends its token (core.ts:350-354).
+ * n_replaced (optional, [n]) receives the replacements each merge performed.  Weights stay with the host. */
+int bpe_apply_merges(bpe_engine* e, const int32_t* ab, int64_t n, int64_t* n_replaced);
 /* Debug / parity: dump the pair histogram (pairs with count > 0, unspecified order). */
 int bpe_pair_counts(bpe_engine* e, int32_t* a, int32_t* b, int64_t* count, int64_t cap, int64_t* n);
 
@@ -182,6 +187,19 @@ int bpe_encode_batch(bpe_engine* e, const int32_t* ids, const int64_t* doc_offse
 int bpe_encode_batch_dev(bpe_engine* e, const int32_t* dev_ids, const int64_t* dev_doc_offsets, int64_t n_docs,
                          int64_t n_ids, int64_t max_doc_len, const int32_t* dev_to_vector_index, int32_t n_tvi,
                          int32_t* dev_out, int64_t* dev_out_offsets, int64_t* dev_first_bad, int64_t* n_out);
+
+/* decodeVector / decodeTokens (core.ts:447-471) for a batch of documents.
+ *   values/doc_offsets          vector indices (from_vector_index != NULL) or raw token indices per document
+ *   from_vector_index           n_fvi entries, -1 = hole: `unknown vector index: ${v}` (core.ts:466-468)
+ *   token_bytes/token_byte_offsets  UTF-8 of every token's chars back to back, [n_tokens+1] offsets
+ *   out/out_cap                 decoded UTF-8 bytes, documents back to back (unknown values contribute nothing)
+ *   out_offsets                 [n_docs+1] byte offsets into out
+ *   first_bad                   optional [n_docs]: -1, or the position within the document of the first unknown value
+ *   n_out                       total bytes written (or required when BPE_E_CAPACITY) */
+int bpe_decode_batch(bpe_engine* e, const int32_t* values, const int64_t* doc_offsets, int64_t n_docs,
+                     const int32_t* from_vector_index, int32_t n_fvi, const uint8_t* token_bytes,
+                     const int64_t* token_byte_offsets, int32_t n_tokens, uint8_t* out, int64_t out_cap,
+                     int64_t* out_offsets, int64_t* first_bad, int64_t* n_out);
 
 /* ---- synthetic corpus (bench / tests; SURVEY.md section 8(d), spec in synth.py) ------------ */
 /* Fills `text` (may be NULL to size) with documents until target_bytes is reached. */

@@ -361,3 +361,89 @@ def test_encode_batch_lane_path_fuzz(seed, lmax, monkeypatch):
     old.fromJSON(gpu.toJSON())
     raw2, roff2, _ = old.encodeBatch(ids, off, vector=False)
     assert np.array_equal(raw, raw2) and np.array_equal(roff, roff2)
+
+
+def test_decode_batch_matches_host_decode():
+    """Device decodeVector (core.ts:455-471): bytes equal the concatenated token chars; the first unknown vector index
+    of a document is reported where the reference throws."""
+    rng = random.Random(31)
+    t, lit = make(), LiteralTokenizer()
+    docs = ["the cat sat on the mat\n" * 30, "café \U0001F600 naïve 中文 " * 20, "", "zzz", "ab" * 100]
+    for d in docs:
+        t.addToCorpus(d)
+        lit.addToCorpus(d)
+    t.mergeUntil({"max_iterations": 60})
+    lit.mergeUntil({"max_iterations": 60})
+    lit.compactVectorIndex()
+    vecs = []
+    for d in docs + ["the mat sat", "", "中文café"]:
+        try:
+            vecs.append(lit.encodeToVector(d))
+        except ValueError:
+            vecs.append([])
+    values = np.array([v for vec in vecs for v in vec], dtype=np.int32)
+    off = np.zeros(len(vecs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(v) for v in vecs])
+    raw, boff, bad = t.decodeBatch(values, off, vector=True)
+    assert (bad == -1).all()
+    for d, vec in enumerate(vecs):
+        assert raw[boff[d]:boff[d + 1]].decode("utf-8") == lit.decodeVector(vec)
+    # raw token indices (decodeTokens semantics)
+    idx = np.array([rng.randrange(len(t.token_table)) for _ in range(500)], dtype=np.int32)
+    raw2, boff2, _ = t.decodeBatch(idx, np.array([0, 200, 200, 500], dtype=np.int64), vector=False)
+    want = ["".join(t.token_table[i].chars for i in idx[a:b]) for a, b in ((0, 200), (200, 200), (200, 500))]
+    assert [raw2[boff2[d]:boff2[d + 1]].decode("utf-8") for d in range(3)] == want
+    # unknown vector indices: first offender per document
+    n_vec = len(lit.from_vector_index)
+    vals = np.array([0, 1, n_vec + 5, 2, -3, 1, 0], dtype=np.int32)
+    _, _, bad3 = t.decodeBatch(vals, np.array([0, 4, 4, 7], dtype=np.int64), vector=True)
+    assert bad3.tolist() == [2, -1, 0]
+    with pytest.raises(ValueError, match="unknown vector index: %d" % (n_vec + 5)):
+        lit.decodeVector(vals[:4].tolist())
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_batched_merge_log_replay_equals_line_by_line(seed):
+    """restoreMerges (one device call, replay mode of the loop kernel) == restoreMerge per line (core.ts:477-494) ==
+    the run that produced the log; pairs that no longer occur, unknown codes and an emptied corpus included."""
+    from bpe_tokenizer_b200 import compactMerge
+
+    rng = random.Random(500 + seed)
+    alphabet = "ab" if seed == 0 else "abcdef "
+    docs = _random_docs(rng, alphabet, rng.randint(2, 9), rng.choice([40, 300]))
+    first = make()
+    for d in docs:
+        first.addToCorpus(d)
+    first.mergeUntil({"max_length": rng.choice([None, 6])})
+    # compactMerge is taken when the merge is found (core.spec.ts:176-183): c.weight == c.original_weight at that moment
+    log = [[a.code, b.code, c.original_weight] for a, b, c in first.merge_tokens]
+    assert compactMerge((first.merge_tokens[0][0], first.merge_tokens[0][1], first.merge_tokens[0][2]))[:2] == log[0][:2]
+    one, batch, lit = make(), make(), LiteralTokenizer()
+    for d in docs:
+        one.addToCorpus(d)
+        batch.addToCorpus(d)
+        lit.addToCorpus(d)
+    for line in log:
+        one.restoreMerge(line)
+        lit.restoreMerge(line)
+    cut = len(log) // 2
+    batch.restoreMerges(log[:cut])  # two calls: the second continues on the rewritten corpus
+    batch.restoreMerges(log[cut:])
+    assert batch.toJSON() == one.toJSON() == lit.toJSON() == first.toJSON()
+    assert batch.corpus_in_code == one.corpus_in_code == lit.corpus_in_code == first.corpus_in_code
+    # the resumed tokenizer keeps merging like the uninterrupted one (the index is rebuilt after a replay)
+    more = docs[0] + docs[-1]
+    for x in (batch, first):
+        x.addToCorpus(more)
+        x.mergeUntil({"max_iterations": 5})
+    assert batch.toJSON() == first.toJSON()
+    # corpus emptied before the replay (example/import-merge-log-to-ram.ts:22): only tables grow
+    empty = make()
+    for d in docs:
+        empty.addToCorpus(d)
+    empty.corpus_in_code = []
+    empty.restoreMerges(log)
+    assert [t.chars for t in empty.token_table] == [t.chars for t in first.token_table][: len(empty.token_table)]
+    assert empty.encodeToCode(docs[0]) == lit.encodeToCode(docs[0])
+    with pytest.raises(ValueError, match="unknown token, a_code"):
+        batch.restoreMerges([["￿", "a", 3]])
