@@ -16,6 +16,7 @@
 #include "encode_lanes.cuh"
 #include "train_kernels.cuh"
 #include "mg_kernels.cuh"
+#include "text_kernels.cuh"
 
 using namespace bpe;
 
@@ -167,6 +168,14 @@ struct bpe_engine {
   DevBuf<uint32_t> mg_mark, mg_touched, mg_tie_sorted, mg_export_n;
   int mg_loop_blocks = 0;
   unsigned long long mg_epoch = 0, mg_tie_epoch = 0;
+
+  // text front end (text_kernels.cuh): code point -> single-character token index, -1 = unknown
+  DevBuf<int32_t> d_cpmap;
+  DevBuf<uint32_t> d_firstpos;
+  DevBuf<uint8_t> x_text;
+  DevBuf<uint32_t> x_tilecnt;
+  DevBuf<uint64_t> x_tileoff;
+  DevBuf<unsigned long long> x_counts;
 
   // staging of the host-buffer encode / restore calls (grow-only, reused across calls)
   DevBuf<int32_t> x_ids, x_out, x_tvi;
@@ -1779,6 +1788,63 @@ int scan_u32(bpe_engine* e, EncodeScratch& sc, const uint32_t* in, uint64_t* out
   return BPE_OK;
 }
 
+
+// ---- text front end: UTF-8 documents -> token indices on the device ----------------------------------------------
+int ensure_cpmap(bpe_engine* e) {
+  if (e->d_cpmap.p) return BPE_OK;
+  CK(e->d_cpmap.reserve(CP_LIMIT));
+  CK(e->d_firstpos.reserve(CP_LIMIT));
+  CK(cudaMemsetAsync(e->d_cpmap.p, 0xFF, (size_t)CP_LIMIT * 4, e->stream));
+  CK(cudaMemsetAsync(e->d_firstpos.p, 0xFF, (size_t)CP_LIMIT * 4, e->stream));
+  return BPE_OK;
+}
+
+// decodes into e->x_ids (placeholders -(cp+1) for unknown code points), document boundaries in code points into
+// e->x_off (device) and e->h_rel (host).  track_new: keep first positions of unknown code points (addToCorpus);
+// otherwise *unknown receives (pos << 32 | cp) of the first unknown code point or ~0.
+int text_to_ids(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_offsets, int64_t n_docs, bool track_new, int64_t* n_chars,
+                unsigned long long* unknown) {
+  TRY(check_offsets(e, doc_byte_offsets, n_docs));
+  TRY(ensure_cpmap(e));
+  int64_t base = n_docs ? doc_byte_offsets[0] : 0, nbytes = n_docs ? doc_byte_offsets[n_docs] - base : 0;
+  if (nbytes > 0 && !utf8) return fail(e, BPE_E_INVALID, "null text");
+  if ((uint64_t)nbytes >= 0xFFFFFFF0ull) return fail(e, BPE_E_DOMAIN, "text batch too large for one call");
+  std::vector<int64_t> rel((size_t)n_docs + 1, 0);
+  for (int64_t d = 0; d < n_docs; d++) rel[d + 1] = doc_byte_offsets[d + 1] - base;
+  uint32_t n_tiles = (uint32_t)((nbytes + TX_TILE - 1) / TX_TILE);
+  CK(e->x_text.reserve((size_t)std::max<int64_t>(nbytes, 1)));
+  CK(e->x_tilecnt.reserve((size_t)n_tiles + 1));
+  CK(e->x_tileoff.reserve((size_t)n_tiles + 2));
+  CK(e->x_ids.reserve((size_t)std::max<int64_t>(nbytes, 1)));  // at most one code point per byte
+  CK(e->x_off.reserve((size_t)n_docs + 1));
+  CK(e->x_ooff.reserve((size_t)n_docs + 1));
+  CK(e->x_flag.reserve(1));
+  if (nbytes) CK(cudaMemcpyAsync(e->x_text.p, utf8 + base, (size_t)nbytes, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->x_ooff.p, rel.data(), (size_t)(n_docs + 1) * 8, cudaMemcpyHostToDevice, e->stream));  // byte offsets
+  CK(cudaMemsetAsync(e->x_flag.p, 0xFF, 8, e->stream));
+  if (n_tiles) {
+    k_utf8_count<<<n_tiles, TX_THREADS, 0, e->stream>>>(e->x_text.p, (uint64_t)nbytes, e->x_tilecnt.p);
+    CKL();
+  }
+  TRY(scan_u32(e, e->x_scratch, e->x_tilecnt.p, e->x_tileoff.p, n_tiles));
+  if (n_tiles) {
+    k_utf8_decode<<<n_tiles, TX_THREADS, 0, e->stream>>>(e->x_text.p, (uint64_t)nbytes, e->x_tileoff.p, e->d_cpmap.p, e->x_ids.p,
+                                                         track_new ? e->d_firstpos.p : nullptr, track_new ? nullptr : e->x_flag.p);
+    CKL();
+  }
+  k_utf8_doc_offsets<<<(int)std::min<int64_t>((n_docs + 1 + 7) / 8, (int64_t)e->grid(8)), 256, 0, e->stream>>>(e->x_text.p, e->x_tileoff.p, e->x_ooff.p, n_docs + 1,
+                                                                                                      e->x_off.p);
+  CKL();
+  e->h_rel.resize((size_t)n_docs + 1);
+  CK(cudaMemcpyAsync(e->h_rel.data(), e->x_off.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+  unsigned long long unk = ~0ull;
+  CK(cudaMemcpyAsync(&unk, e->x_flag.p, 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  *n_chars = n_docs ? e->h_rel[(size_t)n_docs] : 0;
+  if (unknown) *unknown = unk;
+  return BPE_OK;
+}
+
 int bpe_decode_batch(bpe_engine* e, const int32_t* values, const int64_t* doc_offsets, int64_t n_docs, const int32_t* from_vector_index,
                      int32_t n_fvi, const uint8_t* token_bytes, const int64_t* token_byte_offsets, int32_t n_tokens, uint8_t* out,
                      int64_t out_cap, int64_t* out_offsets, int64_t* first_bad, int64_t* n_out) {
@@ -1844,6 +1910,126 @@ int bpe_decode_batch(bpe_engine* e, const int32_t* values, const int64_t* doc_of
     CKL();
     CK(cudaMemcpyAsync(out, d_out.p, (size_t)nbytes, cudaMemcpyDeviceToHost, e->stream));
   }
+  CK(cudaStreamSynchronize(e->stream));
+  return BPE_OK;
+}
+
+
+// ---- text in, tokens out ---------------------------------------------------------------------------------------------
+int bpe_set_chars(bpe_engine* e, const int32_t* code_points, const int32_t* indices, int32_t n) {
+  if (!e || n < 0 || (n > 0 && (!code_points || !indices))) return fail(e, BPE_E_INVALID, "bad character table");
+  CK(cudaSetDevice(e->device));
+  TRY(ensure_cpmap(e));
+  CK(cudaMemsetAsync(e->d_cpmap.p, 0xFF, (size_t)CP_LIMIT * 4, e->stream));
+  if (n) {
+    DevBuf<int32_t> a, b;
+    CK(a.reserve((size_t)n));
+    CK(b.reserve((size_t)n));
+    CK(cudaMemcpyAsync(a.p, code_points, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(b.p, indices, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    k_set_cpmap<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_cpmap.p, a.p, b.p, (uint32_t)n);
+    CKL();
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  return BPE_OK;
+}
+
+int bpe_add_text(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_offsets, int64_t n_docs, int32_t* new_code_points, int32_t new_cap,
+                 int32_t* n_new, int64_t* counts, int64_t counts_cap) {
+  if (!e || !n_new) return fail(e, BPE_E_INVALID, "bad arguments");
+  *n_new = 0;
+  CK(cudaSetDevice(e->device));
+  int64_t n_chars = 0;
+  TRY(text_to_ids(e, utf8, doc_byte_offsets, n_docs, true, &n_chars, nullptr));
+  // unknown code points become tokens in first-appearance order (core.ts:186-199)
+  DevBuf<uint32_t> d_cp, d_pos, d_n;
+  const uint32_t cap = 1u << 16;
+  CK(d_cp.reserve(cap));
+  CK(d_pos.reserve(cap));
+  CK(d_n.reserve(1));
+  CK(cudaMemsetAsync(d_n.p, 0, 4, e->stream));
+  k_collect_new_cps<<<e->grid(4), 256, 0, e->stream>>>(e->d_firstpos.p, d_cp.p, d_pos.p, cap, d_n.p);
+  CKL();
+  uint32_t nn = 0;
+  CK(cudaMemcpyAsync(&nn, d_n.p, 4, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (nn > cap || (int64_t)e->n_tokens + nn > BPE_MAX_TOKENS) return fail(e, BPE_E_DOMAIN, "token table would exceed %d", BPE_MAX_TOKENS);
+  if ((int32_t)nn > new_cap) {
+    *n_new = (int32_t)nn;
+    return fail(e, BPE_E_CAPACITY, "%u new characters, room for %d", nn, new_cap);
+  }
+  std::vector<uint32_t> cps(nn), pos(nn);
+  if (nn) {
+    CK(cudaMemcpy(cps.data(), d_cp.p, (size_t)nn * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pos.data(), d_pos.p, (size_t)nn * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> order(nn);
+    for (uint32_t i = 0; i < nn; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return pos[a] < pos[b]; });
+    std::vector<int32_t> h_cp(nn), h_idx(nn);
+    for (uint32_t k = 0; k < nn; k++) {
+      h_cp[k] = (int32_t)cps[order[k]];
+      h_idx[k] = e->n_tokens + (int32_t)k;
+      new_code_points[k] = h_cp[k];
+      e->h_len16.push_back(h_cp[k] >= 0x10000 ? 2 : 1);  // `chars.length` in UTF-16 units (core.ts:272)
+    }
+    e->n_tokens += (int32_t)nn;
+    e->mt_dirty = e->lt_dirty = true;
+    TRY(sync_len16(e));
+    DevBuf<int32_t> a, b;
+    CK(a.reserve(nn));
+    CK(b.reserve(nn));
+    CK(cudaMemcpyAsync(a.p, h_cp.data(), (size_t)nn * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(b.p, h_idx.data(), (size_t)nn * 4, cudaMemcpyHostToDevice, e->stream));
+    k_set_cpmap<<<(nn + 255) / 256, 256, 0, e->stream>>>(e->d_cpmap.p, a.p, b.p, nn);
+    CKL();
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  *n_new = (int32_t)nn;
+  if (counts_cap < e->n_tokens && counts) return fail(e, BPE_E_CAPACITY, "counts holds %lld entries, need %d", (long long)counts_cap, e->n_tokens);
+  CK(e->x_counts.reserve((size_t)std::max(e->n_tokens, 1)));
+  CK(cudaMemsetAsync(e->x_counts.p, 0, (size_t)std::max(e->n_tokens, 1) * 8, e->stream));
+  if (n_chars) {
+    k_fix_and_count<<<e->grid(8), 256, 0, e->stream>>>(e->x_ids.p, (uint64_t)n_chars, e->d_cpmap.p, e->x_counts.p, (uint32_t)e->n_tokens);
+    CKL();
+  }
+  if (counts) CK(cudaMemcpyAsync(counts, e->x_counts.p, (size_t)e->n_tokens * 8, cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return append_docs_dev(e, e->x_ids.p, e->h_rel.data(), n_docs);
+}
+
+int bpe_encode_text_batch(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_offsets, int64_t n_docs, const int32_t* to_vector_index,
+                          int32_t n_tvi, int32_t* out, int64_t out_cap, int64_t* out_offsets, int64_t* first_bad, int64_t* n_out,
+                          int64_t* unknown_pos, int32_t* unknown_code_point) {
+  if (!e || !n_out || !out_offsets) return fail(e, BPE_E_INVALID, "bad encode arguments");
+  CK(cudaSetDevice(e->device));
+  if (unknown_pos) *unknown_pos = -1;
+  int64_t n_chars = 0;
+  unsigned long long unk = ~0ull;
+  TRY(text_to_ids(e, utf8, doc_byte_offsets, n_docs, false, &n_chars, &unk));
+  if (unk != ~0ull) {  // encodeToCode throws at the first unknown character (core.ts:398-400)
+    if (unknown_pos) *unknown_pos = (int64_t)(unk >> 32);
+    if (unknown_code_point) *unknown_code_point = (int32_t)(unk & 0xFFFFFFFFu);
+    return fail(e, BPE_E_INVALID, "unknown token, char: U+%04X at code point %lld", (unsigned)(unk & 0xFFFFFFFFu), (long long)(unk >> 32));
+  }
+  int64_t max_len = 0;
+  for (int64_t d = 0; d < n_docs; d++) max_len = std::max(max_len, e->h_rel[(size_t)d + 1] - e->h_rel[(size_t)d]);
+  CK(e->x_out.reserve((size_t)std::max<int64_t>(n_chars, 1)));
+  DevBuf<int64_t> d_ooff;
+  CK(d_ooff.reserve((size_t)n_docs + 1));
+  if (first_bad) CK(e->x_bad.reserve((size_t)std::max<int64_t>(n_docs, 1)));
+  if (to_vector_index && n_tvi > 0) {
+    CK(e->x_tvi.reserve((size_t)n_tvi));
+    CK(cudaMemcpyAsync(e->x_tvi.p, to_vector_index, (size_t)n_tvi * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  TRY(encode_dev(e, e->x_scratch, e->x_ids.p, e->x_off.p, n_docs, n_chars, max_len, to_vector_index ? e->x_tvi.p : nullptr, n_tvi, e->x_out.p, d_ooff.p,
+                 first_bad ? e->x_bad.p : nullptr, n_out));
+  CK(cudaMemcpyAsync(out_offsets, d_ooff.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (first_bad && n_docs) CK(cudaMemcpyAsync(first_bad, e->x_bad.p, (size_t)n_docs * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (*n_out > out_cap || (*n_out && !out)) {
+    CK(cudaStreamSynchronize(e->stream));
+    return fail(e, BPE_E_CAPACITY, "output buffer holds %lld values, need %lld", (long long)out_cap, (long long)*n_out);
+  }
+  if (*n_out) CK(cudaMemcpyAsync(out, e->x_out.p, (size_t)*n_out * 4, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return BPE_OK;
 }

@@ -134,6 +134,7 @@ class BPETokenizer:
         self.from_vector_index: Optional[Dict[int, int]] = None  # core.ts:103
         self._pending: List[np.ndarray] = []  # documents added on the host, not yet uploaded
         self._tvi_dev: Optional[np.ndarray] = None
+        self._chars_synced = -1  # entries of char_to_token the engine's character table holds (-1: never pushed)
 
     def __del__(self):
         try:
@@ -265,6 +266,70 @@ class BPETokenizer:
             t.weight += int(counts[i])
             t.original_weight += int(counts[i])
         self._check(self._lib.bpe_add_documents(self._h, p32(ids), p64(doc_offsets), len(doc_offsets) - 1))
+
+    # ---- text front end on the device (csrc/text_kernels.cuh) -----------------------------------------
+    def _sync_chars(self) -> None:
+        if self._chars_synced == len(self.char_to_token):
+            return
+        # only one-code-point keys can match a character of a text; after `addToCorpus` following merges, fromJSON files
+        # multi-character tokens under char_to_token (core.ts:157-159 takes the first char_count entries) -- they are inert
+        items = [(ord(ch), t.index) for ch, t in self.char_to_token.items() if len(ch) == 1]
+        cps = np.array([c for c, _ in items], dtype=np.int32)
+        idx = np.array([i for _, i in items], dtype=np.int32)
+        self._check(self._lib.bpe_set_chars(self._h, p32(cps), p32(idx), len(cps)))
+        self._chars_synced = len(self.char_to_token)
+
+    def addTextBatch(self, utf8: bytes, doc_byte_offsets: np.ndarray) -> None:
+        """addToCorpus (core.ts:182-207) for many documents given as UTF-8 bytes, with the code-point loop, the
+        first-appearance token creation and the weight counts done on the device.  Equivalent to calling
+        ``addToCorpus(doc)`` for every document in order."""
+        self._flush()
+        self._sync_chars()
+        doc_byte_offsets = np.ascontiguousarray(doc_byte_offsets, dtype=np.int64)
+        buf = np.frombuffer(utf8 or b"\0", dtype=np.uint8)
+        new_cps = np.empty(1 << 16, dtype=np.int32)
+        counts = np.zeros(len(self.token_table) + (1 << 16), dtype=np.int64)
+        n_new = C.c_int32()
+        self._check(self._lib.bpe_add_text(self._h, buf.ctypes.data_as(_abi.u8p), p64(doc_byte_offsets), len(doc_byte_offsets) - 1,
+                                           p32(new_cps), new_cps.size, C.byref(n_new), p64(counts), counts.size))
+        for cp in new_cps[: n_new.value].tolist():  # the same tokens the engine just appended (core.ts:188-199)
+            index = len(self.token_table)
+            token = Token(chr(cp), 0, 0, chr(index + 1), index)
+            self.char_to_token[token.chars] = token
+            self.code_to_token[token.code] = token
+            self.token_table.append(token)
+        self._chars_synced = len(self.char_to_token)
+        for i in np.nonzero(counts[: len(self.token_table)])[0]:
+            t = self.token_table[i]
+            t.weight += int(counts[i])
+            t.original_weight += int(counts[i])
+        if n_new.value:
+            self._invalidateVectorIndex()
+
+    def encodeTextBatch(self, utf8: bytes, doc_byte_offsets: np.ndarray, vector: bool = True):
+        """encodeBatch with the char -> index step on the device: -> (values, out_offsets, first_bad)."""
+        self._flush()
+        self._sync_chars()
+        doc_byte_offsets = np.ascontiguousarray(doc_byte_offsets, dtype=np.int64)
+        n_docs = len(doc_byte_offsets) - 1
+        buf = np.frombuffer(utf8 or b"\0", dtype=np.uint8)
+        total = int(doc_byte_offsets[-1] - doc_byte_offsets[0]) if n_docs else 0
+        out = np.empty(max(total, 1), dtype=np.int32)
+        out_off = np.zeros(n_docs + 1, dtype=np.int64)
+        bad = np.full(max(n_docs, 1), -1, dtype=np.int64)
+        n, upos, ucp = C.c_int64(), C.c_int64(-1), C.c_int32()
+        tvi = None
+        if vector:
+            if self.to_vector_index is None:
+                self.compactVectorIndex()
+            tvi = self._tvi_array()
+        rc = self._lib.bpe_encode_text_batch(self._h, buf.ctypes.data_as(_abi.u8p), p64(doc_byte_offsets), n_docs,
+                                             p32(tvi) if tvi is not None else None, len(tvi) if tvi is not None else 0, p32(out), out.size,
+                                             p64(out_off), p64(bad), C.byref(n), C.byref(upos), C.byref(ucp))
+        if rc == _abi.BPE_E_INVALID and upos.value >= 0:
+            raise ValueError("unknown token, char: " + _js_stringify(chr(ucp.value)))  # core.ts:399
+        self._check(rc)
+        return out[: n.value], out_off, bad[:n_docs]
 
     def restoreToCorpus(self, content: str) -> None:  # core.ts:213-216
         ids = self._char_ids(content, create=False)

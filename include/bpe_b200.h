@@ -201,6 +201,25 @@ int bpe_decode_batch(bpe_engine* e, const int32_t* values, const int64_t* doc_of
                      const int64_t* token_byte_offsets, int32_t n_tokens, uint8_t* out, int64_t out_cap,
                      int64_t* out_offsets, int64_t* first_bad, int64_t* n_out);
 
+/* ---- text front end on the device (core.ts:185-205 ingest, :396-402 encode front end) --------------
+ * Documents arrive as UTF-8 bytes (lone surrogates in their generalised 3-byte form); one token per CODE POINT, as
+ * the reference's `for (let char of content)` yields them.  The engine keeps a code point -> token index table. */
+/* Replaces the engine's character table (after fromJSON, or when the host created character tokens itself). */
+int bpe_set_chars(bpe_engine* e, const int32_t* code_points, const int32_t* indices, int32_t n);
+/* addToCorpus for a batch of documents given as text: unknown code points become tokens n_tokens, n_tokens+1, ...
+ * in first-appearance order (core.ts:186-199); new_code_points[0..*n_new) lists them so the host can append the
+ * same tokens.  counts[i] (optional, counts_cap >= the new token count) = occurrences of token i in this batch
+ * (the `weight++ / original_weight++` of core.ts:201-202). */
+int bpe_add_text(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_offsets, int64_t n_docs,
+                 int32_t* new_code_points, int32_t new_cap, int32_t* n_new, int64_t* counts, int64_t counts_cap);
+/* bpe_encode_batch with the char -> index step on the device.  An unknown character fails the call with
+ * BPE_E_INVALID (the reference throws `unknown token, char: ...`, core.ts:398-400); *unknown_pos / *unknown_code_point
+ * (optional) identify the first one (code-point index within the batch). */
+int bpe_encode_text_batch(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_offsets, int64_t n_docs,
+                          const int32_t* to_vector_index, int32_t n_tvi, int32_t* out, int64_t out_cap,
+                          int64_t* out_offsets, int64_t* first_bad, int64_t* n_out, int64_t* unknown_pos,
+                          int32_t* unknown_code_point);
+
 /* ---- synthetic corpus (bench / tests; SURVEY.md section 8(d), spec in synth.py) ------------ */
 /* Fills `text` (may be NULL to size) with documents until target_bytes is reached. */
 int bpe_synth_corpus(int64_t target_bytes, uint64_t seed, int32_t vocab, uint64_t word_seed, uint8_t* text,

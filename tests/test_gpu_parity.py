@@ -447,3 +447,67 @@ def test_batched_merge_log_replay_equals_line_by_line(seed):
     assert empty.encodeToCode(docs[0]) == lit.encodeToCode(docs[0])
     with pytest.raises(ValueError, match="unknown token, a_code"):
         batch.restoreMerges([["￿", "a", 3]])
+
+
+def _utf8_batch(docs):
+    chunks = [d.encode("utf-8", "surrogatepass") for d in docs]
+    off = np.zeros(len(chunks) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(c) for c in chunks])
+    return b"".join(chunks), off
+
+
+def test_device_text_front_end_equals_add_to_corpus():
+    """addTextBatch / encodeTextBatch (UTF-8 decode, first-appearance token creation and weights on the device,
+    csrc/text_kernels.cuh) against addToCorpus / encodeToVector (core.ts:182-207, :392-445): 1- to 4-byte characters,
+    empty documents, characters first seen late, a second batch that adds more characters after merges."""
+    rng = random.Random(77)
+    pool = "abc déf ÿ中文字 \U0001F600\U0001F389\n\r\t" + "".join(chr(c) for c in (0x7F, 0x80, 0x7FF, 0x800, 0xFFFF, 0x10000, 0x10FFFF))
+    docs = ["".join(rng.choice(pool) for _ in range(rng.randint(0, 300))) for _ in range(60)] + ["", "a" * 5000, "ÿ" * 4100]
+    dev, host, lit = make(), make(), LiteralTokenizer()
+    text, off = _utf8_batch(docs)
+    dev.addTextBatch(text, off)
+    for d in docs:
+        host.addToCorpus(d)
+        lit.addToCorpus(d)
+    assert rows(dev) == rows(host) == rows(lit)
+    assert dev.corpus_in_code == host.corpus_in_code == lit.corpus_in_code
+    for x in (dev, host, lit):
+        x.mergeUntil({"max_iterations": 40})
+    assert dev.toJSON() == host.toJSON() == lit.toJSON()
+    # second batch after merges: new characters get indices after the merged tokens (core.ts:188-199, :204)
+    more = ["xyz" + d for d in docs[:10]] + ["§§§ new § chars ¶"]
+    text2, off2 = _utf8_batch(more)
+    dev.addTextBatch(text2, off2)
+    for d in more:
+        host.addToCorpus(d)
+        lit.addToCorpus(d)
+    assert rows(dev) == rows(host) == rows(lit)
+    for x in (dev, host, lit):
+        x.mergeUntil({"max_iterations": 20})
+    assert dev.toJSON() == lit.toJSON()
+    assert dev.corpus_in_code == lit.corpus_in_code
+    # encode from text
+    probe = [d for d in docs[:20]] + ["abc", ""]
+    ptext, poff = _utf8_batch(probe)
+    raw, roff, _ = dev.encodeTextBatch(ptext, poff, vector=False)
+    for d, textd in enumerate(probe):
+        assert raw[roff[d]:roff[d + 1]].tolist() == [ord(ch) - 1 for ch in lit.encodeToCode(textd)], d
+    vals, voff, bad = dev.encodeTextBatch(ptext, poff, vector=True)
+    lit.compactVectorIndex()
+    for d, textd in enumerate(probe):
+        try:
+            want = lit.encodeToVector(textd)
+        except ValueError:
+            assert bad[d] >= 0
+            continue
+        assert bad[d] == -1 and vals[voff[d]:voff[d + 1]].tolist() == want
+    with pytest.raises(ValueError) as ei:
+        dev.encodeTextBatch(*_utf8_batch(["abc", "ab☃c"]))
+    with pytest.raises(ValueError) as ej:
+        lit.encodeToVector("ab☃c")
+    assert str(ei.value) == str(ej.value)
+    # a snapshot restored into a fresh engine knows the characters again
+    back = make()
+    back.fromJSON(dev.toJSON())
+    raw2, roff2, _ = back.encodeTextBatch(ptext, poff, vector=False)
+    assert np.array_equal(raw, raw2) and np.array_equal(roff, roff2)
