@@ -163,6 +163,7 @@ def run_b200(args):
     c2_total = int(text2.size)
     b2 = shard_bounds(np.diff(off2), world)
     lo2, hi2 = b2[rank], b2[rank + 1]
+    text2_host = torch.from_numpy(np.ascontiguousarray(text2[off2[lo2]:off2[hi2]])).pin_memory()  # the raw UTF-8 bytes (ASCII here)
     ids2_host = torch.from_numpy(lut[text2[off2[lo2]:off2[hi2]]]).pin_memory()
     off2 = np.ascontiguousarray(off2[lo2:hi2 + 1] - off2[lo2])
     del text2
@@ -293,6 +294,18 @@ def run_b200(args):
     enc_kernel_ms = stats().ms_encode
     encode_step_host()
     ms_enc_e2e = timed(encode_step_host, e2e_steps)
+
+    # text in (UTF-8 bytes, 1 B/char over PCIe), vectors out: char -> index on the device (csrc/text_kernels.cuh)
+    cps = np.array(alphabet, dtype=np.int32)
+    check(lib.bpe_set_chars(h, p32(cps), p32(np.arange(len(alphabet), dtype=np.int32)), len(alphabet)))
+
+    def encode_step_text():
+        check(lib.bpe_encode_text_batch(h, C.cast(text2_host.data_ptr(), _abi.u8p), p64(off2), n_docs2, p32(tvi), len(tvi),
+                                        C.cast(out_host.data_ptr(), _abi.i32p), out_host.numel(), p64(ooff_host), None, C.byref(n_out), None, None))
+
+    encode_step_text()
+    assert n_out.value == k_out, "text front end disagrees with the id path"
+    ms_enc_text = timed(encode_step_text, e2e_steps)
     clocks = sampler.stop()
 
     # ---- aggregate over ranks -----------------------------------------------------------------------------
@@ -313,6 +326,8 @@ def run_b200(args):
     achieved = scan_bytes / step_s / 1e9 / world  # per GPU
     enc_gbs = allsum(c2 * args.steps) / (ms_enc / 1e3) / 1e9
     enc_e2e_gbs = allsum(c2 * e2e_steps) / (ms_enc_e2e / 1e3) / 1e9
+    enc_text_gbs = allsum(c2 * e2e_steps) / (ms_enc_text / 1e3) / 1e9
+    enc_text_h2d = int(allsum(c2 + off2.nbytes + tvi.nbytes))
     enc_alg_bytes = 4 * c2 + 4 * k_out  # this rank's shard, against this rank's kernel time
     enc_achieved = enc_alg_bytes / (enc_kernel_ms / 1e3) / 1e9
     h2d_total = int(allsum(n0 * 4 + off_host.nbytes))
@@ -361,6 +376,8 @@ def run_b200(args):
                 "metric": "encodeToVector GB/s of input text", "value": enc_gbs, "unit": "GB/s", "ms_per_step": ms_enc / args.steps,
                 "chars": c2_total, "tokens_out": k_out_total, "docs": n_docs2_total, "gpu_launches": int(le1 - le0),
                 "e2e": {"value": enc_e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": enc_h2d_total, "d2h_bytes_per_step": enc_d2h_total},
+                "e2e_text": {"value": enc_text_gbs, "unit": "GB/s", "h2d_bytes_per_step": enc_text_h2d, "d2h_bytes_per_step": enc_d2h_total,
+                             "note": "bpe_encode_text_batch: UTF-8 bytes in (1 B/char), char->index on the device, vectors out"},
                 "roofline": {"bound": "hbm", "achieved": enc_achieved, "peak": peak, "unit": "GB/s", "frac": enc_achieved / peak, "traffic": None,
                              "kernel": "k_range_starts + k_encode_lanes + scan + k_gather_map (ms_encode of the engine, rank 0 shard)", "alg_bytes": enc_alg_bytes},
             },

@@ -176,6 +176,8 @@ struct bpe_engine {
   DevBuf<uint32_t> x_tilecnt;
   DevBuf<uint64_t> x_tileoff;
   DevBuf<unsigned long long> x_counts;
+  DevBuf<uint32_t> x_doccnt;
+  DevBuf<uint64_t> x_docoff;
 
   // staging of the host-buffer encode / restore calls (grow-only, reused across calls)
   DevBuf<int32_t> x_ids, x_out, x_tvi;
@@ -1832,9 +1834,17 @@ int text_to_ids(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_offs
                                                          track_new ? e->d_firstpos.p : nullptr, track_new ? nullptr : e->x_flag.p);
     CKL();
   }
-  k_utf8_doc_offsets<<<(int)std::min<int64_t>((n_docs + 1 + 7) / 8, (int64_t)e->grid(8)), 256, 0, e->stream>>>(e->x_text.p, e->x_tileoff.p, e->x_ooff.p, n_docs + 1,
-                                                                                                      e->x_off.p);
-  CKL();
+  {  // document boundaries in code points: per-document counts, then a scan
+    CK(e->x_doccnt.reserve((size_t)n_docs + 1));
+    CK(e->x_docoff.reserve((size_t)n_docs + 2));
+    if (n_docs) {
+      k_utf8_doc_counts<<<(int)std::min<int64_t>((n_docs + 7) / 8, (int64_t)e->grid(16)), 256, 0, e->stream>>>(e->x_text.p, e->x_ooff.p, n_docs, e->x_doccnt.p);
+      CKL();
+    }
+    TRY(scan_u32(e, e->x_scratch, e->x_doccnt.p, e->x_docoff.p, (uint32_t)n_docs));
+    k_u64_to_i64<<<(int)std::min<int64_t>((n_docs + 256) / 256, (int64_t)e->grid(8)), 256, 0, e->stream>>>(e->x_docoff.p, e->x_off.p, n_docs + 1);
+    CKL();
+  }
   e->h_rel.resize((size_t)n_docs + 1);
   CK(cudaMemcpyAsync(e->h_rel.data(), e->x_off.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
   unsigned long long unk = ~0ull;

@@ -84,22 +84,26 @@ __global__ void __launch_bounds__(TX_THREADS) k_utf8_decode(const uint8_t* __res
   }
 }
 
-// code-point index of every document boundary: lead bytes before byte offset doc_byte_off[d]
-__global__ void k_utf8_doc_offsets(const uint8_t* __restrict__ text, const uint64_t* __restrict__ tile_off, const int64_t* __restrict__ doc_byte_off,
-                                   int64_t n_bounds, int64_t* __restrict__ doc_char_off) {
+// code points per document: lead bytes inside the document's byte range (one warp per document; total work = n bytes)
+__global__ void k_utf8_doc_counts(const uint8_t* __restrict__ text, const int64_t* __restrict__ doc_byte_off, int64_t n_docs,
+                                  uint32_t* __restrict__ doc_chars) {
   int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint32_t lane = threadIdx.x & 31;
   int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t d = wid; d < n_bounds; d += nw) {
-    uint64_t pos = (uint64_t)doc_byte_off[d];
-    uint64_t tile = pos / TX_TILE;
+  for (int64_t d = wid; d < n_docs; d += nw) {
+    uint64_t b0 = (uint64_t)doc_byte_off[d], b1 = (uint64_t)doc_byte_off[d + 1];
     uint32_t c = 0;
-    for (uint64_t p = tile * TX_TILE + lane; p < pos; p += 32)
+    for (uint64_t p = b0 + lane; p < b1; p += 32)
       if (utf8_is_lead(__ldg(text + p))) c++;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-    if (lane == 0) doc_char_off[d] = (int64_t)(tile_off[tile] + c);
+    if (lane == 0) doc_chars[d] = c;
   }
+}
+
+__global__ void k_u64_to_i64(const uint64_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int64_t)in[i];
 }
 
 // unknown code points seen by the last decode, with their first positions
