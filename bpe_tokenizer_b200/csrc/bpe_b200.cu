@@ -165,7 +165,7 @@ struct bpe_engine {
   bool mg_counts_global = false;         // the table's counts are the sum over all ranks (import done for this index)
   uint32_t mg_inbox_stride = 0, mg_tie_cap = 0;
   DevBuf<int32_t> mg_dlt;
-  DevBuf<uint32_t> mg_mark, mg_touched, mg_tie_sorted, mg_export_n;
+  DevBuf<uint32_t> mg_mark, mg_touched, mg_tie_sorted, mg_export_n, mg_newpair;
   int mg_loop_blocks = 0;
   unsigned long long mg_epoch = 0, mg_tie_epoch = 0;
 
@@ -989,6 +989,8 @@ MgArgs mg_args(bpe_engine* e) {
   }
   M.mark = e->mg_mark.p;
   M.tie_sorted = e->mg_tie_sorted.p;
+  M.newpair = e->mg_newpair.p;
+  M.newpair_cap = (uint32_t)e->mg_newpair.cap;
   return M;
 }
 
@@ -1014,6 +1016,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
   CK(e->barrier.reserve(64));
   CK(e->mg_touched.reserve((size_t)4 * BPE_MAX_TOKENS + 64));
   CK(e->mg_tie_sorted.reserve(e->mg_tie_cap));
+  CK(e->mg_newpair.reserve((size_t)2 * BPE_MAX_TOKENS + 64));
   cudaEvent_t t0, t1;
   CK(cudaEventCreate(&t0));
   CK(cudaEventCreate(&t1));

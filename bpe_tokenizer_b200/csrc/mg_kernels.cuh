@@ -40,6 +40,8 @@ struct MgArgs {
   // local scratch
   uint32_t* mark;          // per table slot: last merge (c + 1) that put the pair on the hot list
   uint32_t* tie_sorted;    // candidates (table slots) in canonical key order
+  uint32_t* newpair;       // table slots of the pairs born in the current merge (any rank), deduplicated
+  uint32_t newpair_cap;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -110,53 +112,72 @@ __device__ __forceinline__ unsigned long long* mg_area(const MgArgs& M, int dst,
   return M.inbox[dst] + ((size_t)par * M.world + sender) * M.inbox_stride;
 }
 
+// ---- exchange, executed by warp 0 of block 0: lane q talks to rank q, so its cost does not grow with the world size ----
 // header of a message: 16 u32 (H_* indices) in the first 64 bytes of the area, moved with 128-bit accesses
-__device__ __forceinline__ void mg_write_header(const LoopArgsMg& P, DevState* st, uint32_t par, uint32_t n_rec, uint32_t status) {
+__device__ __forceinline__ void mg_exchange_warp(const LoopArgsMg& P, DevState* st, uint32_t par, uint32_t n_rec, unsigned long long epoch,
+                                                 unsigned long long* const* flags) {
   const MgArgs& M = P.M;
   const LoopArgs& L = P.L;
-  uint32_t h[16];
+  const int q = (int)(threadIdx.x & 31u);
+  const bool peer = q < M.world && q != M.rank;
+  if (q < M.world) {
+    uint32_t cur = ld_cg(&st->pool_cursor);
+    uint32_t h[12];
 #pragma unroll
-  for (int i = 0; i < 16; i++) h[i] = 0;
-  h[H_N] = n_rec;
-  h[H_ERR] = st->err;
-  uint32_t cur = st->pool_cursor;
-  h[H_POOL_FREE] = L.pool_cap > cur ? L.pool_cap - cur : 0;
-  h[H_SITES_CAP] = L.A.sites_cap;
-  h[H_NEW_CAP] = L.A.new_cap;
-  h[H_HOT_CAP] = min(L.hot_cap, L.hot_limit);
-  h[H_LEN16_CAP] = L.len16_cap;
-  h[H_TBL_CAP] = L.tbl_cap;
-  h[H_CAND_CAP] = min(L.cand_cap, M.tie_cap);
-  h[H_STATUS] = status;
-  for (int q = 0; q < M.world; q++) {
+    for (int i = 0; i < 12; i++) h[i] = 0;
+    h[H_N] = n_rec;
+    h[H_ERR] = ld_cg(&st->err);
+    h[H_POOL_FREE] = L.pool_cap > cur ? L.pool_cap - cur : 0;
+    h[H_SITES_CAP] = L.A.sites_cap;
+    h[H_NEW_CAP] = L.A.new_cap;
+    h[H_HOT_CAP] = min(L.hot_cap, L.hot_limit);
+    h[H_LEN16_CAP] = L.len16_cap;
+    h[H_TBL_CAP] = L.tbl_cap;
+    h[H_CAND_CAP] = min(L.cand_cap, M.tie_cap);
     uint4* dst = reinterpret_cast<uint4*>(mg_area(M, q, par, M.rank));
 #pragma unroll
-    for (int i = 0; i < 4; i++) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+    for (int i = 0; i < 3; i++) dst[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+    __threadfence_system();
   }
-  __threadfence_system();
-}
-
-// block 0, thread 0, after the exchange: minima / OR over the G headers -> one 32-byte block every thread reads at once
-struct MgGlobals {
-  uint32_t err, pool_free, sites_cap, new_cap, hot_cap, len16_cap, tbl_cap, cand_cap;
-};
-
-__device__ __forceinline__ void mg_fold_headers(const MgArgs& M, DevState* st, uint32_t par) {
-  uint32_t err = 0;
-  uint32_t mins[16];
-#pragma unroll
-  for (int i = 0; i < 16; i++) mins[i] = 0xFFFFFFFFu;
-  for (int q = 0; q < M.world; q++) {
-    const uint4* h = reinterpret_cast<const uint4*>(mg_area(M, M.rank, par, q));
-    uint4 v0 = ld_cg4(h), v1 = ld_cg4(h + 1), v2 = ld_cg4(h + 2);
-    uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
-    err |= w[H_ERR];
-#pragma unroll
-    for (int i = H_POOL_FREE; i <= H_CAND_CAP; i++) mins[i] = min(mins[i], w[i]);
+  __syncwarp();
+  if (peer) st_release_sys(flags[q] + 16 * M.rank, epoch);
+  if (peer) {
+    const unsigned long long* f = flags[M.rank] + 16 * q;
+    unsigned long long t0 = now_ns();
+    uint32_t ns = 32;
+    while (ld_acquire_sys(f) < epoch) {
+      __nanosleep(ns);
+      if (ns < 1024) ns <<= 1;
+      if (now_ns() - t0 > MG_TIMEOUT_NS) {
+        atomicOr(&st->err, ERR_PEER_TIMEOUT);
+        st->mg_abort = 1;
+        break;
+      }
+    }
   }
-  uint4* g = reinterpret_cast<uint4*>(st->g_vals);
-  g[0] = make_uint4(err, mins[H_POOL_FREE], mins[H_SITES_CAP], mins[H_NEW_CAP]);
-  g[1] = make_uint4(mins[H_HOT_CAP], mins[H_LEN16_CAP], mins[H_TBL_CAP], mins[H_CAND_CAP]);
+  __syncwarp();
+  // fold the G headers: OR of the error flags, minima of the capacities
+  uint32_t w[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) w[i] = (i == H_ERR) ? 0u : 0xFFFFFFFFu;
+  if (q < M.world) {
+    const uint4* hq = reinterpret_cast<const uint4*>(mg_area(M, M.rank, par, q));
+    uint4 v0 = ld_cg4(hq), v1 = ld_cg4(hq + 1), v2 = ld_cg4(hq + 2);
+    w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w; w[8] = v2.x; w[9] = v2.y; w[10] = v2.z; w[11] = v2.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = H_ERR; i <= H_CAND_CAP; i++) {
+      uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, w[i], o);
+      w[i] = (i == H_ERR) ? (w[i] | other) : min(w[i], other);
+    }
+  }
+  if (q == 0) {
+    uint4* g = reinterpret_cast<uint4*>(st->g_vals);
+    g[0] = make_uint4(w[H_ERR], w[H_POOL_FREE], w[H_SITES_CAP], w[H_NEW_CAP]);
+    g[1] = make_uint4(w[H_HOT_CAP], w[H_LEN16_CAP], w[H_TBL_CAP], w[H_CAND_CAP]);
+  }
 }
 
 __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
@@ -182,10 +203,9 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
     st->snap_n_keys = st->n_keys;
     st->snap_hot_n = st->hot_n;
     st->mg_abort = 0;
-    mg_write_header(P, st, (uint32_t)((epoch + 1) & 1u), 0, LOOP_RUNNING);
-    mg_signal_and_wait(M, M.flag_data, epoch + 1, st);
-    mg_fold_headers(M, st, (uint32_t)((epoch + 1) & 1u));
+    st->n_newpair = 0;
   }
+  if (bid == 0 && threadIdx.x < 32) mg_exchange_warp(P, st, (uint32_t)((epoch + 1) & 1u), 0, epoch + 1, M.flag_data);
   epoch++;
   {
     Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
@@ -376,11 +396,10 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
       GRID_BARRIER();
       MGPROF(4)
     }
+    if (bid == 0 && threadIdx.x < 32) mg_exchange_warp(P, st, epar, min(ld_cg(&st->n_out), M.inbox_stride - MG_HDR), epoch + 1, M.flag_data);
     if (lead) {
-      mg_write_header(P, st, epar, min(ld_cg(&st->n_out), M.inbox_stride - MG_HDR), LOOP_RUNNING);
       st->n_out = 0;  // nobody appends before the next merge's P1
-      mg_signal_and_wait(M, M.flag_data, epoch + 1, st);
-      mg_fold_headers(M, st, epar);
+      st->n_newpair = 0;
       st->n_cand = 0;
       st->tie_pos = ~0ull;
       t.cnt[w.slot] = 0;  // every counted occurrence of the winner, on every rank, is being replaced
@@ -401,19 +420,47 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
       return;
     }
     // ---- P2: apply the deltas of all ranks to the replicated counts; lists of the locally new pairs ----
-    for (int q = 0; q < M.world; q++) {
-      const unsigned long long* area = mg_area(M, M.rank, epar, q);
-      const uint32_t nrec = ld_cg(reinterpret_cast<const uint32_t*>(area) + H_N);
-      for (uint32_t i = gtid; i < ((nrec + 31u) & ~31u); i += gthreads) {  // warp-uniform: one n_keys atomic per warp
-        bool ins = false;
-        if (i < nrec) {
-          unsigned long long rec = ld_cg(area + MG_HDR + i);
-          uint32_t s = tbl_find_or_insert_ex(t, (uint32_t)(rec >> 32), &ins);
-          if (s == NOSLOT) atomicOr(&st->err, ERR_TABLE_FULL);
-          else atomicAdd(t.cnt + s, (uint32_t)rec);
+    {
+      // all G record lists as ONE index space, so a thread walks a single record's chain whatever the world size
+      uint32_t pre[MG_MAX_WORLD + 1];
+      pre[0] = 0;
+#pragma unroll
+      for (int q = 0; q < MG_MAX_WORLD; q++)
+        pre[q + 1] = pre[q] + (q < M.world ? ld_cg(reinterpret_cast<const uint32_t*>(mg_area(M, M.rank, epar, q)) + H_N) : 0u);
+      const uint32_t total = pre[MG_MAX_WORLD];
+      const uint32_t lane = lane_id();
+      for (uint32_t j = gtid; j < ((total + 31u) & ~31u); j += gthreads) {  // warp-uniform
+        bool ins = false, born = false;
+        uint32_t s = NOSLOT;
+        if (j < total) {
+          int q = 0;
+#pragma unroll
+          for (int r = 1; r < MG_MAX_WORLD; r++) q += (j >= pre[r]) ? 1 : 0;
+          unsigned long long rec = ld_cg(mg_area(M, M.rank, epar, q) + MG_HDR + (j - pre[q]));
+          uint32_t key = (uint32_t)(rec >> 32);
+          s = tbl_find_or_insert_ex(t, key, &ins);
+          if (s == NOSLOT) {
+            atomicOr(&st->err, ERR_TABLE_FULL);
+          } else {
+            atomicAdd(t.cnt + s, (uint32_t)rec);
+            // a pair born in this merge (it contains c): first record of it on this rank lists it for the hot-list test of P3
+            if (((key >> 16) == c || (key & 0xFFFFu) == c)) born = atomicMax(M.mark + s, c + 1u) < c + 1u;
+          }
         }
         uint32_t im = __ballot_sync(0xFFFFFFFFu, ins);
-        if (im && lane_id() == (uint32_t)(__ffs(im) - 1)) atomicAdd(&st->n_keys, (uint32_t)__popc(im));
+        if (im && lane == (uint32_t)(__ffs(im) - 1)) atomicAdd(&st->n_keys, (uint32_t)__popc(im));
+        uint32_t bm = __ballot_sync(0xFFFFFFFFu, born);
+        if (bm) {
+          uint32_t base = 0;
+          int src = __ffs(bm) - 1;
+          if ((int)lane == src) base = atomicAdd(&st->n_newpair, (uint32_t)__popc(bm));
+          base = __shfl_sync(0xFFFFFFFFu, base, src);
+          if (born) {
+            uint32_t k = base + __popc(bm & ((1u << lane) - 1u));
+            if (k < M.newpair_cap) M.newpair[k] = s;
+            else atomicOr(&st->err, ERR_HOT_OVERFLOW);
+          }
+        }
       }
     }
     phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);
@@ -429,15 +476,10 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
     const uint32_t hot_n0 = ld_cg(&st->snap_hot_n);
     phase_apply(A, wa, wb, c, ld_cg(&st->n_sites[par]), false, bid, nblk);
     Best mine{0ull, NOSLOT, 0};
-    for (int q = 0; q < M.world; q++) {
-      const unsigned long long* area = mg_area(M, M.rank, epar, q);
-      const uint32_t nrec = ld_cg(reinterpret_cast<const uint32_t*>(area) + H_N);
-      for (uint32_t i = gtid; i < nrec; i += gthreads) {
-        uint32_t key = (uint32_t)(ld_cg(area + MG_HDR + i) >> 32);
-        if ((key >> 16) != c && (key & 0xFFFFu) != c) continue;
-        uint32_t s = tbl_find(t, key);
-        if (s == NOSLOT) continue;
-        if (atomicMax(M.mark + s, c + 1u) >= c + 1u) continue;  // another rank's record already handled this pair
+    {
+      const uint32_t nnp = min(ld_cg(&st->n_newpair), M.newpair_cap);
+      for (uint32_t i = gtid; i < nnp; i += gthreads) {
+        uint32_t s = ld_cg(&M.newpair[i]);
         unsigned long long pr = slot_primary(t, A.len16, s, L.max_length);
         if (pr && (uint32_t)(pr >> 20) >= thresh) {
           uint32_t k = atomicAdd(&st->hot_n, 1u);

@@ -59,6 +59,7 @@ struct DevState {
   unsigned long long mg_tie_epoch;  // tie exchanges completed
   uint32_t n_touched[2];            // pairs whose count changed on this rank in the current merge (by iteration parity)
   uint32_t n_out;                   // records in the outgoing delta message
+  uint32_t n_newpair;               // distinct pairs born in the current merge on ANY rank (hot-list candidates)
   uint32_t mg_abort;                // a peer did not answer in time / a rank reported an error: every block leaves
   unsigned long long mg_prof_ns[12];  // block 0: decide, P1, wait, M1, wait, exchange, wait, P2, wait, P3, wait, tie path
   // folded message headers, read by every thread with two 128-bit loads: [0] OR of all ranks' error flags, then the
