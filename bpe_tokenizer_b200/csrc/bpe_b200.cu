@@ -144,6 +144,7 @@ struct bpe_engine {
   DevBuf<Best> partials;
   DevBuf<SiteRec> sites;
   DevBuf<uint32_t> newslots;
+  DevBuf<uint32_t> nd;  // dense accumulator of the pairs born by the current merge (train_kernels.cuh, ND_*)
   DevBuf<uint32_t> hot;
   bool hot_valid = false;
   uint32_t hot_max_length = 0;
@@ -330,6 +331,8 @@ int build_index(bpe_engine* e) {
   if (!e->h_st) CK(cudaHostAlloc((void**)&e->h_st, sizeof(DevState), cudaHostAllocDefault));
   CK(e->d_st.reserve(1));
   CK(e->partials.reserve((size_t)e->grid(8)));
+  if (!e->nd.p) CK(e->nd.reserve((size_t)ND_ROWS * ND_STRIDE));
+  CK(cudaMemsetAsync(e->nd.p, 0, (size_t)ND_ROWS * ND_STRIDE * 4, e->stream));  // all rows zero between merges
   TRY(sync_len16(e));
   uint64_t n = e->n_slots;
   if (n >= 0xFFFFFFF0ull) return fail(e, BPE_E_DOMAIN, "corpus of %llu positions exceeds the 2^32 engine limit", (unsigned long long)n);
@@ -470,6 +473,7 @@ ApplyArgs apply_args(bpe_engine* e) {
   A.sites = e->sites.p;
   A.sites_cap = (uint32_t)std::min<size_t>(e->sites.cap, 0xFFFFFFFFu);
   A.newslots = e->newslots.p;
+  A.nd = e->nd.p;
   A.new_cap = (uint32_t)std::min<size_t>(e->newslots.cap, 0xFFFFFFFFu);
   A.len16 = e->d_len16.p;
   A.scan_mode = e->scan_mode;
@@ -508,8 +512,7 @@ int run_apply(bpe_engine* e, uint32_t a, uint32_t b, uint32_t c, uint32_t bound)
   k_sites<<<blocks, 256, 0, e->stream>>>(A, a, b, c);
   CKL();
   int blocks2 = (int)std::min<uint64_t>((uint64_t)e->grid(8), std::max<uint64_t>(1, (2ull * bound + 255) / 256));
-  k_alloc_new<<<blocks2, 256, 0, e->stream>>>(t, e->newslots.p, e->d_len16.p, e->hot_max_length, e->hot_valid ? 1 : 0, e->hot.p,
-                                              (uint32_t)e->hot.cap, (uint32_t)e->pool.cap, e->d_st.p);
+  k_alloc_new<<<blocks2, 256, 0, e->stream>>>(A, c, e->hot_max_length, e->hot_valid ? 1 : 0, e->hot.p, (uint32_t)e->hot.cap, (uint32_t)e->pool.cap);
   CKL();
   int blocks3 = (int)std::min<uint64_t>((uint64_t)e->grid(8), std::max<uint64_t>(1, ((uint64_t)bound + 255) / 256));
   k_apply<<<blocks3, 256, 0, e->stream>>>(A, a, b, c);

@@ -376,7 +376,35 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
     MGPROF(1)
     GRID_BARRIER();
     MGPROF(2)
-    // ---- M1 (staged mode): one (pair, delta) record per touched pair, stored into every rank's inbox (NVLink) ----
+    // ---- M1: the counts of the pairs born by this merge (dense rows, one record per pair) and, in staged mode, one
+    // (pair, delta) record per touched pair -- stored straight into every rank's inbox (NVLink) ----
+    {
+      const uint32_t lane = lane_id();
+      const uint32_t per_side = c + 1u, total2 = 2u * per_side;
+      for (uint32_t i = gtid; i < ((total2 + 31u) & ~31u); i += gthreads) {
+        uint32_t cntv = 0, key = 0;
+        if (i < total2) {
+          uint32_t side = i >= per_side ? 1u : 0u, tok = i - side * per_side;
+          cntv = ld_cg(A.nd + (size_t)(side ? ND_R_CNT : ND_L_CNT) * ND_STRIDE + tok);
+          key = side ? pair_key(c, tok) : pair_key(tok, c);
+        }
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, cntv != 0);
+        if (!m) continue;
+        uint32_t base = 0;
+        int src = __ffs(m) - 1;
+        if ((int)lane == src) base = atomicAdd(&st->n_out, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, src);
+        if (cntv) {
+          uint32_t k = base + __popc(m & ((1u << lane) - 1u));
+          if (MG_HDR + k >= M.inbox_stride) {
+            atomicOr(&st->err, ERR_INBOX_OVERFLOW);
+          } else {
+            unsigned long long rec = ((unsigned long long)key << 32) | cntv;
+            for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MG_HDR + k] = rec;
+          }
+        }
+      }
+    }
     if (!direct) {
       const uint32_t nt = min(ld_cg(&st->n_touched[par]), A.touched_cap);
       for (uint32_t i = gtid; i < nt; i += gthreads) {
@@ -391,11 +419,11 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
         unsigned long long rec = ((unsigned long long)t.keys[s] << 32) | (uint32_t)d;
         for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MG_HDR + k] = rec;
       }
-      __threadfence_system();
-      MGPROF(3)
-      GRID_BARRIER();
-      MGPROF(4)
     }
+    __threadfence_system();
+    MGPROF(3)
+    GRID_BARRIER();
+    MGPROF(4)
     if (bid == 0 && threadIdx.x < 32) mg_exchange_warp(P, st, epar, min(ld_cg(&st->n_out), M.inbox_stride - MG_HDR), epoch + 1, M.flag_data);
     if (lead) {
       st->n_out = 0;  // nobody appends before the next merge's P1
@@ -463,7 +491,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
         }
       }
     }
-    phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);
+    phase_new_pairs(A, c, A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, true, bid, nblk);
     MGPROF(7)
     GRID_BARRIER();
     MGPROF(8)

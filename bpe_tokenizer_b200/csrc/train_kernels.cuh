@@ -604,11 +604,18 @@ struct ApplyArgs {
   int32_t* dlt;
   uint32_t* touched;
   uint32_t touched_cap;
+  // pairs born by a merge are (x,c) or (c,y): they are accumulated in dense per-token rows (L2-resident, RED atomics, no
+  // hashing) and entered into the pair table once each by phase_new_pairs.  nd[ND_*][tok], row stride ND_STRIDE
+  uint32_t* nd;
   // sharded training, small merges: every (pair, delta) goes straight into the record area of each rank's inbox
   unsigned long long* push[8];
   int push_world;  // 0: staged mode (or single GPU)
   uint32_t push_cap;
 };
+
+constexpr uint32_t ND_STRIDE = 56320;  // >= BPE_MAX_TOKENS + 1
+enum { ND_L_LEN = 0, ND_L_CNT, ND_R_LEN, ND_R_CNT, ND_L_SLOT, ND_R_SLOT, ND_ROWS };
+constexpr uint32_t NOTOKV = 0xFFFFFFFFu;
 
 constexpr uint32_t ERR_TOUCH_OVERFLOW = 128u, ERR_PEER_TIMEOUT = 256u, ERR_INBOX_OVERFLOW = 512u, ERR_PEER = 1024u;
 
@@ -678,43 +685,19 @@ __device__ __forceinline__ void agg_dec(const ApplyArgs& A, uint32_t key, bool h
   cnt_delta_warp(A, leader && s != NOSLOT, s, key, -(int32_t)__popc(peers), par);
 }
 
-// returns the table slot of `key` to every lane with has == true
-__device__ __forceinline__ uint32_t agg_new(const ApplyArgs& A, uint32_t key, bool has, bool counted, uint32_t par) {
-  const PairTable& t = A.t;
-  DevState* st = A.st;
+// One adjacency of a pair BORN by this merge -- (tok, c) for side 0, (c, tok) for side 1 -- per `has` lane: occurrences
+// and counted occurrences go to the dense rows with fire-and-forget atomics (one per distinct token per warp).
+__device__ __forceinline__ void agg_new_dense(const ApplyArgs& A, uint32_t side, uint32_t tok, bool has, bool counted) {
   uint32_t lane = lane_id();
-  uint32_t k = has ? key : (EMPTY_KEY - 1 - lane);
+  uint32_t k = has ? tok : (0xFFFFFF00u + lane);
   uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
   uint32_t cmask = __ballot_sync(0xFFFFFFFFu, has && counted);
-  uint32_t leader = __ffs(peers) - 1;
-  uint32_t s = NOSLOT, nc = 0;
-  bool inserted = false, born = false;
-  if (has && lane == leader) {
-    s = tbl_find_or_insert_ex(t, key, &inserted);
-    if (s == NOSLOT) {
-      atomicOr(&st->err, ERR_TABLE_FULL);
-    } else {
-      nc = __popc(peers & cmask);
-      born = atomicAdd(t.occ_len + s, (uint32_t)__popc(peers)) == 0;  // first adjacency of a pair born in this iteration
-    }
+  if (has && lane == (uint32_t)(__ffs(peers) - 1)) {
+    uint32_t* row = A.nd + (size_t)(side ? ND_R_LEN : ND_L_LEN) * ND_STRIDE;
+    atomicAdd(row + tok, (uint32_t)__popc(peers));
+    uint32_t nc = __popc(peers & cmask);
+    if (nc) atomicAdd(row + ND_STRIDE + tok, nc);
   }
-  cnt_delta_warp(A, nc != 0, s, key, (int32_t)nc, par);
-  // grid-wide counters: one atomic per warp
-  uint32_t im = __ballot_sync(0xFFFFFFFFu, inserted);
-  if (im && lane == (uint32_t)(__ffs(im) - 1)) atomicAdd(&st->n_keys, (uint32_t)__popc(im));
-  uint32_t bm = __ballot_sync(0xFFFFFFFFu, born);
-  if (bm) {
-    uint32_t base = 0;
-    int src = __ffs(bm) - 1;
-    if ((int)lane == src) base = atomicAdd(&st->n_new[par], (uint32_t)__popc(bm));
-    base = __shfl_sync(0xFFFFFFFFu, base, src);
-    if (born) {
-      uint32_t i = base + __popc(bm & ((1u << lane) - 1u));
-      if (i < A.new_cap) A.newslots[i] = s;
-      else atomicOr(&st->err, ERR_SITE_OVERFLOW);
-    }
-  }
-  return __shfl_sync(0xFFFFFFFFu, s, leader);
 }
 
 __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint32_t b, uint32_t c, uint32_t par,
@@ -761,9 +744,9 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
     }
     FINE(1, w + q + koff)
     if (!__any_sync(0xFFFFFFFFu, site)) continue;
-    SiteRec rec{p, NOPOS, NOSLOT, NOSLOT};
+    SiteRec rec{p, NOPOS, NOTOKV, NOTOKV};
     // ---- adjacency on the left of the new token ----
-    uint32_t dec1_key = 0, new1_key = 0;
+    uint32_t dec1_key = 0, new1_tok = 0;
     bool dec1 = false, new1 = false, new1_counted = true;
     if (site) {
       uint32_t lpos;
@@ -796,7 +779,7 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
             dec1 = true;
             dec1_key = pair_key(b, a);
           }
-          new1_key = pair_key(c, c);  // runs of c count every other pair (:285-290)
+          new1_tok = c;  // the pair (c,c): runs of c count every other pair (:285-290)
           new1_counted = (chain_j & 1u) != 0;
           rec.lpos = llpos;
         } else {
@@ -808,19 +791,20 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
             dec1 = true;
             dec1_key = pair_key((uint32_t)x, a);
           }
-          new1_key = pair_key((uint32_t)x, c);
+          new1_tok = (uint32_t)x;  // the pair (x,c)
           rec.lpos = lpos;
         }
       }
     }
-    FINE(2, (uint32_t)dec1_key + new1_key)
+    FINE(2, (uint32_t)dec1_key + new1_tok)
     agg_dec(A, dec1_key, dec1, par);
     FINE(3, 0)
-    rec.lslot = agg_new(A, new1_key, new1, new1_counted, par);
+    agg_new_dense(A, 0, new1_tok, new1, new1_counted);
+    rec.lslot = new1 ? new1_tok : NOTOKV;  // resolved to the pair's table slot by phase_apply (ND_L_SLOT)
     FINE(4, rec.lslot)
 
     // ---- adjacency on the right of the new token (left to the next site when that one is chained) ----
-    uint32_t dec2_key = 0, new2_key = 0;
+    uint32_t dec2_key = 0, new2_tok = 0;
     bool dec2 = false, new2 = false;
     if (site) {
       uint32_t r;
@@ -841,14 +825,15 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
             dec2_key = pair_key(b, (uint32_t)y);
           }
           new2 = true;
-          new2_key = pair_key(c, (uint32_t)y);
+          new2_tok = (uint32_t)y;  // the pair (c,y)
         }
       }
     }
-    FINE(5, (uint32_t)dec2_key + new2_key)
+    FINE(5, (uint32_t)dec2_key + new2_tok)
     agg_dec(A, dec2_key, dec2, par);
     FINE(6, 0)
-    rec.rslot = agg_new(A, new2_key, new2, true, par);
+    agg_new_dense(A, 1, new2_tok, new2, true);
+    rec.rslot = new2 ? new2_tok : NOTOKV;
     FINE(7, rec.rslot)
 
     // ---- record the site (one counter atomic per warp) ----
@@ -866,44 +851,72 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
 #undef FINE
 }
 
-// K3 phase 2: allocate the lists of the pairs born in this iteration; feed the hot list.
-__device__ __forceinline__ void phase_alloc_new(const PairTable& t, const uint32_t* newslots, uint32_t n_new,
-                                                const uint32_t* len16, uint32_t max_length, int hot_valid, uint32_t* hot,
-                                                uint32_t hot_cap, uint32_t pool_cap, DevState* st, uint32_t bid,
-                                                uint32_t nblk) {
-  uint32_t thresh = st->hot_thresh;
+// K3 phase 2: every pair born in this merge -- the non-empty cells of the dense rows -- enters the pair table ONCE:
+// key, occurrence-list length, list space from the pool (one cursor atomic per warp), count (unless the counts travel
+// through the sharded exchange), hot list.  The cells are cleared for the next merge; ND_*_SLOT keeps the table slot for
+// phase_apply.
+__device__ __forceinline__ void phase_new_pairs(const ApplyArgs& A, uint32_t c, const uint32_t* len16, uint32_t max_length,
+                                                int hot_valid, uint32_t* hot, uint32_t hot_cap, uint32_t pool_cap, bool counts_elsewhere,
+                                                uint32_t bid, uint32_t nblk) {
+  const PairTable& t = A.t;
+  DevState* st = A.st;
+  const uint32_t thresh = st->hot_thresh;
   const uint32_t lane = lane_id();
-  const uint32_t n_round = (n_new + 31u) & ~31u;
-  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n_round; i += nblk * blockDim.x) {
-    const bool act = i < n_new;
-    uint32_t s = act ? newslots[i] : 0u;
-    uint32_t len = act ? t.occ_len[s] : 0u;
+  const uint32_t per_side = c + 1u;            // tokens 0..c can be the other half of a new pair
+  const uint32_t total = 2u * per_side;
+  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < ((total + 31u) & ~31u); i += nblk * blockDim.x) {
+    uint32_t side = 0, tok = 0, len = 0, cnt = 0;
+    uint32_t* row = nullptr;
+    if (i < total) {
+      side = i >= per_side ? 1u : 0u;
+      tok = i - side * per_side;
+      row = A.nd + (size_t)(side ? ND_R_LEN : ND_L_LEN) * ND_STRIDE;
+      len = ld_cg(row + tok);
+    }
+    const bool act = len != 0;
+    uint32_t s = NOSLOT;
+    bool ins = false;
+    if (act) {
+      cnt = ld_cg(row + ND_STRIDE + tok);
+      row[tok] = 0;
+      row[ND_STRIDE + tok] = 0;
+      s = tbl_find_or_insert_ex(t, side ? pair_key(c, tok) : pair_key(tok, c), &ins);
+      if (s == NOSLOT) atomicOr(&st->err, ERR_TABLE_FULL);
+    }
+    uint32_t im = __ballot_sync(0xFFFFFFFFu, ins);
+    if (im && lane == (uint32_t)(__ffs(im) - 1)) atomicAdd(&st->n_keys, (uint32_t)__popc(im));
     // one pool_cursor atomic per warp: inclusive scan of the list lengths
-    uint32_t inc = len;
+    uint32_t mylen = (act && s != NOSLOT) ? len : 0u;
+    uint32_t inc = mylen;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
       if ((int)lane >= o) inc += v;
     }
-    uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, inc, 31);
     uint32_t wbase = 0;
-    if (lane == 31 && total) wbase = atomicAdd(&st->pool_cursor, total);
+    if (lane == 31 && wtotal) wbase = atomicAdd(&st->pool_cursor, wtotal);
     wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
-    if (!act) continue;
-    uint32_t start = wbase + (inc - len);
+    if (!act || s == NOSLOT) continue;
+    uint32_t start = wbase + (inc - mylen);
     if (start > pool_cap || len > pool_cap - start) {
       atomicOr(&st->err, ERR_POOL_FULL);
       start = 0;
-      t.occ_len[s] = 0;
+      len = 0;
     }
     t.occ_start[s] = start;
+    t.occ_len[s] = len;
     t.occ_fill[s] = 0;
-    if (hot_valid) {
-      unsigned long long pr = slot_primary(t, len16, s, max_length);
-      if (pr && (uint32_t)(pr >> 20) >= thresh) {
-        uint32_t k = atomicAdd(&st->hot_n, 1u);
-        if (k < hot_cap) hot[k] = s;
-        else atomicOr(&st->err, ERR_HOT_OVERFLOW);
+    A.nd[(size_t)(side ? ND_R_SLOT : ND_L_SLOT) * ND_STRIDE + tok] = s;
+    if (!counts_elsewhere) {
+      t.cnt[s] = cnt;  // the key is new: nobody else touches its count in this phase
+      if (hot_valid) {
+        unsigned long long pr = slot_primary(t, len16, s, max_length);
+        if (pr && (uint32_t)(pr >> 20) >= thresh) {
+          uint32_t k = atomicAdd(&st->hot_n, 1u);
+          if (k < hot_cap) hot[k] = s;
+          else atomicOr(&st->err, ERR_HOT_OVERFLOW);
+        }
       }
     }
   }
@@ -937,8 +950,10 @@ __device__ __forceinline__ void phase_apply(const ApplyArgs& A, uint32_t a, uint
   uint32_t round = (n_sites + 31u) & ~31u;
   for (uint32_t i = bid * blockDim.x + threadIdx.x; i < round; i += nblk * blockDim.x) {
     bool has = i < n_sites;
-    uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(A.sites) + i) : make_uint4(0, NOPOS, NOSLOT, NOSLOT);
-    uint32_t p = rv.x, lpos = rv.y, lslot = rv.z, rslot = rv.w;
+    uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(A.sites) + i) : make_uint4(0, NOPOS, NOTOKV, NOTOKV);
+    uint32_t p = rv.x, lpos = rv.y;
+    uint32_t lslot = (has && rv.z != NOTOKV) ? ld_cg(A.nd + (size_t)ND_L_SLOT * ND_STRIDE + rv.z) : NOSLOT;
+    uint32_t rslot = (has && rv.w != NOTOKV) ? ld_cg(A.nd + (size_t)ND_R_SLOT * ND_STRIDE + rv.w) : NOSLOT;
     if (has) {
       if (p + 8 < n) prefetch_l1(slots + p + 8);
       if (p + 16 < n) prefetch_l1(slots + p + 16);
@@ -974,10 +989,9 @@ __global__ void __launch_bounds__(256) k_sites(ApplyArgs A, uint32_t a, uint32_t
   phase_sites(A, a, b, c, 0, tbl_find(A.t, pair_key(a, b)), blockIdx.x, gridDim.x);
 }
 
-__global__ void k_alloc_new(PairTable t, const uint32_t* __restrict__ newslots, const uint32_t* __restrict__ len16,
-                            uint32_t max_length, int hot_valid, uint32_t* __restrict__ hot, uint32_t hot_cap,
-                            uint32_t pool_cap, DevState* st) {
-  phase_alloc_new(t, newslots, st->n_new[0], len16, max_length, hot_valid, hot, hot_cap, pool_cap, st, blockIdx.x, gridDim.x);
+__global__ void __launch_bounds__(256) k_alloc_new(ApplyArgs A, uint32_t c, uint32_t max_length, int hot_valid, uint32_t* __restrict__ hot,
+                                                    uint32_t hot_cap, uint32_t pool_cap) {
+  phase_new_pairs(A, c, A.len16, max_length, hot_valid, hot, hot_cap, pool_cap, false, blockIdx.x, gridDim.x);
 }
 
 __global__ void __launch_bounds__(256) k_apply(ApplyArgs A, uint32_t a, uint32_t b, uint32_t c) {
@@ -1214,7 +1228,7 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
                                                 // the winner's own pair)
       if (replay) L.log[it].weight = (long long)st->n_sites[par];  // replacements performed (bpe_apply_merge's n_replaced)
     }
-    phase_alloc_new(t, A.newslots, ld_cg(&st->n_new[par]), A.len16, L.max_length, replay ? 0 : 1, L.hot, L.hot_cap, L.pool_cap, st, bid, nblk);
+    phase_new_pairs(A, c, A.len16, L.max_length, replay ? 0 : 1, L.hot, L.hot_cap, L.pool_cap, false, bid, nblk);
 #ifdef BPE_FINE_PROF
     if (prof) st->bucket_ns[bkt][1] += now_ns() - tp0;
 #endif
