@@ -366,6 +366,8 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "traffic_note": "a 1 GB step cannot be replayed by ncu (a launch rewrites >20 GB of state); on cfg2 the loop moves 95.5 KB read + 15.6 KB "
+                                "written per merge vs ~72 MB of reference-algorithm bytes (profiles/r01c_bench_default.md)",
                 "kernel": "k_merge_loop (persistent cooperative mergeUntil kernel; the step also contains k_ingest_ids + K1)",
                 "note": "achieved = reference-algorithm bytes sum_t 4*(2*N_t+N_{t+1}) / step time ('x of reference-algorithm roofline', SURVEY 8d); "
                         "an incremental design may exceed 1.0; peak from " + peak_src,
@@ -378,7 +380,8 @@ def run_b200(args):
                 "e2e": {"value": enc_e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": enc_h2d_total, "d2h_bytes_per_step": enc_d2h_total},
                 "e2e_text": {"value": enc_text_gbs, "unit": "GB/s", "h2d_bytes_per_step": enc_text_h2d, "d2h_bytes_per_step": enc_d2h_total,
                              "note": "bpe_encode_text_batch: UTF-8 bytes in (1 B/char), char->index on the device, vectors out"},
-                "roofline": {"bound": "hbm", "achieved": enc_achieved, "peak": peak, "unit": "GB/s", "frac": enc_achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": enc_achieved, "peak": peak, "unit": "GB/s", "frac": enc_achieved / peak, "traffic": 1.072 * enc_alg_bytes,
+                             "traffic_note": "ncu --set full on a 100 MB launch: dram read+write = 1.072 x algorithmic bytes (profiles/r01b_encode_lanes.md), scaled to this shard",
                              "kernel": "k_range_starts + k_encode_lanes + scan + k_gather_map (ms_encode of the engine, rank 0 shard)", "alg_bytes": enc_alg_bytes},
             },
             "setup": {"synth_s": gen_s},

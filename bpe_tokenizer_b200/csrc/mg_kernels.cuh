@@ -144,10 +144,10 @@ __device__ __forceinline__ void mg_exchange_warp(const LoopArgsMg& P, DevState* 
   if (peer) {
     const unsigned long long* f = flags[M.rank] + 16 * q;
     unsigned long long t0 = now_ns();
-    uint32_t ns = 32;
+    uint32_t ns = 16;
     while (ld_acquire_sys(f) < epoch) {
       __nanosleep(ns);
-      if (ns < 1024) ns <<= 1;
+      if (ns < 128) ns <<= 1;
       if (now_ns() - t0 > MG_TIMEOUT_NS) {
         atomicOr(&st->err, ERR_PEER_TIMEOUT);
         st->mg_abort = 1;
@@ -376,9 +376,9 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
     MGPROF(1)
     GRID_BARRIER();
     MGPROF(2)
-    // ---- M1: the counts of the pairs born by this merge (dense rows, one record per pair) and, in staged mode, one
-    // (pair, delta) record per touched pair -- stored straight into every rank's inbox (NVLink) ----
-    {
+    // ---- M1 (staged mode; small merges pushed everything during P1): the counts of the pairs born by this merge (dense
+    // rows, one record per pair) and one (pair, delta) record per touched pair -- stored into every rank's inbox ----
+    if (!direct) {
       const uint32_t lane = lane_id();
       const uint32_t per_side = c + 1u, total2 = 2u * per_side;
       for (uint32_t i = gtid; i < ((total2 + 31u) & ~31u); i += gthreads) {
@@ -420,10 +420,12 @@ __global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
         for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MG_HDR + k] = rec;
       }
     }
-    __threadfence_system();
-    MGPROF(3)
-    GRID_BARRIER();
-    MGPROF(4)
+    if (!direct) {
+      __threadfence_system();
+      MGPROF(3)
+      GRID_BARRIER();
+      MGPROF(4)
+    }
     if (bid == 0 && threadIdx.x < 32) mg_exchange_warp(P, st, epar, min(ld_cg(&st->n_out), M.inbox_stride - MG_HDR), epoch + 1, M.flag_data);
     if (lead) {
       st->n_out = 0;  // nobody appends before the next merge's P1

@@ -687,17 +687,22 @@ __device__ __forceinline__ void agg_dec(const ApplyArgs& A, uint32_t key, bool h
 
 // One adjacency of a pair BORN by this merge -- (tok, c) for side 0, (c, tok) for side 1 -- per `has` lane: occurrences
 // and counted occurrences go to the dense rows with fire-and-forget atomics (one per distinct token per warp).
-__device__ __forceinline__ void agg_new_dense(const ApplyArgs& A, uint32_t side, uint32_t tok, bool has, bool counted) {
+__device__ __forceinline__ void agg_new_dense(const ApplyArgs& A, uint32_t side, uint32_t tok, uint32_t c, bool has, bool counted,
+                                              uint32_t par) {
   uint32_t lane = lane_id();
   uint32_t k = has ? tok : (0xFFFFFF00u + lane);
   uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
   uint32_t cmask = __ballot_sync(0xFFFFFFFFu, has && counted);
-  if (has && lane == (uint32_t)(__ffs(peers) - 1)) {
+  const bool leader = has && lane == (uint32_t)(__ffs(peers) - 1);
+  uint32_t nc = 0;
+  if (leader) {
     uint32_t* row = A.nd + (size_t)(side ? ND_R_LEN : ND_L_LEN) * ND_STRIDE;
     atomicAdd(row + tok, (uint32_t)__popc(peers));
-    uint32_t nc = __popc(peers & cmask);
-    if (nc) atomicAdd(row + ND_STRIDE + tok, nc);
+    nc = __popc(peers & cmask);
+    if (nc && !A.push_world) atomicAdd(row + ND_STRIDE + tok, nc);
   }
+  // sharded, small merges: the count goes straight to every rank's inbox (partial counts per warp add up on arrival)
+  if (A.push_world) cnt_delta_warp(A, nc != 0, NOSLOT, side ? pair_key(c, tok) : pair_key(tok, c), (int32_t)nc, par);
 }
 
 __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint32_t b, uint32_t c, uint32_t par,
@@ -799,7 +804,7 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
     FINE(2, (uint32_t)dec1_key + new1_tok)
     agg_dec(A, dec1_key, dec1, par);
     FINE(3, 0)
-    agg_new_dense(A, 0, new1_tok, new1, new1_counted);
+    agg_new_dense(A, 0, new1_tok, c, new1, new1_counted, par);
     rec.lslot = new1 ? new1_tok : NOTOKV;  // resolved to the pair's table slot by phase_apply (ND_L_SLOT)
     FINE(4, rec.lslot)
 
@@ -832,7 +837,7 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
     FINE(5, (uint32_t)dec2_key + new2_tok)
     agg_dec(A, dec2_key, dec2, par);
     FINE(6, 0)
-    agg_new_dense(A, 1, new2_tok, new2, true);
+    agg_new_dense(A, 1, new2_tok, c, new2, true, par);
     rec.rslot = new2 ? new2_tok : NOTOKV;
     FINE(7, rec.rslot)
 
