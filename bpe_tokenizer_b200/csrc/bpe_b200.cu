@@ -1769,11 +1769,7 @@ int bpe_encode_batch(bpe_engine* e, const int32_t* ids, const int64_t* doc_offse
   }
   if (*n_out) CK(cudaMemcpyAsync(out, e->x_out.p, (size_t)*n_out * 4, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  if (total > (256ll << 20)) {  // do not sit on GBs of staging after a bulk call
-    e->x_ids.release();
-    e->x_out.release();
-  }
-  return BPE_OK;
+  return BPE_OK;  // the staging buffers stay (grow-only): re-allocating GBs per call costs more than the copies
 }
 
 
