@@ -813,7 +813,12 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop, ML_THREADS, 0));
     if (per_sm < 1) return fail(e, BPE_E_CUDA, "k_merge_loop does not fit on an SM");
-    e->loop_blocks = e->sm_count * std::min(per_sm, 2);
+    // one 512-thread block per SM: measured best on cfg3 (1.28 s vs 1.41 s with two per SM, 1.33 s with half an SM count,
+    // 1.55 s with 1024-thread blocks) -- a merge is latency bound, fewer arrivals per grid barrier and fewer partials win
+    int want = 1;
+    if (const char* v = getenv("BPE_LOOP_PER_SM")) want = std::max(1, atoi(v));  // tuning knob: co-resident blocks per SM
+    e->loop_blocks = e->sm_count * std::min(per_sm, want);
+    if (const char* v = getenv("BPE_LOOP_BLOCKS")) e->loop_blocks = std::max(1, std::min(atoi(v), e->sm_count * per_sm));
   }
   CK(e->partials.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
   CK(e->sites.reserve(1u << 16, 0, e->stream, 1.0));
@@ -1010,7 +1015,9 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_loop_mg, ML_THREADS, 0));
     if (per_sm < 1) return fail(e, BPE_E_CUDA, "k_merge_loop_mg does not fit on an SM");
-    e->mg_loop_blocks = e->sm_count * std::min(per_sm, 2);
+    int want = 1;
+    if (const char* v = getenv("BPE_LOOP_PER_SM")) want = std::max(1, atoi(v));
+    e->mg_loop_blocks = e->sm_count * std::min(per_sm, want);
   }
   CK(e->partials.reserve((size_t)std::max(e->mg_loop_blocks, e->grid(8))));
   CK(e->sites.reserve(1u << 16, 0, e->stream, 1.0));

@@ -180,7 +180,7 @@ __device__ __forceinline__ void mg_exchange_warp(const LoopArgsMg& P, DevState* 
   }
 }
 
-__global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop_mg(LoopArgsMg P) {
+__global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(LoopArgsMg P) {
   __shared__ Best s_best[ML_THREADS / 32];
   __shared__ uint32_t s_max[32];
   const LoopArgs& L = P.L;

@@ -1008,7 +1008,11 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs A, uint32_t a, uint32_t
 // phases are separated by a grid barrier (3 per merge), every block takes the same exit decision from
 // the same published state.  The host is only needed to grow buffers or rebuild the hot list.
 // ------------------------------------------------------------------------------------------------
-constexpr int ML_THREADS = 512;
+#ifndef BPE_ML_THREADS
+#define BPE_ML_THREADS 512
+#endif
+constexpr int ML_THREADS = BPE_ML_THREADS;
+constexpr int ML_MIN_BLOCKS = ML_THREADS >= 1024 ? 1 : 2;
 
 struct LoopArgs {
   ApplyArgs A;
@@ -1073,7 +1077,7 @@ __global__ void k_loop_prepare(DevState* st, uint32_t n_tokens, unsigned long lo
   }
 }
 
-__global__ void __launch_bounds__(ML_THREADS, 2) k_merge_loop(LoopArgs L) {
+__global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopArgs L) {
   __shared__ Best s_best[ML_THREADS / 32];
   __shared__ uint32_t s_max[32];
   const ApplyArgs& A = L.A;
