@@ -494,6 +494,8 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
       }
     }
     phase_new_pairs(A, c, A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, true, bid, nblk);
+    const uint32_t n_sites_now = ld_cg(&st->n_sites[par]);
+    phase_rewrite(A, c, n_sites_now, bid, nblk);  // independent of the table work: fills the wait of the fast blocks
     MGPROF(7)
     GRID_BARRIER();
     MGPROF(8)
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
       st->snap_err = st->err;
     }
     const uint32_t hot_n0 = ld_cg(&st->snap_hot_n);
-    phase_apply(A, wa, wb, c, ld_cg(&st->n_sites[par]), false, bid, nblk);
+    phase_fill(A, n_sites_now, bid, nblk);
     Best mine{0ull, NOSLOT, 0};
     {
       const uint32_t nnp = min(ld_cg(&st->n_newpair), M.newpair_cap);

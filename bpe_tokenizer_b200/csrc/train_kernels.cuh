@@ -939,38 +939,18 @@ __device__ __forceinline__ uint32_t agg_cursor(const PairTable& t, uint32_t slot
   return base + __popc(peers & ((1u << lane) - 1u));
 }
 
-__device__ __forceinline__ void phase_apply(const ApplyArgs& A, uint32_t a, uint32_t b, uint32_t c, uint32_t n_sites,
-                                            bool zero_count, uint32_t bid, uint32_t nblk) {
+// K3 phase 3 comes in two independent halves, so that the loop kernels can run the first one next to phase_new_pairs
+// (neither reads what the other writes): phase_rewrite puts c into the corpus, phase_fill writes the positions of the
+// new adjacencies into the lists phase_new_pairs allocated.
+__device__ __forceinline__ void phase_rewrite(const ApplyArgs& A, uint32_t c, uint32_t n_sites, uint32_t bid, uint32_t nblk) {
   uint32_t* slots = A.slots;
   const uint32_t n = A.n;
-  const PairTable& t = A.t;
   if (bid == 0 && threadIdx.x == 0) {
-    if (zero_count) {
-      uint32_t s = tbl_find(t, pair_key(a, b));
-      if (s != NOSLOT) t.cnt[s] = 0;  // every counted occurrence was replaced
-    }
     A.st->live_tokens -= n_sites;
     A.st->sites_total += n_sites;
   }
-  uint32_t round = (n_sites + 31u) & ~31u;
-  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < round; i += nblk * blockDim.x) {
-    bool has = i < n_sites;
-    uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(A.sites) + i) : make_uint4(0, NOPOS, NOTOKV, NOTOKV);
-    uint32_t p = rv.x, lpos = rv.y;
-    uint32_t lslot = (has && rv.z != NOTOKV) ? ld_cg(A.nd + (size_t)ND_L_SLOT * ND_STRIDE + rv.z) : NOSLOT;
-    uint32_t rslot = (has && rv.w != NOTOKV) ? ld_cg(A.nd + (size_t)ND_R_SLOT * ND_STRIDE + rv.w) : NOSLOT;
-    if (has) {
-      if (p + 8 < n) prefetch_l1(slots + p + 8);
-      if (p + 16 < n) prefetch_l1(slots + p + 16);
-      prefetch_l1(slots + p);
-    }
-    bool hl = has && lslot != NOSLOT && t.occ_len[lslot];
-    bool hr = has && rslot != NOSLOT && t.occ_len[rslot];
-    uint32_t il = agg_cursor(t, lslot, hl);
-    uint32_t ir = agg_cursor(t, rslot, hr);
-    if (hl) A.pool[il] = lpos;
-    if (hr) A.pool[ir] = p;
-    if (!has) continue;
+  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n_sites; i += nblk * blockDim.x) {
+    uint32_t p = ld_cg(&A.sites[i].p);
     // own slots only: [p, e] where e is the last slot of b
     uint32_t q = next_pos(slots, n, p);
     uint32_t e = next_pos(slots, n, q) - 1;
@@ -986,6 +966,34 @@ __device__ __forceinline__ void phase_apply(const ApplyArgs& A, uint32_t a, uint
       slots[e] = mk_back(span - 1);
     }
   }
+}
+
+__device__ __forceinline__ void phase_fill(const ApplyArgs& A, uint32_t n_sites, uint32_t bid, uint32_t nblk) {
+  const PairTable& t = A.t;
+  uint32_t round = (n_sites + 31u) & ~31u;
+  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < round; i += nblk * blockDim.x) {
+    bool has = i < n_sites;
+    uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(A.sites) + i) : make_uint4(0, NOPOS, NOTOKV, NOTOKV);
+    uint32_t p = rv.x, lpos = rv.y;
+    uint32_t lslot = (has && rv.z != NOTOKV) ? ld_cg(A.nd + (size_t)ND_L_SLOT * ND_STRIDE + rv.z) : NOSLOT;
+    uint32_t rslot = (has && rv.w != NOTOKV) ? ld_cg(A.nd + (size_t)ND_R_SLOT * ND_STRIDE + rv.w) : NOSLOT;
+    bool hl = has && lslot != NOSLOT && t.occ_len[lslot];
+    bool hr = has && rslot != NOSLOT && t.occ_len[rslot];
+    uint32_t il = agg_cursor(t, lslot, hl);
+    uint32_t ir = agg_cursor(t, rslot, hr);
+    if (hl) A.pool[il] = lpos;
+    if (hr) A.pool[ir] = p;
+  }
+}
+
+__device__ __forceinline__ void phase_apply(const ApplyArgs& A, uint32_t a, uint32_t b, uint32_t c, uint32_t n_sites,
+                                            bool zero_count, uint32_t bid, uint32_t nblk) {
+  if (zero_count && bid == 0 && threadIdx.x == 0) {
+    uint32_t s = tbl_find(A.t, pair_key(a, b));
+    if (s != NOSLOT) A.t.cnt[s] = 0;  // every counted occurrence was replaced
+  }
+  phase_fill(A, n_sites, bid, nblk);
+  phase_rewrite(A, c, n_sites, bid, nblk);
 }
 
 // ---- stand-alone K3 kernels (applyMerge / restoreMerge one at a time, and the host-driven loop) ----
@@ -1237,7 +1245,19 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
                                                 // the winner's own pair)
       if (replay) L.log[it].weight = (long long)st->n_sites[par];  // replacements performed (bpe_apply_merge's n_replaced)
     }
+    const uint32_t hot_pre = ld_cg(&st->snap_hot_n);  // entries before this merge's pairs join (stable since the last P3)
+    const uint32_t n_sites_now = ld_cg(&st->n_sites[par]);
     phase_new_pairs(A, c, A.len16, L.max_length, replay ? 0 : 1, L.hot, L.hot_cap, L.pool_cap, false, bid, nblk);
+    phase_rewrite(A, c, n_sites_now, bid, nblk);  // independent of the table work above: fills the wait of the fast blocks
+    Best mine{0ull, NOSLOT, 0};
+    if (!replay) {  // arg-max over the pairs that were already hot: their counts are final since the barrier after P1
+      for (uint32_t i = bid * blockDim.x + threadIdx.x; i < hot_pre; i += nblk * blockDim.x) {
+        uint32_t hs = L.hot[i];
+        if (hs == w.slot) continue;  // the winner's count is being zeroed
+        unsigned long long pr = slot_primary(t, A.len16, hs, L.max_length);
+        if (pr) mine = best_merge(mine, Best{pr, hs, 1});
+      }
+    }
 #ifdef BPE_FINE_PROF
     if (prof) st->bucket_ns[bkt][1] += now_ns() - tp0;
 #endif
@@ -1251,9 +1271,15 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
       st->snap_hot_n = st->hot_n;
       st->snap_err = st->err;
     }
-    phase_apply(A, wa, wb, c, ld_cg(&st->n_sites[par]), false, bid, nblk);
-    if (!replay) {
-      Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
+    phase_fill(A, n_sites_now, bid, nblk);
+    if (!replay) {  // the pairs born by this merge that made it onto the hot list
+      const uint32_t hot_now = ld_cg(&st->hot_n);
+      for (uint32_t i = hot_pre + bid * blockDim.x + threadIdx.x; i < hot_now; i += nblk * blockDim.x) {
+        uint32_t hs = L.hot[i];
+        unsigned long long pr = slot_primary(t, A.len16, hs, L.max_length);
+        if (pr) mine = best_merge(mine, Best{pr, hs, 1});
+      }
+      Best v = best_block_reduce(mine, s_best);
       if (threadIdx.x == 0) L.partials[bid] = v;
     }
 #ifdef BPE_FINE_PROF
