@@ -493,9 +493,9 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
         }
       }
     }
-    phase_new_pairs(A, c, A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, true, bid, nblk);
+    phase_new_pairs(A, c, A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, true, gtid, gthreads);
     const uint32_t n_sites_now = ld_cg(&st->n_sites[par]);
-    phase_rewrite(A, c, n_sites_now, bid, nblk);  // independent of the table work: fills the wait of the fast blocks
+    phase_rewrite(A, c, n_sites_now, gtid, gthreads);  // independent of the table work: fills the wait of the fast blocks
     MGPROF(7)
     GRID_BARRIER();
     MGPROF(8)

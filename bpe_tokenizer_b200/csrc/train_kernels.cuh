@@ -862,14 +862,14 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
 // phase_apply.
 __device__ __forceinline__ void phase_new_pairs(const ApplyArgs& A, uint32_t c, const uint32_t* len16, uint32_t max_length,
                                                 int hot_valid, uint32_t* hot, uint32_t hot_cap, uint32_t pool_cap, bool counts_elsewhere,
-                                                uint32_t bid, uint32_t nblk) {
+                                                uint32_t vt, uint32_t nvt) {  // virtual thread id / count (whole warps)
   const PairTable& t = A.t;
   DevState* st = A.st;
   const uint32_t thresh = st->hot_thresh;
   const uint32_t lane = lane_id();
   const uint32_t per_side = c + 1u;            // tokens 0..c can be the other half of a new pair
   const uint32_t total = 2u * per_side;
-  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < ((total + 31u) & ~31u); i += nblk * blockDim.x) {
+  for (uint32_t i = vt; i < ((total + 31u) & ~31u); i += nvt) {
     uint32_t side = 0, tok = 0, len = 0, cnt = 0;
     uint32_t* row = nullptr;
     if (i < total) {
@@ -942,14 +942,14 @@ __device__ __forceinline__ uint32_t agg_cursor(const PairTable& t, uint32_t slot
 // K3 phase 3 comes in two independent halves, so that the loop kernels can run the first one next to phase_new_pairs
 // (neither reads what the other writes): phase_rewrite puts c into the corpus, phase_fill writes the positions of the
 // new adjacencies into the lists phase_new_pairs allocated.
-__device__ __forceinline__ void phase_rewrite(const ApplyArgs& A, uint32_t c, uint32_t n_sites, uint32_t bid, uint32_t nblk) {
+__device__ __forceinline__ void phase_rewrite(const ApplyArgs& A, uint32_t c, uint32_t n_sites, uint32_t vt, uint32_t nvt) {
   uint32_t* slots = A.slots;
   const uint32_t n = A.n;
-  if (bid == 0 && threadIdx.x == 0) {
+  if (vt == 0) {
     A.st->live_tokens -= n_sites;
     A.st->sites_total += n_sites;
   }
-  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n_sites; i += nblk * blockDim.x) {
+  for (uint32_t i = vt; i < n_sites; i += nvt) {
     uint32_t p = ld_cg(&A.sites[i].p);
     // own slots only: [p, e] where e is the last slot of b
     uint32_t q = next_pos(slots, n, p);
@@ -993,7 +993,7 @@ __device__ __forceinline__ void phase_apply(const ApplyArgs& A, uint32_t a, uint
     if (s != NOSLOT) A.t.cnt[s] = 0;  // every counted occurrence was replaced
   }
   phase_fill(A, n_sites, bid, nblk);
-  phase_rewrite(A, c, n_sites, bid, nblk);
+  phase_rewrite(A, c, n_sites, bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
 }
 
 // ---- stand-alone K3 kernels (applyMerge / restoreMerge one at a time, and the host-driven loop) ----
@@ -1004,7 +1004,7 @@ __global__ void __launch_bounds__(256) k_sites(ApplyArgs A, uint32_t a, uint32_t
 
 __global__ void __launch_bounds__(256) k_alloc_new(ApplyArgs A, uint32_t c, uint32_t max_length, int hot_valid, uint32_t* __restrict__ hot,
                                                     uint32_t hot_cap, uint32_t pool_cap) {
-  phase_new_pairs(A, c, A.len16, max_length, hot_valid, hot, hot_cap, pool_cap, false, blockIdx.x, gridDim.x);
+  phase_new_pairs(A, c, A.len16, max_length, hot_valid, hot, hot_cap, pool_cap, false, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 __global__ void __launch_bounds__(256) k_apply(ApplyArgs A, uint32_t a, uint32_t b, uint32_t c) {
@@ -1247,15 +1247,27 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
     }
     const uint32_t hot_pre = ld_cg(&st->snap_hot_n);  // entries before this merge's pairs join (stable since the last P3)
     const uint32_t n_sites_now = ld_cg(&st->n_sites[par]);
-    phase_new_pairs(A, c, A.len16, L.max_length, replay ? 0 : 1, L.hot, L.hot_cap, L.pool_cap, false, bid, nblk);
-    phase_rewrite(A, c, n_sites_now, bid, nblk);  // independent of the table work above: fills the wait of the fast blocks
     Best mine{0ull, NOSLOT, 0};
-    if (!replay) {  // arg-max over the pairs that were already hot: their counts are final since the barrier after P1
-      for (uint32_t i = bid * blockDim.x + threadIdx.x; i < hot_pre; i += nblk * blockDim.x) {
-        uint32_t hs = L.hot[i];
-        if (hs == w.slot) continue;  // the winner's count is being zeroed
-        unsigned long long pr = slot_primary(t, A.len16, hs, L.max_length);
-        if (pr) mine = best_merge(mine, Best{pr, hs, 1});
+    {
+      // Three independent jobs: table inserts of the new pairs, the corpus rewrite, the arg-max over the pairs that were
+      // already hot (their counts are final since the barrier after P1).  Small merges are latency bound, so the warps of
+      // every block split up (8 / 4 / 4) and the three dependency chains run side by side; big merges keep every thread
+      // on every job.
+      const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+      const bool split = n_sites_now <= 16384u && blockDim.x == 512u;
+      const uint32_t gt = bid * blockDim.x + threadIdx.x, gn = nblk * blockDim.x;
+      if (!split || warp < 8)
+        phase_new_pairs(A, c, A.len16, L.max_length, replay ? 0 : 1, L.hot, L.hot_cap, L.pool_cap, false,
+                        split ? (bid * 8 + warp) * 32 + lane : gt, split ? nblk * 256 : gn);
+      if (!split || (warp >= 8 && warp < 12))
+        phase_rewrite(A, c, n_sites_now, split ? (bid * 4 + warp - 8) * 32 + lane : gt, split ? nblk * 128 : gn);
+      if (!replay && (!split || warp >= 12)) {
+        for (uint32_t i = split ? (bid * 4 + warp - 12) * 32 + lane : gt; i < hot_pre; i += split ? nblk * 128 : gn) {
+          uint32_t hs = L.hot[i];
+          if (hs == w.slot) continue;  // the winner's count is being zeroed
+          unsigned long long pr = slot_primary(t, A.len16, hs, L.max_length);
+          if (pr) mine = best_merge(mine, Best{pr, hs, 1});
+        }
       }
     }
 #ifdef BPE_FINE_PROF
