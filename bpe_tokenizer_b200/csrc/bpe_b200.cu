@@ -131,6 +131,7 @@ struct bpe_engine {
   uint32_t lt_cap = 0;
   int32_t lt_c_affine = -1;
   int enc_lmax = 32;     // rows per lane of the lane path (32 or 48); BPE_ENC_LMAX overrides
+  int enc_lmax_forced = 0;
   int enc_force_old = 0; // debug: BPE_ENC_OLD=1 routes every document through the per-document kernel
 
   // pair index
@@ -684,9 +685,11 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
   bool run_old = e->enc_force_old != 0;
   if (n_docs > 0 && !run_old) {
     // lane path: one warp per batch of whole documents; position ranges of `stride` ids name the batches
-    const int lmax = e->enc_lmax;
+    // rows per lane: the smallest batch that still holds the longest document keeps the most warps resident (the kernel is
+    // latency bound: 26.4 GB/s with 20 rows / 32 warps per SM vs 22.5 GB/s with 32 rows / 20 warps on the 1 GB text)
+    int lmax = e->enc_lmax;
+    if (!e->enc_lmax_forced) lmax = max_doc_len <= 512 ? 16 : max_doc_len <= 640 ? 20 : max_doc_len <= 768 ? 24 : max_doc_len <= 1024 ? 32 : 48;
     const uint32_t cap = 32u * (uint32_t)lmax;
-    (void)max_doc_len;
     uint32_t stride = 4u * cap;  // a range = the documents starting in `stride` consecutive positions, packed greedily into batches
     uint64_t nr64 = ((uint64_t)n_ids + stride - 1) / stride;
     if (nr64 == 0) nr64 = 1;
@@ -698,7 +701,13 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
                                                                                                              sc.range_first.p);
     CKL();
     LaneTables lt{e->d_lt.p, e->lt_cap - 1, (uint32_t)(32 - ilog2(e->lt_cap)), e->d_lt_dense.p, e->d_rule_c.p, e->lt_c_affine};
-    if (lmax == 32)
+    if (lmax == 16)
+      TRY((launch_encode_lanes<16, 20>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
+    else if (lmax == 20)
+      TRY((launch_encode_lanes<20, 16>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
+    else if (lmax == 24)
+      TRY((launch_encode_lanes<24, 13>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
+    else if (lmax == 32)
       TRY((launch_encode_lanes<32, 10>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
     else
       TRY((launch_encode_lanes<48, 6>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
@@ -1164,9 +1173,12 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
           rc = fail(e, BPE_E_NOMEM, "pair table cannot grow further");
           break;
         }
+        auto tt = clk();
         if ((rc = grow_table(e, pow2_at_least(want))) != BPE_OK) break;
+        if (trace) fprintf(stderr, "[bpe r%d] grow_table -> %u slots: %.1f ms\n", e->mg_rank, e->tbl_cap, since(tt));
       }
       uint64_t pool_after = (uint64_t)e->h_st->pool_cursor + 4 * w;  // the in-kernel test is one merge conservative
+      auto tp = clk();
       if (pool_after > 0xFFFFFFF0ull) {
         rc = fail(e, BPE_E_DOMAIN, "occurrence pool exceeds 2^32 cells");
         break;
@@ -1179,6 +1191,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
         rc = fail(e, BPE_E_NOMEM, "growing merge buffers: %s", cudaGetErrorString(ce));
         break;
       }
+      if (trace && since(tp) > 1.0) fprintf(stderr, "[bpe r%d] buffer growth (pool %zu cells): %.1f ms\n", e->mg_rank, e->pool.cap, since(tp));
       if (e->h_st->best_mult > e->mg_tie_cap) {
         rc = fail(e, BPE_E_DOMAIN, "%u pairs tie on (weight, index sum): more than the tie mailbox holds (%u)", e->h_st->best_mult, e->mg_tie_cap);
         break;
@@ -1303,7 +1316,8 @@ int bpe_create(int device, bpe_engine** out) {
   e->stream = e->own_stream;
   if (getenv("BPE_HOST_LOOP")) e->host_loop = 1;
   if (getenv("BPE_ENC_OLD")) e->enc_force_old = 1;
-  if (const char* v = getenv("BPE_ENC_LMAX")) e->enc_lmax = (atoi(v) == 48) ? 48 : 32;
+  if (getenv("BPE_ENC_LMAX")) e->enc_lmax_forced = 1;
+  if (const char* v = getenv("BPE_ENC_LMAX")) e->enc_lmax = (atoi(v) == 48 || atoi(v) == 24 || atoi(v) == 20 || atoi(v) == 16) ? atoi(v) : 32;
   *out = e;
   return BPE_OK;
 }

@@ -316,7 +316,7 @@ def test_add_to_corpus_after_merges_appends_raw_ids():
     assert t.corpus_in_code == lit.corpus_in_code
 
 
-@pytest.mark.parametrize("lmax", ["48", "32"])
+@pytest.mark.parametrize("lmax", ["48", "32", "24", "20", "16"])
 @pytest.mark.parametrize("seed", range(6))
 def test_encode_batch_lane_path_fuzz(seed, lmax, monkeypatch):
     """K4 lane path (encode_lanes.cuh): batches of ragged documents -- empty, single-token, runs, documents longer than
