@@ -511,3 +511,55 @@ def test_device_text_front_end_equals_add_to_corpus():
     back.fromJSON(dev.toJSON())
     raw2, roff2, _ = back.encodeTextBatch(ptext, poff, vector=False)
     assert np.array_equal(raw, raw2) and np.array_equal(roff, roff2)
+
+
+def test_scale_properties_64mb():
+    """Size-independent properties at a size the oracle cannot reach in test time (64 MB, 2000 merges): weights equal the
+    live occurrences of every token, token count conservation, encode -> decode round trip of unseen text (byte exact),
+    idempotence of encode on its own decoded output, monotone offsets; plus an oracle check of a slice."""
+    import ctypes as C
+
+    from bpe_tokenizer_b200 import _abi
+    from oracle.int_oracle import IntOracle
+
+    lib = _abi.load_library()
+
+    def synth(target, seed):
+        nb, nd = C.c_int64(), C.c_int64()
+        assert lib.bpe_synth_corpus(target, seed, 50000, 42, None, 0, None, 0, C.byref(nb), C.byref(nd)) == 0
+        text = np.empty(nb.value, dtype=np.uint8)
+        off = np.empty(nd.value + 1, dtype=np.int64)
+        assert lib.bpe_synth_corpus(target, seed, 50000, 42, text.ctypes.data_as(_abi.u8p), text.size, _abi.p64(off), off.size, C.byref(nb), C.byref(nd)) == 0
+        return text, off
+
+    text, off = synth(64_000_000, 43)
+    t = make()
+    t.addTextBatch(text.tobytes(), off)  # device text front end: characters, indices and weights
+    n0 = int(text.size)
+    assert sum(tk.weight for tk in t.token_table) == n0 and len(t.token_table) == 29
+    done = t.mergeUntil({"max_iterations": 2000})
+    assert done == 2000
+    ids, offs = t.corpusIds()
+    weights = np.array([tk.weight for tk in t.token_table])
+    assert np.array_equal(np.bincount(ids, minlength=len(t.token_table)), weights)           # core.ts:201,345-346 bookkeeping
+    assert ids.size == n0 - sum(c.original_weight for _, _, c in t.merge_tokens)              # every replacement removes one token
+    assert np.all(np.diff(offs) >= 0) and offs[-1] == ids.size
+    w = [c.original_weight for _, _, c in t.merge_tokens]
+    assert all(w[i] >= w[i + 1] for i in range(len(w) - 1))                                   # counts never grow: weights are sorted
+    # unseen text: encode -> decode is the identity, encode is idempotent on its own output
+    text2, off2 = synth(32_000_000, 44)
+    raw, roff, _ = t.encodeTextBatch(text2.tobytes(), off2, vector=False)
+    assert np.all(np.diff(roff) >= 0) and roff[-1] == raw.size
+    back, boff, bad = t.decodeBatch(raw, roff, vector=False)
+    assert (bad == -1).all() and back == text2.tobytes() and np.array_equal(boff, off2)
+    raw2, roff2, _ = t.encodeTextBatch(back, boff, vector=False)
+    assert np.array_equal(raw, raw2) and np.array_equal(roff, roff2)
+    # a slice against the compiled oracle (sequential replaceAll per merge, core.ts:404-406)
+    o = IntOracle()
+    o.set_len16(np.ones(len(t.token_table), dtype=np.int32))
+    o.load_merges(np.array([[a.index, b.index, c.index] for a, b, c in t.merge_tokens], dtype=np.int32))
+    lut = np.full(256, -1, dtype=np.int32)
+    for ch, tk in t.char_to_token.items():
+        lut[ord(ch)] = tk.index
+    for d in list(range(0, 40)) + list(range(len(off2) - 41, len(off2) - 1)):
+        assert np.array_equal(raw[roff[d]:roff[d + 1]], o.encode(lut[text2[off2[d]:off2[d + 1]]], fast=True)), d
