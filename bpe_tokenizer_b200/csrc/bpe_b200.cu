@@ -1213,7 +1213,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
     e->stats.sites_merged = (int64_t)e->h_st->sites_total;
     e->stats.tie_breaks = e->h_st->tie_breaks;
     if (getenv("BPE_TRACE") && e->mg_rank == 0) {
-      fprintf(stderr, "[bpe r0] mg phases ms (decide, P1, wait, M1, wait, exchange, wait, P2, wait, P3, wait, tie):");
+      fprintf(stderr, "[bpe r0] mg phases ms (decide, P1, wait, M1, wait, send+local P2, barrier+peer wait, apply, wait, P3, wait, tie):");
       for (int i = 0; i < 12; i++) fprintf(stderr, " %.1f", (double)e->h_st->mg_prof_ns[i] * 1e-6);
       fprintf(stderr, "  total %.1f ms, %lld merges; host ms: hot rebuild %.1f, growth %.1f, launch..fetch %.1f, log %.1f\n", ms, (long long)done,
               host_ms[0], host_ms[1], host_ms[2], host_ms[3]);

@@ -114,8 +114,8 @@ __device__ __forceinline__ unsigned long long* mg_area(const MgArgs& M, int dst,
 
 // ---- exchange, executed by warp 0 of block 0: lane q talks to rank q, so its cost does not grow with the world size ----
 // header of a message: 16 u32 (H_* indices) in the first 64 bytes of the area, moved with 128-bit accesses
-__device__ __forceinline__ void mg_exchange_warp(const LoopArgsMg& P, DevState* st, uint32_t par, uint32_t n_rec, unsigned long long epoch,
-                                                 unsigned long long* const* flags) {
+__device__ __forceinline__ void mg_send_warp(const LoopArgsMg& P, DevState* st, uint32_t par, uint32_t n_rec, unsigned long long epoch,
+                                             unsigned long long* const* flags) {
   const MgArgs& M = P.M;
   const LoopArgs& L = P.L;
   const int q = (int)(threadIdx.x & 31u);
@@ -141,6 +141,14 @@ __device__ __forceinline__ void mg_exchange_warp(const LoopArgsMg& P, DevState* 
   }
   __syncwarp();
   if (peer) st_release_sys(flags[q] + 16 * M.rank, epoch);
+}
+
+// second half: wait for every peer's flag, then fold the G headers (OR of the error flags, minima of the capacities)
+__device__ __forceinline__ void mg_wait_fold_warp(const LoopArgsMg& P, DevState* st, uint32_t par, unsigned long long epoch,
+                                                  unsigned long long* const* flags) {
+  const MgArgs& M = P.M;
+  const int q = (int)(threadIdx.x & 31u);
+  const bool peer = q < M.world && q != M.rank;
   if (peer) {
     const unsigned long long* f = flags[M.rank] + 16 * q;
     unsigned long long t0 = now_ns();
@@ -156,7 +164,6 @@ __device__ __forceinline__ void mg_exchange_warp(const LoopArgsMg& P, DevState* 
     }
   }
   __syncwarp();
-  // fold the G headers: OR of the error flags, minima of the capacities
   uint32_t w[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) w[i] = (i == H_ERR) ? 0u : 0xFFFFFFFFu;
@@ -205,7 +212,10 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
     st->mg_abort = 0;
     st->n_newpair = 0;
   }
-  if (bid == 0 && threadIdx.x < 32) mg_exchange_warp(P, st, (uint32_t)((epoch + 1) & 1u), 0, epoch + 1, M.flag_data);
+  if (bid == 0 && threadIdx.x < 32) {
+    mg_send_warp(P, st, (uint32_t)((epoch + 1) & 1u), 0, epoch + 1, M.flag_data);
+    mg_wait_fold_warp(P, st, (uint32_t)((epoch + 1) & 1u), epoch + 1, M.flag_data);
+  }
   epoch++;
   {
     Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
@@ -426,7 +436,15 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
       GRID_BARRIER();
       MGPROF(4)
     }
-    if (bid == 0 && threadIdx.x < 32) mg_exchange_warp(P, st, epar, min(ld_cg(&st->n_out), M.inbox_stride - MG_HDR), epoch + 1, M.flag_data);
+    // ---- send, then do the LOCAL half of P2 while the peers' messages travel: the pairs born on this shard enter the table
+    // (their counts come with the records), the shard is rewritten.  The wait for the peers sits behind that work. ----
+    if (bid == 0 && threadIdx.x < 32) mg_send_warp(P, st, epar, min(ld_cg(&st->n_out), M.inbox_stride - MG_HDR), epoch + 1, M.flag_data);
+    const uint32_t n_sites_now = ld_cg(&st->n_sites[par]);
+    phase_new_pairs(A, c, A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, true, gtid, gthreads);
+    phase_rewrite(A, c, n_sites_now, gtid, gthreads);
+    MGPROF(5)
+    GRID_BARRIER();
+    if (bid == 0 && threadIdx.x < 32) mg_wait_fold_warp(P, st, epar, epoch + 1, M.flag_data);
     if (lead) {
       st->n_out = 0;  // nobody appends before the next merge's P1
       st->n_newpair = 0;
@@ -436,20 +454,19 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
       st->snap_hot_n = st->hot_n;  // stable: the appends of the previous merge are complete, the next ones come in P3
     }
     epoch++;
-    MGPROF(5)
-    GRID_BARRIER();
     MGPROF(6)
+    GRID_BARRIER();
     if (ld_cg(&st->mg_abort)) {
       if (lead) {
         st->status = LOOP_ERROR;
-        st->iters_done = it;  // the merge was not applied
-        st->n_tokens = n_tokens0 + it;
+        st->iters_done = it + 1;  // the local shard was already rewritten for this merge; the engine is unusable after an abort
+        st->n_tokens = n_tokens0 + it + 1;
         st->mg_epoch = epoch;
         st->mg_tie_epoch = tie_epoch;
       }
       return;
     }
-    // ---- P2: apply the deltas of all ranks to the replicated counts; lists of the locally new pairs ----
+    // ---- P2 (second half): apply the deltas of all ranks to the replicated counts ----
     {
       // all G record lists as ONE index space, so a thread walks a single record's chain whatever the world size
       uint32_t pre[MG_MAX_WORLD + 1];
@@ -493,9 +510,6 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
         }
       }
     }
-    phase_new_pairs(A, c, A.len16, L.max_length, 0, L.hot, L.hot_cap, L.pool_cap, true, gtid, gthreads);
-    const uint32_t n_sites_now = ld_cg(&st->n_sites[par]);
-    phase_rewrite(A, c, n_sites_now, gtid, gthreads);  // independent of the table work: fills the wait of the fast blocks
     MGPROF(7)
     GRID_BARRIER();
     MGPROF(8)
