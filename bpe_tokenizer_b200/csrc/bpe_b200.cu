@@ -183,7 +183,7 @@ struct bpe_engine {
 
   // staging of the host-buffer encode / restore calls (grow-only, reused across calls)
   DevBuf<int32_t> x_ids, x_out, x_tvi;
-  DevBuf<int64_t> x_off, x_ooff, x_bad;
+  DevBuf<int64_t> x_off, x_ooff, x_ooff2, x_bad;
   DevBuf<unsigned long long> x_flag;
   std::vector<int64_t> h_rel;
   EncodeScratch x_scratch;
@@ -2047,7 +2047,7 @@ int bpe_encode_text_batch(bpe_engine* e, const uint8_t* utf8, const int64_t* doc
   int64_t max_len = 0;
   for (int64_t d = 0; d < n_docs; d++) max_len = std::max(max_len, e->h_rel[(size_t)d + 1] - e->h_rel[(size_t)d]);
   CK(e->x_out.reserve((size_t)std::max<int64_t>(n_chars, 1)));
-  DevBuf<int64_t> d_ooff;
+  DevBuf<int64_t>& d_ooff = e->x_ooff2;
   CK(d_ooff.reserve((size_t)n_docs + 1));
   if (first_bad) CK(e->x_bad.reserve((size_t)std::max<int64_t>(n_docs, 1)));
   if (to_vector_index && n_tvi > 0) {
