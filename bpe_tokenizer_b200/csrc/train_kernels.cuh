@@ -685,6 +685,30 @@ __device__ __forceinline__ void agg_dec(const ApplyArgs& A, uint32_t key, bool h
   cnt_delta_warp(A, leader && s != NOSLOT, s, key, -(int32_t)__popc(peers), par);
 }
 
+// Two decrements at once: both first probes are issued before either is consumed (one DRAM round trip instead of two)
+__device__ __forceinline__ void agg_dec2(const ApplyArgs& A, uint32_t key1, bool has1, uint32_t key2, bool has2, uint32_t par) {
+  const PairTable& t = A.t;
+  uint32_t lane = lane_id();
+  uint32_t peers1 = __match_any_sync(0xFFFFFFFFu, has1 ? key1 : (EMPTY_KEY - 1 - lane));
+  uint32_t peers2 = __match_any_sync(0xFFFFFFFFu, has2 ? key2 : (EMPTY_KEY - 1 - lane));
+  bool lead1 = has1 && lane == (uint32_t)(__ffs(peers1) - 1);
+  bool lead2 = has2 && lane == (uint32_t)(__ffs(peers2) - 1);
+  uint32_t h1 = tbl_hash(t, key1), h2 = tbl_hash(t, key2);
+  uint32_t k1 = lead1 ? t.keys[h1] : EMPTY_KEY;
+  uint32_t k2 = lead2 ? t.keys[h2] : EMPTY_KEY;
+  uint32_t s1 = NOSLOT, s2 = NOSLOT;
+  if (lead1) {
+    s1 = (k1 == key1) ? h1 : (k1 == EMPTY_KEY ? NOSLOT : tbl_find(t, key1));
+    if (s1 == NOSLOT) atomicOr(&A.st->err, ERR_MISSING_KEY);
+  }
+  if (lead2) {
+    s2 = (k2 == key2) ? h2 : (k2 == EMPTY_KEY ? NOSLOT : tbl_find(t, key2));
+    if (s2 == NOSLOT) atomicOr(&A.st->err, ERR_MISSING_KEY);
+  }
+  cnt_delta_warp(A, lead1 && s1 != NOSLOT, s1, key1, -(int32_t)__popc(peers1), par);
+  cnt_delta_warp(A, lead2 && s2 != NOSLOT, s2, key2, -(int32_t)__popc(peers2), par);
+}
+
 // One adjacency of a pair BORN by this merge -- (tok, c) for side 0, (c, tok) for side 1 -- per `has` lane: occurrences
 // and counted occurrences go to the dense rows with fire-and-forget atomics (one per distinct token per warp).
 __device__ __forceinline__ void agg_new_dense(const ApplyArgs& A, uint32_t side, uint32_t tok, uint32_t c, bool has, bool counted,
@@ -748,7 +772,11 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
       }
     }
     FINE(1, w + q + koff)
-    if (!__any_sync(0xFFFFFFFFu, site)) continue;
+    // reserve the warp's cells in the site list NOW: the counter's round trip overlaps the neighbour walks below
+    const uint32_t smask = __ballot_sync(0xFFFFFFFFu, site);
+    if (!smask) continue;
+    uint32_t site_base = 0;
+    if (lane == (uint32_t)(__ffs(smask) - 1)) site_base = atomicAdd(&st->n_sites[par], (uint32_t)__popc(smask));
     SiteRec rec{p, NOPOS, NOTOKV, NOTOKV};
     // ---- adjacency on the left of the new token ----
     uint32_t dec1_key = 0, new1_tok = 0;
@@ -802,7 +830,6 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
       }
     }
     FINE(2, (uint32_t)dec1_key + new1_tok)
-    agg_dec(A, dec1_key, dec1, par);
     FINE(3, 0)
     agg_new_dense(A, 0, new1_tok, c, new1, new1_counted, par);
     rec.lslot = new1 ? new1_tok : NOTOKV;  // resolved to the pair's table slot by phase_apply (ND_L_SLOT)
@@ -835,17 +862,14 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
       }
     }
     FINE(5, (uint32_t)dec2_key + new2_tok)
-    agg_dec(A, dec2_key, dec2, par);
+    agg_dec2(A, dec1_key, dec1, dec2_key, dec2, par);
     FINE(6, 0)
     agg_new_dense(A, 1, new2_tok, c, new2, true, par);
     rec.rslot = new2 ? new2_tok : NOTOKV;
     FINE(7, rec.rslot)
 
-    // ---- record the site (one counter atomic per warp) ----
-    uint32_t smask = __ballot_sync(0xFFFFFFFFu, site);
-    uint32_t base = 0;
-    if (lane == (uint32_t)(__ffs(smask) - 1)) base = atomicAdd(&st->n_sites[par], (uint32_t)__popc(smask));
-    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(smask) - 1);
+    // ---- record the site ----
+    uint32_t base = __shfl_sync(0xFFFFFFFFu, site_base, __ffs(smask) - 1);
     if (site) {
       uint32_t k = base + __popc(smask & ((1u << lane) - 1u));
       if (k < A.sites_cap) reinterpret_cast<uint4*>(A.sites)[k] = make_uint4(rec.p, rec.lpos, rec.lslot, rec.rslot);
