@@ -50,7 +50,7 @@ __device__ __forceinline__ uint32_t mt_lookup(const MergeTable& mt, uint32_t a, 
 // left end before time r.  The lowest rank present always qualifies, so every round makes progress.
 // SL and SR are prefix scans of clamp functions x -> max(lo, min(hi, x)), which compose into clamps: one
 // warp-shuffle scan per 32 tokens.  After each round the document is compacted in place, so the work shrinks with
-// the token count.  Prototype + fuzz against the literal oracle: tools/proto_encode_safe.py.
+// the token count.  Prototype + fuzz against the literal oracle: tests/proto/proto_encode_safe.py.
 constexpr uint32_t RK_DIRTY = 0xFFFFFFFEu;
 constexpr uint32_t RINF = 0xFFFFu;
 

@@ -19,7 +19,7 @@
 // run must not grow at its left end before time r).  The lowest rank present always qualifies, so every round makes
 // progress; with the spine bounds the number of rounds is close to the depth of the merge trees (~8 for 32k merges).
 // SL and SR are scans of clamp functions x -> max(lo, min(hi, x)), which compose into clamps.
-// Prototype, fuzzed against the literal oracle: tools/proto_encode_lanes.py.
+// Prototype, fuzzed against the literal oracle: tests/proto/proto_encode_lanes.py.
 #pragma once
 #include "common.cuh"
 

@@ -3,9 +3,9 @@ Per round: pass 2 (right to left) computes SR on the pre-round state, pass 3 wal
 left token `cur` that greedily absorbs the following pre-round tokens while the merge is provably the one the
 sequential process performs (new tokens included: right-cascade), exactly like replaceAll consumes a run."""
 import os, random, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from tools.proto_encode_lanes import Tables, clamp_apply, INF, NONE, BOUNDARY, DIRTY
+from tests.proto.proto_encode_lanes import Tables, clamp_apply, INF, NONE, BOUNDARY, DIRTY
 
 NOBLOCK = 0x1FFFF
 
@@ -261,15 +261,15 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "stats":
         import numpy as np
         from bpe_tokenizer_b200.synth import synth_corpus
-        log = np.load(os.path.join(ROOT, "gpurun_out", "merges_1000000000_32000.npy"))
-        alphabet = np.load(os.path.join(ROOT, "gpurun_out", "alphabet_1000000000.npy"))
+        log = np.load(os.path.join(ROOT, "tools", "data", "merges_cfg3_abc.npy"))
+        alphabet = np.load(os.path.join(ROOT, "tools", "data", "alphabet_cfg3.npy"))
         lut = np.full(256, -1, dtype=np.int64)
         lut[alphabet] = np.arange(len(alphabet))
-        merges = [(int(m["a"]), int(m["b"]), int(m["c"])) for m in log]
+        merges = [tuple(int(x) for x in m) for m in log]
         T = Tables(merges)
         text, off = synth_corpus(120_000, seed=44)
         docs = [lut[text[off[d]:off[d + 1]]].tolist() for d in range(len(off) - 1)]
-        from tools import proto_encode_lanes as base
+        from tests.proto import proto_encode_lanes as base
         for casc in (True, False):
             stats = []
             i = 0

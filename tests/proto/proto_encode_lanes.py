@@ -15,7 +15,7 @@ A pair j of rank r is merged this round iff r <= SL[j] and r <= SR[j+1]; pairs (
 replaceAll parity inside their run and need r <= T[s-1] at the run start s (the run must not grow at its left end).
 """
 import math, os, random, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 INF = 0xFFFF
@@ -271,12 +271,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "stats":
         import numpy as np
         from bpe_tokenizer_b200.synth import synth_corpus
-        log = np.load(os.path.join(ROOT, "gpurun_out", "merges_1000000000_32000.npy"))
-        alphabet = np.load(os.path.join(ROOT, "gpurun_out", "alphabet_1000000000.npy"))
+        log = np.load(os.path.join(ROOT, "tools", "data", "merges_cfg3_abc.npy"))
+        alphabet = np.load(os.path.join(ROOT, "tools", "data", "alphabet_cfg3.npy"))
         lut = np.full(256, -1, dtype=np.int64)
         lut[alphabet] = np.arange(len(alphabet))
         nm = int(sys.argv[2]) if len(sys.argv) > 2 else len(log)
-        merges = [(int(m["a"]), int(m["b"]), int(m["c"])) for m in log[:nm]]
+        merges = [tuple(int(x) for x in m) for m in log[:nm]]
         T = Tables(merges)
         text, off = synth_corpus(120_000, seed=44)
         docs = [lut[text[off[d]:off[d + 1]]].tolist() for d in range(len(off) - 1)]

@@ -2,7 +2,7 @@
 literal oracle.  A pair (x,y) of rank r may be merged NOW iff x cannot be consumed from the left and y cannot be
 consumed from the right strictly before time r (then the sequential process merges exactly this pair at time r)."""
 import os, random, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import LiteralTokenizer
 
