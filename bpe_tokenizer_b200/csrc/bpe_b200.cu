@@ -289,9 +289,7 @@ int alloc_table(bpe_engine* e, uint32_t cap) {
   }
   if (e->mg_world > 1) {  // per-slot side arrays of the sharded loop follow the table (all zero between merges)
     CK(e->mg_dlt.reserve(cap));
-    CK(e->mg_mark.reserve(cap));
     CK(cudaMemsetAsync(e->mg_dlt.p, 0, (size_t)cap * 4, e->stream));
-    CK(cudaMemsetAsync(e->mg_mark.p, 0, (size_t)cap * 4, e->stream));
   }
   return BPE_OK;
 }
@@ -475,6 +473,8 @@ ApplyArgs apply_args(bpe_engine* e) {
   A.sites_cap = (uint32_t)std::min<size_t>(e->sites.cap, 0xFFFFFFFFu);
   A.newslots = e->newslots.p;
   A.nd = e->nd.p;
+  A.newpair = nullptr;
+  A.newpair_cap = 0;
   A.new_cap = (uint32_t)std::min<size_t>(e->newslots.cap, 0xFFFFFFFFu);
   A.len16 = e->d_len16.p;
   A.scan_mode = e->scan_mode;
@@ -1004,7 +1004,6 @@ MgArgs mg_args(bpe_engine* e) {
     M.inbox[q] = reinterpret_cast<unsigned long long*>(base + 2 * flags_bytes);
     M.tiebox[q] = reinterpret_cast<uint32_t*>(base + 2 * flags_bytes + inbox_bytes);
   }
-  M.mark = e->mg_mark.p;
   M.tie_sorted = e->mg_tie_sorted.p;
   M.newpair = e->mg_newpair.p;
   M.newpair_cap = (uint32_t)e->mg_newpair.cap;
@@ -1073,6 +1072,8 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
     LoopArgsMg P;
     LoopArgs& L = P.L;
     L.A = apply_args(e);
+    L.A.newpair = e->mg_newpair.p;
+    L.A.newpair_cap = (uint32_t)e->mg_newpair.cap;
     L.A.dlt = e->mg_dlt.p;
     L.A.touched = e->mg_touched.p;
     L.A.touched_cap = (uint32_t)e->mg_touched.cap;

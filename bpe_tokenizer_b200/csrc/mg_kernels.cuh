@@ -38,7 +38,6 @@ struct MgArgs {
   unsigned long long* inbox[MG_MAX_WORLD];      // [2][world][inbox_stride]
   uint32_t* tiebox[MG_MAX_WORLD];               // [2][world][tie_cap]
   // local scratch
-  uint32_t* mark;          // per table slot: last merge (c + 1) that put the pair on the hot list
   uint32_t* tie_sorted;    // candidates (table slots) in canonical key order
   uint32_t* newpair;       // table slots of the pairs born in the current merge (any rank), deduplicated
   uint32_t newpair_cap;
@@ -367,6 +366,7 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
       st->n_sites[par ^ 1u] = 0;
       st->n_new[par ^ 1u] = 0;
       st->n_touched[par ^ 1u] = 0;
+      st->n_newpair = 0;  // consumed by the previous merge's P3
       if (w.mult > 1) st->tie_breaks++;
     }
     const uint32_t epar = (uint32_t)((epoch + 1) & 1u);
@@ -447,7 +447,6 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
     if (bid == 0 && threadIdx.x < 32) mg_wait_fold_warp(P, st, epar, epoch + 1, M.flag_data);
     if (lead) {
       st->n_out = 0;  // nobody appends before the next merge's P1
-      st->n_newpair = 0;
       st->n_cand = 0;
       st->tie_pos = ~0ull;
       t.cnt[w.slot] = 0;  // every counted occurrence of the winner, on every rank, is being replaced
@@ -490,8 +489,7 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
             atomicOr(&st->err, ERR_TABLE_FULL);
           } else {
             atomicAdd(t.cnt + s, (uint32_t)rec);
-            // a pair born in this merge (it contains c): first record of it on this rank lists it for the hot-list test of P3
-            if (((key >> 16) == c || (key & 0xFFFFu) == c)) born = atomicMax(M.mark + s, c + 1u) < c + 1u;
+            born = ins;  // a pair born on another shard only: whoever inserts the key lists it for the hot-list test of P3
           }
         }
         uint32_t im = __ballot_sync(0xFFFFFFFFu, ins);

@@ -607,6 +607,10 @@ struct ApplyArgs {
   // pairs born by a merge are (x,c) or (c,y): they are accumulated in dense per-token rows (L2-resident, RED atomics, no
   // hashing) and entered into the pair table once each by phase_new_pairs.  nd[ND_*][tok], row stride ND_STRIDE
   uint32_t* nd;
+  // sharded training: table slots of the pairs born by the current merge on ANY rank (candidates for the hot list); a
+  // pair is listed by whoever inserts its key -- phase_new_pairs for pairs born on this shard, the record pass otherwise
+  uint32_t* newpair;
+  uint32_t newpair_cap;
   // sharded training, small merges: every (pair, delta) goes straight into the record area of each rank's inbox
   unsigned long long* push[8];
   int push_world;  // 0: staged mode (or single GPU)
@@ -937,7 +941,13 @@ __device__ __forceinline__ void phase_new_pairs(const ApplyArgs& A, uint32_t c, 
     t.occ_len[s] = len;
     t.occ_fill[s] = 0;
     A.nd[(size_t)(side ? ND_R_SLOT : ND_L_SLOT) * ND_STRIDE + tok] = s;
-    if (!counts_elsewhere) {
+    if (counts_elsewhere) {
+      if (ins) {  // (the counts arrive with the records of the exchange; P3 tests the pair against the hot-list threshold)
+        uint32_t k = atomicAdd(&st->n_newpair, 1u);
+        if (k < A.newpair_cap) A.newpair[k] = s;
+        else atomicOr(&st->err, ERR_HOT_OVERFLOW);
+      }
+    } else {
       t.cnt[s] = cnt;  // the key is new: nobody else touches its count in this phase
       if (hot_valid) {
         unsigned long long pr = slot_primary(t, len16, s, max_length);
