@@ -465,7 +465,9 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
       }
       return;
     }
-    // ---- P2 (second half): apply the deltas of all ranks to the replicated counts ----
+    // ---- P2 (second half): apply the deltas of all ranks to the replicated counts; the lists of the pairs born on this
+    // shard are filled next to it (independent work: positions only) ----
+    phase_fill(A, n_sites_now, bid, nblk);
     {
       // all G record lists as ONE index space, so a thread walks a single record's chain whatever the world size
       uint32_t pre[MG_MAX_WORLD + 1];
@@ -518,7 +520,6 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
       st->snap_err = st->err;
     }
     const uint32_t hot_n0 = ld_cg(&st->snap_hot_n);
-    phase_fill(A, n_sites_now, bid, nblk);
     Best mine{0ull, NOSLOT, 0};
     {
       const uint32_t nnp = min(ld_cg(&st->n_newpair), M.newpair_cap);
