@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -72,6 +73,25 @@ struct DevBuf {
     p = q;
     cap = want;
     return cudaSuccess;
+  }
+};
+
+// grow-only pinned host buffer (staging of the small per-document arrays of the encode pipeline)
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~PinBuf() {
+    if (p) cudaFreeHost(p);
+  }
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t err = cudaHostAlloc((void**)&p, n * sizeof(T), cudaHostAllocDefault);
+    if (err == cudaSuccess) cap = n;
+    return err;
   }
 };
 
@@ -187,6 +207,12 @@ struct bpe_engine {
   DevBuf<unsigned long long> x_flag;
   std::vector<int64_t> h_rel;
   EncodeScratch x_scratch;
+  // the host-buffer encode calls run as a three-stream pipeline over chunks of whole documents: copy in | encode | copy out
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_done = nullptr, ev_res[2] = {nullptr, nullptr};
+  unsigned long long* h_pipe = nullptr;  // pinned: 3 slots x 4 words of per-chunk flags, [12..13] flags of the lane kernel
+  PinBuf<int64_t> h_in_off, h_out_off, h_bad;  // pinned staging of document offsets in, output offsets and first offenders out
+  int64_t enc_chunk = 64ll << 20;        // input units (ids or bytes) per chunk; BPE_ENC_CHUNK overrides
 
   // scratch
   DevBuf<int32_t> stage_ids;
@@ -667,10 +693,25 @@ int launch_encode_lanes(bpe_engine* e, const int32_t* dev_ids, const int64_t* de
 }
 
 
+// streams, events and pinned flag words of the host-buffer encode pipeline (encode_pipeline below)
+int ensure_pipe(bpe_engine* e) {
+  if (e->h_pipe) return BPE_OK;
+  CK(cudaStreamCreateWithFlags(&e->s_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->s_out, cudaStreamNonBlocking));
+  for (cudaEvent_t* ev : {&e->ev_in[0], &e->ev_in[1], &e->ev_in[2], &e->ev_done, &e->ev_res[0], &e->ev_res[1]})
+    CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+  if (const char* v = getenv("BPE_ENC_CHUNK"))
+    if (atoll(v) > 0) e->enc_chunk = atoll(v);
+  CK(cudaHostAlloc((void**)&e->h_pipe, 16 * sizeof(unsigned long long), cudaHostAllocDefault));
+  return BPE_OK;
+}
+
 // device-resident encode; leaves compacted output in dev_out / dev_out_offsets
 int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const int64_t* dev_doc_off, int64_t n_docs,
                int64_t n_ids, int64_t max_doc_len, const int32_t* dev_tvi, int32_t n_tvi, int32_t* dev_out,
-               int64_t* dev_out_offsets, int64_t* dev_first_bad, int64_t* n_out) {
+               int64_t* dev_out_offsets, int64_t* dev_first_bad, int64_t* n_out, const std::function<int()>* overlap = nullptr) {
+  // `overlap`: host work of the caller that runs while the lane kernel does (the encode pipeline prepares its next chunk there)
+  int overlap_rc = BPE_OK;
   if (e->h_merges.size() / 3 > EL_MAX_RANK + 1) return fail(e, BPE_E_DOMAIN, "merge list too long");
   TRY(ensure_lane_tables(e));
   CK(sc.out_tmp.reserve((size_t)std::max<int64_t>(n_ids, 1)));
@@ -711,9 +752,15 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
       TRY((launch_encode_lanes<32, 10>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
     else
       TRY((launch_encode_lanes<48, 6>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
-    uint32_t hf[2] = {0, 0};
-    CK(cudaMemcpyAsync(hf, sc.flags.p, sizeof hf, cudaMemcpyDeviceToHost, e->stream));
+    TRY(ensure_pipe(e));
+    volatile uint32_t* hf = reinterpret_cast<volatile uint32_t*>(e->h_pipe + 12);  // pinned: the copy below does not block the host
+    CK(cudaMemcpyAsync((void*)hf, sc.flags.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (overlap) {
+      overlap_rc = (*overlap)();
+      overlap = nullptr;
+    }
     CK(cudaStreamSynchronize(e->stream));
+    if (overlap_rc != BPE_OK) return overlap_rc;
     if (hf[1]) return fail(e, BPE_E_INTERNAL, "encode rounds did not converge");
     run_old = hf[0] != 0;
   }
@@ -754,9 +801,11 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
     CKL();
   }
   CK(cudaEventRecord(e->ev1, e->stream));
+  if (overlap) overlap_rc = (*overlap)();  // the lane kernel did not run
   uint64_t total = 0;
   CK(cudaMemcpyAsync(&total, sc.out_off.p + n_docs, sizeof total, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
+  if (overlap_rc != BPE_OK) return overlap_rc;
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->stats.ms_encode = ms;
@@ -1337,6 +1386,11 @@ void bpe_destroy(bpe_engine* e) {
   if (e->h_st) cudaFreeHost(e->h_st);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  for (cudaEvent_t ev : {e->ev_in[0], e->ev_in[1], e->ev_in[2], e->ev_done, e->ev_res[0], e->ev_res[1]})
+    if (ev) cudaEventDestroy(ev);
+  if (e->s_in) cudaStreamDestroy(e->s_in);
+  if (e->s_out) cudaStreamDestroy(e->s_out);
+  if (e->h_pipe) cudaFreeHost(e->h_pipe);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -1769,29 +1823,17 @@ int stage_encode_inputs(bpe_engine* e, const int32_t* ids, const int64_t* doc_of
   return BPE_OK;
 }
 
+int encode_host(bpe_engine* e, bool is_text, const int32_t* ids, const uint8_t* utf8, const int64_t* off, int64_t n_docs, const int32_t* to_vector_index,
+                int32_t n_tvi, int32_t* out, int64_t out_cap, int64_t* out_offsets, int64_t* first_bad, int64_t* n_out, int64_t* unknown_pos,
+                int32_t* unknown_code_point);
+
 int bpe_encode_batch(bpe_engine* e, const int32_t* ids, const int64_t* doc_offsets, int64_t n_docs, const int32_t* to_vector_index,
                      int32_t n_tvi, int32_t* out, int64_t out_cap, int64_t* out_offsets, int64_t* first_bad, int64_t* n_out) {
   if (!e || !n_out || !out_offsets) return fail(e, BPE_E_INVALID, "bad encode arguments");
-  TRY(check_offsets(e, doc_offsets, n_docs));
+  if (n_docs < 0 || (!doc_offsets && n_docs > 0)) return fail(e, BPE_E_INVALID, "bad document offsets");
+  if (n_docs > 0 && doc_offsets[n_docs] > doc_offsets[0] && !ids) return fail(e, BPE_E_INVALID, "null ids");
   CK(cudaSetDevice(e->device));
-  int64_t total = 0, max_len = 0;
-  TRY(stage_encode_inputs(e, ids, doc_offsets, n_docs, &total, &max_len));
-  if (first_bad) CK(e->x_bad.reserve((size_t)std::max<int64_t>(n_docs, 1)));
-  if (to_vector_index && n_tvi > 0) {
-    CK(e->x_tvi.reserve((size_t)n_tvi));
-    CK(cudaMemcpyAsync(e->x_tvi.p, to_vector_index, (size_t)n_tvi * 4, cudaMemcpyHostToDevice, e->stream));
-  }
-  TRY(encode_dev(e, e->x_scratch, e->x_ids.p, e->x_off.p, n_docs, total, max_len, to_vector_index ? e->x_tvi.p : nullptr, n_tvi, e->x_out.p,
-                 e->x_ooff.p, first_bad ? e->x_bad.p : nullptr, n_out));
-  CK(cudaMemcpyAsync(out_offsets, e->x_ooff.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
-  if (first_bad && n_docs) CK(cudaMemcpyAsync(first_bad, e->x_bad.p, (size_t)n_docs * 8, cudaMemcpyDeviceToHost, e->stream));
-  if (*n_out > out_cap || (*n_out && !out)) {
-    CK(cudaStreamSynchronize(e->stream));
-    return fail(e, BPE_E_CAPACITY, "output buffer holds %lld values, need %lld", (long long)out_cap, (long long)*n_out);
-  }
-  if (*n_out) CK(cudaMemcpyAsync(out, e->x_out.p, (size_t)*n_out * 4, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  return BPE_OK;  // the staging buffers stay (grow-only): re-allocating GBs per call costs more than the copies
+  return encode_host(e, false, ids, nullptr, doc_offsets, n_docs, to_vector_index, n_tvi, out, out_cap, out_offsets, first_bad, n_out, nullptr, nullptr);
 }
 
 
@@ -1825,9 +1867,47 @@ int ensure_cpmap(bpe_engine* e) {
   return BPE_OK;
 }
 
-// decodes into e->x_ids (placeholders -(cp+1) for unknown code points), document boundaries in code points into
-// e->x_off (device) and e->h_rel (host).  track_new: keep first positions of unknown code points (addToCorpus);
-// otherwise *unknown receives (pos << 32 | cp) of the first unknown code point or ~0.
+// launches only, no synchronisation: the UTF-8 bytes of whole documents (d_text, boundaries d_byte_off relative to it) become
+// ids (placeholders -(cp+1) for unknown code points) and document boundaries in code points (d_char_off, n_docs + 1).
+// track_new: keep the first positions of unknown code points (addToCorpus); otherwise d_flags[0] receives
+// (pos << 32 | cp) of the first unknown code point or ~0.  d_flags[1] = code points of the longest document,
+// d_flags[2] = code points in total.
+int text_decode_dev(bpe_engine* e, const uint8_t* d_text, int64_t nbytes, const int64_t* d_byte_off, int64_t n_docs, int32_t* d_ids,
+                    int64_t* d_char_off, bool track_new, unsigned long long* d_flags) {
+  if ((uint64_t)nbytes >= 0xFFFFFFF0ull) return fail(e, BPE_E_DOMAIN, "text batch too large for one call");
+  uint32_t n_tiles = (uint32_t)((nbytes + TX_TILE - 1) / TX_TILE);
+  CK(e->x_tilecnt.reserve((size_t)n_tiles + 1));
+  CK(e->x_tileoff.reserve((size_t)n_tiles + 2));
+  CK(e->x_doccnt.reserve((size_t)n_docs + 1));
+  CK(e->x_docoff.reserve((size_t)n_docs + 2));
+  CK(cudaMemsetAsync(d_flags, 0xFF, 8, e->stream));
+  CK(cudaMemsetAsync(d_flags + 1, 0, 8, e->stream));
+  if (n_tiles) {
+    k_utf8_count<<<n_tiles, TX_THREADS, 0, e->stream>>>(d_text, (uint64_t)nbytes, e->x_tilecnt.p);
+    CKL();
+  }
+  TRY(scan_u32(e, e->x_scratch, e->x_tilecnt.p, e->x_tileoff.p, n_tiles));
+  if (n_tiles) {
+    k_utf8_decode<<<n_tiles, TX_THREADS, 0, e->stream>>>(d_text, (uint64_t)nbytes, e->x_tileoff.p, e->d_cpmap.p, d_ids,
+                                                         track_new ? e->d_firstpos.p : nullptr, track_new ? nullptr : d_flags);
+    CKL();
+  }
+  // document boundaries in code points: per-document counts, then a scan
+  if (n_docs) {
+    k_utf8_doc_counts<<<(int)std::min<int64_t>((n_docs + 7) / 8, (int64_t)e->grid(16)), 256, 0, e->stream>>>(d_text, d_byte_off, n_docs, e->x_doccnt.p);
+    CKL();
+    k_max_u32<<<(int)std::min<int64_t>((n_docs + 255) / 256, (int64_t)e->grid(4)), 256, 0, e->stream>>>(e->x_doccnt.p, n_docs, d_flags + 1);
+    CKL();
+  }
+  TRY(scan_u32(e, e->x_scratch, e->x_doccnt.p, e->x_docoff.p, (uint32_t)n_docs));
+  k_u64_to_i64<<<(int)std::min<int64_t>((n_docs + 256) / 256, (int64_t)e->grid(8)), 256, 0, e->stream>>>(e->x_docoff.p, d_char_off, n_docs + 1);
+  CKL();
+  CK(cudaMemcpyAsync(d_flags + 2, e->x_docoff.p + n_docs, 8, cudaMemcpyDeviceToDevice, e->stream));
+  return BPE_OK;
+}
+
+// one un-pipelined batch (bpe_add_text): decodes into e->x_ids, document boundaries in code points into e->x_off (device)
+// and e->h_rel (host)
 int text_to_ids(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_offsets, int64_t n_docs, bool track_new, int64_t* n_chars,
                 unsigned long long* unknown) {
   TRY(check_offsets(e, doc_byte_offsets, n_docs));
@@ -1837,38 +1917,14 @@ int text_to_ids(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_offs
   if ((uint64_t)nbytes >= 0xFFFFFFF0ull) return fail(e, BPE_E_DOMAIN, "text batch too large for one call");
   std::vector<int64_t> rel((size_t)n_docs + 1, 0);
   for (int64_t d = 0; d < n_docs; d++) rel[d + 1] = doc_byte_offsets[d + 1] - base;
-  uint32_t n_tiles = (uint32_t)((nbytes + TX_TILE - 1) / TX_TILE);
   CK(e->x_text.reserve((size_t)std::max<int64_t>(nbytes, 1)));
-  CK(e->x_tilecnt.reserve((size_t)n_tiles + 1));
-  CK(e->x_tileoff.reserve((size_t)n_tiles + 2));
   CK(e->x_ids.reserve((size_t)std::max<int64_t>(nbytes, 1)));  // at most one code point per byte
   CK(e->x_off.reserve((size_t)n_docs + 1));
   CK(e->x_ooff.reserve((size_t)n_docs + 1));
-  CK(e->x_flag.reserve(1));
+  CK(e->x_flag.reserve(8));
   if (nbytes) CK(cudaMemcpyAsync(e->x_text.p, utf8 + base, (size_t)nbytes, cudaMemcpyHostToDevice, e->stream));
   CK(cudaMemcpyAsync(e->x_ooff.p, rel.data(), (size_t)(n_docs + 1) * 8, cudaMemcpyHostToDevice, e->stream));  // byte offsets
-  CK(cudaMemsetAsync(e->x_flag.p, 0xFF, 8, e->stream));
-  if (n_tiles) {
-    k_utf8_count<<<n_tiles, TX_THREADS, 0, e->stream>>>(e->x_text.p, (uint64_t)nbytes, e->x_tilecnt.p);
-    CKL();
-  }
-  TRY(scan_u32(e, e->x_scratch, e->x_tilecnt.p, e->x_tileoff.p, n_tiles));
-  if (n_tiles) {
-    k_utf8_decode<<<n_tiles, TX_THREADS, 0, e->stream>>>(e->x_text.p, (uint64_t)nbytes, e->x_tileoff.p, e->d_cpmap.p, e->x_ids.p,
-                                                         track_new ? e->d_firstpos.p : nullptr, track_new ? nullptr : e->x_flag.p);
-    CKL();
-  }
-  {  // document boundaries in code points: per-document counts, then a scan
-    CK(e->x_doccnt.reserve((size_t)n_docs + 1));
-    CK(e->x_docoff.reserve((size_t)n_docs + 2));
-    if (n_docs) {
-      k_utf8_doc_counts<<<(int)std::min<int64_t>((n_docs + 7) / 8, (int64_t)e->grid(16)), 256, 0, e->stream>>>(e->x_text.p, e->x_ooff.p, n_docs, e->x_doccnt.p);
-      CKL();
-    }
-    TRY(scan_u32(e, e->x_scratch, e->x_doccnt.p, e->x_docoff.p, (uint32_t)n_docs));
-    k_u64_to_i64<<<(int)std::min<int64_t>((n_docs + 256) / 256, (int64_t)e->grid(8)), 256, 0, e->stream>>>(e->x_docoff.p, e->x_off.p, n_docs + 1);
-    CKL();
-  }
+  TRY(text_decode_dev(e, e->x_text.p, nbytes, e->x_ooff.p, n_docs, e->x_ids.p, e->x_off.p, track_new, e->x_flag.p));
   e->h_rel.resize((size_t)n_docs + 1);
   CK(cudaMemcpyAsync(e->h_rel.data(), e->x_off.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
   unsigned long long unk = ~0ull;
@@ -1877,6 +1933,198 @@ int text_to_ids(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_offs
   *n_chars = n_docs ? e->h_rel[(size_t)n_docs] : 0;
   if (unknown) *unknown = unk;
   return BPE_OK;
+}
+
+// ---- host buffers in, host buffers out: chunks of whole documents flow through three streams ----------------------------
+// copy in (s_in) | front end + encode (e->stream) | copy out (s_out).  Chunk c+1 is uploaded while chunk c is encoded and the
+// vectors of chunk c-1 travel back; every chunk owns its own region of the staging buffers, so no stage waits for a buffer.
+// With pinned host buffers the call costs max(PCIe in, encode, PCIe out) instead of their sum; with pageable buffers the
+// copies are synchronous and the call degrades to the serial order.
+struct PipeChunk {
+  int64_t d0 = 0, d1 = 0;    // documents [d0, d1)
+  int64_t in0 = 0, in1 = 0;  // input units (ids or bytes) relative to the first document of the batch
+  int64_t max_len = 0;       // longest document in input units
+  int64_t reg = 0, oreg = 0; // where the chunk lives in the unit staging buffers / the offset staging buffers
+};
+
+// the next chunk starting at document d0: about `target` input units, at least one document.  The offsets are checked on the
+// way (nothing is read through an offset that was not) and written, relative to the chunk, to `rel` (d1 - d0 + 1 values).
+int next_chunk(bpe_engine* e, const int64_t* off, int64_t n_docs, int64_t d0, int64_t target, int64_t* rel, PipeChunk* c) {
+  const int64_t first = off[d0], limit = first + target;
+  int64_t d = d0, max_len = 0;
+  rel[0] = 0;
+  while (d < n_docs && (d == d0 || off[d + 1] <= limit)) {
+    int64_t len = off[d + 1] - off[d];
+    if (len < 0) return fail(e, BPE_E_INVALID, "document offsets must be non-decreasing (doc %lld)", (long long)d);
+    max_len = std::max(max_len, len);
+    d++;
+    rel[d - d0] = off[d] - first;
+  }
+  c->d0 = d0;
+  c->d1 = d;
+  c->in0 = first - off[0];
+  c->in1 = off[d] - off[0];
+  c->max_len = max_len;
+  return BPE_OK;
+}
+
+int encode_pipeline(bpe_engine* e, const bool is_text, const int32_t* ids, const uint8_t* utf8, const int64_t* off, int64_t n_docs,
+                    const int32_t* to_vector_index, int32_t n_tvi, int32_t* out, int64_t out_cap, int64_t* out_offsets, int64_t* first_bad,
+                    int64_t* n_out, int64_t* unknown_pos, int32_t* unknown_code_point) {
+  const int64_t base = off[0], target = std::max<int64_t>(e->enc_chunk, 1), pad = 256;
+  if (off[n_docs] < base) return fail(e, BPE_E_INVALID, "document offsets must be non-decreasing");
+  const int64_t total = off[n_docs] - base;
+  // two consecutive chunks always hold more than `target` units, which bounds their number
+  const int64_t max_chunks = std::min<int64_t>(2 * (total / target) + 4, n_docs + 1);
+  const size_t unit_cap = (size_t)(total + pad * max_chunks), off_cap = (size_t)(n_docs + max_chunks + 1);
+  // everything a chunk in flight may touch is allocated before the first copy starts
+  if (is_text) {
+    TRY(ensure_cpmap(e));
+    CK(e->x_text.reserve(unit_cap));
+    CK(e->x_ooff2.reserve(off_cap));
+  }
+  CK(e->x_ids.reserve(unit_cap));  // text: at most one code point per byte
+  CK(e->x_out.reserve(unit_cap));
+  CK(e->x_off.reserve(off_cap));
+  CK(e->x_ooff.reserve(off_cap));
+  CK(e->x_flag.reserve(12));
+  CK(e->h_in_off.reserve(off_cap));
+  CK(e->h_out_off.reserve((size_t)n_docs + 1));
+  if (first_bad) {
+    CK(e->x_bad.reserve((size_t)n_docs));
+    CK(e->h_bad.reserve((size_t)n_docs));
+  }
+  const int32_t* d_tvi = nullptr;
+  if (to_vector_index && n_tvi > 0) {
+    CK(e->x_tvi.reserve((size_t)n_tvi));
+    CK(cudaMemcpyAsync(e->x_tvi.p, to_vector_index, (size_t)n_tvi * 4, cudaMemcpyHostToDevice, e->stream));
+  }
+  if (to_vector_index) d_tvi = e->x_tvi.p;
+  int64_t* d_in_off = is_text ? e->x_ooff.p : e->x_off.p;  // the caller's offsets relative to the chunk (text: in bytes)
+  int64_t* d_out_off = is_text ? e->x_ooff2.p : e->x_ooff.p;
+
+  // s_in: the chunk after `prev` goes to the device (units, offsets; ids are checked against the token table there)
+  auto upload_next = [&](const PipeChunk& prev, int slot, PipeChunk* c) -> int {
+    const int64_t reg = (prev.reg + (prev.in1 - prev.in0) + pad - 1) / pad * pad, oreg = prev.oreg + (prev.d1 - prev.d0) + (prev.d1 ? 1 : 0);
+    TRY(next_chunk(e, off, n_docs, prev.d1, target, e->h_in_off.p + oreg, c));
+    c->reg = reg;
+    c->oreg = oreg;
+    const int64_t len = c->in1 - c->in0, nd = c->d1 - c->d0;
+    CK(cudaMemcpyAsync(d_in_off + oreg, e->h_in_off.p + oreg, (size_t)(nd + 1) * 8, cudaMemcpyHostToDevice, e->s_in));
+    if (len && is_text) CK(cudaMemcpyAsync(e->x_text.p + reg, utf8 + base + c->in0, (size_t)len, cudaMemcpyHostToDevice, e->s_in));
+    if (len && !is_text) CK(cudaMemcpyAsync(e->x_ids.p + reg, ids + base + c->in0, (size_t)len * 4, cudaMemcpyHostToDevice, e->s_in));
+    if (!is_text) {  // ids must name existing tokens; the first offender is reported like the reference's left-to-right scan would
+      CK(cudaMemsetAsync(e->x_flag.p + slot * 4, 0xFF, 8, e->s_in));
+      if (len) {
+        k_first_bad_id<<<e->grid(8), 256, 0, e->s_in>>>(e->x_ids.p + reg, (uint64_t)len, (uint32_t)e->n_tokens, e->x_flag.p + slot * 4);
+        CKL();
+      }
+      CK(cudaMemcpyAsync(e->h_pipe + slot * 4, e->x_flag.p + slot * 4, 8, cudaMemcpyDeviceToHost, e->s_in));
+    }
+    CK(cudaEventRecord(e->ev_in[slot], e->s_in));
+    return BPE_OK;
+  };
+  // the per-document results of a finished chunk leave the pinned staging for the caller's arrays
+  auto deliver = [&](const PipeChunk& c, int res_slot, bool last) -> int {
+    CK(cudaEventSynchronize(e->ev_res[res_slot]));
+    const int64_t nd = c.d1 - c.d0;
+    memcpy(out_offsets + c.d0, e->h_out_off.p + c.d0, (size_t)(nd + (last ? 1 : 0)) * 8);
+    if (first_bad) memcpy(first_bad + c.d0, e->h_bad.p + c.d0, (size_t)nd * 8);
+    return BPE_OK;
+  };
+
+  PipeChunk chunks[3], done;  // chunks[c % 3]: current, next, the one after
+  int64_t n_up = 0, cum = 0, char_cum = 0;
+  bool overflow = false, have_done = false;
+  float ms_sum = 0;
+  TRY(upload_next(PipeChunk(), 0, &chunks[0]));
+  n_up = 1;
+  if (chunks[0].d1 < n_docs) {
+    TRY(upload_next(chunks[0], 1, &chunks[1]));
+    n_up = 2;
+  }
+  for (int64_t c = 0;; c++) {
+    const PipeChunk cur = chunks[c % 3];
+    const int slot = (int)(c % 3);
+    const int64_t nd = cur.d1 - cur.d0, len = cur.in1 - cur.in0;
+    const bool last = cur.d1 >= n_docs;
+    int64_t n_units = len, max_len = cur.max_len;
+    if (!is_text) {
+      CK(cudaEventSynchronize(e->ev_in[slot]));
+      unsigned long long fb = e->h_pipe[slot * 4];
+      if (fb != ~0ull)
+        return fail(e, BPE_E_INVALID, "id %d at %lld outside the token table", ids[base + cur.in0 + (int64_t)fb], (long long)(cur.in0 + (int64_t)fb));
+    } else {
+      CK(cudaStreamWaitEvent(e->stream, e->ev_in[slot], 0));
+      TRY(text_decode_dev(e, e->x_text.p + cur.reg, len, d_in_off + cur.oreg, nd, e->x_ids.p + cur.reg, e->x_off.p + cur.oreg, false,
+                          e->x_flag.p + slot * 4));
+      CK(cudaMemcpyAsync(e->h_pipe + slot * 4, e->x_flag.p + slot * 4, 3 * 8, cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      unsigned long long unk = e->h_pipe[slot * 4];
+      if (unk != ~0ull) {  // encodeToCode throws at the first unknown character (core.ts:398-400)
+        int64_t pos = char_cum + (int64_t)(unk >> 32);
+        if (unknown_pos) *unknown_pos = pos;
+        if (unknown_code_point) *unknown_code_point = (int32_t)(unk & 0xFFFFFFFFu);
+        return fail(e, BPE_E_INVALID, "unknown token, char: U+%04X at code point %lld", (unsigned)(unk & 0xFFFFFFFFu), (long long)pos);
+      }
+      max_len = (int64_t)e->h_pipe[slot * 4 + 1];
+      n_units = (int64_t)e->h_pipe[slot * 4 + 2];
+    }
+    // host work hidden under the encode kernel: the chunk after the next one starts its way in, the previous one is handed over
+    const std::function<int()> overlap = [&]() -> int {
+      if (n_up == c + 2 && chunks[(c + 1) % 3].d1 < n_docs) {
+        TRY(upload_next(chunks[(c + 1) % 3], (int)((c + 2) % 3), &chunks[(c + 2) % 3]));
+        n_up++;
+      }
+      if (have_done) TRY(deliver(done, (int)((c - 1) & 1), false));
+      have_done = false;
+      return BPE_OK;
+    };
+    int64_t k = 0;
+    TRY(encode_dev(e, e->x_scratch, e->x_ids.p + cur.reg, e->x_off.p + cur.oreg, nd, n_units, max_len, d_tvi, n_tvi, e->x_out.p + cur.reg,
+                   d_out_off + cur.oreg, first_bad ? e->x_bad.p + cur.d0 : nullptr, &k, &overlap));
+    ms_sum += e->stats.ms_encode;
+    if (cum) {  // the chunk's output offsets take their place in the batch
+      k_shift_i64<<<(int)std::min<int64_t>((nd + 256) / 256, (int64_t)e->grid(4)), 256, 0, e->stream>>>(d_out_off + cur.oreg, nd + 1, cum);
+      CKL();
+    }
+    CK(cudaEventRecord(e->ev_done, e->stream));
+    CK(cudaStreamWaitEvent(e->s_out, e->ev_done, 0));
+    CK(cudaMemcpyAsync(e->h_out_off.p + cur.d0, d_out_off + cur.oreg, (size_t)(nd + (last ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, e->s_out));
+    if (first_bad && nd) CK(cudaMemcpyAsync(e->h_bad.p + cur.d0, e->x_bad.p + cur.d0, (size_t)nd * 8, cudaMemcpyDeviceToHost, e->s_out));
+    CK(cudaEventRecord(e->ev_res[c & 1], e->s_out));
+    if (cum + k > out_cap || (k && !out)) overflow = true;  // keep going: the caller learns the size it needs
+    if (!overflow && k) CK(cudaMemcpyAsync(out + cum, e->x_out.p + cur.reg, (size_t)k * 4, cudaMemcpyDeviceToHost, e->s_out));
+    cum += k;
+    char_cum += n_units;
+    done = cur;
+    have_done = true;
+    if (last) {
+      TRY(deliver(done, (int)(c & 1), true));
+      break;
+    }
+  }
+  *n_out = cum;
+  e->stats.ms_encode = ms_sum;
+  if (overflow) return fail(e, BPE_E_CAPACITY, "output buffer holds %lld values, need %lld", (long long)out_cap, (long long)cum);
+  return BPE_OK;
+}
+
+int encode_host(bpe_engine* e, bool is_text, const int32_t* ids, const uint8_t* utf8, const int64_t* off, int64_t n_docs, const int32_t* to_vector_index,
+                int32_t n_tvi, int32_t* out, int64_t out_cap, int64_t* out_offsets, int64_t* first_bad, int64_t* n_out, int64_t* unknown_pos,
+                int32_t* unknown_code_point) {
+  *n_out = 0;
+  if (n_docs == 0) {
+    out_offsets[0] = 0;
+    return BPE_OK;
+  }
+  TRY(ensure_pipe(e));
+  int rc = encode_pipeline(e, is_text, ids, utf8, off, n_docs, to_vector_index, n_tvi, out, out_cap, out_offsets, first_bad, n_out, unknown_pos, unknown_code_point);
+  // whatever happened, nothing may still read or write the caller's buffers when the call returns
+  cudaError_t c0 = cudaStreamSynchronize(e->s_in), c1 = cudaStreamSynchronize(e->stream), c2 = cudaStreamSynchronize(e->s_out);
+  if (rc == BPE_OK && (c0 != cudaSuccess || c1 != cudaSuccess || c2 != cudaSuccess))
+    rc = fail(e, BPE_E_CUDA, "encode pipeline: %s", cudaGetErrorString(c0 != cudaSuccess ? c0 : c1 != cudaSuccess ? c1 : c2));
+  return rc;
 }
 
 int bpe_decode_batch(bpe_engine* e, const int32_t* values, const int64_t* doc_offsets, int64_t n_docs, const int32_t* from_vector_index,
@@ -2035,37 +2283,12 @@ int bpe_encode_text_batch(bpe_engine* e, const uint8_t* utf8, const int64_t* doc
                           int32_t n_tvi, int32_t* out, int64_t out_cap, int64_t* out_offsets, int64_t* first_bad, int64_t* n_out,
                           int64_t* unknown_pos, int32_t* unknown_code_point) {
   if (!e || !n_out || !out_offsets) return fail(e, BPE_E_INVALID, "bad encode arguments");
-  CK(cudaSetDevice(e->device));
+  if (n_docs < 0 || (!doc_byte_offsets && n_docs > 0)) return fail(e, BPE_E_INVALID, "bad document offsets");
   if (unknown_pos) *unknown_pos = -1;
-  int64_t n_chars = 0;
-  unsigned long long unk = ~0ull;
-  TRY(text_to_ids(e, utf8, doc_byte_offsets, n_docs, false, &n_chars, &unk));
-  if (unk != ~0ull) {  // encodeToCode throws at the first unknown character (core.ts:398-400)
-    if (unknown_pos) *unknown_pos = (int64_t)(unk >> 32);
-    if (unknown_code_point) *unknown_code_point = (int32_t)(unk & 0xFFFFFFFFu);
-    return fail(e, BPE_E_INVALID, "unknown token, char: U+%04X at code point %lld", (unsigned)(unk & 0xFFFFFFFFu), (long long)(unk >> 32));
-  }
-  int64_t max_len = 0;
-  for (int64_t d = 0; d < n_docs; d++) max_len = std::max(max_len, e->h_rel[(size_t)d + 1] - e->h_rel[(size_t)d]);
-  CK(e->x_out.reserve((size_t)std::max<int64_t>(n_chars, 1)));
-  DevBuf<int64_t>& d_ooff = e->x_ooff2;
-  CK(d_ooff.reserve((size_t)n_docs + 1));
-  if (first_bad) CK(e->x_bad.reserve((size_t)std::max<int64_t>(n_docs, 1)));
-  if (to_vector_index && n_tvi > 0) {
-    CK(e->x_tvi.reserve((size_t)n_tvi));
-    CK(cudaMemcpyAsync(e->x_tvi.p, to_vector_index, (size_t)n_tvi * 4, cudaMemcpyHostToDevice, e->stream));
-  }
-  TRY(encode_dev(e, e->x_scratch, e->x_ids.p, e->x_off.p, n_docs, n_chars, max_len, to_vector_index ? e->x_tvi.p : nullptr, n_tvi, e->x_out.p, d_ooff.p,
-                 first_bad ? e->x_bad.p : nullptr, n_out));
-  CK(cudaMemcpyAsync(out_offsets, d_ooff.p, (size_t)(n_docs + 1) * 8, cudaMemcpyDeviceToHost, e->stream));
-  if (first_bad && n_docs) CK(cudaMemcpyAsync(first_bad, e->x_bad.p, (size_t)n_docs * 8, cudaMemcpyDeviceToHost, e->stream));
-  if (*n_out > out_cap || (*n_out && !out)) {
-    CK(cudaStreamSynchronize(e->stream));
-    return fail(e, BPE_E_CAPACITY, "output buffer holds %lld values, need %lld", (long long)out_cap, (long long)*n_out);
-  }
-  if (*n_out) CK(cudaMemcpyAsync(out, e->x_out.p, (size_t)*n_out * 4, cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
-  return BPE_OK;
+  if (!utf8 && n_docs > 0 && doc_byte_offsets[n_docs] > doc_byte_offsets[0]) return fail(e, BPE_E_INVALID, "null text");
+  CK(cudaSetDevice(e->device));
+  return encode_host(e, true, nullptr, utf8, doc_byte_offsets, n_docs, to_vector_index, n_tvi, out, out_cap, out_offsets, first_bad, n_out, unknown_pos,
+                     unknown_code_point);
 }
 
 int bpe_restore_documents(bpe_engine* e, const int32_t* ids, const int64_t* doc_offsets, int64_t n_docs) {

@@ -106,6 +106,23 @@ __global__ void k_u64_to_i64(const uint64_t* __restrict__ in, int64_t* __restric
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int64_t)in[i];
 }
 
+// offsets[i] += delta: rebases the caller's document offsets to the start of a chunk, and a chunk's output offsets to their
+// place in the whole batch (the host-buffer encode pipeline of bpe_b200.cu)
+__global__ void k_shift_i64(int64_t* __restrict__ p, int64_t n, int64_t delta) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] += delta;
+}
+
+// *out = max(*out, max of in[0..n))
+__global__ void k_max_u32(const uint32_t* __restrict__ in, int64_t n, unsigned long long* __restrict__ out) {
+  uint32_t m = 0;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = max(m, __ldg(in + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, (unsigned long long)m);
+}
+
 // unknown code points seen by the last decode, with their first positions
 __global__ void k_collect_new_cps(uint32_t* __restrict__ first_pos, uint32_t* __restrict__ out_cp, uint32_t* __restrict__ out_pos, uint32_t cap,
                                   uint32_t* __restrict__ n_out) {

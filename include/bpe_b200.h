@@ -73,7 +73,7 @@ typedef struct bpe_stats {
   double ms_index_build;       /* K1 histogram + occurrence lists                                 */
   double ms_argmax;            /* K2 (only when timing is enabled)                                */
   double ms_apply;             /* K3                                                              */
-  double ms_encode;            /* K4 + K5, last bpe_encode_batch* call                            */
+  double ms_encode;            /* K4 + K5, last bpe_encode_batch* call (summed over its chunks)   */
   double ms_last_merge_until;  /* device time of the last bpe_merge_until call                    */
   double ms_loop_phase[8];     /* k_merge_loop as seen by block 0, cumulative since the last index build:
                                   decide, P1 sites, P1 barrier wait, P2 alloc, P2 wait, P3 apply+argmax, P3 wait, tie path */
@@ -177,7 +177,12 @@ int bpe_mg_import_counts(bpe_engine* e, const uint32_t* dev_keys, const uint32_t
  *   first_bad            optional [n_docs]: -1, or the offset WITHIN the document's output of the
  *                        first token whose to_vector_index is a hole (the reference throws
  *                        `unknown token index: ${index}` there); out holds -(index+1) at holes.
- *   n_out                total values written (or required when BPE_E_CAPACITY) */
+ *   n_out                total values written (or required when BPE_E_CAPACITY; out_offsets and
+ *                        first_bad are complete in that case as well)
+ * The call is a three-stream pipeline over chunks of whole documents (copy in | encode | copy out;
+ * BPE_ENC_CHUNK = input units per chunk, default 64 Mi): with page-locked `ids` / `out` buffers it costs
+ * max(PCIe in, encode, PCIe out); pageable buffers are correct but their copies serialise.  The small
+ * per-document arrays are staged through pinned memory of the engine either way. */
 int bpe_encode_batch(bpe_engine* e, const int32_t* ids, const int64_t* doc_offsets, int64_t n_docs,
                      const int32_t* to_vector_index, int32_t n_tvi, int32_t* out, int64_t out_cap,
                      int64_t* out_offsets, int64_t* first_bad, int64_t* n_out);

@@ -363,6 +363,87 @@ def test_encode_batch_lane_path_fuzz(seed, lmax, monkeypatch):
     assert np.array_equal(raw, raw2) and np.array_equal(roff, roff2)
 
 
+@pytest.mark.parametrize("chunk", ["1", "97", "1000", "5000"])
+def test_host_buffer_encode_pipeline_chunks(chunk, monkeypatch):
+    """bpe_encode_batch / bpe_encode_text_batch run as a three-stream pipeline over chunks of whole documents
+    (copy in | encode | copy out, bpe_b200.cu encode_pipeline).  Forced to tiny chunks, the vectors, offsets and
+    first-offender reports must equal the one-chunk call and the sequential replaceAll of core.ts:404-406; errors keep
+    their batch-relative positions when they occur in a late chunk."""
+    import ctypes as C
+
+    from bpe_tokenizer_b200 import _abi
+    from bpe_tokenizer_b200.tokenizer import BpeError
+
+    rng = random.Random(4242)
+    alphabet = "abcdé中 \n"
+    train = _random_docs(rng, alphabet, 8, 400)
+    lit, one = LiteralTokenizer(), make()
+    for d in train:
+        lit.addToCorpus(d)
+        one.addToCorpus(d)
+    lit.mergeUntil({"max_iterations": 60})
+    one.mergeUntil({"max_iterations": 60})
+    assert one.toJSON() == lit.toJSON()
+    known = [ch for ch in alphabet if ch in lit.char_to_token]
+    docs = []
+    for _ in range(300):
+        kind = rng.random()
+        n = 0 if kind < 0.1 else rng.randint(1, 12) if kind < 0.4 else rng.randint(1, 300) if kind < 0.95 else rng.randint(1100, 2600)
+        docs.append("".join(rng.choice(known) for _ in range(n)))
+    docs += ["", ""]  # the batch ends with empty documents
+    ids = np.array([lit.char_to_token[ch].index for d in docs for ch in d], dtype=np.int32)
+    off = np.zeros(len(docs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(d) for d in docs])
+    text, boff = _utf8_batch(docs)
+    want = [one.encodeBatch(ids, off, vector=v) for v in (False, True)] + [one.encodeTextBatch(text, boff, vector=v) for v in (False, True)]
+    for d, doc in enumerate(docs[:40]):
+        raw, roff, _ = want[0]
+        assert raw[roff[d]:roff[d + 1]].tolist() == [ord(ch) - 1 for ch in lit.encodeToCode(doc)], d
+    assert all(np.array_equal(a, b) for a, b in zip(want[0], want[2])) and all(np.array_equal(a, b) for a, b in zip(want[1], want[3]))
+
+    monkeypatch.setenv("BPE_ENC_CHUNK", chunk)
+    t = make()
+    t.fromJSON(one.toJSON())
+    got = [t.encodeBatch(ids, off, vector=v) for v in (False, True)] + [t.encodeTextBatch(text, boff, vector=v) for v in (False, True)]
+    for g, w in zip(got, want):
+        assert all(np.array_equal(a, b) for a, b in zip(g, w))
+    # a window of the batch (offsets that do not start at zero)
+    lo, hi = 17, 203
+    raw, roff, _ = t.encodeBatch(ids, off[lo:hi + 1], vector=False)
+    w_raw, w_off, _ = want[0]
+    assert np.array_equal(raw, w_raw[w_off[lo]:w_off[hi]]) and np.array_equal(roff, w_off[lo:hi + 1] - w_off[lo])
+    # an id outside the table / an unknown character in a late chunk: position relative to the batch
+    bad_at = int(off[250]) + 1
+    assert off[251] > bad_at
+    ids_bad = ids.copy()
+    ids_bad[bad_at] = 60000
+    with pytest.raises(BpeError, match="id 60000 at %d outside" % bad_at):
+        t.encodeBatch(ids_bad, off, vector=False)
+    docs_bad = list(docs)
+    docs_bad[250] = docs_bad[250][:1] + "☃" + docs_bad[250][1:]
+    with pytest.raises(ValueError, match="unknown token, char"):
+        t.encodeTextBatch(*_utf8_batch(docs_bad), vector=False)
+    tb, ob = _utf8_batch(docs_bad)
+    buf = np.frombuffer(tb, dtype=np.uint8)
+    out = np.empty(len(tb), dtype=np.int32)
+    ooff = np.zeros(len(docs) + 1, dtype=np.int64)
+    n, upos, ucp = C.c_int64(), C.c_int64(-1), C.c_int32()
+    rc = t._lib.bpe_encode_text_batch(t._h, buf.ctypes.data_as(_abi.u8p), _abi.p64(ob), len(docs), None, 0, _abi.p32(out), out.size, _abi.p64(ooff),
+                                      None, C.byref(n), C.byref(upos), C.byref(ucp))
+    assert rc == _abi.BPE_E_INVALID and upos.value == bad_at and ucp.value == ord("☃")
+    # an output buffer that is too small: BPE_E_CAPACITY and the size that is needed
+    small = np.empty(10, dtype=np.int32)
+    rc = t._lib.bpe_encode_batch(t._h, _abi.p32(ids), _abi.p64(off), len(docs), None, 0, _abi.p32(small), small.size, _abi.p64(ooff), None, C.byref(n))
+    assert rc == _abi.BPE_E_CAPACITY and n.value == want[0][0].size and np.array_equal(ooff, want[0][1])
+    # offsets that go backwards are refused before anything is read through them
+    off_bad = off.copy()
+    off_bad[260] = off_bad[259] - 1
+    with pytest.raises(BpeError, match="non-decreasing"):
+        t.encodeBatch(ids, off_bad, vector=False)
+    # the engine still works after the failed calls
+    assert all(np.array_equal(a, b) for a, b in zip(t.encodeBatch(ids, off, vector=True), want[1]))
+
+
 def test_decode_batch_matches_host_decode():
     """Device decodeVector (core.ts:455-471): bytes equal the concatenated token chars; the first unknown vector index
     of a document is reported where the reference throws."""
