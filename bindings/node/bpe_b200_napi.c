@@ -28,7 +28,7 @@
 
 #include "bpe_b200.h"
 
-#define MAX_ARGS 8
+#define MAX_ARGS 10
 
 typedef struct {
   napi_env env;
@@ -284,7 +284,7 @@ static napi_value ApplyMerge(napi_env env, napi_callback_info info) {
   return rc == BPE_OK ? num(env, n) : throw_rc(env, c.e, rc);
 }
 
-/* (e, Int32Array ab /* 2 per merge *​/) : a whole merge log in one call (example/import-merge-log-to-ram.ts:24-31) */
+/* (e, Int32Array ab [2 per merge]) : a whole merge log in one call (example/import-merge-log-to-ram.ts:24-31) */
 static napi_value ApplyMerges(napi_env env, napi_callback_info info) {
   call_t c = begin(env, info, 2);
   void* ab;
@@ -294,7 +294,7 @@ static napi_value ApplyMerges(napi_env env, napi_callback_info info) {
   return rc == BPE_OK ? undefined(env) : throw_rc(env, c.e, rc);
 }
 
-/* (e, min_weight, max_length, max_iterations, Int32Array abc /* 3 per merge *​/, Float64Array weights) -> n_done
+/* (e, min_weight, max_length, max_iterations, Int32Array abc [3 per merge], Float64Array weights) -> n_done
  * mergeUntil core.ts:365-383 as ONE device-resident loop; the class replays abc/weights into token_table. */
 static napi_value MergeUntil(napi_env env, napi_callback_info info) {
   call_t c = begin(env, info, 6);
