@@ -212,7 +212,7 @@ struct bpe_engine {
   cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_done = nullptr, ev_res[2] = {nullptr, nullptr};
   unsigned long long* h_pipe = nullptr;  // pinned: 3 slots x 4 words of per-chunk flags, [12..13] flags of the lane kernel
   PinBuf<int64_t> h_in_off, h_out_off, h_bad;  // pinned staging of document offsets in, output offsets and first offenders out
-  int64_t enc_chunk = 64ll << 20;        // input units (ids or bytes) per chunk; BPE_ENC_CHUNK overrides
+  int64_t enc_chunk = 128ll << 20;       // input units (ids or bytes) per full-size chunk; BPE_ENC_CHUNK overrides
 
   // scratch
   DevBuf<int32_t> stage_ids;
@@ -702,7 +702,7 @@ int ensure_pipe(bpe_engine* e) {
     CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   if (const char* v = getenv("BPE_ENC_CHUNK"))
     if (atoll(v) > 0) e->enc_chunk = atoll(v);
-  CK(cudaHostAlloc((void**)&e->h_pipe, 16 * sizeof(unsigned long long), cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&e->h_pipe, 16 * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
   return BPE_OK;
 }
 
@@ -714,6 +714,7 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
   int overlap_rc = BPE_OK;
   if (e->h_merges.size() / 3 > EL_MAX_RANK + 1) return fail(e, BPE_E_DOMAIN, "merge list too long");
   TRY(ensure_lane_tables(e));
+  TRY(ensure_pipe(e));
   CK(sc.out_tmp.reserve((size_t)std::max<int64_t>(n_ids, 1)));
   CK(sc.out_len.reserve((size_t)n_docs + 1));
   CK(sc.out_off.reserve((size_t)n_docs + 2));
@@ -752,9 +753,9 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
       TRY((launch_encode_lanes<32, 10>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
     else
       TRY((launch_encode_lanes<48, 6>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
-    TRY(ensure_pipe(e));
-    volatile uint32_t* hf = reinterpret_cast<volatile uint32_t*>(e->h_pipe + 12);  // pinned: the copy below does not block the host
-    CK(cudaMemcpyAsync((void*)hf, sc.flags.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    volatile uint32_t* hf = reinterpret_cast<volatile uint32_t*>(e->h_pipe + 12);  // flags[0..1], written by the device (k_copy_u64)
+    k_copy_u64<<<1, 32, 0, e->stream>>>(e->h_pipe + 12, reinterpret_cast<const unsigned long long*>(sc.flags.p), 1);
+    CKL();
     if (overlap) {
       overlap_rc = (*overlap)();
       overlap = nullptr;
@@ -802,10 +803,11 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
   }
   CK(cudaEventRecord(e->ev1, e->stream));
   if (overlap) overlap_rc = (*overlap)();  // the lane kernel did not run
-  uint64_t total = 0;
-  CK(cudaMemcpyAsync(&total, sc.out_off.p + n_docs, sizeof total, cudaMemcpyDeviceToHost, e->stream));
+  k_copy_u64<<<1, 32, 0, e->stream>>>(e->h_pipe + 13, reinterpret_cast<const unsigned long long*>(sc.out_off.p + n_docs), 1);
+  CKL();
   CK(cudaStreamSynchronize(e->stream));
   if (overlap_rc != BPE_OK) return overlap_rc;
+  const uint64_t total = *reinterpret_cast<volatile unsigned long long*>(e->h_pipe + 13);
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->stats.ms_encode = ms;
@@ -1974,8 +1976,11 @@ int encode_pipeline(bpe_engine* e, const bool is_text, const int32_t* ids, const
   const int64_t base = off[0], target = std::max<int64_t>(e->enc_chunk, 1), pad = 256;
   if (off[n_docs] < base) return fail(e, BPE_E_INVALID, "document offsets must be non-decreasing");
   const int64_t total = off[n_docs] - base;
-  // two consecutive chunks always hold more than `target` units, which bounds their number
-  const int64_t max_chunks = std::min<int64_t>(2 * (total / target) + 4, n_docs + 1);
+  // The first chunks are small and double up to `target` (the first copy in is exposed), the last ones halve again (so
+  // are the last encode and the last copy out).  Two consecutive chunks always hold more than the smallest chunk target,
+  // which bounds their number.
+  const int64_t min_target = std::max<int64_t>(target / 8, 1);
+  const int64_t max_chunks = std::min<int64_t>(2 * (total / min_target) + 8, n_docs + 1);
   const size_t unit_cap = (size_t)(total + pad * max_chunks), off_cap = (size_t)(n_docs + max_chunks + 1);
   // everything a chunk in flight may touch is allocated before the first copy starts
   if (is_text) {
@@ -2003,10 +2008,13 @@ int encode_pipeline(bpe_engine* e, const bool is_text, const int32_t* ids, const
   int64_t* d_in_off = is_text ? e->x_ooff.p : e->x_off.p;  // the caller's offsets relative to the chunk (text: in bytes)
   int64_t* d_out_off = is_text ? e->x_ooff2.p : e->x_ooff.p;
 
+  int64_t n_up = 0;  // chunks sent so far
   // s_in: the chunk after `prev` goes to the device (units, offsets; ids are checked against the token table there)
   auto upload_next = [&](const PipeChunk& prev, int slot, PipeChunk* c) -> int {
     const int64_t reg = (prev.reg + (prev.in1 - prev.in0) + pad - 1) / pad * pad, oreg = prev.oreg + (prev.d1 - prev.d0) + (prev.d1 ? 1 : 0);
-    TRY(next_chunk(e, off, n_docs, prev.d1, target, e->h_in_off.p + oreg, c));
+    int64_t want = target >> std::max<int64_t>(0, 3 - n_up);                               // ramp up: 1/8, 1/4, 1/2, 1
+    want = std::min(want, std::max((total - prev.in1) / 2, min_target));                      // ramp down
+    TRY(next_chunk(e, off, n_docs, prev.d1, std::max(want, min_target), e->h_in_off.p + oreg, c));
     c->reg = reg;
     c->oreg = oreg;
     const int64_t len = c->in1 - c->in0, nd = c->d1 - c->d0;
@@ -2019,7 +2027,8 @@ int encode_pipeline(bpe_engine* e, const bool is_text, const int32_t* ids, const
         k_first_bad_id<<<e->grid(8), 256, 0, e->s_in>>>(e->x_ids.p + reg, (uint64_t)len, (uint32_t)e->n_tokens, e->x_flag.p + slot * 4);
         CKL();
       }
-      CK(cudaMemcpyAsync(e->h_pipe + slot * 4, e->x_flag.p + slot * 4, 8, cudaMemcpyDeviceToHost, e->s_in));
+      k_copy_u64<<<1, 32, 0, e->s_in>>>(e->h_pipe + slot * 4, e->x_flag.p + slot * 4, 1);
+      CKL();
     }
     CK(cudaEventRecord(e->ev_in[slot], e->s_in));
     return BPE_OK;
@@ -2034,7 +2043,7 @@ int encode_pipeline(bpe_engine* e, const bool is_text, const int32_t* ids, const
   };
 
   PipeChunk chunks[3], done;  // chunks[c % 3]: current, next, the one after
-  int64_t n_up = 0, cum = 0, char_cum = 0;
+  int64_t cum = 0, char_cum = 0;
   bool overflow = false, have_done = false;
   float ms_sum = 0;
   TRY(upload_next(PipeChunk(), 0, &chunks[0]));
@@ -2051,24 +2060,26 @@ int encode_pipeline(bpe_engine* e, const bool is_text, const int32_t* ids, const
     int64_t n_units = len, max_len = cur.max_len;
     if (!is_text) {
       CK(cudaEventSynchronize(e->ev_in[slot]));
-      unsigned long long fb = e->h_pipe[slot * 4];
+      unsigned long long fb = *static_cast<volatile unsigned long long*>(e->h_pipe + slot * 4);
       if (fb != ~0ull)
         return fail(e, BPE_E_INVALID, "id %d at %lld outside the token table", ids[base + cur.in0 + (int64_t)fb], (long long)(cur.in0 + (int64_t)fb));
     } else {
       CK(cudaStreamWaitEvent(e->stream, e->ev_in[slot], 0));
       TRY(text_decode_dev(e, e->x_text.p + cur.reg, len, d_in_off + cur.oreg, nd, e->x_ids.p + cur.reg, e->x_off.p + cur.oreg, false,
                           e->x_flag.p + slot * 4));
-      CK(cudaMemcpyAsync(e->h_pipe + slot * 4, e->x_flag.p + slot * 4, 3 * 8, cudaMemcpyDeviceToHost, e->stream));
+      k_copy_u64<<<1, 32, 0, e->stream>>>(e->h_pipe + slot * 4, e->x_flag.p + slot * 4, 3);
+      CKL();
       CK(cudaStreamSynchronize(e->stream));
-      unsigned long long unk = e->h_pipe[slot * 4];
+      const volatile unsigned long long* hp = e->h_pipe;
+      unsigned long long unk = hp[slot * 4];
       if (unk != ~0ull) {  // encodeToCode throws at the first unknown character (core.ts:398-400)
         int64_t pos = char_cum + (int64_t)(unk >> 32);
         if (unknown_pos) *unknown_pos = pos;
         if (unknown_code_point) *unknown_code_point = (int32_t)(unk & 0xFFFFFFFFu);
         return fail(e, BPE_E_INVALID, "unknown token, char: U+%04X at code point %lld", (unsigned)(unk & 0xFFFFFFFFu), (long long)pos);
       }
-      max_len = (int64_t)e->h_pipe[slot * 4 + 1];
-      n_units = (int64_t)e->h_pipe[slot * 4 + 2];
+      max_len = (int64_t)hp[slot * 4 + 1];
+      n_units = (int64_t)hp[slot * 4 + 2];
     }
     // host work hidden under the encode kernel: the chunk after the next one starts its way in, the previous one is handed over
     const std::function<int()> overlap = [&]() -> int {

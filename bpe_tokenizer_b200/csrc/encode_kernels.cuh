@@ -305,6 +305,13 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_tiles(const uint32_t* __res
   if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = tile_off[n_tiles];
 }
 
+// A few result words go to PINNED HOST memory straight from a kernel (unified addressing: the device writes through the
+// mapped pointer).  A cudaMemcpyAsync of 8 bytes would queue on the device-to-host copy engine behind the tens of MB of
+// vectors the encode pipeline is streaming out at the same time, and stall the host for that long at every chunk.
+__global__ void k_copy_u64(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+
 // first position whose id lies outside [0, n_tokens): the reference throws at the FIRST offending character (core.ts:396-402)
 __global__ void k_first_bad_id(const int32_t* __restrict__ ids, uint64_t n, uint32_t n_tokens, unsigned long long* __restrict__ first_bad) {
   unsigned long long best = ~0ull;

@@ -180,7 +180,8 @@ int bpe_mg_import_counts(bpe_engine* e, const uint32_t* dev_keys, const uint32_t
  *   n_out                total values written (or required when BPE_E_CAPACITY; out_offsets and
  *                        first_bad are complete in that case as well)
  * The call is a three-stream pipeline over chunks of whole documents (copy in | encode | copy out;
- * BPE_ENC_CHUNK = input units per chunk, default 64 Mi): with page-locked `ids` / `out` buffers it costs
+ * BPE_ENC_CHUNK = input units per full-size chunk, default 128 Mi;
+ * the first and last chunks are smaller): with page-locked `ids` / `out` buffers it costs
  * max(PCIe in, encode, PCIe out); pageable buffers are correct but their copies serialise.  The small
  * per-document arrays are staged through pinned memory of the engine either way. */
 int bpe_encode_batch(bpe_engine* e, const int32_t* ids, const int64_t* doc_offsets, int64_t n_docs,

@@ -31,3 +31,33 @@ for rep in range(reps):
     assert rc == 0, lib.bpe_last_error(h)
     s = bpe_stats(); lib.bpe_get_stats(h, C.byref(s))
     print("encode %d chars (%d docs, max %d) -> %d tokens in %.2f ms = %.2f GB/s" % (ids2.numel(), len(off2) - 1, maxdoc, n_out.value, s.ms_encode, ids2.numel() / s.ms_encode / 1e6), flush=True)
+
+# ---- host-buffer calls (three-stream pipeline): E2E_CHUNKS="16M 64M ..." times bpe_encode_batch / bpe_encode_text_batch from pinned
+# buffers for each chunk size (BPE_ENC_CHUNK is read when an engine first encodes from host buffers, so one engine per setting)
+if os.environ.get("E2E_CHUNKS"):
+    ids_host = torch.from_numpy(ids2h).pin_memory()
+    text_host = torch.from_numpy(np.ascontiguousarray(text2)).pin_memory()
+    out_host = torch.empty(ids2h.size, dtype=torch.int32).pin_memory()
+    ooff_host = np.zeros(len(off2), dtype=np.int64)
+    for spec in os.environ["E2E_CHUNKS"].split():
+        os.environ["BPE_ENC_CHUNK"] = str(int(float(spec[:-1]) * (1 << 20)) if spec.endswith("M") else int(spec))
+        g = C.c_void_p(); assert lib.bpe_create(0, C.byref(g)) == 0
+        assert lib.bpe_set_tokens(g, p32(len16), n_tok) == 0 and lib.bpe_load_merges(g, p32(abc.reshape(-1)), nm) == 0
+        cps = np.asarray(alphabet, dtype=np.int32); idx = np.arange(len(alphabet), dtype=np.int32)
+        assert lib.bpe_set_chars(g, p32(cps), p32(idx), len(cps)) == 0
+        for name in ("ids", "text"):
+            best = 1e9
+            for rep in range(reps + 1):
+                t0 = time.perf_counter()
+                if name == "ids":
+                    rc = lib.bpe_encode_batch(g, C.cast(ids_host.data_ptr(), _abi.i32p), p64(off2), len(off2) - 1, None, 0,
+                                              C.cast(out_host.data_ptr(), _abi.i32p), out_host.numel(), p64(ooff_host), None, C.byref(n_out))
+                else:
+                    rc = lib.bpe_encode_text_batch(g, C.cast(text_host.data_ptr(), _abi.u8p), p64(off2), len(off2) - 1, None, 0,
+                                                   C.cast(out_host.data_ptr(), _abi.i32p), out_host.numel(), p64(ooff_host), None, C.byref(n_out), None, None)
+                dt = time.perf_counter() - t0
+                assert rc == 0, lib.bpe_last_error(g)
+                if rep: best = min(best, dt)
+            s = bpe_stats(); lib.bpe_get_stats(g, C.byref(s))
+            print("e2e chunk %s from %s: %.2f ms = %.2f GB/s (encode kernels %.2f ms, %d tokens)" % (spec, name, best * 1e3, ids2h.size / best / 1e9, s.ms_encode, n_out.value), flush=True)
+        lib.bpe_destroy(g)
