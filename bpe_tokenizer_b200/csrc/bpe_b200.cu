@@ -163,7 +163,7 @@ struct bpe_engine {
   DevBuf<DevState> d_st;
   DevState* h_st = nullptr;  // pinned
   DevBuf<Best> partials;
-  DevBuf<SiteRec> sites;
+  DevBuf<SiteRec> sites, sites2;  // k_merge_loop alternates between the two (deferred list filling)
   DevBuf<uint32_t> newslots;
   DevBuf<uint32_t> nd;  // dense accumulator of the pairs born by the current merge (train_kernels.cuh, ND_*)
   DevBuf<uint32_t> hot;
@@ -497,6 +497,7 @@ ApplyArgs apply_args(bpe_engine* e) {
   A.st = e->d_st.p;
   A.sites = e->sites.p;
   A.sites_cap = (uint32_t)std::min<size_t>(e->sites.cap, 0xFFFFFFFFu);
+  if (e->sites2.p) A.sites_cap = (uint32_t)std::min<size_t>(A.sites_cap, e->sites2.cap);
   A.newslots = e->newslots.p;
   A.nd = e->nd.p;
   A.newpair = nullptr;
@@ -882,6 +883,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
   }
   CK(e->partials.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
   CK(e->sites.reserve(1u << 16, 0, e->stream, 1.0));
+  CK(e->sites2.reserve(std::max<size_t>(e->sites.cap, 1u << 16), 0, e->stream, 1.0));
   CK(e->newslots.reserve(1u << 16, 0, e->stream, 1.0));
   CK(e->cands.reserve(4096, 0, e->stream, 1.0));
   CK(e->barrier.reserve(64));
@@ -930,6 +932,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     L.min_weight = (uint32_t)std::min<int64_t>(mw, 0xFFFFFFFFll);
     L.max_tokens = BPE_MAX_TOKENS;
     L.tbl_cap = e->tbl_cap;
+    L.sites2 = e->sites2.p;
     L.replay = dev_replay ? dev_replay + 2 * done : nullptr;
     if (dev_replay) e->hot_valid = false;  // replayed merges do not feed the hot list
     static const bool trace = getenv("BPE_TRACE") != nullptr;
@@ -1010,6 +1013,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       }
       if ((ce = e->pool.reserve((size_t)pool_after, e->h_st->pool_cursor, e->stream, 1.5)) != cudaSuccess ||
           (ce = e->sites.reserve((size_t)w, 0, e->stream, 1.25)) != cudaSuccess ||
+          (ce = e->sites2.reserve(e->sites.cap, 0, e->stream, 1.0)) != cudaSuccess ||
           (ce = e->newslots.reserve((size_t)new_keys, 0, e->stream, 1.25)) != cudaSuccess ||
           (ce = e->hot.reserve((size_t)e->h_st->hot_n + new_keys, e->h_st->hot_n, e->stream, 1.5)) != cudaSuccess ||
           (ce = e->cands.reserve((size_t)e->h_st->best_mult, 0, e->stream, 1.5)) != cudaSuccess) {

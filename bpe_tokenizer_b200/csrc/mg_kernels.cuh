@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
         Ad.push_world = M.world;
         Ad.push_cap = M.inbox_stride - MG_HDR;
       }
-      phase_sites(Ad, wa, wb, c, par, w.slot, bid, nblk);
+      phase_sites(Ad, wa, wb, c, par, w.slot, bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
       if (direct) __threadfence_system();
     }
     MGPROF(1)
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop_mg(Loo
     }
     // ---- P2 (second half): apply the deltas of all ranks to the replicated counts; the lists of the pairs born on this
     // shard are filled next to it (independent work: positions only) ----
-    phase_fill(A, n_sites_now, bid, nblk);
+    phase_fill(A, n_sites_now, bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
     {
       // all G record lists as ONE index space, so a thread walks a single record's chain whatever the world size
       uint32_t pre[MG_MAX_WORLD + 1];

@@ -733,8 +733,11 @@ __device__ __forceinline__ void agg_new_dense(const ApplyArgs& A, uint32_t side,
   if (A.push_world) cnt_delta_warp(A, nc != 0, NOSLOT, side ? pair_key(c, tok) : pair_key(tok, c), (int32_t)nc, par);
 }
 
+// vt / nvt: virtual thread id and count (whole warps), so that a loop kernel can give the phase a subset of its warps;
+// site_buf: where the site records go (the loop kernel alternates between two buffers), A.sites when null.
 __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint32_t b, uint32_t c, uint32_t par,
-                                            uint32_t pair_slot, uint32_t bid, uint32_t nblk) {
+                                            uint32_t pair_slot, uint32_t vt, uint32_t nvt, SiteRec* site_buf = nullptr) {
+  SiteRec* const site_out = site_buf ? site_buf : A.sites;
   const uint32_t* slots = A.slots;
   const uint32_t n = A.n;
   const PairTable& t = A.t;
@@ -748,7 +751,7 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
   uint32_t lane = lane_id();
   uint32_t total_round = (total + 31u) & ~31u;
 #ifdef BPE_FINE_PROF
-  const bool fine = (bid == 0 && threadIdx.x == 0);
+  const bool fine = (vt == 0);
   unsigned long long ft0 = fine ? now_ns() : 0, ft1;
 #define FINE(k, dep)                                   \
   if (fine) {                                          \
@@ -760,7 +763,7 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
 #else
 #define FINE(k, dep)
 #endif
-  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < total_round; i += nblk * blockDim.x) {
+  for (uint32_t i = vt; i < total_round; i += nvt) {
     bool site = false;
     uint32_t p = 0, w = 0, q = 0, koff = 0;
     if (i < total) {
@@ -876,7 +879,7 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
     uint32_t base = __shfl_sync(0xFFFFFFFFu, site_base, __ffs(smask) - 1);
     if (site) {
       uint32_t k = base + __popc(smask & ((1u << lane) - 1u));
-      if (k < A.sites_cap) reinterpret_cast<uint4*>(A.sites)[k] = make_uint4(rec.p, rec.lpos, rec.lslot, rec.rslot);
+      if (k < A.sites_cap) reinterpret_cast<uint4*>(site_out)[k] = make_uint4(rec.p, rec.lpos, rec.lslot, rec.rslot);
       else atomicOr(&st->err, ERR_SITE_OVERFLOW);
     }
     FINE(8, base)
@@ -890,7 +893,8 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
 // phase_apply.
 __device__ __forceinline__ void phase_new_pairs(const ApplyArgs& A, uint32_t c, const uint32_t* len16, uint32_t max_length,
                                                 int hot_valid, uint32_t* hot, uint32_t hot_cap, uint32_t pool_cap, bool counts_elsewhere,
-                                                uint32_t vt, uint32_t nvt) {  // virtual thread id / count (whole warps)
+                                                uint32_t vt, uint32_t nvt,  // virtual thread id / count (whole warps)
+                                                Best* mine = nullptr) {     // arg-max candidate of the caller: pairs that go onto the hot list join it
   const PairTable& t = A.t;
   DevState* st = A.st;
   const uint32_t thresh = st->hot_thresh;
@@ -955,6 +959,7 @@ __device__ __forceinline__ void phase_new_pairs(const ApplyArgs& A, uint32_t c, 
           uint32_t k = atomicAdd(&st->hot_n, 1u);
           if (k < hot_cap) hot[k] = s;
           else atomicOr(&st->err, ERR_HOT_OVERFLOW);
+          if (mine) *mine = best_merge(*mine, Best{pr, s, 1});
         }
       }
     }
@@ -976,7 +981,9 @@ __device__ __forceinline__ uint32_t agg_cursor(const PairTable& t, uint32_t slot
 // K3 phase 3 comes in two independent halves, so that the loop kernels can run the first one next to phase_new_pairs
 // (neither reads what the other writes): phase_rewrite puts c into the corpus, phase_fill writes the positions of the
 // new adjacencies into the lists phase_new_pairs allocated.
-__device__ __forceinline__ void phase_rewrite(const ApplyArgs& A, uint32_t c, uint32_t n_sites, uint32_t vt, uint32_t nvt) {
+__device__ __forceinline__ void phase_rewrite(const ApplyArgs& A, uint32_t c, uint32_t n_sites, uint32_t vt, uint32_t nvt,
+                                              const SiteRec* site_buf = nullptr) {
+  const SiteRec* const sites = site_buf ? site_buf : A.sites;
   uint32_t* slots = A.slots;
   const uint32_t n = A.n;
   if (vt == 0) {
@@ -984,7 +991,7 @@ __device__ __forceinline__ void phase_rewrite(const ApplyArgs& A, uint32_t c, ui
     A.st->sites_total += n_sites;
   }
   for (uint32_t i = vt; i < n_sites; i += nvt) {
-    uint32_t p = ld_cg(&A.sites[i].p);
+    uint32_t p = ld_cg(&sites[i].p);
     // own slots only: [p, e] where e is the last slot of b
     uint32_t q = next_pos(slots, n, p);
     uint32_t e = next_pos(slots, n, q) - 1;
@@ -1002,12 +1009,13 @@ __device__ __forceinline__ void phase_rewrite(const ApplyArgs& A, uint32_t c, ui
   }
 }
 
-__device__ __forceinline__ void phase_fill(const ApplyArgs& A, uint32_t n_sites, uint32_t bid, uint32_t nblk) {
+__device__ __forceinline__ void phase_fill(const ApplyArgs& A, uint32_t n_sites, uint32_t vt, uint32_t nvt, const SiteRec* site_buf = nullptr) {
   const PairTable& t = A.t;
+  const SiteRec* const sites = site_buf ? site_buf : A.sites;
   uint32_t round = (n_sites + 31u) & ~31u;
-  for (uint32_t i = bid * blockDim.x + threadIdx.x; i < round; i += nblk * blockDim.x) {
+  for (uint32_t i = vt; i < round; i += nvt) {
     bool has = i < n_sites;
-    uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(A.sites) + i) : make_uint4(0, NOPOS, NOTOKV, NOTOKV);
+    uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(sites) + i) : make_uint4(0, NOPOS, NOTOKV, NOTOKV);
     uint32_t p = rv.x, lpos = rv.y;
     uint32_t lslot = (has && rv.z != NOTOKV) ? ld_cg(A.nd + (size_t)ND_L_SLOT * ND_STRIDE + rv.z) : NOSLOT;
     uint32_t rslot = (has && rv.w != NOTOKV) ? ld_cg(A.nd + (size_t)ND_R_SLOT * ND_STRIDE + rv.w) : NOSLOT;
@@ -1026,14 +1034,14 @@ __device__ __forceinline__ void phase_apply(const ApplyArgs& A, uint32_t a, uint
     uint32_t s = tbl_find(A.t, pair_key(a, b));
     if (s != NOSLOT) A.t.cnt[s] = 0;  // every counted occurrence was replaced
   }
-  phase_fill(A, n_sites, bid, nblk);
+  phase_fill(A, n_sites, bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
   phase_rewrite(A, c, n_sites, bid * blockDim.x + threadIdx.x, nblk * blockDim.x);
 }
 
 // ---- stand-alone K3 kernels (applyMerge / restoreMerge one at a time, and the host-driven loop) ----
 __global__ void __launch_bounds__(256) k_sites(ApplyArgs A, uint32_t a, uint32_t b, uint32_t c) {
   if (blockIdx.x == 0 && threadIdx.x == 0) A.len16[c] = A.len16[a] + A.len16[b];  // chars = a.chars + b.chars (:318)
-  phase_sites(A, a, b, c, 0, tbl_find(A.t, pair_key(a, b)), blockIdx.x, gridDim.x);
+  phase_sites(A, a, b, c, 0, tbl_find(A.t, pair_key(a, b)), blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 __global__ void __launch_bounds__(256) k_alloc_new(ApplyArgs A, uint32_t c, uint32_t max_length, int hot_valid, uint32_t* __restrict__ hot,
@@ -1047,8 +1055,18 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs A, uint32_t a, uint32_t
 
 // ------------------------------------------------------------------------------------------------
 // mergeUntil (core.ts:365-383) as ONE persistent cooperative kernel: every block runs the same loop,
-// phases are separated by a grid barrier (3 per merge), every block takes the same exit decision from
+// phases are separated by a grid barrier (2 per merge), every block takes the same exit decision from
 // the same published state.  The host is only needed to grow buffers or rebuild the hot list.
+//
+//   decide(t)                      fold the arg-max partials; same winner, same status in every block
+//   P1(t)  ||  fill(t-1)           sites + count deltas of merge t; the occurrence lists of the pairs BORN by merge t-1 are
+//                                  written next to it (software pipelining: nothing before P1(t+1) reads those lists, unless
+//                                  the winner of t contains the token merge t-1 created, or a tie must be broken by position
+//                                  -- then fill(t-1) is finished, with a barrier of its own, first)
+//   ---- barrier ----
+//   P2(t)                          born pairs enter the table / get list space / join the hot list and the arg-max, the corpus
+//                                  is rewritten, the arg-max runs over the pairs that were already hot -> partials
+//   ---- barrier ----
 // ------------------------------------------------------------------------------------------------
 #ifndef BPE_ML_THREADS
 #define BPE_ML_THREADS 512
@@ -1073,6 +1091,8 @@ struct LoopArgs {
   uint32_t min_weight;
   uint32_t max_tokens;
   uint32_t tbl_cap;
+  SiteRec* sites2;     // second site buffer (capacity A.sites_cap): merges alternate, so that the list filling of merge t
+                       // can run next to the site pass of merge t+1
   // replay mode (batched restoreMerge, core.ts:477-494): the winners are GIVEN -- (a,b) of merge i at replay[2i..2i+1]
   // -- instead of found by the arg-max; the hot list is neither read nor fed
   const int32_t* replay;
@@ -1134,12 +1154,7 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
   __shared__ uint32_t s_rslot;
 
   // first arg-max partials
-  if (bid == 0 && threadIdx.x == 0) {
-    st->snap_n_keys = st->n_keys;
-    st->snap_pool_cursor = st->pool_cursor;
-    st->snap_hot_n = st->hot_n;
-    st->snap_err = st->err;
-  }
+  if (bid == 0 && threadIdx.x == 0) st->snap_err = st->err;
   if (!replay) {
     Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
     if (threadIdx.x == 0) L.partials[bid] = v;
@@ -1154,13 +1169,21 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
     st->prof_ns[i] += tp1 - tp0;     \
     tp0 = tp1;                       \
   }
+  const uint32_t gt = bid * blockDim.x + threadIdx.x, gn = nblk * blockDim.x;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  // deferred phase_fill: the sites of the previous merge whose new adjacencies are not in their lists yet
+  uint32_t fill_n = 0;
+  const SiteRec* fill_sites = nullptr;
   for (uint32_t it = 0;; it++) {
     const uint32_t par = it & 1u;
+    SiteRec* const my_sites = par ? L.sites2 : A.sites;
     // ---- every block folds the partials and takes the same decision ----
+    // n_keys, pool_cursor and hot_n only change in P2, err is snapshot by block 0 in P2: all stable here
     Best w{0ull, NOSLOT, 0};
     uint32_t status = LOOP_RUNNING;
     uint32_t wa = 0, wb = 0, wcnt = 0;
     const uint32_t c = n_tokens0 + it;
+    const uint32_t hot_pre = ld_cg(&st->hot_n);  // entries before this merge's pairs join
     if (replay) {
       // the logged pair; it may not occur at all (a merge whose pair is absent still appends its token, core.ts:350-354)
       if (it < L.log_cap) {
@@ -1202,7 +1225,12 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
       // tie on (weight, a.index+b.index): the pair whose last counted occurrence comes first wins (core.ts:294-305)
       if (w.mult > L.cand_cap) status = LOOP_NEED_HOST;
       else {
-        phase_collect(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), w.primary, L.cands, L.cand_cap, st, bid, nblk);
+        if (fill_n) {  // the tie-break reads occurrence lists: those of the last merge must be complete
+          phase_fill(A, fill_n, gt, gn, fill_sites);
+          fill_n = 0;
+          grid_barrier(L.barrier, ++epoch * nblk);
+        }
+        phase_collect(t, A.len16, L.max_length, 1, L.hot, hot_pre, w.primary, L.cands, L.cand_cap, st, bid, nblk);
         grid_barrier(L.barrier, ++epoch * nblk);
         phase_tie(A.slots, A.n, t, A.pool, L.cands, ld_cg(&st->n_cand), st, s_max, bid, nblk);
         grid_barrier(L.barrier, ++epoch * nblk);
@@ -1222,13 +1250,14 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
       // capacity the host guarantees: sites = wcnt; new pairs are (x,c) or (c,y), so at most 2*(c+1) of them and
       // at most 2 per site; new list cells <= 2 per site
       unsigned long long new_keys = min(2ull * wcnt + 2ull, 2ull * (c + 1ull) + 2ull);
-      if ((unsigned long long)ld_cg(&st->snap_n_keys) + new_keys > (unsigned long long)(L.tbl_cap >> 1)) status = LOOP_NEED_HOST;
-      else if ((unsigned long long)ld_cg(&st->snap_pool_cursor) + 2ull * wcnt > L.pool_cap) status = LOOP_NEED_HOST;
+      if ((unsigned long long)ld_cg(&st->n_keys) + new_keys > (unsigned long long)(L.tbl_cap >> 1)) status = LOOP_NEED_HOST;
+      else if ((unsigned long long)ld_cg(&st->pool_cursor) + 2ull * wcnt > L.pool_cap) status = LOOP_NEED_HOST;
       else if (wcnt > A.sites_cap || new_keys > A.new_cap) status = LOOP_NEED_HOST;
-      else if (!replay && (unsigned long long)ld_cg(&st->snap_hot_n) + new_keys > min(L.hot_cap, L.hot_limit)) status = LOOP_NEED_REBUILD;
+      else if (!replay && (unsigned long long)hot_pre + new_keys > min(L.hot_cap, L.hot_limit)) status = LOOP_NEED_REBUILD;
       else if (c + 1 > L.len16_cap) status = LOOP_NEED_HOST;
     }
     if (status != LOOP_RUNNING) {
+      if (fill_n) phase_fill(A, fill_n, gt, gn, fill_sites);  // the kernel leaves every list complete
       if (bid == 0 && threadIdx.x == 0) {
         st->status = status;
         st->iters_done = it;
@@ -1245,7 +1274,13 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
       }
       return;
     }
-    // ---- P1: sites + deltas ----
+    if (fill_n && it && (wa == c - 1u || wb == c - 1u)) {
+      // the winner was born by the previous merge: its list is exactly what fill(t-1) still has to write
+      phase_fill(A, fill_n, gt, gn, fill_sites);
+      fill_n = 0;
+      grid_barrier(L.barrier, ++epoch * nblk);
+    }
+    // ---- P1: sites + deltas, next to the list filling of the previous merge ----
     if (bid == 0 && threadIdx.x == 0) {
       A.len16[c] = A.len16[wa] + A.len16[wb];  // chars = a.chars + b.chars (:318)
       MergeRec r;
@@ -1259,7 +1294,15 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
       st->n_new[par ^ 1u] = 0;
       if (w.mult > 1) st->tie_breaks++;
     }
-    phase_sites(A, wa, wb, c, par, w.slot, bid, nblk);
+    if (fill_n && fill_n <= 8192u && wcnt <= 16384u && blockDim.x == 512u) {
+      // both latency bound: 12 warps of every block walk the sites, 4 fill the lists
+      if (warp < 12) phase_sites(A, wa, wb, c, par, w.slot, (bid * 12 + warp) * 32 + lane, nblk * 384, my_sites);
+      else phase_fill(A, fill_n, (bid * 4 + warp - 12) * 32 + lane, nblk * 128, fill_sites);
+    } else {
+      if (fill_n) phase_fill(A, fill_n, gt, gn, fill_sites);
+      phase_sites(A, wa, wb, c, par, w.slot, gt, gn, my_sites);
+    }
+    fill_n = 0;
 #ifdef BPE_FINE_PROF
     const int bkt = 31 - __clz(wcnt | 1u);
     if (prof) {
@@ -1270,31 +1313,26 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
     PROF(1)
     grid_barrier(L.barrier, ++epoch * nblk);
     PROF(2)
-    // ---- P2: lists of the new pairs, hot list ----
+    // ---- P2: the born pairs (table, list space, hot list, arg-max), the corpus rewrite, the arg-max over the old hot pairs ----
     if (bid == 0 && threadIdx.x == 0) {
       st->n_cand = 0;
       st->tie_pos = ~0ull;
-      if (w.slot != NOSLOT) t.cnt[w.slot] = 0;  // every counted occurrence of the winner is being replaced; must be visible
-                                                // before the next arg-max partials are taken in P3 (no delta of P1 touches
-                                                // the winner's own pair)
+      st->snap_err = st->err;  // what every block will act on at the next decision (errors of this phase: one merge later)
+      if (w.slot != NOSLOT) t.cnt[w.slot] = 0;  // every counted occurrence of the winner is being replaced (no delta of P1
+                                                // touches the winner's own pair); the arg-max below skips the slot
       if (replay) L.log[it].weight = (long long)st->n_sites[par];  // replacements performed (bpe_apply_merge's n_replaced)
     }
-    const uint32_t hot_pre = ld_cg(&st->snap_hot_n);  // entries before this merge's pairs join (stable since the last P3)
     const uint32_t n_sites_now = ld_cg(&st->n_sites[par]);
     Best mine{0ull, NOSLOT, 0};
     {
-      // Three independent jobs: table inserts of the new pairs, the corpus rewrite, the arg-max over the pairs that were
-      // already hot (their counts are final since the barrier after P1).  Small merges are latency bound, so the warps of
-      // every block split up (8 / 4 / 4) and the three dependency chains run side by side; big merges keep every thread
-      // on every job.
-      const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+      // Three independent jobs.  Small merges are latency bound, so the warps of every block split up (8 / 4 / 4) and the
+      // three dependency chains run side by side; big merges keep every thread on every job.
       const bool split = n_sites_now <= 16384u && blockDim.x == 512u;
-      const uint32_t gt = bid * blockDim.x + threadIdx.x, gn = nblk * blockDim.x;
       if (!split || warp < 8)
         phase_new_pairs(A, c, A.len16, L.max_length, replay ? 0 : 1, L.hot, L.hot_cap, L.pool_cap, false,
-                        split ? (bid * 8 + warp) * 32 + lane : gt, split ? nblk * 256 : gn);
+                        split ? (bid * 8 + warp) * 32 + lane : gt, split ? nblk * 256 : gn, &mine);
       if (!split || (warp >= 8 && warp < 12))
-        phase_rewrite(A, c, n_sites_now, split ? (bid * 4 + warp - 8) * 32 + lane : gt, split ? nblk * 128 : gn);
+        phase_rewrite(A, c, n_sites_now, split ? (bid * 4 + warp - 8) * 32 + lane : gt, split ? nblk * 128 : gn, my_sites);
       if (!replay && (!split || warp >= 12)) {
         for (uint32_t i = split ? (bid * 4 + warp - 12) * 32 + lane : gt; i < hot_pre; i += split ? nblk * 128 : gn) {
           uint32_t hs = L.hot[i];
@@ -1304,36 +1342,18 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
         }
       }
     }
+    if (!replay) {
+      Best v = best_block_reduce(mine, s_best);
+      if (threadIdx.x == 0) L.partials[bid] = v;
+    }
+    fill_n = n_sites_now;
+    fill_sites = my_sites;
 #ifdef BPE_FINE_PROF
     if (prof) st->bucket_ns[bkt][1] += now_ns() - tp0;
 #endif
     PROF(3)
     grid_barrier(L.barrier, ++epoch * nblk);
     PROF(4)
-    // ---- P3: rewrite + next arg-max partials ----
-    if (bid == 0 && threadIdx.x == 0) {
-      st->snap_n_keys = st->n_keys;
-      st->snap_pool_cursor = st->pool_cursor;
-      st->snap_hot_n = st->hot_n;
-      st->snap_err = st->err;
-    }
-    phase_fill(A, n_sites_now, bid, nblk);
-    if (!replay) {  // the pairs born by this merge that made it onto the hot list
-      const uint32_t hot_now = ld_cg(&st->hot_n);
-      for (uint32_t i = hot_pre + bid * blockDim.x + threadIdx.x; i < hot_now; i += nblk * blockDim.x) {
-        uint32_t hs = L.hot[i];
-        unsigned long long pr = slot_primary(t, A.len16, hs, L.max_length);
-        if (pr) mine = best_merge(mine, Best{pr, hs, 1});
-      }
-      Best v = best_block_reduce(mine, s_best);
-      if (threadIdx.x == 0) L.partials[bid] = v;
-    }
-#ifdef BPE_FINE_PROF
-    if (prof) st->bucket_ns[bkt][2] += now_ns() - tp0;
-#endif
-    PROF(5)
-    grid_barrier(L.barrier, ++epoch * nblk);
-    PROF(6)
   }
 #undef PROF
 }

@@ -1,4 +1,4 @@
-import os, sys, time, ctypes as C
+import hashlib, os, sys, time, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
@@ -24,4 +24,5 @@ for rep in range(3):
     t2 = time.time()
     s = bpe_stats(); lib.bpe_get_stats(h, C.byref(s))
     print("rep", rep, "rc", rc, "ingest %.1f ms" % ((t1 - t0) * 1e3), "merge_until wall %.1f ms" % ((t2 - t1) * 1e3), "k1 total ms %.1f" % s.ms_index_build,
-          "phases", [round(x, 1) for x in s.ms_loop_phase], "launches", s.kernel_launches, "rebuilds", s.hot_rebuilds, file=sys.stderr)
+          "phases", [round(x, 1) for x in s.ms_loop_phase], "launches", s.kernel_launches, "rebuilds", s.hot_rebuilds,
+          "sha1", hashlib.sha1(log[: nd.value].tobytes()).hexdigest()[:12], file=sys.stderr)
