@@ -933,6 +933,8 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     L.max_tokens = BPE_MAX_TOKENS;
     L.tbl_cap = e->tbl_cap;
     L.sites2 = e->sites2.p;
+    const char* pf = getenv("BPE_LOOP_PREFETCH");  // read per launch: a tuning knob
+    L.prefetch = pf ? std::max(0, std::min(atoi(pf), 2)) : 1;
     L.replay = dev_replay ? dev_replay + 2 * done : nullptr;
     if (dev_replay) e->hot_valid = false;  // replayed merges do not feed the hot list
     static const bool trace = getenv("BPE_TRACE") != nullptr;

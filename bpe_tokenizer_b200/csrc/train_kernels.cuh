@@ -1096,6 +1096,7 @@ struct LoopArgs {
   // replay mode (batched restoreMerge, core.ts:477-494): the winners are GIVEN -- (a,b) of merge i at replay[2i..2i+1]
   // -- instead of found by the arg-max; the hot list is neither read nor fed
   const int32_t* replay;
+  int prefetch;  // speculative L2 prefetch of the sites of this many runner-ups (prefetch_runner_up); BPE_LOOP_PREFETCH=0..2
 };
 
 // Grid barrier for the co-resident (cooperative) launch.  The arrival counter lives in its own 128-byte line, away
@@ -1120,6 +1121,35 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
     __threadfence();
   }
   __syncthreads();
+}
+
+// Speculation: the runner-up of a decision is the most likely next winner (its count only changes when it neighbours a site
+// of the current merge; 97.6 % of the cfg3 winners are pairs that existed before the previous merge).  While a block walks
+// the sites of the current merge, its spare warps pull the corpus lines around the runner-up's occurrences into L2, so that
+// the next site pass -- a chain of dependent loads -- finds them there instead of in DRAM.  Hints only: nothing depends on them.
+__device__ __forceinline__ void prefetch_runner_up(const LoopArgs& L, uint32_t winner_slot, uint32_t nblk, uint32_t vt, uint32_t nvt) {
+  const PairTable& t = L.A.t;
+  uint32_t skip = winner_slot;
+  for (int cand = 0; cand < L.prefetch; cand++) {  // the best L.prefetch candidates below the winner
+    Best r{0ull, NOSLOT, 0};
+    for (uint32_t i = lane_id(); i < nblk; i += 32) {
+      Best pb{ld_cg(&L.partials[i].primary), ld_cg(&L.partials[i].slot), 1};
+      if (pb.slot != winner_slot && pb.slot != skip && pb.slot != NOSLOT) r = best_merge(r, pb);
+    }
+    r = best_warp_reduce(r);
+    if (!r.primary || r.slot == NOSLOT) return;
+    skip = r.slot;
+    const uint32_t start = t.occ_start[r.slot], len = t.occ_len[r.slot];
+    if (len > 32768u) continue;  // a merge of that size is throughput bound
+    for (uint32_t i = vt; i < len; i += nvt) {
+      const uint32_t p = ld_cg(L.A.pool + start + i);
+      if (p >= L.A.n) continue;
+      const uint32_t* q = L.A.slots + p;  // the site, the token on its left, the two tokens on its right
+      prefetch_l2(q);
+      if (p >= 16u) prefetch_l2(q - 16);
+      if (p + 24u < L.A.n) prefetch_l2(q + 24);
+    }
+  }
 }
 
 __global__ void k_loop_prepare(DevState* st, uint32_t n_tokens, unsigned long long* barrier) {
@@ -1294,10 +1324,15 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
       st->n_new[par ^ 1u] = 0;
       if (w.mult > 1) st->tie_breaks++;
     }
-    if (fill_n && fill_n <= 8192u && wcnt <= 16384u && blockDim.x == 512u) {
-      // both latency bound: 12 warps of every block walk the sites, 4 fill the lists
-      if (warp < 12) phase_sites(A, wa, wb, c, par, w.slot, (bid * 12 + warp) * 32 + lane, nblk * 384, my_sites);
-      else phase_fill(A, fill_n, (bid * 4 + warp - 12) * 32 + lane, nblk * 128, fill_sites);
+    if (fill_n <= 8192u && wcnt <= 16384u && blockDim.x == 512u) {
+      // latency bound: 12 warps of every block walk the sites, 4 fill the lists of the last merge and then warm the L2
+      // for the next one
+      if (warp < 12) {
+        phase_sites(A, wa, wb, c, par, w.slot, (bid * 12 + warp) * 32 + lane, nblk * 384, my_sites);
+      } else {
+        if (fill_n) phase_fill(A, fill_n, (bid * 4 + warp - 12) * 32 + lane, nblk * 128, fill_sites);
+        if (L.prefetch && !replay) prefetch_runner_up(L, w.slot, nblk, (bid * 4 + warp - 12) * 32 + lane, nblk * 128);
+      }
     } else {
       if (fill_n) phase_fill(A, fill_n, gt, gn, fill_sites);
       phase_sites(A, wa, wb, c, par, w.slot, gt, gn, my_sites);
