@@ -163,6 +163,7 @@ struct bpe_engine {
   DevBuf<DevState> d_st;
   DevState* h_st = nullptr;  // pinned
   DevBuf<Best> partials;
+  DevBuf<uint32_t> partial_keys;
   DevBuf<SiteRec> sites, sites2;  // k_merge_loop alternates between the two (deferred list filling)
   DevBuf<uint32_t> newslots;
   DevBuf<uint32_t> nd;  // dense accumulator of the pairs born by the current merge (train_kernels.cuh, ND_*)
@@ -882,6 +883,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     if (const char* v = getenv("BPE_LOOP_BLOCKS")) e->loop_blocks = std::max(1, std::min(atoi(v), e->sm_count * per_sm));
   }
   CK(e->partials.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
+  CK(e->partial_keys.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
   CK(e->sites.reserve(1u << 16, 0, e->stream, 1.0));
   CK(e->sites2.reserve(std::max<size_t>(e->sites.cap, 1u << 16), 0, e->stream, 1.0));
   CK(e->newslots.reserve(1u << 16, 0, e->stream, 1.0));
@@ -925,6 +927,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     L.cands = e->cands.p;
     L.cand_cap = (uint32_t)std::min<size_t>(e->cands.cap, 0xFFFFFFF0u);
     L.partials = e->partials.p;
+    L.partial_keys = e->partial_keys.p;
     L.barrier = e->barrier.p;
     L.log = e->dev_log.p;
     L.log_cap = chunk;

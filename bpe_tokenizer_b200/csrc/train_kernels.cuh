@@ -398,6 +398,19 @@ __device__ __forceinline__ unsigned long long slot_primary(const PairTable& t, c
   return make_primary(c, a, b);
 }
 
+// the same, also handing out the pair's key
+__device__ __forceinline__ unsigned long long slot_primary_k(const PairTable& t, const uint32_t* len16, uint32_t s, uint32_t max_length,
+                                                             uint32_t* key_out) {
+  uint32_t key = t.keys[s];
+  *key_out = key;
+  if (key == EMPTY_KEY) return 0ull;
+  uint32_t c = t.cnt[s];
+  if (c == 0) return 0ull;
+  uint32_t a = key >> 16, b = key & 0xFFFFu;
+  if (max_length && len16[a] + len16[b] > max_length) return 0ull;
+  return make_primary(c, a, b);
+}
+
 // per-thread partial over this block's stripe of the hot list (use_hot) or of the whole table
 __device__ __forceinline__ Best argmax_stripe(const PairTable& t, const uint32_t* len16, uint32_t max_length, int use_hot,
                                               const uint32_t* hot, uint32_t n, uint32_t bid, uint32_t nblk) {
@@ -894,7 +907,8 @@ __device__ __forceinline__ void phase_sites(const ApplyArgs& A, uint32_t a, uint
 __device__ __forceinline__ void phase_new_pairs(const ApplyArgs& A, uint32_t c, const uint32_t* len16, uint32_t max_length,
                                                 int hot_valid, uint32_t* hot, uint32_t hot_cap, uint32_t pool_cap, bool counts_elsewhere,
                                                 uint32_t vt, uint32_t nvt,  // virtual thread id / count (whole warps)
-                                                Best* mine = nullptr) {     // arg-max candidate of the caller: pairs that go onto the hot list join it
+                                                Best* mine = nullptr,       // arg-max candidate of the caller: pairs that go onto the hot list join it
+                                                uint32_t* mine_key = nullptr) {  // ... and the key of that candidate
   const PairTable& t = A.t;
   DevState* st = A.st;
   const uint32_t thresh = st->hot_thresh;
@@ -909,12 +923,12 @@ __device__ __forceinline__ void phase_new_pairs(const ApplyArgs& A, uint32_t c, 
       tok = i - side * per_side;
       row = A.nd + (size_t)(side ? ND_R_LEN : ND_L_LEN) * ND_STRIDE;
       len = ld_cg(row + tok);
+      cnt = ld_cg(row + ND_STRIDE + tok);  // both cells in flight together (the count is only used when len != 0)
     }
     const bool act = len != 0;
     uint32_t s = NOSLOT;
     bool ins = false;
     if (act) {
-      cnt = ld_cg(row + ND_STRIDE + tok);
       row[tok] = 0;
       row[ND_STRIDE + tok] = 0;
       s = tbl_find_or_insert_ex(t, side ? pair_key(c, tok) : pair_key(tok, c), &ins);
@@ -954,12 +968,18 @@ __device__ __forceinline__ void phase_new_pairs(const ApplyArgs& A, uint32_t c, 
     } else {
       t.cnt[s] = cnt;  // the key is new: nobody else touches its count in this phase
       if (hot_valid) {
-        unsigned long long pr = slot_primary(t, len16, s, max_length);
+        // = slot_primary(t, len16, s, max_length), from what this thread already holds (no re-read of the cells it just wrote)
+        const uint32_t pa = side ? c : tok, pb = side ? tok : c;
+        unsigned long long pr = (cnt && !(max_length && len16[pa] + len16[pb] > max_length)) ? make_primary(cnt, pa, pb) : 0ull;
         if (pr && (uint32_t)(pr >> 20) >= thresh) {
           uint32_t k = atomicAdd(&st->hot_n, 1u);
           if (k < hot_cap) hot[k] = s;
           else atomicOr(&st->err, ERR_HOT_OVERFLOW);
-          if (mine) *mine = best_merge(*mine, Best{pr, s, 1});
+          if (mine) {
+            const uint32_t before = mine->slot;
+            *mine = best_merge(*mine, Best{pr, s, 1});
+            if (mine_key && mine->slot != before) *mine_key = pair_key(pa, pb);
+          }
         }
       }
     }
@@ -1084,6 +1104,7 @@ struct LoopArgs {
   uint32_t* cands;
   uint32_t cand_cap;
   Best* partials;
+  uint32_t* partial_keys;       // key (a << 16 | b) of partials[i].slot: the decision does not have to go back to the table for it
   unsigned long long* barrier;  // arrival counter, zeroed before the launch
   MergeRec* log;       // device merge log for this launch
   uint32_t log_cap;    // max merges this launch may apply
@@ -1181,13 +1202,16 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
   const uint32_t thresh = ld_cg(&st->hot_thresh);
 
   const bool replay = L.replay != nullptr;
-  __shared__ uint32_t s_rslot;
+  __shared__ uint32_t s_rslot, s_wkey;
 
   // first arg-max partials
   if (bid == 0 && threadIdx.x == 0) st->snap_err = st->err;
   if (!replay) {
     Best v = best_block_reduce(argmax_stripe(t, A.len16, L.max_length, 1, L.hot, ld_cg(&st->hot_n), bid, nblk), s_best);
-    if (threadIdx.x == 0) L.partials[bid] = v;
+    if (threadIdx.x == 0) {
+      L.partials[bid] = v;
+      L.partial_keys[bid] = v.primary ? t.keys[v.slot] : 0u;
+    }
   }
   grid_barrier(L.barrier, ++epoch * nblk);
 
@@ -1228,16 +1252,23 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
         if (w.slot != NOSLOT) wcnt = max(t.cnt[w.slot], t.occ_len[w.slot]);  // bound on the sites (the list may hold stale entries)
       }
     } else {
+      uint32_t my_key = 0;
       for (uint32_t i = threadIdx.x; i < nblk; i += blockDim.x) {
         Best pb;
         pb.primary = ld_cg(&L.partials[i].primary);
         pb.slot = ld_cg(&L.partials[i].slot);
         pb.mult = ld_cg(&L.partials[i].mult);
+        const uint32_t pk = ld_cg(&L.partial_keys[i]);
+        const uint32_t before = w.slot;
         w = best_merge(w, pb);
+        if (w.slot != before) my_key = pk;
       }
+      const Best mine_w = w;
       w = best_block_reduce(w, s_best);
-      if (w.primary) {
-        uint32_t key = t.keys[w.slot];
+      if (w.primary) {  // block-uniform: the thread that holds the winning partial hands out its key
+        if (mine_w.primary == w.primary && mine_w.slot == w.slot) s_wkey = my_key;
+        __syncthreads();
+        const uint32_t key = s_wkey;
         wa = key >> 16;
         wb = key & 0xFFFFu;
         wcnt = (uint32_t)(w.primary >> 20);
@@ -1359,27 +1390,33 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
     }
     const uint32_t n_sites_now = ld_cg(&st->n_sites[par]);
     Best mine{0ull, NOSLOT, 0};
+    uint32_t mine_key = 0;
     {
       // Three independent jobs.  Small merges are latency bound, so the warps of every block split up (8 / 4 / 4) and the
       // three dependency chains run side by side; big merges keep every thread on every job.
       const bool split = n_sites_now <= 16384u && blockDim.x == 512u;
       if (!split || warp < 8)
         phase_new_pairs(A, c, A.len16, L.max_length, replay ? 0 : 1, L.hot, L.hot_cap, L.pool_cap, false,
-                        split ? (bid * 8 + warp) * 32 + lane : gt, split ? nblk * 256 : gn, &mine);
+                        split ? (bid * 8 + warp) * 32 + lane : gt, split ? nblk * 256 : gn, &mine, &mine_key);
       if (!split || (warp >= 8 && warp < 12))
         phase_rewrite(A, c, n_sites_now, split ? (bid * 4 + warp - 8) * 32 + lane : gt, split ? nblk * 128 : gn, my_sites);
       if (!replay && (!split || warp >= 12)) {
         for (uint32_t i = split ? (bid * 4 + warp - 12) * 32 + lane : gt; i < hot_pre; i += split ? nblk * 128 : gn) {
-          uint32_t hs = L.hot[i];
+          uint32_t hs = L.hot[i], hk;
           if (hs == w.slot) continue;  // the winner's count is being zeroed
-          unsigned long long pr = slot_primary(t, A.len16, hs, L.max_length);
-          if (pr) mine = best_merge(mine, Best{pr, hs, 1});
+          unsigned long long pr = slot_primary_k(t, A.len16, hs, L.max_length, &hk);
+          if (pr) {
+            const uint32_t before = mine.slot;
+            mine = best_merge(mine, Best{pr, hs, 1});
+            if (mine.slot != before) mine_key = hk;
+          }
         }
       }
     }
     if (!replay) {
       Best v = best_block_reduce(mine, s_best);
       if (threadIdx.x == 0) L.partials[bid] = v;
+      if (mine.primary == v.primary && mine.slot == v.slot) L.partial_keys[bid] = mine_key;  // the owner of the block's best
     }
     fill_n = n_sites_now;
     fill_sites = my_sites;
