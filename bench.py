@@ -366,8 +366,8 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "traffic_note": "a 1 GB step cannot be replayed by ncu (a launch rewrites >20 GB of state); on cfg2 the loop moves 95.5 KB read + 15.6 KB "
-                                "written per merge vs ~72 MB of reference-algorithm bytes (profiles/r01c_bench_default.md)",
+                "traffic_note": "a 1 GB step cannot be replayed by ncu (a launch rewrites >20 GB of state); on cfg2 the loop moves 94.5 KB read + 15.5 KB "
+                                "written per merge vs ~72 MB of reference-algorithm bytes (profiles/r01h_bench_after_two_barrier_loop.md)",
                 "kernel": "k_merge_loop (persistent cooperative mergeUntil kernel; the step also contains k_ingest_ids + K1)",
                 "note": "achieved = reference-algorithm bytes sum_t 4*(2*N_t+N_{t+1}) / step time ('x of reference-algorithm roofline', SURVEY 8d); "
                         "an incremental design may exceed 1.0; peak from " + peak_src,
