@@ -936,6 +936,21 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     L.max_tokens = BPE_MAX_TOKENS;
     L.tbl_cap = e->tbl_cap;
     L.sites2 = e->sites2.p;
+    {  // warp split of the latency-bound phases and barrier back-off (tuning knobs, read per launch)
+      // measured on cfg3 (profiles/r01i): born pairs / rewrite / old-hot arg-max = 10/2/4 warps beats 8/4/4 by 1 %, 6/x loses 1-2 %;
+      // 10..14 site warps and 64..512 ns of back-off are all within noise
+      int a = 12, b = 10, c = 2, ns = 256;
+      if (const char* v = getenv("BPE_LOOP_P1_SITES")) a = atoi(v);
+      if (const char* v = getenv("BPE_LOOP_P2_NEW")) b = atoi(v);
+      if (const char* v = getenv("BPE_LOOP_P2_RW")) c = atoi(v);
+      if (const char* v = getenv("BPE_LOOP_BAR_NS")) ns = atoi(v);
+      if (a < 1 || a > 15) a = 12;
+      if (b < 1 || c < 1 || b + c > 15) b = 10, c = 2;
+      L.p1_sites = (uint32_t)a;
+      L.p2_new = (uint32_t)b;
+      L.p2_rw = (uint32_t)c;
+      L.bar_ns = (uint32_t)std::max(32, std::min(ns, 4096));
+    }
     const char* pf = getenv("BPE_LOOP_PREFETCH");  // read per launch: a tuning knob
     L.prefetch = pf ? std::max(0, std::min(atoi(pf), 2)) : 1;
     L.replay = dev_replay ? dev_replay + 2 * done : nullptr;

@@ -1117,6 +1117,11 @@ struct LoopArgs {
   // replay mode (batched restoreMerge, core.ts:477-494): the winners are GIVEN -- (a,b) of merge i at replay[2i..2i+1]
   // -- instead of found by the arg-max; the hot list is neither read nor fed
   const int32_t* replay;
+  // how the 16 warps of a block share the latency-bound phases of small merges (tuning knobs, defaults in merge_until_device):
+  // P1: p1_sites warps walk the sites, the others fill the previous merge's lists and prefetch; P2: p2_new warps enter the
+  // born pairs, p2_rw warps rewrite the corpus, the others run the arg-max over the old hot pairs
+  uint32_t p1_sites, p2_new, p2_rw;
+  uint32_t bar_ns;  // longest back-off of a barrier poll
   int prefetch;  // speculative L2 prefetch of the sites of this many runner-ups (prefetch_runner_up); BPE_LOOP_PREFETCH=0..2
 };
 
@@ -1129,7 +1134,7 @@ __device__ __forceinline__ unsigned long long now_ns() {
   return t;
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target, uint32_t max_ns = 256) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -1137,7 +1142,7 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
     uint32_t ns = 32;
     while (ld_volatile_u64(ctr) < target) {
       __nanosleep(ns);
-      if (ns < 256) ns <<= 1;
+      if (ns < max_ns) ns <<= 1;
     }
     __threadfence();
   }
@@ -1213,7 +1218,7 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
       L.partial_keys[bid] = v.primary ? t.keys[v.slot] : 0u;
     }
   }
-  grid_barrier(L.barrier, ++epoch * nblk);
+  grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
 
   const bool prof = (bid == 0 && threadIdx.x == 0);
   unsigned long long tp0 = prof ? now_ns() : 0, tp1;
@@ -1289,12 +1294,12 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
         if (fill_n) {  // the tie-break reads occurrence lists: those of the last merge must be complete
           phase_fill(A, fill_n, gt, gn, fill_sites);
           fill_n = 0;
-          grid_barrier(L.barrier, ++epoch * nblk);
+          grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
         }
         phase_collect(t, A.len16, L.max_length, 1, L.hot, hot_pre, w.primary, L.cands, L.cand_cap, st, bid, nblk);
-        grid_barrier(L.barrier, ++epoch * nblk);
+        grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
         phase_tie(A.slots, A.n, t, A.pool, L.cands, ld_cg(&st->n_cand), st, s_max, bid, nblk);
-        grid_barrier(L.barrier, ++epoch * nblk);
+        grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
         unsigned long long tp = ld_cg(&st->tie_pos);
         if (tp == ~0ull) status = LOOP_ERROR;
         else {
@@ -1339,7 +1344,7 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
       // the winner was born by the previous merge: its list is exactly what fill(t-1) still has to write
       phase_fill(A, fill_n, gt, gn, fill_sites);
       fill_n = 0;
-      grid_barrier(L.barrier, ++epoch * nblk);
+      grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
     }
     // ---- P1: sites + deltas, next to the list filling of the previous merge ----
     if (bid == 0 && threadIdx.x == 0) {
@@ -1358,11 +1363,12 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
     if (fill_n <= 8192u && wcnt <= 16384u && blockDim.x == 512u) {
       // latency bound: 12 warps of every block walk the sites, 4 fill the lists of the last merge and then warm the L2
       // for the next one
-      if (warp < 12) {
-        phase_sites(A, wa, wb, c, par, w.slot, (bid * 12 + warp) * 32 + lane, nblk * 384, my_sites);
+      const uint32_t ws = L.p1_sites, wh = 16u - ws;
+      if (warp < ws) {
+        phase_sites(A, wa, wb, c, par, w.slot, (bid * ws + warp) * 32 + lane, nblk * ws * 32, my_sites);
       } else {
-        if (fill_n) phase_fill(A, fill_n, (bid * 4 + warp - 12) * 32 + lane, nblk * 128, fill_sites);
-        if (L.prefetch && !replay) prefetch_runner_up(L, w.slot, nblk, (bid * 4 + warp - 12) * 32 + lane, nblk * 128);
+        if (fill_n) phase_fill(A, fill_n, (bid * wh + warp - ws) * 32 + lane, nblk * wh * 32, fill_sites);
+        if (L.prefetch && !replay) prefetch_runner_up(L, w.slot, nblk, (bid * wh + warp - ws) * 32 + lane, nblk * wh * 32);
       }
     } else {
       if (fill_n) phase_fill(A, fill_n, gt, gn, fill_sites);
@@ -1377,7 +1383,7 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
     }
 #endif
     PROF(1)
-    grid_barrier(L.barrier, ++epoch * nblk);
+    grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
     PROF(2)
     // ---- P2: the born pairs (table, list space, hot list, arg-max), the corpus rewrite, the arg-max over the old hot pairs ----
     if (bid == 0 && threadIdx.x == 0) {
@@ -1392,16 +1398,17 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
     Best mine{0ull, NOSLOT, 0};
     uint32_t mine_key = 0;
     {
-      // Three independent jobs.  Small merges are latency bound, so the warps of every block split up (8 / 4 / 4) and the
+      // Three independent jobs.  Small merges are latency bound, so the warps of every block split up (p2_new / p2_rw / rest) and the
       // three dependency chains run side by side; big merges keep every thread on every job.
       const bool split = n_sites_now <= 16384u && blockDim.x == 512u;
-      if (!split || warp < 8)
+      const uint32_t wn = L.p2_new, wr = L.p2_rw, wm = 16u - wn - wr;
+      if (!split || warp < wn)
         phase_new_pairs(A, c, A.len16, L.max_length, replay ? 0 : 1, L.hot, L.hot_cap, L.pool_cap, false,
-                        split ? (bid * 8 + warp) * 32 + lane : gt, split ? nblk * 256 : gn, &mine, &mine_key);
-      if (!split || (warp >= 8 && warp < 12))
-        phase_rewrite(A, c, n_sites_now, split ? (bid * 4 + warp - 8) * 32 + lane : gt, split ? nblk * 128 : gn, my_sites);
-      if (!replay && (!split || warp >= 12)) {
-        for (uint32_t i = split ? (bid * 4 + warp - 12) * 32 + lane : gt; i < hot_pre; i += split ? nblk * 128 : gn) {
+                        split ? (bid * wn + warp) * 32 + lane : gt, split ? nblk * wn * 32 : gn, &mine, &mine_key);
+      if (!split || (warp >= wn && warp < wn + wr))
+        phase_rewrite(A, c, n_sites_now, split ? (bid * wr + warp - wn) * 32 + lane : gt, split ? nblk * wr * 32 : gn, my_sites);
+      if (!replay && (!split || warp >= wn + wr)) {
+        for (uint32_t i = split ? (bid * wm + warp - wn - wr) * 32 + lane : gt; i < hot_pre; i += split ? nblk * wm * 32 : gn) {
           uint32_t hs = L.hot[i], hk;
           if (hs == w.slot) continue;  // the winner's count is being zeroed
           unsigned long long pr = slot_primary_k(t, A.len16, hs, L.max_length, &hk);
@@ -1424,7 +1431,7 @@ __global__ void __launch_bounds__(ML_THREADS, ML_MIN_BLOCKS) k_merge_loop(LoopAr
     if (prof) st->bucket_ns[bkt][1] += now_ns() - tp0;
 #endif
     PROF(3)
-    grid_barrier(L.barrier, ++epoch * nblk);
+    grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
     PROF(4)
   }
 #undef PROF

@@ -18,9 +18,10 @@ log = np.zeros(merges, dtype=MERGE_DTYPE); nd = C.c_int64()
 sweep = os.environ.get("ENVSWEEP", "").split()  # e.g. "BPE_LOOP_PREFETCH=0 BPE_LOOP_PREFETCH=1": rep i runs with entry i % len
 for rep in range(int(os.environ.get("REPS", "3"))):
     if sweep:
-        k, v = sweep[rep % len(sweep)].split("=")
-        os.environ[k] = v
-        print("rep", rep, "with", k, "=", v, file=sys.stderr)
+        for kv in sweep[rep % len(sweep)].split(","):  # "A=1,B=2": several knobs per rep
+            k, v = kv.split("=")
+            os.environ[k] = v
+        print("rep", rep, "with", sweep[rep % len(sweep)], file=sys.stderr)
     t0 = time.time()
     lib.bpe_clear_corpus(h); lib.bpe_set_tokens(h, p32(len16), len(len16)); lib.bpe_load_merges(h, None, 0)
     assert lib.bpe_add_documents_dev(h, C.c_void_p(ids.data_ptr()), p64(off), len(off) - 1) == 0
