@@ -498,7 +498,6 @@ ApplyArgs apply_args(bpe_engine* e) {
   A.st = e->d_st.p;
   A.sites = e->sites.p;
   A.sites_cap = (uint32_t)std::min<size_t>(e->sites.cap, 0xFFFFFFFFu);
-  if (e->sites2.p) A.sites_cap = (uint32_t)std::min<size_t>(A.sites_cap, e->sites2.cap);
   A.newslots = e->newslots.p;
   A.nd = e->nd.p;
   A.newpair = nullptr;
@@ -936,6 +935,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     L.max_tokens = BPE_MAX_TOKENS;
     L.tbl_cap = e->tbl_cap;
     L.sites2 = e->sites2.p;
+    L.A.sites_cap = (uint32_t)std::min<size_t>(L.A.sites_cap, e->sites2.cap);  // (only this kernel alternates between the two)
     {  // warp split of the latency-bound phases and barrier back-off (tuning knobs, read per launch)
       // measured on cfg3 (profiles/r01i): born pairs / rewrite / old-hot arg-max = 10/2/4 warps beats 8/4/4 by 1 %, 6/x loses 1-2 %;
       // 10..14 site warps and 64..512 ns of back-off are all within noise
