@@ -338,6 +338,8 @@ def run_b200(args):
 
     if rank == 0:
         cpu = cpu_baseline(args, merges_sample=8) if world == 1 else None  # timed on rank 0 at N=1 only
+        # (out_host / ooff_host hold the result of the last host-buffer encode call: raw token indices, tvi being the identity)
+        enc_cpu = cpu_encode_baseline(log, done, ids2_host.numpy(), off2, out_host.numpy(), ooff_host) if world == 1 else None
         line = {
             "metric": "mergeUntil merges/sec",
             "value": value,
@@ -388,6 +390,8 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if enc_cpu is not None:
+            line["encode"]["cpu_baseline"] = enc_cpu
         print(json.dumps(line))
     lib.bpe_destroy(h)
     if world > 1:
@@ -427,6 +431,30 @@ def cpu_baseline(args, merges_sample=8):
         "sample": "C++ restatement of core.ts (Node/V8 absent), 1 thread of %d: first %d merges on the first %d chars took %.2f s (%.3f merges/s); "
                   "per-merge cost is linear in corpus size, value = that x %.4f (sample/workload size)" % (os.cpu_count() or 1, done, n, dt, rate, scale),
     }
+
+
+def cpu_encode_baseline(log, done, ids, off, gpu_out, gpu_off, sample_bytes=1_000_000):
+    """encodeToCode (core.ts:404-406: every merge in training order, replaceAll over the document) by the CPU restatement, one call per
+    document, on the first ~1 MB of the encode text -- and the check that the vectors the GPU produced for those documents are identical."""
+    try:
+        from oracle.int_oracle import IntOracle
+
+        o = IntOracle()
+        o.load_merges(np.stack([log["a"][:done], log["b"][:done], log["c"][:done]], axis=1).astype(np.int32))
+        d = max(1, min(int(np.searchsorted(off, off[0] + sample_bytes, side="left")), len(off) - 1))
+        same, k = True, 0
+        t0 = time.perf_counter()
+        for i in range(d):
+            want = o.encode(ids[off[i]:off[i + 1]])
+            k += want.size
+            same = same and np.array_equal(want, gpu_out[gpu_off[i]:gpu_off[i + 1]])
+        dt = time.perf_counter() - t0
+        chars = int(off[d] - off[0])
+        return {"value": chars / dt / 1e9, "unit": "GB/s", "cores": 1, "kind": "port", "matches_gpu_output": bool(same),
+                "sample": "C++ restatement of core.ts encodeToCode (Node/V8 absent), 1 thread of %d: the first %d documents (%d chars -> %d tokens) of the "
+                          "encode text with the %d merges just learned took %.2f s" % (os.cpu_count() or 1, d, chars, k, done, dt)}
+    except Exception as e:  # the baseline must never take the GPU line down
+        return {"value": None, "unit": "GB/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
 
 
 def run_reference(args):
