@@ -1994,18 +1994,43 @@ int next_chunk(bpe_engine* e, const int64_t* off, int64_t n_docs, int64_t d0, in
   return BPE_OK;
 }
 
+// Sizes of the pipeline for a batch of `total` input units in n_docs documents.  The first chunks are small and double up to
+// `target` (the first copy in is exposed), the last ones halve again (so are the last encode and the last copy out).  A chunk
+// closes when the next document would pass its target, so two consecutive chunks always hold more than the smallest target
+// -- which bounds their number and with it the staging buffers (tests/test_abi_symbols.py checks the bound through
+// bpe_debug_plan_chunks).
+struct PipePlan {
+  int64_t target, min_target, max_chunks, pad;
+  size_t unit_cap, off_cap;
+};
+
+PipePlan pipe_plan(int64_t total, int64_t n_docs, int64_t chunk_units) {
+  PipePlan P;
+  P.target = std::min<int64_t>(std::max<int64_t>(chunk_units, 1), 1ll << 40);
+  P.min_target = std::max<int64_t>(P.target / 8, 1);
+  P.max_chunks = std::min<int64_t>(2 * (total / P.min_target) + 8, n_docs + 1);
+  P.pad = 256;  // every chunk's region of the unit buffers starts on a multiple of this
+  P.unit_cap = (size_t)(total + P.pad * P.max_chunks);
+  P.off_cap = (size_t)(n_docs + P.max_chunks + 1);
+  return P;
+}
+
+// target of chunk number `index` when `remaining` units are left
+int64_t pipe_want(const PipePlan& P, int64_t index, int64_t remaining) {
+  int64_t want = P.target >> std::max<int64_t>(0, 3 - index);          // ramp up: 1/8, 1/4, 1/2, 1
+  want = std::min(want, std::max(remaining / 2, P.min_target));        // ramp down
+  return std::max(want, P.min_target);
+}
+
 int encode_pipeline(bpe_engine* e, const bool is_text, const int32_t* ids, const uint8_t* utf8, const int64_t* off, int64_t n_docs,
                     const int32_t* to_vector_index, int32_t n_tvi, int32_t* out, int64_t out_cap, int64_t* out_offsets, int64_t* first_bad,
                     int64_t* n_out, int64_t* unknown_pos, int32_t* unknown_code_point) {
-  const int64_t base = off[0], target = std::max<int64_t>(e->enc_chunk, 1), pad = 256;
+  const int64_t base = off[0];
   if (off[n_docs] < base) return fail(e, BPE_E_INVALID, "document offsets must be non-decreasing");
   const int64_t total = off[n_docs] - base;
-  // The first chunks are small and double up to `target` (the first copy in is exposed), the last ones halve again (so
-  // are the last encode and the last copy out).  Two consecutive chunks always hold more than the smallest chunk target,
-  // which bounds their number.
-  const int64_t min_target = std::max<int64_t>(target / 8, 1);
-  const int64_t max_chunks = std::min<int64_t>(2 * (total / min_target) + 8, n_docs + 1);
-  const size_t unit_cap = (size_t)(total + pad * max_chunks), off_cap = (size_t)(n_docs + max_chunks + 1);
+  const PipePlan P = pipe_plan(total, n_docs, e->enc_chunk);
+  const int64_t pad = P.pad;
+  const size_t unit_cap = P.unit_cap, off_cap = P.off_cap;
   // everything a chunk in flight may touch is allocated before the first copy starts
   if (is_text) {
     TRY(ensure_cpmap(e));
@@ -2036,9 +2061,7 @@ int encode_pipeline(bpe_engine* e, const bool is_text, const int32_t* ids, const
   // s_in: the chunk after `prev` goes to the device (units, offsets; ids are checked against the token table there)
   auto upload_next = [&](const PipeChunk& prev, int slot, PipeChunk* c) -> int {
     const int64_t reg = (prev.reg + (prev.in1 - prev.in0) + pad - 1) / pad * pad, oreg = prev.oreg + (prev.d1 - prev.d0) + (prev.d1 ? 1 : 0);
-    int64_t want = target >> std::max<int64_t>(0, 3 - n_up);                               // ramp up: 1/8, 1/4, 1/2, 1
-    want = std::min(want, std::max((total - prev.in1) / 2, min_target));                      // ramp down
-    TRY(next_chunk(e, off, n_docs, prev.d1, std::max(want, min_target), e->h_in_off.p + oreg, c));
+    TRY(next_chunk(e, off, n_docs, prev.d1, pipe_want(P, n_up, total - prev.in1), e->h_in_off.p + oreg, c));
     c->reg = reg;
     c->oreg = oreg;
     const int64_t len = c->in1 - c->in0, nd = c->d1 - c->d0;
@@ -2324,6 +2347,34 @@ int bpe_encode_text_batch(bpe_engine* e, const uint8_t* utf8, const int64_t* doc
   CK(cudaSetDevice(e->device));
   return encode_host(e, true, nullptr, utf8, doc_byte_offsets, n_docs, to_vector_index, n_tvi, out, out_cap, out_offsets, first_bad, n_out, unknown_pos,
                      unknown_code_point);
+}
+
+int bpe_debug_plan_chunks(const int64_t* doc_offsets, int64_t n_docs, int64_t chunk_units, int64_t* first_doc, int64_t cap, int64_t* n_chunks,
+                          int64_t* bounds) {
+  if (!doc_offsets || n_docs <= 0 || !n_chunks || !bounds) return BPE_E_INVALID;
+  if (doc_offsets[n_docs] < doc_offsets[0]) return BPE_E_INVALID;
+  const int64_t total = doc_offsets[n_docs] - doc_offsets[0];
+  const PipePlan P = pipe_plan(total, n_docs, chunk_units);
+  std::vector<int64_t> rel((size_t)n_docs + 2);
+  PipeChunk prev, c;
+  int64_t n = 0, reg = 0, oreg = 0;
+  while (prev.d1 < n_docs) {
+    reg = (prev.reg + (prev.in1 - prev.in0) + P.pad - 1) / P.pad * P.pad;
+    oreg = prev.oreg + (prev.d1 - prev.d0) + (prev.d1 ? 1 : 0);
+    TRY(next_chunk(nullptr, doc_offsets, n_docs, prev.d1, pipe_want(P, n, total - prev.in1), rel.data(), &c));
+    c.reg = reg;
+    c.oreg = oreg;
+    if (first_doc && n < cap) first_doc[n] = c.d0;
+    n++;
+    prev = c;
+  }
+  *n_chunks = n;
+  bounds[0] = P.max_chunks;
+  bounds[1] = (int64_t)P.unit_cap;
+  bounds[2] = prev.reg + (prev.in1 - prev.in0);       // units of the staging buffers the last chunk reaches
+  bounds[3] = (int64_t)P.off_cap;
+  bounds[4] = prev.oreg + (prev.d1 - prev.d0) + 1;    // offset entries the last chunk reaches
+  return BPE_OK;
 }
 
 int bpe_restore_documents(bpe_engine* e, const int32_t* ids, const int64_t* doc_offsets, int64_t n_docs) {

@@ -207,6 +207,13 @@ int bpe_decode_batch(bpe_engine* e, const int32_t* values, const int64_t* doc_of
                      const int64_t* token_byte_offsets, int32_t n_tokens, uint8_t* out, int64_t out_cap,
                      int64_t* out_offsets, int64_t* first_bad, int64_t* n_out);
 
+/* Debug / test: how the host-buffer encode calls above would cut a batch into chunks of whole documents
+ * (chunk_units = full-size chunk; no device work, no engine).  first_doc[0..min(*n_chunks, cap)) receives the first
+ * document of every chunk; bounds[5] = {chunk-count bound, unit capacity of the staging buffers, units reached by the
+ * last chunk, offset-entry capacity, offset entries reached}: the reached values must not exceed the capacities. */
+int bpe_debug_plan_chunks(const int64_t* doc_offsets, int64_t n_docs, int64_t chunk_units, int64_t* first_doc, int64_t cap,
+                          int64_t* n_chunks, int64_t* bounds);
+
 /* ---- text front end on the device (core.ts:185-205 ingest, :396-402 encode front end) --------------
  * Documents arrive as UTF-8 bytes (lone surrogates in their generalised 3-byte form); one token per CODE POINT, as
  * the reference's `for (let char of content)` yields them.  The engine keeps a code point -> token index table. */
