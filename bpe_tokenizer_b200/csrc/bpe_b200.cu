@@ -595,22 +595,25 @@ int ensure_merge_table(bpe_engine* e) {
 }
 
 // ---- pair table of the lane path: rank + spine bounds per pair (see encode_lanes.cuh) ---------------------------
-int ensure_lane_tables(bpe_engine* e) {
-  if (!e->lt_dirty && e->d_lt.p) return BPE_OK;
-  size_t m = e->h_merges.size() / 3;
+// rank, token and spine bounds of every pair that is a rule or lies on a spine of one (encode_lanes.cuh) -- pure host work,
+// also reachable without a device through bpe_debug_lane_table (CPU parity test against the prototype of the algorithm)
+struct LaneEnt {
+  uint16_t rk = 0xFFFF, c = 0, rs = 0xFFFF, ls = 0xFFFF;
+};
+
+int build_lane_entries(bpe_engine* e, const std::vector<int32_t>& merges, int32_t n_tokens, std::unordered_map<uint32_t, LaneEnt>& M,
+                       std::vector<uint16_t>& rule_c) {
+  size_t m = merges.size() / 3;
   if (m > EL_MAX_RANK + 1) return fail(e, BPE_E_DOMAIN, "merge list too long");
-  const int32_t nt = std::max(e->n_tokens, 1);
-  struct Ent {
-    uint16_t rk = 0xFFFF, c = 0, rs = 0xFFFF, ls = 0xFFFF;
-  };
-  std::unordered_map<uint32_t, Ent> M;
+  const int32_t nt = std::max(n_tokens, 1);
+  M.clear();
   M.reserve(m * 3 + 16);
   // definition of every merged token (core.ts:315-325: c is a fresh index, so each c has one definition)
   std::vector<int32_t> def_a((size_t)nt, -1), def_b((size_t)nt, -1);
   std::vector<uint8_t> first(m, 0);
-  std::vector<uint16_t> rule_c(std::max<size_t>(m, 1), 0);
+  rule_c.assign(std::max<size_t>(m, 1), 0);
   for (size_t r = 0; r < m; r++) {
-    int32_t a = e->h_merges[3 * r], b = e->h_merges[3 * r + 1], c = e->h_merges[3 * r + 2];
+    int32_t a = merges[3 * r], b = merges[3 * r + 1], c = merges[3 * r + 2];
     if (a < 0 || b < 0 || c < 0 || a >= nt || b >= nt || c >= nt)
       return fail(e, BPE_E_INVALID, "merge %zu refers to a token outside the table", r);
     rule_c[r] = (uint16_t)c;
@@ -620,7 +623,7 @@ int ensure_lane_tables(bpe_engine* e) {
     } else if (def_a[c] >= 0 && (def_a[c] != a || def_b[c] != b)) {
       return fail(e, BPE_E_INVALID, "token %d is produced by two different merges", c);
     }
-    Ent& x = M[pair_key((uint32_t)a, (uint32_t)b)];
+    LaneEnt& x = M[pair_key((uint32_t)a, (uint32_t)b)];
     if (x.rk == 0xFFFF) {  // a second rule for the same pair can never fire (the first one removed every occurrence)
       x.rk = (uint16_t)r;
       x.c = (uint16_t)c;
@@ -629,27 +632,36 @@ int ensure_lane_tables(bpe_engine* e) {
   }
   for (size_t r = 0; r < m; r++) {
     if (!first[r]) continue;
-    int32_t a = e->h_merges[3 * r], b = e->h_merges[3 * r + 1];
+    int32_t a = merges[3 * r], b = merges[3 * r + 1];
     for (int32_t u = a;;) {  // every token on the right spine of a: anything ending in u may grow into a
-      Ent& x = M[pair_key((uint32_t)u, (uint32_t)b)];
+      LaneEnt& x = M[pair_key((uint32_t)u, (uint32_t)b)];
       if (x.rs > r) x.rs = (uint16_t)r;
       if (def_a[u] < 0) break;
       u = def_b[u];
     }
     for (int32_t w = b;;) {  // every token on the left spine of b
-      Ent& x = M[pair_key((uint32_t)a, (uint32_t)w)];
+      LaneEnt& x = M[pair_key((uint32_t)a, (uint32_t)w)];
       if (x.ls > r) x.ls = (uint16_t)r;
       if (def_a[w] < 0) break;
       w = def_a[w];
     }
   }
+  return BPE_OK;
+}
+
+int ensure_lane_tables(bpe_engine* e) {
+  if (!e->lt_dirty && e->d_lt.p) return BPE_OK;
+  size_t m = e->h_merges.size() / 3;
+  std::unordered_map<uint32_t, LaneEnt> M;
+  std::vector<uint16_t> rule_c;
+  TRY(build_lane_entries(e, e->h_merges, e->n_tokens, M, rule_c));
   uint32_t cap = pow2_at_least(std::max<size_t>(2 * M.size(), 1024));
   std::vector<uint4> h(cap, make_uint4(EMPTY_KEY, EL_NONE, 0xFFFFFFFFu, 0));
   std::vector<uint2> dense((size_t)EL_DENSE * EL_DENSE, make_uint2(EL_NONE, 0xFFFFFFFFu));
   int shift = 32 - ilog2(cap);
   for (auto& kv : M) {
     uint32_t key = kv.first;
-    const Ent& x = kv.second;
+    const LaneEnt& x = kv.second;
     uint32_t y = (uint32_t)x.rk | ((uint32_t)x.c << 16), z = (uint32_t)x.rs | ((uint32_t)x.ls << 16);
     uint32_t a = key >> 16, b = key & 0xFFFFu;
     if (a < (uint32_t)EL_DENSE && b < (uint32_t)EL_DENSE) dense[a * EL_DENSE + b] = make_uint2(y, z);
@@ -2347,6 +2359,28 @@ int bpe_encode_text_batch(bpe_engine* e, const uint8_t* utf8, const int64_t* doc
   CK(cudaSetDevice(e->device));
   return encode_host(e, true, nullptr, utf8, doc_byte_offsets, n_docs, to_vector_index, n_tvi, out, out_cap, out_offsets, first_bad, n_out, unknown_pos,
                      unknown_code_point);
+}
+
+int bpe_debug_lane_table(const int32_t* abc, int64_t n_merges, int32_t n_tokens, int32_t* a, int32_t* b, int32_t* rank, int32_t* c,
+                         int32_t* right_spine_bound, int32_t* left_spine_bound, int64_t cap, int64_t* n) {
+  if (n_merges < 0 || (n_merges > 0 && !abc) || !n) return BPE_E_INVALID;
+  std::vector<int32_t> merges(abc, abc + 3 * n_merges);
+  std::unordered_map<uint32_t, LaneEnt> M;
+  std::vector<uint16_t> rule_c;
+  TRY(build_lane_entries(nullptr, merges, n_tokens, M, rule_c));
+  *n = (int64_t)M.size();
+  if ((int64_t)M.size() > cap) return BPE_E_CAPACITY;
+  int64_t i = 0;
+  for (const auto& kv : M) {
+    a[i] = (int32_t)(kv.first >> 16);
+    b[i] = (int32_t)(kv.first & 0xFFFFu);
+    rank[i] = kv.second.rk == 0xFFFF ? -1 : (int32_t)kv.second.rk;
+    c[i] = kv.second.rk == 0xFFFF ? -1 : (int32_t)kv.second.c;
+    right_spine_bound[i] = kv.second.rs == 0xFFFF ? -1 : (int32_t)kv.second.rs;
+    left_spine_bound[i] = kv.second.ls == 0xFFFF ? -1 : (int32_t)kv.second.ls;
+    i++;
+  }
+  return BPE_OK;
 }
 
 int bpe_debug_plan_chunks(const int64_t* doc_offsets, int64_t n_docs, int64_t chunk_units, int64_t* first_doc, int64_t cap, int64_t* n_chunks,

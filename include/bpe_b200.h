@@ -207,6 +207,12 @@ int bpe_decode_batch(bpe_engine* e, const int32_t* values, const int64_t* doc_of
                      const int64_t* token_byte_offsets, int32_t n_tokens, uint8_t* out, int64_t out_cap,
                      int64_t* out_offsets, int64_t* first_bad, int64_t* n_out);
 
+/* Debug / test: the pair table the encode kernel works from (csrc/encode_lanes.cuh), built from a merge list abc[3*i..] =
+ * (a, b, c) without touching a device: for every pair that is a rule or lies on a spine of one, its rank and token (-1: no
+ * rule) and the lowest rank of any rule that can consume its right / left half through a spine (-1: none).
+ * *n = number of pairs (BPE_E_CAPACITY when cap is smaller); unspecified order. */
+int bpe_debug_lane_table(const int32_t* abc, int64_t n_merges, int32_t n_tokens, int32_t* a, int32_t* b, int32_t* rank, int32_t* c,
+                         int32_t* right_spine_bound, int32_t* left_spine_bound, int64_t cap, int64_t* n);
 /* Debug / test: how the host-buffer encode calls above would cut a batch into chunks of whole documents
  * (chunk_units = full-size chunk; no device work, no engine).  first_doc[0..min(*n_chunks, cap)) receives the first
  * document of every chunk; bounds[5] = {chunk-count bound, unit capacity of the staging buffers, units reached by the
