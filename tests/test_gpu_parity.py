@@ -229,6 +229,38 @@ def test_zipf_1mb_500_merges_bit_exact():
             assert vals[ooff[d]:ooff[d + 1]].tolist() == [orc.to_vector_index[x] for x in want_raw.tolist()]
 
 
+def test_cfg2_full_size_merge_log_matches_the_oracle():
+    """BASELINE config 2 at FULL size (10 MB seeded Zipf corpus, 4 000 merges, SURVEY.md section 8(d) "cfg2: full bit-exact"): the
+    product's merge log -- pairs, new indices and weights, in the byte layout bench.py hashes -- equals the one the CPU restatement
+    of core.ts produced offline (tests/golden/make_cfg2_golden.py, minutes of CPU; the fixture keeps its SHA-1 and both ends)."""
+    import hashlib
+
+    from bpe_tokenizer_b200._abi import MERGE_DTYPE
+    from bpe_tokenizer_b200.synth import first_appearance_ids, synth_corpus
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "cfg2_merge_log.json")) as f:
+        golden = json.load(f)
+    text, off = synth_corpus(10_000_000, seed=43)
+    ids, alphabet = first_appearance_ids(text)
+    assert len(alphabet) == golden["alphabet"] and "%d B" % text.size in golden["workload"] and "%d docs" % (len(off) - 1) in golden["workload"]
+    gpu = make()
+    gpu.addToCorpus("".join(chr(c) for c in alphabet))  # the single-character tokens in first-appearance order
+    gpu._pending = []
+    for tk in gpu.token_table:
+        tk.weight = tk.original_weight = 0
+    gpu.addDocuments(ids, off)
+    assert gpu.mergeUntil({"max_iterations": golden["merges"]}) == golden["merges"]
+    log = np.zeros(golden["merges"], dtype=MERGE_DTYPE)
+    log["a"] = [a.index for a, _, _ in gpu.merge_tokens]
+    log["b"] = [b.index for _, b, _ in gpu.merge_tokens]
+    log["c"] = [c.index for _, _, c in gpu.merge_tokens]
+    log["weight"] = [c.original_weight for _, _, c in gpu.merge_tokens]
+    assert [[int(r["a"]), int(r["b"]), int(r["weight"])] for r in log[:8]] == golden["first"]
+    assert [[int(r["a"]), int(r["b"]), int(r["weight"])] for r in log[-4:]] == golden["last"]
+    assert hashlib.sha1(log["weight"].astype(np.int64).tobytes()).hexdigest() == golden["weights_sha1"]
+    assert hashlib.sha1(log.tobytes()).hexdigest() == golden["sha1"]
+
+
 def test_resume_routes_equal_uninterrupted_run():
     """cfg5 shape at test size: max_length=8, split run resumed (a) via toJSON -> fromJSON -> restoreToCorpus and
     (b) via addToCorpus + restoreMerge(compactMerge(...)); both must equal the uninterrupted run."""
