@@ -145,3 +145,32 @@ def test_committed_golden_fixtures_still_match_literal_oracle():
                 except ValueError as e:
                     got = "throws: " + str(e)
                 assert got == want, (case["name"], text)
+
+
+def test_cfg3_gpu_merge_table_starts_like_the_oracle_on_the_full_corpus():
+    """SURVEY.md section 8(d), parity at scale (1): the first merges of BASELINE config 3 -- pairs, new indices AND weights on the full
+    1 GB corpus -- as the CPU restatement computes them (tests/golden/make_cfg3_prefix_golden.py, ~8 s per merge, run offline) equal
+    the head of the merge log the GPU run produced (tools/data/merges_cfg3_abc.npy + merges_cfg3_weights.npy, written from
+    tools/dump_merges.py's output).  That log is the one every cfg3 bench line reports: its SHA-1 is profiles/*bench*.json's."""
+    import hashlib
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from bpe_tokenizer_b200._abi import MERGE_DTYPE
+
+    abc = np.load(os.path.join(root, "tools", "data", "merges_cfg3_abc.npy"))
+    weights = np.load(os.path.join(root, "tools", "data", "merges_cfg3_weights.npy"))
+    alphabet = np.load(os.path.join(root, "tools", "data", "alphabet_cfg3.npy"))
+    log = np.zeros(len(abc), dtype=MERGE_DTYPE)
+    log["a"], log["b"], log["c"], log["weight"] = abc[:, 0], abc[:, 1], abc[:, 2], weights
+    sha = hashlib.sha1(log.tobytes()).hexdigest()
+    with open(os.path.join(root, "profiles", "r01_bench_n1.json")) as f:
+        assert json.load(f)["config"]["merge_log_sha1"] == sha == "add92aa1a96c276f03b63e3a952370ef04cb60f0"
+    with open(os.path.join(root, "tests", "golden", "cfg3_prefix.json")) as f:
+        golden = json.load(f)
+    assert golden["alphabet"] == alphabet.tolist()
+    n = len(golden["merges"])
+    assert n >= 8
+    assert [[int(r["a"]), int(r["b"]), int(r["c"]), int(r["weight"])] for r in log[:n]] == golden["merges"]
+    # weights never increase from one merge to the next (a born pair occurs at most as often as the pair that bore it)
+    assert np.all(np.diff(weights.astype(np.int64)) <= 0)
