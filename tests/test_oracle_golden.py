@@ -174,3 +174,74 @@ def test_cfg3_gpu_merge_table_starts_like_the_oracle_on_the_full_corpus():
     assert [[int(r["a"]), int(r["b"]), int(r["c"]), int(r["weight"])] for r in log[:n]] == golden["merges"]
     # weights never increase from one merge to the next (a born pair occurs at most as often as the pair that bore it)
     assert np.all(np.diff(weights.astype(np.int64)) <= 0)
+
+
+# ---- the incremental oracle (oracle/fast_oracle.cpp) is pinned to the literal restatement ------------------------------------
+def _int_vs_fast(docs, nsym, mw, ml, mi, len16_chars=None, cap=400):
+    from oracle.fast_oracle import FastOracle
+    from oracle.int_oracle import IntOracle
+
+    ids = np.array([t for d in docs for t in d], dtype=np.int32)
+    off = np.zeros(len(docs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(d) for d in docs])
+    len16 = np.ones(nsym + cap + 1, dtype=np.int32)
+    if len16_chars is not None:
+        len16[:nsym] = len16_chars
+    lit, fast = IntOracle(), FastOracle()
+    lit.set_len16(len16)
+    lit.add_documents(ids, off)
+    fast.set_len16(len16[:nsym])
+    fast.add_documents(ids, off)
+    want, got = lit.merge_until(mw, ml, mi, nsym, cap), fast.merge_until(mw, ml, mi, nsym, cap)
+    assert all(np.array_equal(x, y) for x, y in zip(want, got)), ([x[:12].tolist() for x in want], [x[:12].tolist() for x in got])
+    corpus = np.concatenate([lit.document(d) for d in range(lit.num_documents())]) if lit.num_documents() else np.zeros(0, np.int32)
+    assert np.array_equal(corpus, fast.corpus())
+    return len(want[0])
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_fast_oracle_equals_literal_oracle_fuzz(chunk):
+    """tiny alphabets (ties on weight and index sum, runs like 'aaa', chains like 'abab'), empty and one-token documents, every
+    option: same merges, same weights, same final corpus as the literal restatement"""
+    total = 0
+    for seed in range(chunk * 120, (chunk + 1) * 120):
+        rng = random.Random(40000 + seed)
+        nsym = rng.choice([1, 2, 2, 3, 3, 5, 8])
+        docs = [[rng.randrange(nsym) for _ in range(rng.choice([0, 1, 2, 5, 20, 60, 200]))] for _ in range(rng.randint(1, 6))]
+        chars = [rng.choice([1, 2]) for _ in range(nsym)] if rng.random() < 0.3 else None
+        total += _int_vs_fast(docs, nsym, rng.choice([1, 2, 2, 3, 5]), rng.choice([0, 0, 3, 4, 8]), rng.choice([0, 0, 1, 5, 40]), chars)
+    assert total > 300  # the cases do merge
+
+
+def test_fast_oracle_equals_literal_oracle_on_zipf_text():
+    from bpe_tokenizer_b200.synth import first_appearance_ids, synth_corpus
+
+    text, off = synth_corpus(200_000, seed=43)
+    ids, alphabet = first_appearance_ids(text)
+    docs = [ids[off[d]:off[d + 1]].tolist() for d in range(len(off) - 1)]
+    assert _int_vs_fast(docs, len(alphabet), 2, 0, 300, cap=300) == 300
+    assert _int_vs_fast(docs, len(alphabet), 2, 6, 200, cap=200) == 200
+
+
+def test_fast_oracle_reproduces_the_cfg2_golden_log():
+    """10 MB, 4 000 merges: the incremental oracle (seconds) gives the SHA-1 the literal restatement needed 34 minutes for
+    (tests/golden/cfg2_merge_log.json) -- and the GPU gives (test_gpu_parity.py)"""
+    import hashlib
+    import json
+
+    from bpe_tokenizer_b200._abi import MERGE_DTYPE
+    from bpe_tokenizer_b200.synth import first_appearance_ids, synth_corpus
+    from oracle.fast_oracle import FastOracle
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "cfg2_merge_log.json")) as f:
+        golden = json.load(f)
+    text, off = synth_corpus(10_000_000, seed=43)
+    ids, alphabet = first_appearance_ids(text)
+    o = FastOracle()
+    o.set_len16(np.ones(len(alphabet), dtype=np.int32))
+    o.add_documents(ids, off)
+    la, lb, lw = o.merge_until(2, 0, golden["merges"], len(alphabet), golden["merges"])
+    log = np.zeros(len(la), dtype=MERGE_DTYPE)
+    log["a"], log["b"], log["weight"] = la, lb, lw
+    log["c"] = len(alphabet) + np.arange(len(la))
+    assert hashlib.sha1(log.tobytes()).hexdigest() == golden["sha1"]
