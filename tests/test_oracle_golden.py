@@ -245,3 +245,29 @@ def test_fast_oracle_reproduces_the_cfg2_golden_log():
     log["a"], log["b"], log["weight"] = la, lb, lw
     log["c"] = len(alphabet) + np.arange(len(la))
     assert hashlib.sha1(log.tobytes()).hexdigest() == golden["sha1"]
+
+
+def test_cfg3_full_run_was_checked_against_the_incremental_oracle():
+    """BASELINE config 3 at FULL size: tests/golden/check_cfg3_full.py ran oracle/fast_oracle.cpp over the 1 GB corpus (14 minutes of CPU,
+    ~40 GB of RAM -- too heavy for this suite) and found all 32 000 merges and weights of the GPU's log equal; the fixture records
+    that run.  Here: the fixture belongs to the committed GPU table and to the SHA-1 the cfg3 bench lines report."""
+    import hashlib
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from bpe_tokenizer_b200._abi import MERGE_DTYPE
+
+    with open(os.path.join(root, "tests", "golden", "cfg3_full_check.json")) as f:
+        check = json.load(f)
+    assert check["equals_gpu_merge_log"] is True and check["merges"] == 32000 and "first_difference" not in check
+    abc = np.load(os.path.join(root, "tools", "data", "merges_cfg3_abc.npy"))
+    log = np.zeros(len(abc), dtype=MERGE_DTYPE)
+    log["a"], log["b"], log["c"] = abc[:, 0], abc[:, 1], abc[:, 2]
+    log["weight"] = np.load(os.path.join(root, "tools", "data", "merges_cfg3_weights.npy"))
+    assert hashlib.sha1(log.tobytes()).hexdigest() == check["sha1"]
+    with open(os.path.join(root, "profiles", "r01_bench_n1.json")) as f:
+        bench_line = json.load(f)
+    assert bench_line["config"]["merge_log_sha1"] == check["sha1"]
+    # token conservation: every merge removes exactly `weight` tokens
+    n0 = int(check["workload"].split(" B ")[0])
+    assert n0 - int(log["weight"].sum()) == check["tokens_left"]
