@@ -29,6 +29,11 @@ def sha(t):
 opts = {"max_length": 8}
 t0 = time.time(); A = fresh(); A.addDocuments(ids, off); n = A.mergeUntil(dict(opts, max_iterations=2 * half)); tA = time.time() - t0
 print("A uninterrupted: %d merges, %.1f s, sha %s" % (n, tA, sha(A)), flush=True)
+golden_path = os.path.join(ROOT, "tests", "golden", "cfg5_merge_log.json")  # the incremental CPU oracle's log of this exact run
+if size == 256_000_000 and half == 4096 and os.path.exists(golden_path):
+    import json
+    golden = json.load(open(golden_path))
+    print("A equals the CPU oracle's merge log (%s): %s" % (golden["sha16_of_repr"], golden["sha16_of_repr"] == sha(A) and golden["merges"] == n), flush=True)
 t0 = time.time(); B1 = fresh(); B1.addDocuments(ids, off); B1.mergeUntil(dict(opts, max_iterations=half)); snap = B1.toJSON()
 log = [[a.code, b.code, c.original_weight] for a, b, c in B1.merge_tokens]; B1.close()
 B = BPETokenizer(); B.fromJSON(snap); B.restoreDocuments(ids, off); B.mergeUntil(dict(opts, max_iterations=half)); tB = time.time() - t0
