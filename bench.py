@@ -340,6 +340,8 @@ def run_b200(args):
         cpu = cpu_baseline(args, merges_sample=8) if world == 1 else None  # timed on rank 0 at N=1 only
         # (out_host / ooff_host hold the result of the last host-buffer encode call: raw token indices, tvi being the identity)
         enc_cpu = cpu_encode_baseline(log, done, ids2_host.numpy(), off2, out_host.numpy(), ooff_host) if world == 1 else None
+        if enc_cpu is not None:
+            enc_cpu["full_output"] = full_encode_check(out_host.numpy(), ooff_host, c2, done)
         line = {
             "metric": "mergeUntil merges/sec",
             "value": value,
@@ -431,6 +433,39 @@ def cpu_baseline(args, merges_sample=8):
         "sample": "C++ restatement of core.ts (Node/V8 absent), 1 thread of %d: first %d merges on the first %d chars took %.2f s (%.3f merges/s); "
                   "per-merge cost is linear in corpus size, value = that x %.4f (sample/workload size)" % (os.cpu_count() or 1, done, n, dt, rate, scale),
     }
+
+
+def stream_sha1(values, offsets, block_docs=65536):
+    """SHA-1 over the per-block SHA-1 digests of an int32 token stream (blocks of `block_docs` documents): the form in which
+    tests/golden/make_cfg4_encode_golden.py records the CPU restatement's encoding of the whole 1 GB text."""
+    import hashlib
+
+    h = hashlib.sha1()
+    n_docs = len(offsets) - 1
+    for d0 in range(0, n_docs, block_docs):
+        d1 = min(n_docs, d0 + block_docs)
+        h.update(hashlib.sha1(np.ascontiguousarray(values[offsets[d0]:offsets[d1]], dtype=np.int32).tobytes()).digest())
+    return h.hexdigest()
+
+
+def full_encode_check(gpu_out, gpu_off, chars, merges_done):
+    """The GPU's vectors for the WHOLE encode text against what the CPU restatement produced offline for the same text and merge table
+    (tests/golden/cfg4_encode.json, ~3.5 core-hours; BASELINE config 4): token count, per-document lengths and the token stream."""
+    try:
+        import hashlib
+
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "cfg4_encode.json")
+        out = {"output_sha1": stream_sha1(gpu_out, gpu_off),
+               "doc_lengths_sha1": hashlib.sha1(np.diff(gpu_off).astype(np.int32).tobytes()).hexdigest()}
+        if os.path.exists(path):
+            with open(path) as f:
+                golden = json.load(f)
+            if ("%d B" % chars) in golden["workload"] and merges_done == 32000:
+                out["matches_cpu_golden"] = bool(golden["output_sha1"] == out["output_sha1"] and golden["doc_lengths_sha1"] == out["doc_lengths_sha1"]
+                                                 and golden["tokens_out"] == int(gpu_off[-1] - gpu_off[0]))
+        return out
+    except Exception as e:  # never take the GPU line down
+        return {"failed": repr(e)}
 
 
 def cpu_encode_baseline(log, done, ids, off, gpu_out, gpu_off, sample_bytes=1_000_000):
