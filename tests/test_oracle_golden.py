@@ -271,3 +271,19 @@ def test_cfg3_full_run_was_checked_against_the_incremental_oracle():
     # token conservation: every merge removes exactly `weight` tokens
     n0 = int(check["workload"].split(" B ")[0])
     assert n0 - int(log["weight"].sum()) == check["tokens_left"]
+
+
+def test_cfg4_full_encode_token_count_equals_the_cpu_golden():
+    """BASELINE config 4 at FULL size: the literal encodeToCode restatement, one call per document over the whole 1 GB seed-44 text
+    (tests/golden/make_cfg4_encode_golden.py, ~4 core-hours), produced exactly as many tokens as the GPU reports for the same text
+    and merge table in its bench line; bench.py compares the token stream itself by SHA-1 (encode.cpu_baseline.full_output)."""
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "tests", "golden", "cfg4_encode.json")) as f:
+        golden = json.load(f)
+    with open(os.path.join(root, "profiles", "r01_bench_n1.json")) as f:
+        line = json.load(f)
+    assert line["config"]["merges_done"] == 32000 and line["config"]["merge_log_sha1"] == "add92aa1a96c276f03b63e3a952370ef04cb60f0"
+    assert ("%d B" % line["encode"]["chars"]) in golden["workload"] and ("%d docs" % line["encode"]["docs"]) in golden["workload"]
+    assert golden["tokens_out"] == line["encode"]["tokens_out"] == 176384677
