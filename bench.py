@@ -46,14 +46,11 @@ def measured_peak():
 
 
 def synth(lib, target, seed):
-    from bpe_tokenizer_b200 import _abi
+    """Seeded Zipf text from the stand-alone generator library (libbpe_synth.so: host code only).  `lib` is unused and kept
+    for the tools that pass it: neither arm needs the CUDA product library to make its input."""
+    from bpe_tokenizer_b200.synth import native_corpus
 
-    nb, nd = C.c_int64(), C.c_int64()
-    assert lib.bpe_synth_corpus(target, seed, VOCAB, WORD_SEED, None, 0, None, 0, C.byref(nb), C.byref(nd)) == 0
-    text = np.empty(nb.value, dtype=np.uint8)
-    off = np.empty(nd.value + 1, dtype=np.int64)
-    assert lib.bpe_synth_corpus(target, seed, VOCAB, WORD_SEED, text.ctypes.data_as(_abi.u8p), text.size, _abi.p64(off), off.size, C.byref(nb), C.byref(nd)) == 0
-    return text, off
+    return native_corpus(target, seed, VOCAB, WORD_SEED)
 
 
 def alphabet_lut(text):
@@ -262,7 +259,7 @@ def run_b200(args):
         dist.all_gather_object(digests, digest)
         assert all(d == digest for d in digests), "ranks disagree on the merge log: %r" % (digests,)
     # ---- train: end to end from host buffers ----------------------------------------------------------
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, args.steps)
     train_step(True)
     ms_train_e2e = timed(lambda: train_step(True), e2e_steps)
 
@@ -316,9 +313,17 @@ def run_b200(args):
         dist.all_reduce(t)
         return float(t.item())
 
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     import hashlib
 
     log_sha1 = hashlib.sha1(log[:done].tobytes()).hexdigest()
+    golden_log = merge_log_golden(args.workload, n0_total, done)
+    if golden_log is not None:  # a wrong merge sequence must not print a throughput
+        assert log_sha1 == golden_log["sha1"], "merge log differs from the CPU oracle's (%s vs %s)" % (log_sha1, golden_log["sha1"])
     step_s = ms_train / 1e3 / args.steps
     value = done * args.steps / (ms_train / 1e3)  # ONE merge sequence for the whole (sharded) corpus
     e2e_value = done * e2e_steps / (ms_train_e2e / 1e3)
@@ -336,12 +341,42 @@ def run_b200(args):
     enc_h2d_total = int(allsum(c2 * 4 + off2.nbytes + tvi.nbytes))
     enc_d2h_total = int(allsum(k_out * 4 + off2.nbytes))
 
+    # (out_host / ooff_host hold the result of the last host-buffer encode call: raw token indices, tvi being the identity)
+    enc_full = None
+    if world > 1:
+        # the shards' vectors, gathered on rank 0 in document order (ranks own contiguous document ranges), are hashed exactly
+        # like the single-GPU output and compared with the CPU golden of the whole text
+        kmax = int(max_over_ranks(k_out))
+        dmax = int(max_over_ranks(n_docs2 + 1))
+        pad_v = torch.zeros(kmax, dtype=torch.int32, device="cuda")
+        pad_v[:k_out] = out_host[:k_out].cuda()
+        pad_o = torch.zeros(dmax, dtype=torch.int64, device="cuda")
+        pad_o[:n_docs2 + 1] = torch.from_numpy(ooff_host).cuda()
+        meta = torch.tensor([k_out, n_docs2], dtype=torch.int64, device="cuda")
+        gv = [torch.empty_like(pad_v) for _ in range(world)] if rank == 0 else None
+        go = [torch.empty_like(pad_o) for _ in range(world)] if rank == 0 else None
+        gm = [torch.empty_like(meta) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad_v, gv, dst=0)
+        dist.gather(pad_o, go, dst=0)
+        dist.gather(meta, gm, dst=0)
+        if rank == 0:
+            vals, offs, base = [], [np.zeros(1, dtype=np.int64)], 0
+            for q in range(world):
+                kq, dq = (int(x) for x in gm[q].tolist())
+                vals.append(gv[q][:kq].cpu().numpy())
+                oq = go[q][:dq + 1].cpu().numpy()
+                offs.append(oq[1:] - oq[0] + base)
+                base += kq
+            enc_full = full_encode_check(np.concatenate(vals), np.concatenate(offs), c2_total, done)
+            del gv, go, vals
     if rank == 0:
         cpu = cpu_baseline(args, merges_sample=8) if world == 1 else None  # timed on rank 0 at N=1 only
-        # (out_host / ooff_host hold the result of the last host-buffer encode call: raw token indices, tvi being the identity)
+        cpu_inc = cpu_incremental_baseline(args) if world == 1 else None
         enc_cpu = cpu_encode_baseline(log, done, ids2_host.numpy(), off2, out_host.numpy(), ooff_host) if world == 1 else None
         if enc_cpu is not None:
             enc_cpu["full_output"] = full_encode_check(out_host.numpy(), ooff_host, c2, done)
+        if enc_full is not None and enc_full.get("matches_cpu_golden") is False:
+            raise AssertionError("encode output of the %d shards differs from the CPU golden: %r" % (world, enc_full))
         line = {
             "metric": "mergeUntil merges/sec",
             "value": value,
@@ -360,6 +395,8 @@ def run_b200(args):
                             % (args.workload, n0_total, TRAIN_SEED, n_docs_total, merges),
                 "merges_done": done,
                 "merge_log_sha1": log_sha1,
+                "merge_log_matches_cpu_golden": (None if golden_log is None else True),
+                "merge_log_golden": (None if golden_log is None else golden_log["file"]),
                 "sharding": ("corpus sharded by document over %d GPUs (contiguous, token-balanced); global pair counts replicated, "
                              "per-merge count deltas exchanged GPU-to-GPU over NVLink inside the persistent kernel" % world) if world > 1 else "single GPU",
                 "l2": "corpus (4 B/char) and occurrence pool are larger than the 126 MB L2" if n0 * 4 > 126e6 else "inputs smaller than L2; every step re-ingests and rebuilds the index (cold tables)",
@@ -392,6 +429,10 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if cpu_inc is not None:
+            line["cpu_baseline_incremental"] = cpu_inc
+        if enc_full is not None:
+            line["encode"]["full_output"] = enc_full
         if enc_cpu is not None:
             line["encode"]["cpu_baseline"] = enc_cpu
         print(json.dumps(line))
@@ -403,13 +444,11 @@ def run_b200(args):
 # ------------------------------------------------------------------------------------------------------
 def cpu_sample(args, merges_sample):
     """The CPU restatement of core.ts (oracle/int_oracle.cpp, 1 thread) on a bounded slice of the same workload."""
-    from bpe_tokenizer_b200 import _abi
     from oracle.int_oracle import IntOracle
 
-    lib = _abi.load_library()
     train_bytes, merges, encode_bytes = WORKLOADS[args.workload]
     sample_bytes = min(train_bytes, 16_000_000)
-    text, off = synth(lib, sample_bytes, TRAIN_SEED)
+    text, off = synth(None, sample_bytes, TRAIN_SEED)
     lut, alphabet = alphabet_lut(text)
     ids = lut[text]
     o = IntOracle()
@@ -423,6 +462,38 @@ def cpu_sample(args, merges_sample):
     return rate_sample, scale, ids.size, len(la), dt
 
 
+def cpu_incremental_baseline(args, sample_bytes=16_000_000, merges_sample=2000):
+    """A second CPU point: the INCREMENTAL oracle (oracle/fast_oracle.cpp -- same results, work per merge proportional to the
+    occurrences touched; not the reference's algorithm) timed live on a bounded slice, next to the committed full-size figure."""
+    try:
+        from oracle.fast_oracle import FastOracle
+
+        train_bytes, merges, _ = WORKLOADS[args.workload]
+        text, off = synth(None, min(train_bytes, sample_bytes), TRAIN_SEED)
+        lut, alphabet = alphabet_lut(text)
+        ids = lut[text]
+        o = FastOracle()
+        o.set_len16(np.ones(len(alphabet), dtype=np.int32))
+        t0 = time.perf_counter()
+        o.add_documents(ids, off)
+        la, _, _ = o.merge_until(2, 0, merges_sample, len(alphabet), merges_sample)
+        dt = time.perf_counter() - t0
+        out = {"value": len(la) / dt, "unit": "merges/s", "cores": 1, "kind": "port (incremental algorithm, not core.ts's)",
+               "sample": "oracle/fast_oracle.cpp, 1 thread of %d: index build + first %d merges on the first %d chars took %.2f s"
+                         % (os.cpu_count() or 1, len(la), ids.size, dt)}
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "cfg3_full_check.json")) as f:
+                g = json.load(f)
+            out["full_size_committed"] = {"value": g["merges"] / g["oracle_seconds"], "unit": "merges/s",
+                                          "note": "the same oracle over the whole cfg3 workload, offline: %d merges in %.0f s (%s)"
+                                                  % (g["merges"], g["oracle_seconds"], "tests/golden/cfg3_full_check.json")}
+        except Exception:
+            pass
+        return out
+    except Exception as e:  # never take the GPU line down
+        return {"value": None, "unit": "merges/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+
+
 def cpu_baseline(args, merges_sample=8):
     try:
         rate, scale, n, done, dt = cpu_sample(args, merges_sample)
@@ -433,6 +504,22 @@ def cpu_baseline(args, merges_sample=8):
         "sample": "C++ restatement of core.ts (Node/V8 absent), 1 thread of %d: first %d merges on the first %d chars took %.2f s (%.3f merges/s); "
                   "per-merge cost is linear in corpus size, value = that x %.4f (sample/workload size)" % (os.cpu_count() or 1, done, n, dt, rate, scale),
     }
+
+
+def merge_log_golden(workload, n0_total, done):
+    """SHA-1 of the CPU oracle's merge log for this exact workload, when a committed fixture holds one: cfg3 = the incremental
+    oracle's full 32 000-merge run (tests/golden/cfg3_full_check.json), cfg2 = the literal restatement's (cfg2_merge_log.json)."""
+    try:
+        name = {"cfg3": "cfg3_full_check.json", "cfg2": "cfg2_merge_log.json"}.get(workload)
+        if not name:
+            return None
+        with open(os.path.join(ROOT, "tests", "golden", name)) as f:
+            g = json.load(f)
+        if int(g.get("merges", -1)) != int(done) or ("%d B" % n0_total) not in g.get("workload", ""):
+            return None
+        return {"sha1": g["sha1"], "file": "tests/golden/" + name}
+    except Exception:
+        return None
 
 
 def stream_sha1(values, offsets, block_docs=65536):

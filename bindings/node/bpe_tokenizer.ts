@@ -297,7 +297,7 @@ export class BPETokenizer {
       t.weight += n
       t.original_weight += n
     })
-    if (n_new) this.invalidateVectorIndex()
+    // like addToCorpus (core.ts:182-207), no vector-index invalidation: a stale index throws `unknown token index`
   }
 
   // ---- vector index: core.ts:222-241 ---------------------------------------------------------------------------------------

@@ -48,5 +48,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+SYNTH_LIB = os.path.join(HERE, "libbpe_synth.so")
+
+
+def build_synth(force: bool = False) -> str:
+    """The corpus generator alone (csrc/synth.cpp, host only, plain g++): bench.py's reference arm and the tests
+    generate the synthetic text through this library so that they never map the CUDA product library."""
+    src = os.path.join(CSRC, "synth.cpp")
+    if not force and os.path.exists(SYNTH_LIB) and os.path.getmtime(SYNTH_LIB) >= os.path.getmtime(src):
+        return SYNTH_LIB
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    r = subprocess.run([cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", SYNTH_LIB, src], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed on synth.cpp (%d)" % r.returncode)
+    return SYNTH_LIB
+
+
 if __name__ == "__main__":
+    build_synth(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

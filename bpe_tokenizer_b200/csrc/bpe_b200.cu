@@ -57,9 +57,13 @@ struct DevBuf {
     T* q = nullptr;
     cudaError_t err = cudaMalloc(&q, want * sizeof(T));
     if (err != cudaSuccess) {
+      (void)cudaGetLastError();  // the runtime keeps the failure as its "last error": the next launch check must not see it
       want = n;
       err = cudaMalloc(&q, want * sizeof(T));
-      if (err != cudaSuccess) return err;
+      if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        return err;
+      }
     }
     if (p && keep_n) {
       err = cudaMemcpyAsync(q, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, s);
@@ -91,6 +95,7 @@ struct PinBuf {
     cap = 0;
     cudaError_t err = cudaHostAlloc((void**)&p, n * sizeof(T), cudaHostAllocDefault);
     if (err == cudaSuccess) cap = n;
+    else (void)cudaGetLastError();
     return err;
   }
 };
@@ -208,6 +213,9 @@ struct bpe_engine {
   DevBuf<unsigned long long> x_flag;
   std::vector<int64_t> h_rel;
   EncodeScratch x_scratch;
+  EncodeScratch dev_scratch;             // scratch of bpe_encode_batch_dev (device buffers in, device buffers out)
+  uint32_t lanes_attr_set = 0;           // bit per k_encode_lanes instantiation whose dynamic shared memory limit was raised on
+                                         // THIS engine's device (the attribute is per device, not per process)
   // the host-buffer encode calls run as a three-stream pipeline over chunks of whole documents: copy in | encode | copy out
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_done = nullptr, ev_res[2] = {nullptr, nullptr};
@@ -690,10 +698,10 @@ int launch_encode_lanes(bpe_engine* e, const int32_t* dev_ids, const int64_t* de
                         uint32_t* next_range) {
   size_t smem = (size_t)2 * EL_DENSE * EL_DENSE * 4 + (size_t)WARPS * (LMAX * 32 * 2 + LMAX * 16) * 4;
   auto kern = k_encode_lanes<LMAX, WARPS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  const uint32_t inst_bit = 1u << (LMAX / 4 - 4);  // LMAX = 16, 20, 24, 32, 48 (one WARPS each): bits 0, 1, 2, 4, 8
+  if (!(e->lanes_attr_set & inst_bit)) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    e->lanes_attr_set |= inst_bit;
   }
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -1611,6 +1619,8 @@ int bpe_get_corpus(bpe_engine* e, int64_t doc_begin, int64_t doc_end, int32_t* o
 int bpe_find_next_merge(bpe_engine* e, int64_t min_weight, int32_t max_length, bpe_merge* out, int* found) {
   if (!e || !out || !found) return BPE_E_INVALID;
   *found = 0;
+  // a shard alone would answer with ITS best pair, not the corpus's (core.ts:265-310 counts over all documents)
+  if (e->mg_world > 1) return fail(e, BPE_E_INVALID, "bpe_find_next_merge is not available on a sharded engine; use bpe_merge_until(max_iterations = 1)");
   CK(cudaSetDevice(e->device));
   if (e->n_slots == 0) return BPE_OK;
   TRY(ensure_index(e));
@@ -1645,6 +1655,8 @@ int bpe_apply_merge(bpe_engine* e, int32_t a, int32_t b, int32_t c, int64_t* n_r
     e->index_valid = false;
     return BPE_OK;
   }
+  // a single step would update this shard's counts with its local deltas only (the sharded loop exchanges them)
+  if (e->mg_world > 1) return fail(e, BPE_E_INVALID, "bpe_apply_merge on a corpus is not available on a sharded engine; use bpe_merge_until");
   TRY(ensure_index(e));
   k_lookup_pair<<<1, 32, 0, e->stream>>>(e->table(), (uint32_t)a, (uint32_t)b, e->d_st.p);
   CKL();
@@ -1823,9 +1835,9 @@ int bpe_encode_batch_dev(bpe_engine* e, const int32_t* dev_ids, const int64_t* d
   if (!e || !n_out || n_docs < 0 || n_ids < 0 || !dev_doc_offsets || !dev_out_offsets || (n_ids > 0 && (!dev_ids || !dev_out)))
     return fail(e, BPE_E_INVALID, "bad encode arguments");
   CK(cudaSetDevice(e->device));
-  static thread_local EncodeScratch* tls = nullptr;  // reused across calls so steady-state encode does not allocate
-  if (!tls) tls = new EncodeScratch();
-  return encode_dev(e, *tls, dev_ids, dev_doc_offsets, n_docs, n_ids, max_doc_len, dev_to_vector_index, n_tvi, dev_out,
+  // scratch owned by the engine (freed by bpe_destroy, on the engine's device): reused across calls so that steady-state
+  // encode does not allocate
+  return encode_dev(e, e->dev_scratch, dev_ids, dev_doc_offsets, n_docs, n_ids, max_doc_len, dev_to_vector_index, n_tvi, dev_out,
                     dev_out_offsets, dev_first_bad, n_out);
 }
 

@@ -100,7 +100,6 @@ class ShardedBPETokenizer(BPETokenizer):
             device = torch.cuda.current_device()
         super().__init__(device)
         self._torch_device = torch.device("cuda", device)
-        self._uploaded = False
         if self.world > _abi.MG_MAX_WORLD:
             raise BpeError(_abi.BPE_E_INVALID, "at most %d ranks (one NVLink domain)" % _abi.MG_MAX_WORLD)
         if self.world > 1:
@@ -112,21 +111,74 @@ class ShardedBPETokenizer(BPETokenizer):
             dist.barrier(group=group)
 
     # ---- corpus: keep only this rank's shard ------------------------------------------------------
-    def _flush(self) -> None:
-        self._sync_tokens()
-        if not self._pending:
-            return
+    _ONCE = ("sharded corpus: add every document before the first merge/encode of the corpus "
+             "(a later batch would break the global document order); clear the corpus first")
+
+    def _reset_host(self) -> None:
+        super()._reset_host()
+        self._pending_restore: List[np.ndarray] = []  # restoreToCorpus documents (raw character ids), not yet uploaded
+        self._uploaded = False  # fromJSON drops the corpus (core.ts:138-146)
+
+    def _upload_shard(self, docs: List[np.ndarray], restore: bool) -> None:
+        """Every rank holds ALL `docs` (SPMD); it uploads the contiguous, token-balanced range it owns."""
         if self._uploaded:
-            raise BpeError(_abi.BPE_E_INVALID, "sharded corpus: add every document before the first merge/encode of the corpus "
-                                              "(a later batch would break the global document order); clear the corpus first")
-        docs, self._pending = self._pending, []
+            raise BpeError(_abi.BPE_E_INVALID, self._ONCE)
         b = shard_bounds([d.size for d in docs], self.world)
         mine = docs[b[self.rank]:b[self.rank + 1]]
         offsets = np.zeros(len(mine) + 1, dtype=np.int64)
         np.cumsum([d.size for d in mine], out=offsets[1:])
         ids = np.concatenate(mine) if offsets[-1] else np.zeros(0, dtype=np.int32)
-        self._check(self._lib.bpe_add_documents(self._h, p32(np.ascontiguousarray(ids, dtype=np.int32)), p64(offsets), len(mine)))
+        fn = self._lib.bpe_restore_documents if restore else self._lib.bpe_add_documents
+        self._check(fn(self._h, p32(np.ascontiguousarray(ids, dtype=np.int32)), p64(offsets), len(mine)))
         self._uploaded = True
+
+    def _flush(self) -> None:
+        self._sync_tokens()
+        if self._pending and self._pending_restore:
+            raise BpeError(_abi.BPE_E_INVALID, "sharded corpus: addToCorpus and restoreToCorpus documents cannot be mixed in one upload")
+        if self._pending:
+            docs, self._pending = self._pending, []
+            self._upload_shard(docs, restore=False)
+        elif self._pending_restore:
+            docs, self._pending_restore = self._pending_restore, []
+            self._upload_shard(docs, restore=True)
+
+    def restoreToCorpus(self, content: str) -> None:  # core.ts:213-216, called with EVERY document on EVERY rank
+        self._pending_restore.append(self._char_ids(content, create=False))
+
+    def restoreDocuments(self, ids: np.ndarray, doc_offsets: np.ndarray, local_shard: bool = False) -> None:
+        """Bulk restoreToCorpus.  local_shard=False: every rank passes ALL documents and keeps its shard;
+        local_shard=True: the arrays hold only this rank's documents (ranks in document order)."""
+        self._flush()
+        if self._uploaded:
+            raise BpeError(_abi.BPE_E_INVALID, self._ONCE)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        doc_offsets = np.ascontiguousarray(doc_offsets, dtype=np.int64)
+        self._check_offsets(doc_offsets, ids.size)
+        lo, hi = 0, len(doc_offsets) - 1
+        if not local_shard:
+            b = shard_bounds(np.diff(doc_offsets), self.world)
+            lo, hi = b[self.rank], b[self.rank + 1]
+        off = np.ascontiguousarray(doc_offsets[lo:hi + 1])
+        self._check(self._lib.bpe_restore_documents(self._h, p32(ids), p64(off), hi - lo))
+        self._uploaded = True
+
+    def addTextBatch(self, utf8: bytes, doc_byte_offsets: np.ndarray) -> None:
+        # the device-side ingest assigns first-appearance indices over the documents it is given; a rank that only sees
+        # its shard cannot reproduce the global order of core.ts:186-199
+        raise BpeError(_abi.BPE_E_INVALID, "addTextBatch is not available on a sharded corpus; use addToCorpus or addDocuments")
+
+    @property
+    def corpus_in_code(self) -> List[str]:  # this rank's shard (corpusIdsAllRanks gathers every shard)
+        return BPETokenizer.corpus_in_code.fget(self)
+
+    @corpus_in_code.setter
+    def corpus_in_code(self, value: Sequence[str]) -> None:  # every rank passes ALL documents, `[]` clears
+        self.clearCorpus()
+        self._sync_tokens()
+        docs = [np.fromiter((ord(ch) - 1 for ch in s), dtype=np.int32, count=len(s)) for s in value]
+        if docs:
+            self._upload_shard(docs, restore=False)
 
     def addDocuments(self, ids: np.ndarray, doc_offsets: np.ndarray, local_shard: bool = False) -> None:
         """Bulk addToCorpus.  local_shard=False: every rank passes ALL documents and keeps its shard;
@@ -138,6 +190,7 @@ class ShardedBPETokenizer(BPETokenizer):
             raise BpeError(_abi.BPE_E_INVALID, "sharded corpus: documents were already uploaded; clear the corpus first")
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         doc_offsets = np.ascontiguousarray(doc_offsets, dtype=np.int64)
+        self._check_offsets(doc_offsets, ids.size)
         n_docs = len(doc_offsets) - 1
         counts = np.bincount(ids[doc_offsets[0]:doc_offsets[-1]], minlength=len(self.token_table)).astype(np.int64)
         if counts.size > len(self.token_table):
@@ -166,6 +219,8 @@ class ShardedBPETokenizer(BPETokenizer):
         import torch
 
         self._flush()
+        if self._uploaded:
+            raise BpeError(_abi.BPE_E_INVALID, self._ONCE)
         counts = np.asarray(char_counts, dtype=np.int64)
         if self.world > 1:
             t = torch.from_numpy(counts.copy()).to(self._torch_device)
@@ -181,6 +236,7 @@ class ShardedBPETokenizer(BPETokenizer):
 
     def clearCorpus(self) -> None:
         self._pending = []
+        self._pending_restore = []
         self._check(self._lib.bpe_clear_corpus(self._h))
         self._uploaded = False
 

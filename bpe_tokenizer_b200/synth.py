@@ -114,6 +114,34 @@ def synth_corpus(target_bytes: int, seed: int = TRAIN_SEED, vocab: int = V_DEFAU
     return text, offsets
 
 
+_native = None
+
+
+def native_corpus(target_bytes: int, seed: int = TRAIN_SEED, vocab: int = V_DEFAULT, word_seed: int = WORD_SEED):
+    """Same text as synth_corpus, from the compiled generator (csrc/synth.cpp built on its own as libbpe_synth.so --
+    host code only, no CUDA): -> (text_bytes uint8[n], doc_offsets int64[D+1]).  For the 10 MB .. 1 GB corpora."""
+    import ctypes as C
+
+    global _native
+    if _native is None:
+        from . import build as _build
+
+        lib = C.CDLL(_build.build_synth())
+        lib.bpe_synth_corpus.restype = C.c_int
+        lib.bpe_synth_corpus.argtypes = [C.c_int64, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        _native = lib
+    nb, nd = C.c_int64(), C.c_int64()
+    if _native.bpe_synth_corpus(target_bytes, seed, vocab, word_seed, None, 0, None, 0, C.byref(nb), C.byref(nd)) != 0:
+        raise RuntimeError("bpe_synth_corpus (sizing) failed")
+    text = np.empty(nb.value, dtype=np.uint8)
+    off = np.empty(nd.value + 1, dtype=np.int64)
+    if _native.bpe_synth_corpus(target_bytes, seed, vocab, word_seed, text.ctypes.data, text.size, off.ctypes.data, off.size,
+                                C.byref(nb), C.byref(nd)) != 0:
+        raise RuntimeError("bpe_synth_corpus failed")
+    return text, off
+
+
 def first_appearance_ids(text: np.ndarray):
     """Map bytes to token indices in first-appearance order, as addToCorpus does
     (reference core.ts:186-199).  -> (ids int32[n], alphabet list[int] by index)."""

@@ -151,6 +151,15 @@ class BPETokenizer:
         if rc != _abi.BPE_OK:
             raise BpeError(rc, (self._lib.bpe_last_error(self._h) or b"").decode("utf-8", "replace"))
 
+    @staticmethod
+    def _check_offsets(doc_offsets: np.ndarray, n_units: int) -> None:
+        """The C ABI carries no length for `ids` / `utf8`: the offsets are the only bound, so they must stay inside the
+        array the caller handed over (and be non-decreasing) before a pointer to it crosses the boundary."""
+        if doc_offsets.ndim != 1 or doc_offsets.size < 1:
+            raise ValueError("doc_offsets must hold n_docs + 1 entries")
+        if int(doc_offsets[0]) < 0 or int(doc_offsets[-1]) > n_units or (doc_offsets.size > 1 and bool(np.any(np.diff(doc_offsets) < 0))):
+            raise ValueError("doc_offsets must be non-decreasing and lie inside the ids / bytes array (0 .. %d)" % n_units)
+
     def _dev_num_tokens(self) -> int:
         n = C.c_int32()
         self._check(self._lib.bpe_num_tokens(self._h, C.byref(n)))
@@ -258,6 +267,7 @@ class BPETokenizer:
         self._flush()
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         doc_offsets = np.ascontiguousarray(doc_offsets, dtype=np.int64)
+        self._check_offsets(doc_offsets, ids.size)
         counts = np.bincount(ids[doc_offsets[0]:doc_offsets[-1]], minlength=len(self.token_table))
         if counts.size > len(self.token_table):
             raise ValueError("document holds an index outside token_table")
@@ -286,6 +296,7 @@ class BPETokenizer:
         self._flush()
         self._sync_chars()
         doc_byte_offsets = np.ascontiguousarray(doc_byte_offsets, dtype=np.int64)
+        self._check_offsets(doc_byte_offsets, len(utf8))
         buf = np.frombuffer(utf8 or b"\0", dtype=np.uint8)
         new_cps = np.empty(1 << 16, dtype=np.int32)
         counts = np.zeros(len(self.token_table) + (1 << 16), dtype=np.int64)
@@ -303,14 +314,15 @@ class BPETokenizer:
             t = self.token_table[i]
             t.weight += int(counts[i])
             t.original_weight += int(counts[i])
-        if n_new.value:
-            self._invalidateVectorIndex()
+        # like addToCorpus (core.ts:182-207) this does NOT invalidate the vector index: a following encodeToVector with a
+        # stale index throws `unknown token index` for the new characters, exactly as the reference does
 
     def encodeTextBatch(self, utf8: bytes, doc_byte_offsets: np.ndarray, vector: bool = True):
         """encodeBatch with the char -> index step on the device: -> (values, out_offsets, first_bad)."""
         self._flush()
         self._sync_chars()
         doc_byte_offsets = np.ascontiguousarray(doc_byte_offsets, dtype=np.int64)
+        self._check_offsets(doc_byte_offsets, len(utf8))
         n_docs = len(doc_byte_offsets) - 1
         buf = np.frombuffer(utf8 or b"\0", dtype=np.uint8)
         total = int(doc_byte_offsets[-1] - doc_byte_offsets[0]) if n_docs else 0
@@ -342,6 +354,7 @@ class BPETokenizer:
         self._flush()
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         doc_offsets = np.ascontiguousarray(doc_offsets, dtype=np.int64)
+        self._check_offsets(doc_offsets, ids.size)
         self._check(self._lib.bpe_restore_documents(self._h, p32(ids), p64(doc_offsets), len(doc_offsets) - 1))
 
     def corpusIds(self) -> Tuple[np.ndarray, np.ndarray]:
@@ -506,6 +519,7 @@ class BPETokenizer:
         self._flush()
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         doc_offsets = np.ascontiguousarray(doc_offsets, dtype=np.int64)
+        self._check_offsets(doc_offsets, ids.size)
         n_docs = len(doc_offsets) - 1
         total = int(doc_offsets[-1] - doc_offsets[0]) if n_docs else 0
         out = np.empty(max(total, 1), dtype=np.int32)
@@ -550,6 +564,7 @@ class BPETokenizer:
         self._flush()
         values = np.ascontiguousarray(values, dtype=np.int32)
         doc_offsets = np.ascontiguousarray(doc_offsets, dtype=np.int64)
+        self._check_offsets(doc_offsets, values.size)
         n_docs = len(doc_offsets) - 1
         fvi = None
         if vector:

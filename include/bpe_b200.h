@@ -152,7 +152,9 @@ int bpe_pair_counts(bpe_engine* e, int32_t* a, int32_t* b, int64_t* count, int64
  *   -> bpe_mg_connect -> bpe_set_tokens / bpe_add_documents* (this rank's shard)
  *   -> bpe_mg_export_counts -> (all-gather the (pair,count) lists) -> bpe_mg_import_counts per peer
  *   -> bpe_merge_until (collective: all ranks, same arguments).
- * Single-step bpe_find_next_merge / bpe_apply_merge stay local to the shard. */
+ * Single-step bpe_find_next_merge / bpe_apply_merge (on a non-empty corpus) / bpe_apply_merges return BPE_E_INVALID on
+ * an engine initialised with world > 1: a shard alone cannot answer for the whole corpus; bpe_merge_until(max_iterations
+ * = 1) is the exact single step. */
 #define BPE_MG_MAX_WORLD 8
 /* Allocates this rank's mailbox (peers store count deltas into it over NVLink) and writes its
  * cudaIpcMemHandle_t (64 bytes) to handle_out. */

@@ -262,50 +262,72 @@ def test_cfg2_full_size_merge_log_matches_the_oracle():
 
 
 def test_resume_routes_equal_uninterrupted_run():
-    """cfg5 shape at test size: max_length=8, split run resumed (a) via toJSON -> fromJSON -> restoreToCorpus and
-    (b) via addToCorpus + restoreMerge(compactMerge(...)); both must equal the uninterrupted run."""
-    from bpe_tokenizer_b200 import compactMerge
+    """cfg5 shape at test size: max_length=8, split run resumed (a) via toJSON -> fromJSON -> restoreToCorpus
+    (core.ts:213-216) and (b) via addToCorpus + restoreMerge(compactMerge(...)) (core.ts:477-494); both must equal the
+    uninterrupted run -- and every stage must equal the ORACLE doing the same thing (the compiled restatement for the
+    mergeUntil stages, the literal one for restoreToCorpus / restoreMerge on a sample)."""
     from bpe_tokenizer_b200.synth import synth_corpus
 
     text, off = synth_corpus(200_000)
     docs = [bytes(text[off[d]:off[d + 1]]).decode() for d in range(len(off) - 1)]
     opts = {"max_length": 8, "max_iterations": 60}
-    full = make()
-    for d in docs:
-        full.addToCorpus(d)
-    full.mergeUntil({"max_length": 8, "max_iterations": 120})
-    first = make()
-    for d in docs:
-        first.addToCorpus(d)
-    first.mergeUntil(opts)
+
+    def run(factory, n):
+        t = factory()
+        for d in docs:
+            t.addToCorpus(d)
+        t.mergeUntil({"max_length": 8, "max_iterations": n})
+        return t
+
+    full, o_full = run(make, 120), run(IntOracleTokenizer, 120)
+    assert full.toJSON() == o_full.toJSON()
+    assert full.corpus_in_code == o_full.corpus_in_code
+    first, o_first = run(make, 60), run(IntOracleTokenizer, 60)
+    assert first.toJSON() == o_first.toJSON()
+    assert first.corpus_in_code == o_first.corpus_in_code
     snap = json.loads(json.dumps(first.toJSON()))
     # the reference logs compactMerge(merge) at findNextMerge time, when c.weight is still its original weight
     log = [[a.code, b.code, c.original_weight] for a, b, c in first.merge_tokens]
-    # route (a)
-    a = make()
-    a.fromJSON(snap)
-    for d in docs:
-        a.restoreToCorpus(d)
-    assert a.corpus_in_code == first.corpus_in_code
+    assert log == [[a.code, b.code, c.original_weight] for a, b, c in o_first.merge_tokens]
+    # route (a): the GPU and the oracle both restore every document from the same snapshot
+    a, o_a = make(), IntOracleTokenizer()
+    for t in (a, o_a):
+        t.fromJSON(json.loads(json.dumps(snap)))
+        for d in docs:
+            t.restoreToCorpus(d)
+    assert a.corpus_in_code == o_a.corpus_in_code == first.corpus_in_code
+    assert a.toJSON() == o_a.toJSON()
+    lit = LiteralTokenizer()  # the string-level restatement's restoreToCorpus on a sample of the documents (it is slow)
+    lit.fromJSON(json.loads(json.dumps(snap)))
+    for d in docs[:40]:
+        lit.restoreToCorpus(d)
+    assert lit.corpus_in_code == a.corpus_in_code[:40]
     a.mergeUntil(opts)
-    assert a.toJSON() == full.toJSON()
-    assert a.corpus_in_code == full.corpus_in_code
-    # route (b)
-    b = make()
-    for d in docs:
-        b.addToCorpus(d)
-    for m in log:
-        b.restoreMerge(m)
-    assert b.toJSON() == first.toJSON()
+    o_a.mergeUntil(opts)
+    assert a.toJSON() == o_a.toJSON() == full.toJSON()
+    assert a.corpus_in_code == o_a.corpus_in_code == full.corpus_in_code
+    # route (b): replay the merge log line by line
+    b, o_b = make(), IntOracleTokenizer()
+    for t in (b, o_b):
+        for d in docs:
+            t.addToCorpus(d)
+        for m in log:
+            t.restoreMerge(list(m))
+    assert b.toJSON() == o_b.toJSON() == first.toJSON()
+    assert b.corpus_in_code == o_b.corpus_in_code
     b.mergeUntil(opts)
-    assert b.toJSON() == full.toJSON()
+    o_b.mergeUntil(opts)
+    assert b.toJSON() == o_b.toJSON() == full.toJSON()
+    assert b.corpus_in_code == o_b.corpus_in_code
     # merge log replay with the corpus emptied (example/import-merge-log-to-ram.ts:22-31)
-    c = make()
-    for d in docs[:50]:
-        c.addToCorpus(d)
-    c.corpus_in_code = []
-    for m in log:
-        c.restoreMerge(m)
+    c, o_c = make(), LiteralTokenizer()
+    for t in (c, o_c):
+        for d in docs[:50]:
+            t.addToCorpus(d)
+        t.corpus_in_code = []
+        for m in log:
+            t.restoreMerge(list(m))
+    assert c.toJSON() == o_c.toJSON()
     assert [t.chars for t in c.token_table] == [t.chars for t in first.token_table]
 
 
