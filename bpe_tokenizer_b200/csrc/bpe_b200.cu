@@ -17,6 +17,7 @@
 #include "encode_lanes.cuh"
 #include "train_kernels.cuh"
 #include "mg_kernels.cuh"
+#include "round_kernels.cuh"
 #include "text_kernels.cuh"
 
 using namespace bpe;
@@ -181,6 +182,13 @@ struct bpe_engine {
   DevBuf<MergeRec> dev_log;
   DevBuf<unsigned long long> barrier;  // own 128-byte line
   int loop_blocks = 0;   // co-resident grid of k_merge_loop
+  // several exact merges per barrier round (round_kernels.cuh): dense delta rows, site buffers of merges 1.., per-block top-2 partials
+  DevBuf<uint32_t> r_rows;
+  DevBuf<SiteRec> r_bsites;
+  DevBuf<uint4> r_gp;
+  DevBuf<uint32_t> r_gk;
+  DevBuf<RoundState> r_state;
+  int round_blocks = 0;  // co-resident grid of k_merge_rounds
   int host_loop = 0;     // debug: drive mergeUntil from the host, one launch per phase
   int scan_mode = 0;     // debug: walk all slots instead of occurrence lists
 
@@ -901,6 +909,32 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     e->loop_blocks = e->sm_count * std::min(per_sm, want);
     if (const char* v = getenv("BPE_LOOP_BLOCKS")) e->loop_blocks = std::max(1, std::min(atoi(v), e->sm_count * per_sm));
   }
+  // several exact merges per barrier round (round_kernels.cuh) unless a merge list is replayed; BPE_LOOP_ROUNDS=0 keeps k_merge_loop
+  bool use_rounds = !dev_replay && ML_THREADS == 512;
+  int round_k = RB;
+  if (const char* v = getenv("BPE_LOOP_ROUNDS")) use_rounds = use_rounds && atoi(v) != 0;
+  if (const char* v = getenv("BPE_LOOP_K")) round_k = std::max(1, std::min(atoi(v), (int)RB));
+  if (use_rounds) {
+    if (!e->round_blocks) {
+      int per_sm = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_rounds, ML_THREADS, 0));
+      if (per_sm < 1) return fail(e, BPE_E_CUDA, "k_merge_rounds does not fit on an SM");
+      // (a decision folds two partial entries per block with one thread each)
+      const int most = std::min({e->sm_count * per_sm, (int)(R_QCAP / 2), ML_THREADS / 2});
+      e->round_blocks = std::min(e->sm_count, most);
+      if (const char* v = getenv("BPE_LOOP_BLOCKS")) e->round_blocks = std::max(1, std::min(atoi(v), most));
+    }
+    if (!e->r_rows.p) {
+      const size_t cells = (size_t)2 * RB * RW_ROWS * ND_STRIDE;
+      CK(e->r_rows.reserve(cells));
+      CK(cudaMemsetAsync(e->r_rows.p, 0, cells * 4, e->stream));  // the kernel keeps the rows zero between launches
+      CK(e->r_bsites.reserve((size_t)2 * RB * R_SMALL));
+      CK(e->r_state.reserve(1));
+      CK(cudaMemsetAsync(e->r_state.p, 0, sizeof(RoundState), e->stream));
+    }
+    CK(e->r_gp.reserve((size_t)2 * e->round_blocks));
+    CK(e->r_gk.reserve((size_t)2 * e->round_blocks));
+  }
   CK(e->partials.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
   CK(e->partial_keys.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
   CK(e->sites.reserve(1u << 16, 0, e->stream, 1.0));
@@ -979,10 +1013,25 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     auto tw0 = std::chrono::steady_clock::now();
     k_loop_prepare<<<1, 32, 0, e->stream>>>(e->d_st.p, (uint32_t)e->n_tokens, e->barrier.p);
     e->stats.kernel_launches++;
-    void* args[] = {&L};
-    ce = cudaLaunchCooperativeKernel((void*)k_merge_loop, dim3(e->loop_blocks), dim3(ML_THREADS), args, 0, e->stream);
+    if (use_rounds) {
+      RoundArgs RA;
+      RA.L = L;
+      RA.rows = e->r_rows.p;
+      RA.bsites = e->r_bsites.p;
+      RA.gp = e->r_gp.p;
+      RA.gk = e->r_gk.p;
+      RA.rs = e->r_state.p;
+      RA.kmax = (uint32_t)round_k;
+      k_rounds_prepare<<<1, 32, 0, e->stream>>>(e->r_state.p);
+      e->stats.kernel_launches++;
+      void* rargs[] = {&RA};
+      ce = cudaLaunchCooperativeKernel((void*)k_merge_rounds, dim3(e->round_blocks), dim3(ML_THREADS), rargs, 0, e->stream);
+    } else {
+      void* args[] = {&L};
+      ce = cudaLaunchCooperativeKernel((void*)k_merge_loop, dim3(e->loop_blocks), dim3(ML_THREADS), args, 0, e->stream);
+    }
     if (ce != cudaSuccess) {
-      rc = fail(e, BPE_E_CUDA, "cooperative launch of k_merge_loop: %s", cudaGetErrorString(ce));
+      rc = fail(e, BPE_E_CUDA, "cooperative launch of the mergeUntil kernel: %s", cudaGetErrorString(ce));
       break;
     }
     e->stats.kernel_launches++;
@@ -1076,6 +1125,27 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     e->live_tokens = e->h_st->live_tokens;
     e->stats.sites_merged = (int64_t)e->h_st->sites_total;
     e->stats.tie_breaks = e->h_st->tie_breaks;
+    if (use_rounds) {
+      RoundState hrs;
+      CK(cudaMemcpyAsync(&hrs, e->r_state.p, sizeof(RoundState), cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      e->stats.loop_rounds = (int64_t)hrs.rounds;
+      e->stats.loop_round_merges = (int64_t)hrs.round_merges;
+      e->stats.loop_round_tried = (int64_t)hrs.tried;
+      e->stats.loop_rounds_cut = (int64_t)hrs.rounds_cut_born;
+      static const bool trace_r = getenv("BPE_TRACE") != nullptr;
+      if (trace_r)
+        fprintf(stderr, "[bpe] rounds %llu, merges %llu (tried %llu), cut by the born-pair bound %llu, single %llu; batch ends: cap %llu, no-candidate %llu, tie %llu, big %llu, "
+                        "token %llu, fresh-token %llu, limits %llu\n", hrs.rounds, hrs.round_merges, hrs.tried, hrs.rounds_cut_born, hrs.rounds_single, hrs.stop_reason[0],
+                hrs.stop_reason[1], hrs.stop_reason[2], hrs.stop_reason[3], hrs.stop_reason[4], hrs.stop_reason[5], hrs.stop_reason[6]);
+      if (trace_r) {
+        const unsigned long long* f = e->h_st->fine_ns;
+        const double ns = std::max(1.0, (double)f[5]), nb = std::max(1.0, (double)f[11]);
+        fprintf(stderr, "[bpe] block 0, us per round of small merges (%.0f rounds): decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f; per round of one big merge (%.0f): "
+                        "decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f\n", (double)f[5], f[0] / ns * 1e-3, f[1] / ns * 1e-3, f[2] / ns * 1e-3, f[3] / ns * 1e-3, f[4] / ns * 1e-3,
+                (double)f[11], f[6] / nb * 1e-3, f[7] / nb * 1e-3, f[8] / nb * 1e-3, f[9] / nb * 1e-3, f[10] / nb * 1e-3);
+      }
+    }
   }
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);

@@ -156,9 +156,9 @@ class BPETokenizer:
         """The C ABI carries no length for `ids` / `utf8`: the offsets are the only bound, so they must stay inside the
         array the caller handed over (and be non-decreasing) before a pointer to it crosses the boundary."""
         if doc_offsets.ndim != 1 or doc_offsets.size < 1:
-            raise ValueError("doc_offsets must hold n_docs + 1 entries")
+            raise BpeError(_abi.BPE_E_INVALID, "doc_offsets must hold n_docs + 1 entries")
         if int(doc_offsets[0]) < 0 or int(doc_offsets[-1]) > n_units or (doc_offsets.size > 1 and bool(np.any(np.diff(doc_offsets) < 0))):
-            raise ValueError("doc_offsets must be non-decreasing and lie inside the ids / bytes array (0 .. %d)" % n_units)
+            raise BpeError(_abi.BPE_E_INVALID, "document offsets must be non-decreasing and lie inside the ids / bytes array (0 .. %d)" % n_units)
 
     def _dev_num_tokens(self) -> int:
         n = C.c_int32()

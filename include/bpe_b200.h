@@ -45,7 +45,7 @@ extern "C" {
 
 #define BPE_MAX_TOKENS 56319 /* reference is well-defined only for token_table.length <= 56319 */
 
-#define BPE_ABI_VERSION 1
+#define BPE_ABI_VERSION 2
 
 typedef struct bpe_engine bpe_engine;
 
@@ -75,8 +75,13 @@ typedef struct bpe_stats {
   double ms_apply;             /* K3                                                              */
   double ms_encode;            /* K4 + K5, last bpe_encode_batch* call (summed over its chunks)   */
   double ms_last_merge_until;  /* device time of the last bpe_merge_until call                    */
-  double ms_loop_phase[8];     /* k_merge_loop as seen by block 0, cumulative since the last index build:
-                                  decide, P1 sites, P1 barrier wait, P2 alloc, P2 wait, P3 apply+argmax, P3 wait, tie path */
+  double ms_loop_phase[8];     /* the mergeUntil kernel as seen by block 0, cumulative since the last index build:
+                                  decide, P1 sites, P1 barrier wait, P2, P2 barrier wait, (unused), (unused), tie path */
+  /* bpe_merge_until commits several exact merges per pair of grid barriers (csrc/round_kernels.cuh); cumulative: */
+  int64_t loop_rounds;         /* barrier rounds                                                  */
+  int64_t loop_round_merges;   /* merges those rounds committed (/ loop_rounds = merges per round) */
+  int64_t loop_round_tried;    /* merges whose site pass ran (committed + dropped by the born-pair bound) */
+  int64_t loop_rounds_cut;     /* rounds that dropped a tail of their batch                       */
 } bpe_stats;
 
 int bpe_abi_version(void);

@@ -26,13 +26,13 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(_abi.SYMBOLS) == declared
-    assert lib.bpe_abi_version() == 1
+    assert lib.bpe_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_abi.bpe_merge) == 24
     assert _abi.MERGE_DTYPE.itemsize == 24
-    assert C.sizeof(_abi.bpe_stats) == 23 * 8
+    assert C.sizeof(_abi.bpe_stats) == 27 * 8
 
 
 def test_no_cpu_fallback_without_device():

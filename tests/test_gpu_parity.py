@@ -229,6 +229,44 @@ def test_zipf_1mb_500_merges_bit_exact():
             assert vals[ooff[d]:ooff[d + 1]].tolist() == [orc.to_vector_index[x] for x in want_raw.tolist()]
 
 
+@pytest.mark.parametrize("opts", [{}, {"max_length": 6}, {"min_weight": 150}], ids=["plain", "max_length6", "min_weight150"])
+@pytest.mark.parametrize("k", ["16", "4", "1", "off"])
+def test_merge_rounds_equal_the_oracle(k, opts, monkeypatch):
+    """mergeUntil commits several merges per barrier round (csrc/round_kernels.cuh): whatever the batch size (BPE_LOOP_K;
+    "off" = the one-merge-per-iteration kernel), the merge log, weights and corpus must equal the incremental CPU oracle's
+    (core.ts:365-383 semantics, pinned to the literal restatement by tests/test_oracle_golden.py)."""
+    from oracle.fast_oracle import FastOracle
+
+    if k == "off":
+        monkeypatch.setenv("BPE_LOOP_ROUNDS", "0")
+    else:
+        monkeypatch.setenv("BPE_LOOP_K", k)
+    text, off, ids, alphabet = _zipf_pair(6_000_000)
+    merges = 3000
+    gpu = make()
+    gpu.addToCorpus("".join(chr(c) for c in alphabet))
+    gpu.corpus_in_code = []
+    for tk in gpu.token_table:
+        tk.weight = tk.original_weight = 0
+    gpu.addDocuments(ids, off)
+    n = gpu.mergeUntil(dict(opts, max_iterations=merges))
+    o = FastOracle()
+    o.set_len16(np.ones(len(alphabet), dtype=np.int32))
+    o.add_documents(ids, off)
+    la, lb, lw = o.merge_until(int(opts.get("min_weight", 2)), int(opts.get("max_length", 0)), merges, len(alphabet), merges)
+    got = [[a.index, b.index, c.original_weight] for a, b, c in gpu.merge_tokens]
+    want = [[int(a), int(b), int(w)] for a, b, w in zip(la, lb, lw)]
+    first_bad = next((i for i, (g, w) in enumerate(zip(got, want)) if g != w), None)
+    assert first_bad is None, (first_bad, got[first_bad], want[first_bad])
+    assert n == len(want)
+    got_ids, _ = gpu.corpusIds()
+    assert np.array_equal(got_ids, o.corpus())
+    st = gpu.stats()
+    if k not in ("off", "1") and not opts:
+        assert st["loop_rounds"] > 0 and st["loop_round_merges"] == n
+        assert st["loop_round_merges"] > 1.5 * st["loop_rounds"], st  # the batches really are batches
+
+
 def test_cfg2_full_size_merge_log_matches_the_oracle():
     """BASELINE config 2 at FULL size (10 MB seeded Zipf corpus, 4 000 merges, SURVEY.md section 8(d) "cfg2: full bit-exact"): the
     product's merge log -- pairs, new indices and weights, in the byte layout bench.py hashes -- equals the one the CPU restatement
