@@ -92,9 +92,10 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
 
         if _build.needs_build():
             _build.build()
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m bpe_tokenizer_b200.build` (no CPU fallback exists)")
-    lib = C.CDLL(LIB_PATH)
+    path = os.environ.get("BPE_LIB") or LIB_PATH  # BPE_LIB: a differently tuned build of the same library (A/B timing)
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m bpe_tokenizer_b200.build` (no CPU fallback exists)")
+    lib = C.CDLL(path)
     for name, (restype, argtypes) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError here = header and library disagree
         fn.restype = restype

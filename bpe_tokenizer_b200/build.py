@@ -33,19 +33,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = LIB) -> str:
+    if not force and out == LIB and not needs_build():
         return LIB
     extra = ["-DBPE_FINE_PROF"] if os.environ.get("BPE_FINE_PROF") else []  # debug: sub-step timers inside phase_sites
     if os.environ.get("BPE_ML_THREADS"):
         extra.append("-DBPE_ML_THREADS=" + os.environ["BPE_ML_THREADS"])  # tuning: threads per block of the loop kernels
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+    if os.environ.get("BPE_RD_THREADS"):
+        extra.append("-DBPE_RD_THREADS=" + os.environ["BPE_RD_THREADS"])  # tuning: threads per block of k_merge_rounds
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed (%d)" % r.returncode)
-    return LIB
+    return out
 
 
 SYNTH_LIB = os.path.join(HERE, "libbpe_synth.so")

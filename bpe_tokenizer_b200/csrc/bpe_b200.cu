@@ -185,6 +185,7 @@ struct bpe_engine {
   // several exact merges per barrier round (round_kernels.cuh): dense delta rows, site buffers of merges 1.., per-block top-2 partials
   DevBuf<uint32_t> r_rows;
   DevBuf<SiteRec> r_bsites;
+  DevBuf<uint32_t> r_bits;
   DevBuf<uint4> r_gp;
   DevBuf<uint32_t> r_gk;
   DevBuf<RoundState> r_state;
@@ -910,17 +911,17 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     if (const char* v = getenv("BPE_LOOP_BLOCKS")) e->loop_blocks = std::max(1, std::min(atoi(v), e->sm_count * per_sm));
   }
   // several exact merges per barrier round (round_kernels.cuh) unless a merge list is replayed; BPE_LOOP_ROUNDS=0 keeps k_merge_loop
-  bool use_rounds = !dev_replay && ML_THREADS == 512;
+  bool use_rounds = !dev_replay;
   int round_k = RB;
   if (const char* v = getenv("BPE_LOOP_ROUNDS")) use_rounds = use_rounds && atoi(v) != 0;
   if (const char* v = getenv("BPE_LOOP_K")) round_k = std::max(1, std::min(atoi(v), (int)RB));
   if (use_rounds) {
     if (!e->round_blocks) {
       int per_sm = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_rounds, ML_THREADS, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_rounds, RD_THREADS, 0));
       if (per_sm < 1) return fail(e, BPE_E_CUDA, "k_merge_rounds does not fit on an SM");
       // (a decision folds two partial entries per block with one thread each)
-      const int most = std::min({e->sm_count * per_sm, (int)(R_QCAP / 2), ML_THREADS / 2});
+      const int most = std::min({e->sm_count * per_sm, (int)(R_QCAP / 2), RD_THREADS / 2});
       e->round_blocks = std::min(e->sm_count, most);
       if (const char* v = getenv("BPE_LOOP_BLOCKS")) e->round_blocks = std::max(1, std::min(atoi(v), most));
     }
@@ -929,6 +930,8 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       CK(e->r_rows.reserve(cells));
       CK(cudaMemsetAsync(e->r_rows.p, 0, cells * 4, e->stream));  // the kernel keeps the rows zero between launches
       CK(e->r_bsites.reserve((size_t)2 * RB * R_SMALL));
+      CK(e->r_bits.reserve((size_t)2 * RB * 2 * R_BW));
+      CK(cudaMemsetAsync(e->r_bits.p, 0, (size_t)2 * RB * 2 * R_BW * 4, e->stream));
       CK(e->r_state.reserve(1));
       CK(cudaMemsetAsync(e->r_state.p, 0, sizeof(RoundState), e->stream));
     }
@@ -1022,10 +1025,13 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       RA.gk = e->r_gk.p;
       RA.rs = e->r_state.p;
       RA.kmax = (uint32_t)round_k;
+      RA.bits = e->r_bits.p;
+      RA.bar_mode = 1;
+      if (const char* v = getenv("BPE_LOOP_BAR")) RA.bar_mode = atoi(v) ? 1 : 0;
       k_rounds_prepare<<<1, 32, 0, e->stream>>>(e->r_state.p);
       e->stats.kernel_launches++;
       void* rargs[] = {&RA};
-      ce = cudaLaunchCooperativeKernel((void*)k_merge_rounds, dim3(e->round_blocks), dim3(ML_THREADS), rargs, 0, e->stream);
+      ce = cudaLaunchCooperativeKernel((void*)k_merge_rounds, dim3(e->round_blocks), dim3(RD_THREADS), rargs, 0, e->stream);
     } else {
       void* args[] = {&L};
       ce = cudaLaunchCooperativeKernel((void*)k_merge_loop, dim3(e->loop_blocks), dim3(ML_THREADS), args, 0, e->stream);

@@ -40,11 +40,21 @@
 
 namespace bpe {
 
+#ifndef BPE_RD_THREADS
+#define BPE_RD_THREADS 512
+#endif
+constexpr int RD_THREADS = BPE_RD_THREADS;  // threads per block of k_merge_rounds (one block per SM)
 constexpr int RB = 16;                   // merges per round at most
-constexpr uint32_t R_SMALL = 16384;      // a merge with more counted occurrences than this runs alone
+constexpr uint32_t R_SMALL = 1u << 18;   // a merge with more counted occurrences than this runs alone
+constexpr uint32_t R_BATCH_SITES = 1u << 19;  // ... and a batch stops growing past this many sites (a dropped tail wastes its site pass)
+constexpr uint32_t R_LAT = 16384;        // below this many sites a merge is latency bound (profile classes, warp splits)
+constexpr uint32_t R_BW = ND_STRIDE / 32;  // words of one touched-token bitmap
 enum { RW_DEC_L = 0, RW_DEC_R, RW_NL_LEN, RW_NL_CNT, RW_NR_LEN, RW_NR_CNT, RW_NL_SLOT, RW_NR_SLOT, RW_ROWS };
 constexpr int RW_CLEAR_ROWS = 6;         // rows that accumulate (the SLOT rows are written before they are read)
-constexpr uint32_t R_QCAP = 640;         // per-block top-2 entries a decision can fold (2 x blocks)
+constexpr uint32_t R_QCAP = 384;         // per-block top-2 entries a decision can fold (2 x blocks)
+constexpr uint32_t R_LOW = 1024;         // tokens below this are frequent neighbours: their bitmap bits are set once per BLOCK (shared-memory filter)
+constexpr uint32_t R_CHUNK = 128;        // bitmap words a block expands per pass of P2's job 1
+constexpr uint32_t R_CELLS = R_CHUNK * 32;  // ... and the touched cells they can hold
 constexpr uint32_t ERR_ROUND_MISMATCH = 2048u;  // a merge of a round found a different number of sites than its count
 
 struct RoundState {
@@ -58,6 +68,8 @@ struct RoundArgs {
   LoopArgs L;
   uint32_t* rows;    // [2][RB][RW_ROWS][ND_STRIDE]
   SiteRec* bsites;   // [2][RB][R_SMALL]: merges 1.. of a round (merge 0 uses L.A.sites / L.sites2, which the host sizes)
+  uint32_t* bits;    // [2][RB][2][R_BW]: tokens whose cells of a merge's left / right rows were touched by the site pass
+  int bar_mode;      // 0: k_merge_loop's barrier (two sequentially consistent fences); 1: release arrival + acquire poll
   uint4* gp;         // [2 * blocks] per-block top-2: (primary lo, primary hi, slot, mult)
   uint32_t* gk;      // [2 * blocks] ... and the pair key of that slot
   RoundState* rs;
@@ -66,6 +78,39 @@ struct RoundArgs {
 
 __device__ __forceinline__ uint32_t* round_row(const RoundArgs& R, uint32_t par, uint32_t j, int row) {
   return R.rows + (((size_t)par * RB + j) * RW_ROWS + (size_t)row) * ND_STRIDE;
+}
+__device__ __forceinline__ uint32_t* round_bits(const RoundArgs& R, uint32_t par, uint32_t j, uint32_t side) {
+  return R.bits + (((size_t)par * RB + j) * 2u + side) * R_BW;
+}
+
+// Site record of a round: x = p, y = position of the left token of the born left adjacency (NOPOS: none),
+// z = left token | right token << 16 of the born pairs (R_NOTOK: none), w = what the rewrite needs without walking the corpus
+// again: DOCSTART of p << 31 | overflow << 30 | (q - p) << 15 | (e - p)   (q = start of b, e = last slot of b).
+constexpr uint32_t R_NOTOK = 0xFFFFu;
+__device__ __forceinline__ uint32_t round_pack_span(uint32_t w, uint32_t p, uint32_t q, uint32_t e) {
+  const uint32_t dq = q - p, de = e - p;
+  const uint32_t doc = (w & DOCSTART) ? 0x80000000u : 0u;
+  if (de >= 32768u) return doc | 0x40000000u;
+  return doc | (dq << 15) | de;
+}
+
+// grid barrier with a release arrival and an acquire poll (no sequentially consistent fence): everything the block wrote
+// before its __syncthreads is ordered before thread 0's release; what thread 0 acquires is ordered before the reads of the
+// block after the second __syncthreads (acquire at gpu scope invalidates L1)
+__device__ __forceinline__ void grid_barrier_ra(unsigned long long* ctr, unsigned long long target, uint32_t max_ns) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+    uint32_t ns = 32;
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
+      __nanosleep(ns);
+      if (ns < max_ns) ns <<= 1;
+    }
+  }
+  __syncthreads();
 }
 
 // ---- top-2 groups: the two largest DISTINCT primaries, each with the number of pairs that share it and the smallest slot ----
@@ -114,7 +159,10 @@ struct RoundSm {
   unsigned long long qp[R_QCAP];
   uint32_t qs[R_QCAP], qm[R_QCAP], qk[R_QCAP];
   unsigned long long cp[RB];
-  uint32_t cs[RB], cm[RB], ck[RB], cls[RB], cll[RB];
+  uint32_t cs[RB], cm[RB], ck[RB], cls[RB], cll[RB], clen[RB];
+  uint32_t g_n_keys, g_pool_cursor, g_snap_err, ncell;
+  uint32_t lowbits[RB][2][R_LOW / 32];  // bits of the touched-token bitmaps this block has already set (tokens < R_LOW)
+  uint32_t cell[R_CELLS];               // P2 job 1: (merge * 2 + side) << 16 | token of the touched cells of the current chunk
   Top2 t2[32];
   unsigned long long red[32];
   uint32_t s_max[32];
@@ -152,18 +200,31 @@ __device__ __forceinline__ Top2 top2_block_reduce(Top2 v, Top2* s_t2) {
 
 // all 32 lanes call; `has` lanes add one to row[tok]; lanes that agree on tok elect a leader which issues ONE atomic.
 // Returns, in the leader lane, the number of lanes it stands for (0 elsewhere).
-__device__ __forceinline__ uint32_t row_add_warp(uint32_t* row, uint32_t tok, bool has) {
+// set the token's bit in the merge's touched-token bitmap.  Frequent neighbours (low token indices) would receive one
+// atomic per warp of every site pass on a handful of words: each block sets those bits once (shared-memory filter).
+__device__ __forceinline__ void round_mark(uint32_t* bits, uint32_t* low, uint32_t tok) {
+  const uint32_t m = 1u << (tok & 31u);
+  if (tok < R_LOW) {
+    uint32_t* lw = low + (tok >> 5);
+    if (*reinterpret_cast<volatile uint32_t*>(lw) & m) return;
+    atomicOr(lw, m);
+  }
+  atomicOr(bits + (tok >> 5), m);
+}
+
+__device__ __forceinline__ uint32_t row_add_warp(uint32_t* row, uint32_t* bits, uint32_t* low, uint32_t tok, bool has) {
   const uint32_t lane = lane_id();
   const uint32_t peers = __match_any_sync(0xFFFFFFFFu, has ? tok : (0xFFFFFF00u + lane));
   const bool leader = has && lane == (uint32_t)(__ffs(peers) - 1);
   if (!leader) return 0;
   const uint32_t n = (uint32_t)__popc(peers);
   atomicAdd(row + tok, n);
+  round_mark(bits, low, tok);
   return n;
 }
 
 // the born pair (tok, c) / (c, tok): occurrences and counted occurrences; returns the leader's counted lanes (0 elsewhere)
-__device__ __forceinline__ uint32_t row_new_warp(uint32_t* len_row, uint32_t* cnt_row, uint32_t tok, bool has, bool counted) {
+__device__ __forceinline__ uint32_t row_new_warp(uint32_t* len_row, uint32_t* cnt_row, uint32_t* bits, uint32_t* low, uint32_t tok, bool has, bool counted) {
   const uint32_t lane = lane_id();
   const uint32_t peers = __match_any_sync(0xFFFFFFFFu, has ? tok : (0xFFFFFF00u + lane));
   const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, has && counted);
@@ -172,13 +233,14 @@ __device__ __forceinline__ uint32_t row_new_warp(uint32_t* len_row, uint32_t* cn
   atomicAdd(len_row + tok, (uint32_t)__popc(peers));
   const uint32_t nc = (uint32_t)__popc(peers & cmask);
   if (nc) atomicAdd(cnt_row + tok, nc);
+  round_mark(bits, low, tok);
   return nc;
 }
 
 // One warp-iteration of the site pass of merge j of the round: 32 entries of its occurrence list.
 // The logic of the neighbourhoods is phase_sites' (train_kernels.cuh); what differs is where the deltas go (the merge's
 // dense rows) and the virtual neighbours c_i of the earlier merges of the batch.
-__device__ __forceinline__ void round_sites_iter(const RoundArgs& R, const RoundSm& S, uint32_t par, uint32_t j, uint32_t c_first,
+__device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S, uint32_t par, uint32_t j, uint32_t c_first,
                                                  uint32_t i, SiteRec* site_out, uint32_t sites_cap) {
   const ApplyArgs& A = R.L.A;
   const uint32_t* slots = A.slots;
@@ -206,7 +268,7 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, const Round
   if (!smask) return;
   uint32_t site_base = 0;
   if (lane == (uint32_t)(__ffs(smask) - 1)) site_base = atomicAdd(&R.rs->n_sites[par][j], (uint32_t)__popc(smask));
-  SiteRec rec{p, NOPOS, NOTOKV, NOTOKV};
+  SiteRec rec{p, NOPOS, R_NOTOK, R_NOTOK};
   // ---- adjacency on the left of the new token ----
   uint32_t dec1_tok = 0, new1_tok = 0;
   bool dec1 = false, new1 = false, new1_counted = true;
@@ -283,15 +345,20 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, const Round
       }
     }
   }
-  const uint32_t nc1 = row_new_warp(round_row(R, par, j, RW_NL_LEN), round_row(R, par, j, RW_NL_CNT), new1_tok, new1, new1_counted);
-  rec.lslot = new1 ? new1_tok : NOTOKV;
+  uint32_t* const bits_l = round_bits(R, par, j, 0);
+  uint32_t* const bits_r = round_bits(R, par, j, 1);
+  uint32_t* const low_l = S.lowbits[j][0];
+  uint32_t* const low_r = S.lowbits[j][1];
+  const uint32_t nc1 = row_new_warp(round_row(R, par, j, RW_NL_LEN), round_row(R, par, j, RW_NL_CNT), bits_l, low_l, new1_tok, new1, new1_counted);
+  rec.lslot = new1 ? new1_tok : R_NOTOK;
 
   // ---- adjacency on the right of the new token (left to the next site when that one is chained) ----
-  uint32_t dec2_tok = 0, new2_tok = 0;
+  uint32_t dec2_tok = 0, new2_tok = 0, span_word = 0;
   bool dec2 = false, new2 = false;
   if (site) {
     uint32_t r;
     int y = right_token(slots, n, q, &r);
+    span_word = round_pack_span(w, p, q, r - 1u);  // r = first slot after b (n when b ends the corpus)
     if (y != NOTOK) {
       bool chained_right = false;
       if ((uint32_t)y == a) {
@@ -326,10 +393,10 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, const Round
       }
     }
   }
-  row_add_warp(dec_l, dec1_tok, dec1);
-  row_add_warp(dec_r, dec2_tok, dec2);
-  const uint32_t nc2 = row_new_warp(round_row(R, par, j, RW_NR_LEN), round_row(R, par, j, RW_NR_CNT), new2_tok, new2, true);
-  rec.rslot = new2 ? new2_tok : NOTOKV;
+  row_add_warp(dec_l, bits_l, low_l, dec1_tok, dec1);
+  row_add_warp(dec_r, bits_r, low_r, dec2_tok, dec2);
+  const uint32_t nc2 = row_new_warp(round_row(R, par, j, RW_NR_LEN), round_row(R, par, j, RW_NR_CNT), bits_r, low_r, new2_tok, new2, true);
+  rec.rslot = new2 ? new2_tok : R_NOTOK;
   // upper bounds of the born pairs' counts: the largest group of lanes that share a neighbour, summed over the warps
   const uint32_t u1 = __reduce_max_sync(0xFFFFFFFFu, nc1), u2 = __reduce_max_sync(0xFFFFFFFFu, nc2);
   if (lane == 0) {
@@ -340,7 +407,7 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, const Round
   const uint32_t base = __shfl_sync(0xFFFFFFFFu, site_base, __ffs(smask) - 1);
   if (site) {
     const uint32_t k = base + __popc(smask & ((1u << lane) - 1u));
-    if (k < sites_cap) reinterpret_cast<uint4*>(site_out)[k] = make_uint4(rec.p, rec.lpos, rec.lslot, rec.rslot);
+    if (k < sites_cap) reinterpret_cast<uint4*>(site_out)[k] = make_uint4(rec.p, rec.lpos, rec.lslot | (rec.rslot << 16), span_word);
     else atomicOr(&st->err, ERR_SITE_OVERFLOW);
   }
 }
@@ -352,9 +419,10 @@ __device__ __forceinline__ void round_fill(const ApplyArgs& A, const uint32_t* l
   const uint32_t round = (n_sites + 31u) & ~31u;
   for (uint32_t i = vt; i < round; i += nvt) {
     const bool has = i < n_sites;
-    const uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(sites) + i) : make_uint4(0, NOPOS, NOTOKV, NOTOKV);
-    const uint32_t lslot = (has && rv.z != NOTOKV) ? ld_cg(lrow + rv.z) : NOSLOT;
-    const uint32_t rslot = (has && rv.w != NOTOKV) ? ld_cg(rrow + rv.w) : NOSLOT;
+    const uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(sites) + i) : make_uint4(0, NOPOS, R_NOTOK | (R_NOTOK << 16), 0);
+    const uint32_t ltok = rv.z & 0xFFFFu, rtok = rv.z >> 16;
+    const uint32_t lslot = (has && ltok != R_NOTOK) ? ld_cg(lrow + ltok) : NOSLOT;
+    const uint32_t rslot = (has && rtok != R_NOTOK) ? ld_cg(rrow + rtok) : NOSLOT;
     const bool hl = has && lslot != NOSLOT && t.occ_len[lslot];
     const bool hr = has && rslot != NOSLOT && t.occ_len[rslot];
     const uint32_t il = agg_cursor(t, lslot, hl);
@@ -373,21 +441,56 @@ struct RoundFill {  // what the previous round left to do
   uint32_t v, par, k, c_first;  // merges committed / row parity / merges tried (rows to clear) / first token it created
 };
 
-// the lists of the pairs born by the previous round's merges (runs on the helper warps next to P1, or on everybody)
+// the lists of the pairs born by the previous round's merges, as ONE index space over all their sites (32-aligned per merge),
+// so that the threads of the job share the work evenly whatever the sizes of the merges (runs on the helper warps next to
+// P1, or on everybody)
 __device__ __forceinline__ void round_fill_all(const RoundArgs& R, const RoundSm& S, const RoundFill& F, uint32_t vt, uint32_t nvt) {
-  for (uint32_t j = 0; j < F.v; j++)
-    if (S.fill_n[j])
-      round_fill(R.L.A, round_row(R, F.par, j, RW_NL_SLOT), round_row(R, F.par, j, RW_NR_SLOT), round_sites_buf(R, F.par, j), S.fill_n[j], vt, nvt);
+  const ApplyArgs& A = R.L.A;
+  const PairTable& t = A.t;
+  uint32_t total = 0;
+  for (uint32_t j = 0; j < F.v; j++) total += (S.fill_n[j] + 31u) & ~31u;
+  for (uint32_t i = vt; i < total; i += nvt) {
+    uint32_t j = 0, off = i;  // (warp-uniform: merge boundaries are 32-aligned)
+    while (off >= ((S.fill_n[j] + 31u) & ~31u)) {
+      off -= (S.fill_n[j] + 31u) & ~31u;
+      j++;
+    }
+    const bool has = off < S.fill_n[j];
+    const uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(round_sites_buf(R, F.par, j)) + off) : make_uint4(0, NOPOS, R_NOTOK | (R_NOTOK << 16), 0);
+    const uint32_t ltok = rv.z & 0xFFFFu, rtok = rv.z >> 16;
+    const uint32_t lslot = (has && ltok != R_NOTOK) ? ld_cg(round_row(R, F.par, j, RW_NL_SLOT) + ltok) : NOSLOT;
+    const uint32_t rslot = (has && rtok != R_NOTOK) ? ld_cg(round_row(R, F.par, j, RW_NR_SLOT) + rtok) : NOSLOT;
+    const bool hl = has && lslot != NOSLOT && t.occ_len[lslot];
+    const bool hr = has && rslot != NOSLOT && t.occ_len[rslot];
+    const uint32_t il = agg_cursor(t, lslot, hl);
+    const uint32_t ir = agg_cursor(t, rslot, hr);
+    if (hl) A.pool[il] = rv.y;
+    if (hr) A.pool[ir] = rv.x;
+  }
 }
 
-// zero the accumulating rows of a finished round (only needed when no later round's scan does it: at kernel exit)
+// zero the cells a finished round touched (its bitmaps say which) and the bitmaps themselves; runs next to the site pass of
+// the following round -- which writes the rows of the OTHER parity -- or at kernel exit
 __device__ __forceinline__ void round_clear_rows(const RoundArgs& R, uint32_t par, uint32_t k, uint32_t c_hi, uint32_t vt, uint32_t nvt) {
-  const uint32_t T = (c_hi + 31u) & ~31u;
-  for (uint32_t j = 0; j < k; j++)
-    for (int row = 0; row < RW_CLEAR_ROWS; row++) {
-      uint32_t* r = round_row(R, par, j, row);
-      for (uint32_t i = vt; i < T; i += nvt) r[i] = 0;
+  const uint32_t W = (c_hi + 31u) >> 5;  // bitmap words in use
+  const uint32_t total = k * 2u * W;
+  for (uint32_t i = vt; i < total; i += nvt) {
+    const uint32_t js = i / W, wi = i - js * W, j = js >> 1, side = js & 1u;
+    uint32_t* bw = round_bits(R, par, j, side) + wi;
+    uint32_t word = ld_cg(bw);
+    if (!word) continue;
+    *bw = 0;
+    uint32_t* r0 = round_row(R, par, j, side ? RW_DEC_R : RW_DEC_L) + wi * 32u;
+    uint32_t* r1 = round_row(R, par, j, side ? RW_NR_LEN : RW_NL_LEN) + wi * 32u;
+    uint32_t* r2 = round_row(R, par, j, side ? RW_NR_CNT : RW_NL_CNT) + wi * 32u;
+    while (word) {
+      const uint32_t bpos = (uint32_t)__ffs(word) - 1u;
+      word &= word - 1u;
+      r0[bpos] = 0;
+      r1[bpos] = 0;
+      r2[bpos] = 0;
     }
+  }
 }
 
 __global__ void k_rounds_prepare(RoundState* rs) {
@@ -400,7 +503,26 @@ __global__ void k_rounds_prepare(RoundState* rs) {
   }
 }
 
-__global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
+// how the 16 warps of a block share three independent, latency-bound jobs of n1/n2/n3 items whose dependent chains cost
+// about l1/l2/l3 (same unit): greedy on the number of passes each job needs
+__device__ __forceinline__ void round_split(uint32_t n1, uint32_t n2, uint32_t n3, uint32_t l1, uint32_t l2, uint32_t l3, uint32_t lanes_per_warp_grid,
+                                            uint32_t nwarps, uint32_t* w1, uint32_t* w2, uint32_t* w3) {
+  uint32_t a = 1, b = 1, c = 1;
+  for (uint32_t i = 3; i < nwarps; i++) {
+    const uint32_t ca = ((n1 + lanes_per_warp_grid * a - 1) / (lanes_per_warp_grid * a)) * l1;
+    const uint32_t cb = ((n2 + lanes_per_warp_grid * b - 1) / (lanes_per_warp_grid * b)) * l2;
+    const uint32_t cc = ((n3 + lanes_per_warp_grid * c - 1) / (lanes_per_warp_grid * c)) * l3;
+    // the job that would gain most from one more warp: largest cost first; among equals the one with most items per warp
+    if (ca >= cb && ca >= cc) a++;
+    else if (cb >= cc) b++;
+    else c++;
+  }
+  *w1 = a;
+  *w2 = b;
+  *w3 = c;
+}
+
+__global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
   __shared__ RoundSm S;
   const LoopArgs& L = R.L;
   const ApplyArgs& A = L.A;
@@ -415,6 +537,12 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
   const uint32_t n_tokens0 = ld_cg(&st->n_tokens);
   const uint32_t thresh = ld_cg(&st->hot_thresh);
   const bool lead = (bid == 0 && tid == 0);
+#define RBARRIER()                                                        \
+  do {                                                                    \
+    ++epoch;                                                              \
+    if (R.bar_mode) grid_barrier_ra(L.barrier, epoch * nblk, L.bar_ns);   \
+    else grid_barrier(L.barrier, epoch * nblk, L.bar_ns);                 \
+  } while (0)
 
   // ---- first partials: per-block top-2 over the hot list ----
   if (lead) st->snap_err = st->err;
@@ -436,12 +564,12 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
     }
     if (tid < RB) S.fill_n[tid] = 0;
   }
-  grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
+  RBARRIER();
 
   const bool prof = lead;
   unsigned long long tp0 = prof ? now_ns() : 0, tp1;
-  // block 0's view, per phase (decide, P1, wait, P2, wait, -, -, tie path); fine_ns splits it into rounds of small merges
-  // ([0..4], rounds in [5]) and rounds of one big merge ([6..10], rounds in [11])
+  // block 0's view, per phase (decide, P1, wait, P2, wait, -, -, tie path); fine_ns splits it into rounds of latency-bound
+  // merges ([0..4], rounds in [5]) and rounds whose first merge has more than R_LAT sites ([6..10], rounds in [11])
   uint32_t prof_big = 0;
 #define RPROF(i)                                              \
   if (prof) {                                                 \
@@ -472,6 +600,10 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
         S.cp[tid] = 0;
         S.cm[tid] = 0;
       }
+      for (uint32_t i = tid; i < RB * 2u * (R_LOW / 32u); i += blockDim.x) (&S.lowbits[0][0][0])[i] = 0;
+      if (tid == 320) S.g_n_keys = ld_cg(&st->n_keys);  // (stable here: they only change in P2)
+      if (tid == 321) S.g_pool_cursor = ld_cg(&st->pool_cursor);
+      if (tid == 322) S.g_snap_err = ld_cg(&st->snap_err);
       // the list of candidates is exact down to the largest second-best primary any block published
       const unsigned long long Lcut = block_max_u64((tid & 1u) ? myp : 0ull, S.red);  // (syncs inside: qn / cp are visible)
       if (myp && myp >= Lcut) {
@@ -504,86 +636,107 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
           S.cs[rank] = slot;
           S.cm[rank] = mult;
           S.ck[rank] = key;
+          // what the batch builder needs of this candidate, loaded side by side by the candidates' own threads
+          S.cls[rank] = t.occ_start[slot];
+          S.cll[rank] = t.occ_len[slot];
+          S.clen[rank] = A.len16[key >> 16] + A.len16[key & 0xFFFFu];
         }
       }
       __syncthreads();
-      if (tid < RB && S.cp[tid]) {  // list of every candidate, loaded side by side
-        S.cls[tid] = t.occ_start[S.cs[tid]];
-        S.cll[tid] = t.occ_len[S.cs[tid]];
-      }
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t status = LOOP_RUNNING, k = 0;
+      if (warp == 0) {
+        // lane j judges candidate j on its own; the batch is the longest prefix nobody objects to
+        const uint32_t j = lane;
         const unsigned long long p0 = S.cp[0];
         const uint32_t w0 = (uint32_t)(p0 >> 20);
-        const uint32_t n_keys = ld_cg(&st->n_keys), pool_cursor = ld_cg(&st->pool_cursor);
-        if (ld_cg(&st->snap_err)) status = LOOP_ERROR;
+        const uint32_t n_keys = S.g_n_keys, pool_cursor = S.g_pool_cursor;
+        uint32_t status = LOOP_RUNNING;
+        if (S.g_snap_err) status = LOOP_ERROR;
         else if (!p0) status = (thresh <= 1) ? LOOP_EMPTY : LOOP_NEED_REBUILD;
         else if (w0 < thresh) status = LOOP_NEED_REBUILD;
         else if (w0 < L.min_weight) status = LOOP_DONE;  // core.ts:313
         else if (it >= L.log_cap) status = LOOP_LIMIT;
         else if (c_first >= L.max_tokens) status = LOOP_NEED_HOST;
-        unsigned long long keys_sum = 0, w_sum = 0;
-        int stop = 0;
-        if (status == LOOP_RUNNING) {
-          for (uint32_t j = 0; j < R.kmax; j++) {
-            const unsigned long long pj = S.cp[j];
-            if (!pj) { stop = 1; break; }
-            const uint32_t wj = (uint32_t)(pj >> 20), key = S.ck[j];
-            const uint32_t aj = key >> 16, bj = key & 0xFFFFu, cj = c_first + j;
-            const unsigned long long new_keys = min(2ull * wj + 2ull, 2ull * (cj + 1ull) + 2ull);
-            bool ok = true;
-            uint32_t why = LOOP_NEED_HOST;
-            // capacity the host guarantees (k_merge_loop's checks, cumulative over the batch)
-            if ((unsigned long long)n_keys + keys_sum + new_keys > (unsigned long long)(L.tbl_cap >> 1)) ok = false;
-            else if ((unsigned long long)pool_cursor + 2ull * (w_sum + wj) > L.pool_cap) ok = false;
-            else if (j == 0 && wj > A.sites_cap) ok = false;
-            else if ((unsigned long long)hot_pre + keys_sum + new_keys > min(L.hot_cap, L.hot_limit)) { ok = false; why = LOOP_NEED_REBUILD; }
-            else if (cj + 1 > L.len16_cap) ok = false;
-            if (j == 0) {
-              if (!ok) { status = why; break; }
-              if (S.cm[0] > 1 && S.cm[0] > L.cand_cap) { status = LOOP_NEED_HOST; break; }
-            } else {
-              if (!ok) { stop = 6; break; }
-              if (S.cm[0] > 1 || S.cm[j] > 1) { stop = 2; break; }       // position tie-breaks run alone
-              if (S.w[0] > R_SMALL) { stop = 3; break; }                  // a big merge keeps the whole grid
-              if (wj < thresh || wj < L.min_weight) { stop = 6; break; }  // the next decision handles the status
-              if (it + j >= L.log_cap || cj >= L.max_tokens) { stop = 6; break; }
-              bool shares = false;
-              for (uint32_t i2 = 0; i2 < j; i2++) shares = shares || aj == S.a[i2] || aj == S.b[i2] || bj == S.a[i2] || bj == S.b[i2];
-              if (shares) { stop = 4; break; }
-              if (F.v && (aj >= F.c_first || bj >= F.c_first)) { stop = 5; break; }  // its list is still being written
-            }
-            S.a[j] = aj;
-            S.b[j] = bj;
-            S.w[j] = wj;
-            S.slot[j] = S.cs[j];
-            S.lstart[j] = S.cls[j];
-            S.llen[j] = S.cll[j];
-            S.lenc[j] = A.len16[aj] + A.len16[bj];
-            keys_sum += new_keys;
-            w_sum += wj;
-            k = j + 1;
+        const unsigned long long pj = (j < RB) ? S.cp[j] : 0ull;
+        const uint32_t wj = (uint32_t)(pj >> 20), key = (j < RB) ? S.ck[j] : 0u;
+        const uint32_t aj = key >> 16, bj = key & 0xFFFFu, cj = c_first + j;
+        const unsigned long long new_keys = pj ? min(2ull * wj + 2ull, 2ull * (cj + 1ull) + 2ull) : 0ull;
+        unsigned long long keys_incl = new_keys, w_incl = pj ? wj : 0u;  // cumulative over candidates 0..j (the batch is a prefix)
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, keys_incl, o), y = __shfl_up_sync(0xFFFFFFFFu, w_incl, o);
+          if ((int)lane >= o) {
+            keys_incl += x;
+            w_incl += y;
           }
-          if (status == LOOP_RUNNING && k == R.kmax) stop = 0;
         }
-        S.iter0[0] = 0;
-        for (uint32_t j = 0; j < k; j++) S.iter0[j + 1] = S.iter0[j] + ((S.llen[j] + 31u) >> 5);
-        S.k = k;
-        S.status = status;
-        S.mult0 = S.cm[0];
-        if (lead && status == LOOP_RUNNING) {
-          rs->rounds++;
-          rs->tried += k;
-          rs->stop_reason[stop]++;
-          if (k == 1) rs->rounds_single++;
+        // capacity the host guarantees (k_merge_loop's checks, cumulative over the batch)
+        uint32_t cap_fail = 0;  // 0 fine, else the status it would mean for candidate 0
+        if ((unsigned long long)n_keys + keys_incl > (unsigned long long)(L.tbl_cap >> 1)) cap_fail = LOOP_NEED_HOST;
+        else if ((unsigned long long)pool_cursor + 2ull * w_incl > L.pool_cap) cap_fail = LOOP_NEED_HOST;
+        else if (j == 0 && wj > A.sites_cap) cap_fail = LOOP_NEED_HOST;
+        else if ((unsigned long long)hot_pre + keys_incl > min(L.hot_cap, L.hot_limit)) cap_fail = LOOP_NEED_REBUILD;
+        else if (cj + 1 > L.len16_cap) cap_fail = LOOP_NEED_HOST;
+        const uint32_t mult0 = S.cm[0];
+        if (status == LOOP_RUNNING) {
+          const uint32_t cf0 = __shfl_sync(0xFFFFFFFFu, cap_fail, 0);
+          if (cf0) status = cf0;
+          else if (mult0 > 1 && mult0 > L.cand_cap) status = LOOP_NEED_HOST;
+        }
+        // why candidate j >= 1 cannot join (0: it can); same codes as RoundState::stop_reason
+        uint32_t stop = 0;
+        if (j >= R.kmax) stop = 7;  // (the cap: reported as reason 0)
+        else if (!pj) stop = 1;
+        else if (cap_fail) stop = 6;
+        else if (mult0 > 1 || S.cm[j] > 1) stop = 2;                                   // position tie-breaks run alone
+        else if (w0 > R_SMALL || w_incl > R_BATCH_SITES) stop = 3;                     // a big merge keeps the whole grid
+        else if (wj < thresh || wj < L.min_weight) stop = 6;                           // the next decision handles the status
+        else if (it + j >= L.log_cap || cj >= L.max_tokens) stop = 6;
+        else if (F.v && (aj >= F.c_first || bj >= F.c_first)) stop = 5;                // its list is still being written
+        else {
+          for (uint32_t i2 = 0; i2 < j; i2++) {  // shares a token with an earlier candidate
+            const uint32_t k2 = S.ck[i2], a2 = k2 >> 16, b2 = k2 & 0xFFFFu;
+            if (aj == a2 || aj == b2 || bj == a2 || bj == b2) stop = 4;
+          }
+        }
+        if (j == 0) stop = 0;
+        const uint32_t objections = __ballot_sync(0xFFFFFFFFu, stop != 0);
+        uint32_t k = objections ? (uint32_t)__ffs(objections) - 1u : 32u;  // first candidate that cannot join
+        const uint32_t why = __shfl_sync(0xFFFFFFFFu, stop, k & 31u);
+        if (status != LOOP_RUNNING) k = 0;
+        if (j < k) {
+          S.a[j] = aj;
+          S.b[j] = bj;
+          S.w[j] = wj;
+          S.slot[j] = S.cs[j];
+          S.lstart[j] = S.cls[j];
+          S.llen[j] = S.cll[j];
+          S.lenc[j] = S.clen[j];
+        }
+        uint32_t it_incl = (j < k) ? ((S.cll[j] + 31u) >> 5) : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, it_incl, o);
+          if ((int)lane >= o) it_incl += x;
+        }
+        if (j < RB) S.iter0[j + 1] = it_incl;
+        if (j == 0) {
+          S.iter0[0] = 0;
+          S.k = k;
+          S.status = status;
+          S.mult0 = mult0;
+          if (bid == 0 && status == LOOP_RUNNING) {
+            rs->rounds++;
+            rs->tried += k;
+            rs->stop_reason[why == 7 ? 0 : why]++;
+            if (k == 1) rs->rounds_single++;
+          }
         }
       }
       __syncthreads();
     }
     uint32_t status = S.status;
     uint32_t k = S.k;
-    prof_big = (status == LOOP_RUNNING && S.w[0] > R_SMALL) ? 1u : 0u;
+    prof_big = (status == LOOP_RUNNING && S.w[0] > R_LAT) ? 1u : 0u;
     if (prof && status == LOOP_RUNNING) st->fine_ns[prof_big ? 11 : 5] += 1;
     RPROF(0)
     // ---- tie on (weight, a.index+b.index): the pair whose last counted occurrence comes first wins (core.ts:294-305) ----
@@ -593,12 +746,12 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
         __syncthreads();
         if (tid < RB) S.fill_n[tid] = 0;
         F.v = 0;  // (the rows of that round still wait for their clearing: F.k stays)
-        grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
+        RBARRIER();
       }
       phase_collect(t, A.len16, L.max_length, 1, L.hot, hot_pre, S.cp[0], L.cands, L.cand_cap, st, bid, nblk);
-      grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
+      RBARRIER();
       phase_tie(A.slots, A.n, t, A.pool, L.cands, ld_cg(&st->n_cand), st, S.s_max, bid, nblk);
-      grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
+      RBARRIER();
       const unsigned long long tp = ld_cg(&st->tie_pos);
       __syncthreads();
       if (tp == ~0ull) {
@@ -638,12 +791,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
       __syncthreads();
       if (tid < RB) S.fill_n[tid] = 0;
       F.v = 0;
-      grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
-      if (tid == 0) {  // (the list length was read before the fill; it does not change, the start neither)
-        S.lstart[0] = t.occ_start[S.slot[0]];
-        S.llen[0] = t.occ_len[S.slot[0]];
-      }
-      __syncthreads();
+      RBARRIER();
     }
     // ================= P1: the site passes of the batch, next to the list filling of the previous round =================
     if (lead) {
@@ -658,21 +806,29 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
       const uint32_t iters = S.iter0[k];
       uint32_t fill_total = 0;
       for (uint32_t j = 0; j < F.v; j++) fill_total += S.fill_n[j];
-      const bool split = fill_total <= 8192u * 4u && S.w[0] <= R_SMALL && blockDim.x == 512u;
-      const uint32_t ws = split ? L.p1_sites : 16u, wh = 16u - ws;
+      // latency bound: some warps of every block walk the sites, the others fill the lists of the previous round's pairs and
+      // zero the cells that round touched; throughput bound: everybody does everything
+      const bool split = iters <= 3u * nblk * ((L.p1_sites * (blockDim.x >> 5)) / 16u) && fill_total <= 65536u;
+      const uint32_t NW = blockDim.x >> 5;
+      const uint32_t ws = split ? (L.p1_sites * NW) / 16u : NW, wh = NW - ws;
       if (warp < ws) {
         for (uint32_t wi = bid * ws + warp; wi < iters; wi += nblk * ws) {
           uint32_t j = 0;
           while (j + 1 < k && wi >= S.iter0[j + 1]) j++;
           round_sites_iter(R, S, par, j, c_first, (wi - S.iter0[j]) * 32u + lane, round_sites_buf(R, par, j), j == 0 ? A.sites_cap : R_SMALL);
         }
-        if (!split && F.v) round_fill_all(R, S, F, gt, gn);
-      } else if (F.v) {
-        round_fill_all(R, S, F, (bid * wh + warp - ws) * 32u + lane, nblk * wh * 32u);
+        if (!split) {
+          if (F.v) round_fill_all(R, S, F, gt, gn);
+          if (F.k) round_clear_rows(R, F.par, F.k, F.c_first + F.k, gt, gn);
+        }
+      } else {
+        const uint32_t hvt = (bid * wh + warp - ws) * 32u + lane, hnvt = nblk * wh * 32u;
+        if (F.v) round_fill_all(R, S, F, hvt, hnvt);
+        if (F.k) round_clear_rows(R, F.par, F.k, F.c_first + F.k, hvt, hnvt);
       }
     }
     RPROF(1)
-    grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
+    RBARRIER();
     RPROF(2)
     // ================= P2 =================
     // valid prefix: no pair born by an earlier merge of the batch may reach the count of a later one
@@ -688,15 +844,14 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
         }
       }
     }
-    uint32_t ns[RB];
+    // sites per merge (lane j of every warp holds merge j's), their sum
+    const uint32_t ns_lane = (lane < v) ? ld_cg(&rs->n_sites[par][lane]) : 0u;
+    uint32_t sites_all = ns_lane;
 #pragma unroll
-    for (int j = 0; j < RB; j++) ns[j] = ((uint32_t)j < v) ? ld_cg(&rs->n_sites[par][j]) : 0u;
+    for (int o = 16; o > 0; o >>= 1) sites_all += __shfl_xor_sync(0xFFFFFFFFu, sites_all, o);
     if (lead) {
-      unsigned long long live = 0;
       uint32_t bad = 0;
-#pragma unroll
-      for (int j = 0; j < RB; j++) {
-        if ((uint32_t)j >= v) break;
+      for (uint32_t j = 0; j < v; j++) {
         MergeRec r;
         r.a = (int32_t)S.a[j];
         r.b = (int32_t)S.b[j];
@@ -705,11 +860,10 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
         r.weight = (long long)S.w[j];
         L.log[it + j] = r;
         t.cnt[S.slot[j]] = 0;  // every counted occurrence of the winner is being replaced
-        live += ns[j];
-        bad |= ns[j] != S.w[j];
+        bad |= ld_cg(&rs->n_sites[par][j]) != S.w[j];
       }
-      st->live_tokens -= live;
-      st->sites_total += live;
+      st->live_tokens -= sites_all;
+      st->sites_total += sites_all;
       st->n_cand = 0;
       st->tie_pos = ~0ull;
       if (bad) atomicOr(&st->err, ERR_ROUND_MISMATCH);
@@ -719,66 +873,55 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
     }
     Top2 mine = top2_empty();
     {
-      const uint32_t sites_all = [&] { uint32_t s = 0;
-#pragma unroll
-        for (int j = 0; j < RB; j++) s += ns[j];
-        return s; }();
-      const bool split = sites_all <= 4u * 16384u && S.w[0] <= R_SMALL && blockDim.x == 512u;
-      const uint32_t wn = L.p2_new, wr = L.p2_rw, wm = 16u - wn - wr;
-      // ---- job 1: the dense rows -> born pairs and decrements of the valid merges; the previous round's rows are zeroed ----
+      const bool split = sites_all <= 8u * R_LAT;
+      const uint32_t NW = blockDim.x >> 5;
+      uint32_t wn = NW, wr = NW, wm = NW;
+      if (split) round_split(sites_all, sites_all, hot_pre, 8, 2, 5, nblk * 32u, NW, &wn, &wr, &wm);
+      // ---- job 1: the cells the site passes touched -> born pairs and decrements of the valid merges.  Block b owns the
+      // bitmap words f = b, b + blocks, ... of the flattened (merge, side, word) space (interleaved: the dense low-token words
+      // spread over all blocks), expands R_CHUNK of them at a time into a shared-memory list and hands one cell to each lane ----
       if (!split || warp < wn) {
-        const uint32_t vt = split ? (bid * wn + warp) * 32u + lane : gt, nvt = split ? nblk * wn * 32u : gn;
+        const uint32_t n1t = split ? wn * 32u : blockDim.x;  // threads of this block on the job
+        const uint32_t lt = tid;                              // (job 1 owns the first warps)
         const uint32_t c_hi = c_first + k;
-        const uint32_t T = (c_hi + 31u) & ~31u;
-        const uint32_t kk = max(k, F.k);
-        const uint32_t total = kk * 2u * T;
-        const uint32_t opar = par ^ 1u;
-        for (uint32_t i0 = vt; i0 < total; i0 += 4u * nvt) {
-          uint32_t dec[4], len[4], cnt[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const uint32_t i = i0 + (uint32_t)u * nvt;
-            dec[u] = len[u] = cnt[u] = 0;
-            if (i < total) {
-              const uint32_t qd = i / T, tok = i - qd * T, jj = qd >> 1, side = qd & 1u;
-              if (jj < v) {
-                dec[u] = ld_cg(round_row(R, par, jj, side ? RW_DEC_R : RW_DEC_L) + tok);
-                len[u] = ld_cg(round_row(R, par, jj, side ? RW_NR_LEN : RW_NL_LEN) + tok);
-                cnt[u] = ld_cg(round_row(R, par, jj, side ? RW_NR_CNT : RW_NL_CNT) + tok);
-              }
-              if (jj < F.k) {  // rows of the round before this one (the other parity): nobody reads them any more
-                round_row(R, opar, jj, side ? RW_DEC_R : RW_DEC_L)[tok] = 0;
-                round_row(R, opar, jj, side ? RW_NR_LEN : RW_NL_LEN)[tok] = 0;
-                round_row(R, opar, jj, side ? RW_NR_CNT : RW_NL_CNT)[tok] = 0;
-              }
+        const uint32_t W = (c_hi + 31u) >> 5;
+        const uint32_t nwords = v * 2u * W;
+        const uint32_t M = nwords > bid ? (nwords - bid + nblk - 1u) / nblk : 0u;  // words this block owns
+        for (uint32_t m0 = 0; m0 < M; m0 += R_CHUNK) {
+          if (lt == 0) S.ncell = 0;
+          asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");
+          for (uint32_t m = m0 + lt; m < min(M, m0 + R_CHUNK); m += n1t) {
+            const uint32_t f = bid + nblk * m;
+            const uint32_t js = f / W, wi = f - js * W;
+            uint32_t word = ld_cg(round_bits(R, par, js >> 1, js & 1u) + wi);
+            if (!word) continue;
+            uint32_t pos = atomicAdd(&S.ncell, (uint32_t)__popc(word));
+            while (word) {
+              const uint32_t bpos = (uint32_t)__ffs(word) - 1u;
+              word &= word - 1u;
+              S.cell[pos++] = (js << 16) | (wi * 32u + bpos);
             }
           }
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const uint32_t i = i0 + (uint32_t)u * nvt;
-            if (!__any_sync(0xFFFFFFFFu, (dec[u] | len[u]) != 0)) continue;
-            const uint32_t qd = i / T, tok = i - qd * T, jj = min(qd >> 1, (uint32_t)RB - 1u), side = qd & 1u;
+          asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");
+          const uint32_t ncell = S.ncell;
+          for (uint32_t base = 0; base < ncell; base += n1t) {
+            const uint32_t idx = base + lt;
+            const bool act = idx < ncell;
+            const uint32_t ent = act ? S.cell[idx] : 0u;
+            const uint32_t jj = (ent >> 17) & (RB - 1u), side = (ent >> 16) & 1u, tok = ent & 0xFFFFu;
             const uint32_t cj = c_first + jj;
+            const uint32_t ajj = S.a[jj], bjj = S.b[jj];
+            uint32_t dec = 0, len = 0, cntv = 0;
+            if (act) {
+              dec = ld_cg(round_row(R, par, jj, side ? RW_DEC_R : RW_DEC_L) + tok);
+              len = ld_cg(round_row(R, par, jj, side ? RW_NR_LEN : RW_NL_LEN) + tok);
+              cntv = ld_cg(round_row(R, par, jj, side ? RW_NR_CNT : RW_NL_CNT) + tok);
+            }
             // ---- a pair born by merge jj: (tok, c) or (c, tok) ----
             {
-              const bool act = len[u] != 0;
-              uint32_t s = NOSLOT, cntv = cnt[u];
-              bool ins = false;
-              if (act) {
-                // adjacencies a LATER valid merge of the batch took away again (its virtual neighbour c_jj)
-                for (uint32_t j2 = jj + 1; j2 < v; j2++) {
-                  if (side) {
-                    if (tok == S.a[j2]) cntv -= ld_cg(round_row(R, par, j2, RW_DEC_L) + cj);
-                  } else {
-                    if (tok == S.b[j2]) cntv -= ld_cg(round_row(R, par, j2, RW_DEC_R) + cj);
-                  }
-                }
-                s = tbl_find_or_insert_ex(t, side ? pair_key(cj, tok) : pair_key(tok, cj), &ins);
-                if (s == NOSLOT) atomicOr(&st->err, ERR_TABLE_FULL);
-              }
-              const uint32_t im = __ballot_sync(0xFFFFFFFFu, ins);
-              if (im && lane == (uint32_t)(__ffs(im) - 1)) atomicAdd(&st->n_keys, (uint32_t)__popc(im));
-              uint32_t mylen = (act && s != NOSLOT) ? len[u] : 0u;
+              const bool born = len != 0;
+              // list space first (one cursor atomic per warp): its round trip overlaps the table probe below
+              uint32_t mylen = born ? len : 0u;
               uint32_t inc = mylen;
 #pragma unroll
               for (int o = 1; o < 32; o <<= 1) {
@@ -788,8 +931,33 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
               const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, inc, 31);
               uint32_t wbase = 0;
               if (lane == 31 && wtotal) wbase = atomicAdd(&st->pool_cursor, wtotal);
+              uint32_t s = NOSLOT;
+              bool ins = false;
+              if (born) {
+                // adjacencies a LATER valid merge of the batch took away again (its virtual neighbour c_jj)
+                for (uint32_t j2 = jj + 1; j2 < v; j2++) {
+                  if (side) {
+                    if (tok == S.a[j2]) cntv -= ld_cg(round_row(R, par, j2, RW_DEC_L) + cj);
+                  } else {
+                    if (tok == S.b[j2]) cntv -= ld_cg(round_row(R, par, j2, RW_DEC_R) + cj);
+                  }
+                }
+                // the key is new (it holds a token this round creates): claim the home slot with one CAS, probe on only when taken
+                const uint32_t key = side ? pair_key(cj, tok) : pair_key(tok, cj);
+                const uint32_t h = tbl_hash(t, key);
+                const uint32_t was = atomicCAS(t.keys + h, EMPTY_KEY, key);
+                if (was == EMPTY_KEY) {
+                  s = h;
+                  ins = true;
+                } else {
+                  s = tbl_find_or_insert_ex(t, key, &ins);
+                }
+                if (s == NOSLOT) atomicOr(&st->err, ERR_TABLE_FULL);
+              }
+              const uint32_t im = __ballot_sync(0xFFFFFFFFu, ins);
+              if (im && lane == (uint32_t)(__ffs(im) - 1)) atomicAdd(&st->n_keys, (uint32_t)__popc(im));
               wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
-              if (act && s != NOSLOT) {
+              if (born && s != NOSLOT) {
                 uint32_t start = wbase + (inc - mylen);
                 if (start > L.pool_cap || mylen > L.pool_cap - start) {
                   atomicOr(&st->err, ERR_POOL_FULL);
@@ -813,24 +981,30 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
               }
             }
             // ---- decrements of an OLD pair: (tok, a_jj) on the left side, (b_jj, tok) on the right side ----
-            if (dec[u] != 0 && tok < c_first) {
-              uint32_t totald = dec[u];
+            if (dec != 0 && tok < c_first) {
+              uint32_t totald = dec;
               bool handle = true;
-              const uint32_t ajj = S.a[jj], bjj = S.b[jj];
               if (side) {  // (b_jj, tok): also decremented from the left side of the valid merge whose a is tok
                 for (uint32_t j2 = 0; j2 < v; j2++)
                   if (tok == S.a[j2]) totald += ld_cg(round_row(R, par, j2, RW_DEC_L) + bjj);
-              } else {     // (tok, a_jj): when tok is the b of a valid merge and that merge's right side holds the pair too, it handles both
+              } else {     // (tok, a_jj): when tok is the b of a valid merge whose right side holds the pair too, that side handles both
                 for (uint32_t j2 = 0; j2 < v; j2++)
                   if (tok == S.b[j2] && ld_cg(round_row(R, par, j2, RW_DEC_R) + ajj) != 0) handle = false;
               }
               if (handle) {
                 const uint32_t pa = side ? bjj : tok, pb = side ? tok : ajj;
-                const uint32_t s = tbl_find(t, pair_key(pa, pb));
+                // home slot: key and count are requested together (one round trip when the first probe hits)
+                const uint32_t key = pair_key(pa, pb), h = tbl_hash(t, key);
+                const uint32_t k0 = t.keys[h];
+                uint32_t old = t.cnt[h];
+                uint32_t s = h;
+                if (k0 != key) {
+                  s = (k0 == EMPTY_KEY) ? NOSLOT : tbl_find(t, key);
+                  if (s != NOSLOT) old = t.cnt[s];
+                }
                 if (s == NOSLOT) {
                   atomicOr(&st->err, ERR_MISSING_KEY);
                 } else {
-                  const uint32_t old = t.cnt[s];
                   if (old < totald) atomicOr(&st->err, ERR_ROUND_MISMATCH);
                   const uint32_t nv = old - totald;
                   t.cnt[s] = nv;  // this thread is the only one that touches the pair in this phase
@@ -839,25 +1013,31 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
               }
             }
           }
+          asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");  // the list is reused by the next chunk
         }
       }
-      // ---- job 2: rewrite the corpus at the sites of the valid merges ----
+      // ---- job 2: rewrite the corpus at the sites of the valid merges (the records carry the spans) ----
       if (!split || (warp >= wn && warp < wn + wr)) {
         const uint32_t vt = split ? (bid * wr + warp - wn) * 32u + lane : gt, nvt = split ? nblk * wr * 32u : gn;
-#pragma unroll
-        for (int j = 0; j < RB; j++) {
-          if ((uint32_t)j >= v) break;
-          const SiteRec* sites = round_sites_buf(R, par, j);
-          uint32_t* slots = A.slots;
+        uint32_t* slots = A.slots;
+        for (uint32_t j = 0; j < v; j++) {
+          const uint4* sites = reinterpret_cast<const uint4*>(round_sites_buf(R, par, j));
+          const uint32_t nsj = __shfl_sync(0xFFFFFFFFu, ns_lane, j);
           const uint32_t cj = c_first + j;
-          for (uint32_t i = vt; i < ns[j]; i += nvt) {
-            const uint32_t p = ld_cg(&sites[i].p);
-            const uint32_t q = next_pos(slots, A.n, p);
-            const uint32_t e = next_pos(slots, A.n, q) - 1;
+          for (uint32_t i = vt; i < nsj; i += nvt) {
+            const uint4 rv = ld_cg4(sites + i);
+            const uint32_t p = rv.x;
+            uint32_t q, e;
+            if (rv.w & 0x40000000u) {  // span too long for the record: walk
+              q = next_pos(slots, A.n, p);
+              e = next_pos(slots, A.n, q) - 1;
+            } else {
+              q = p + ((rv.w >> 15) & 0x7FFFu);
+              e = p + (rv.w & 0x7FFFu);
+            }
             const uint32_t span = e - p + 1;
-            const uint32_t w = ld_slot(slots + p);
             if (span > VAL_MASK) atomicOr(&st->err, ERR_SPAN_OVERFLOW);
-            slots[p] = (w & DOCSTART) | cj;
+            slots[p] = (rv.w & DOCSTART) | cj;
             if (span == 2) {
               slots[p + 1] = mk_back(1);
             } else {
@@ -875,6 +1055,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
           const uint32_t hs = L.hot[i];
           const uint32_t key = t.keys[hs];
           if (key == EMPTY_KEY) continue;
+          const uint32_t cv = t.cnt[hs];  // (in flight next to the role test)
           const uint32_t x = key >> 16, y = key & 0xFFFFu;
           bool skip = false;
           for (uint32_t j2 = 0; j2 < v; j2++) {
@@ -882,9 +1063,7 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
             if (y == S.a[j2] && ld_cg(round_row(R, par, j2, RW_DEC_L) + x) != 0) skip = true;  // job 1 hands in its new count
             if (x == S.b[j2] && ld_cg(round_row(R, par, j2, RW_DEC_R) + y) != 0) skip = true;
           }
-          if (skip) continue;
-          const uint32_t cv = t.cnt[hs];
-          if (!cv) continue;
+          if (skip || !cv) continue;
           if (L.max_length && A.len16[x] + A.len16[y] > L.max_length) continue;
           top2_add(mine, make_primary(cv, x, y), hs, 1, key);
         }
@@ -906,10 +1085,11 @@ __global__ void __launch_bounds__(ML_THREADS, 1) k_merge_rounds(RoundArgs R) {
     F.c_first = c_first;
     it += v;
     RPROF(3)
-    grid_barrier(L.barrier, ++epoch * nblk, L.bar_ns);
+    RBARRIER();
     RPROF(4)
   }
 #undef RPROF
+#undef RBARRIER
 }
 
 }  // namespace bpe
