@@ -39,6 +39,8 @@ def build(force: bool = False, verbose: bool = False, out: str = LIB) -> str:
     extra = ["-DBPE_FINE_PROF"] if os.environ.get("BPE_FINE_PROF") else []  # debug: sub-step timers inside phase_sites
     if os.environ.get("BPE_ML_THREADS"):
         extra.append("-DBPE_ML_THREADS=" + os.environ["BPE_ML_THREADS"])  # tuning: threads per block of the loop kernels
+    if os.environ.get("BPE_TBL_STRIDE"):
+        extra.append("-DBPE_TBL_STRIDE=" + os.environ["BPE_TBL_STRIDE"])  # tuning: 8 = one 32-byte entry per pair-table slot
     if os.environ.get("BPE_RD_THREADS"):
         extra.append("-DBPE_RD_THREADS=" + os.environ["BPE_RD_THREADS"])  # tuning: threads per block of k_merge_rounds
     cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]

@@ -183,9 +183,9 @@ struct bpe_engine {
   DevBuf<unsigned long long> barrier;  // own 128-byte line
   int loop_blocks = 0;   // co-resident grid of k_merge_loop
   // several exact merges per barrier round (round_kernels.cuh): dense delta rows, site buffers of merges 1.., per-block top-2 partials
-  DevBuf<uint32_t> r_rows;
+  DevBuf<unsigned long long> r_cells;
+  DevBuf<uint32_t> r_slotrows, r_lists;
   DevBuf<SiteRec> r_bsites;
-  DevBuf<uint32_t> r_bits;
   DevBuf<uint4> r_gp;
   DevBuf<uint32_t> r_gk;
   DevBuf<RoundState> r_state;
@@ -925,13 +925,13 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       e->round_blocks = std::min(e->sm_count, most);
       if (const char* v = getenv("BPE_LOOP_BLOCKS")) e->round_blocks = std::max(1, std::min(atoi(v), most));
     }
-    if (!e->r_rows.p) {
-      const size_t cells = (size_t)2 * RB * RW_ROWS * ND_STRIDE;
-      CK(e->r_rows.reserve(cells));
-      CK(cudaMemsetAsync(e->r_rows.p, 0, cells * 4, e->stream));  // the kernel keeps the rows zero between launches
+    if (!e->r_cells.p) {
+      const size_t cells = (size_t)2 * RB * 2 * ND_STRIDE;
+      CK(e->r_cells.reserve(cells));
+      CK(cudaMemsetAsync(e->r_cells.p, 0, cells * 8, e->stream));  // the kernel keeps the cells zero between launches
+      CK(e->r_slotrows.reserve(cells));
+      CK(e->r_lists.reserve((size_t)2 * e->round_blocks * R_LISTCAP));
       CK(e->r_bsites.reserve((size_t)2 * RB * R_SMALL));
-      CK(e->r_bits.reserve((size_t)2 * RB * 2 * R_BW));
-      CK(cudaMemsetAsync(e->r_bits.p, 0, (size_t)2 * RB * 2 * R_BW * 4, e->stream));
       CK(e->r_state.reserve(1));
       CK(cudaMemsetAsync(e->r_state.p, 0, sizeof(RoundState), e->stream));
     }
@@ -951,6 +951,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
   CK(cudaEventRecord(t0, e->stream));
   int rc = BPE_OK;
   int64_t done = 0;
+  bool legacy_above = false;
   std::vector<MergeRec> tmp;
   for (;;) {
     int64_t remaining = log_cap - done;
@@ -1016,16 +1017,23 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
     auto tw0 = std::chrono::steady_clock::now();
     k_loop_prepare<<<1, 32, 0, e->stream>>>(e->d_st.p, (uint32_t)e->n_tokens, e->barrier.p);
     e->stats.kernel_launches++;
-    if (use_rounds) {
+    if (use_rounds && legacy_above) {
+      // the winner has more sites than the packed delta cells of a round can count: k_merge_loop takes the merges above
+      // R_HUGE (it stops, "done", at the first winner at or below it) and the rounds continue from there
+      L.min_weight = (uint32_t)std::max<int64_t>(mw, (int64_t)R_HUGE + 1);
+      void* args[] = {&L};
+      ce = cudaLaunchCooperativeKernel((void*)k_merge_loop, dim3(e->loop_blocks), dim3(ML_THREADS), args, 0, e->stream);
+    } else if (use_rounds) {
       RoundArgs RA;
       RA.L = L;
-      RA.rows = e->r_rows.p;
+      RA.cells = e->r_cells.p;
+      RA.slotrows = e->r_slotrows.p;
+      RA.lists = e->r_lists.p;
       RA.bsites = e->r_bsites.p;
       RA.gp = e->r_gp.p;
       RA.gk = e->r_gk.p;
       RA.rs = e->r_state.p;
       RA.kmax = (uint32_t)round_k;
-      RA.bits = e->r_bits.p;
       RA.bar_mode = 1;
       if (const char* v = getenv("BPE_LOOP_BAR")) RA.bar_mode = atoi(v) ? 1 : 0;
       k_rounds_prepare<<<1, 32, 0, e->stream>>>(e->r_state.p);
@@ -1074,6 +1082,14 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       e->stats.merges_applied += iters;
     }
     uint32_t status = e->h_st->status;
+    if (use_rounds && legacy_above && status == LOOP_DONE && (int64_t)e->h_st->best_cnt >= mw) {
+      legacy_above = false;  // below R_HUGE now: back to the rounds
+      continue;
+    }
+    if (status == LOOP_NEED_LEGACY) {
+      legacy_above = true;
+      continue;
+    }
     if (status == LOOP_DONE || status == LOOP_EMPTY) break;
     if (status == LOOP_LIMIT) continue;
     if (status == LOOP_NEED_REBUILD) {
@@ -1102,6 +1118,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
         if ((rc = grow_table(e, pow2_at_least(want))) != BPE_OK) break;
       }
       uint64_t pool_after = (uint64_t)e->h_st->pool_cursor + 2 * w;
+      if (use_rounds) pool_after += (uint64_t)e->round_blocks * R_POOL_CHUNK;  // every block of k_merge_rounds may open a private chunk
       if (pool_after > 0xFFFFFFF0ull) {
         rc = fail(e, BPE_E_DOMAIN, "occurrence pool exceeds 2^32 cells");
         break;
@@ -1144,6 +1161,15 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
         fprintf(stderr, "[bpe] rounds %llu, merges %llu (tried %llu), cut by the born-pair bound %llu, single %llu; batch ends: cap %llu, no-candidate %llu, tie %llu, big %llu, "
                         "token %llu, fresh-token %llu, limits %llu\n", hrs.rounds, hrs.round_merges, hrs.tried, hrs.rounds_cut_born, hrs.rounds_single, hrs.stop_reason[0],
                 hrs.stop_reason[1], hrs.stop_reason[2], hrs.stop_reason[3], hrs.stop_reason[4], hrs.stop_reason[5], hrs.stop_reason[6]);
+      if (trace_r)
+        fprintf(stderr, "[bpe] P1 warp-iterations small %llu big %llu; touched cells small %llu big %llu; sites small %llu big %llu\n", hrs.iters_small, hrs.iters_big,
+                hrs.cells_small, hrs.cells_big, hrs.sites_small, hrs.sites_big);
+      if (trace_r) {
+        const unsigned long long* m = e->h_st->mg_prof_ns;
+        const double n = std::max(1.0, (double)m[4]);
+        fprintf(stderr, "[bpe] P2 of rounds of small merges, block 0, us after the barrier: cells done %.1f, rewrite done %.1f, arg-max done %.1f, partials out %.1f\n",
+                m[0] / n * 1e-3, m[1] / n * 1e-3, m[2] / n * 1e-3, m[3] / n * 1e-3);
+      }
       if (trace_r) {
         const unsigned long long* f = e->h_st->fine_ns;
         const double ns = std::max(1.0, (double)f[5]), nb = std::max(1.0, (double)f[11]);

@@ -121,7 +121,10 @@ __device__ __forceinline__ uint32_t run_right(const uint32_t* slots, uint32_t n,
 // in one DRAM sector) was measured on the 1 GB corpus and LOST 8 %: linear probing then pays one sector per probe
 // instead of one per eight, and the hot-list / threshold scans read four times the bytes.  TblField keeps the
 // `t.cnt[i]` / `t.cnt + i` notation either way.
-constexpr uint32_t TBL_STRIDE = 1;  // u32 words between consecutive slots of one field
+#ifndef BPE_TBL_STRIDE
+#define BPE_TBL_STRIDE 1
+#endif
+constexpr uint32_t TBL_STRIDE = BPE_TBL_STRIDE;  // u32 words between consecutive slots of one field
 struct TblField {
   uint32_t* p;
   __host__ __device__ __forceinline__ uint32_t& operator[](uint32_t i) const { return p[(size_t)i * TBL_STRIDE]; }

@@ -48,27 +48,47 @@ constexpr int RB = 16;                   // merges per round at most
 constexpr uint32_t R_SMALL = 1u << 18;   // a merge with more counted occurrences than this runs alone
 constexpr uint32_t R_BATCH_SITES = 1u << 19;  // ... and a batch stops growing past this many sites (a dropped tail wastes its site pass)
 constexpr uint32_t R_LAT = 16384;        // below this many sites a merge is latency bound (profile classes, warp splits)
-constexpr uint32_t R_BW = ND_STRIDE / 32;  // words of one touched-token bitmap
-enum { RW_DEC_L = 0, RW_DEC_R, RW_NL_LEN, RW_NL_CNT, RW_NR_LEN, RW_NR_CNT, RW_NL_SLOT, RW_NR_SLOT, RW_ROWS };
-constexpr int RW_CLEAR_ROWS = 6;         // rows that accumulate (the SLOT rows are written before they are read)
+
+// One 64-bit cell per (merge of the round, side, other token): decrements of the old pair | occurrences of the born pair
+// << 21 | counted occurrences of the born pair << 42 -- ONE atomic per warp and distinct neighbour carries all three.
+constexpr uint32_t R_FIELD = 21;
+constexpr unsigned long long R_FMASK = (1ull << R_FIELD) - 1ull;
+constexpr uint32_t R_HUGE = 1u << 20;    // merges with more counted occurrences overflow the fields: they run through k_merge_loop
+constexpr uint32_t R_POOL_CHUNK = 1u << 16;  // occurrence-pool cells a block reserves at a time
+constexpr uint32_t R_LISTCAP = 32768;    // touched cells a block can list per round (more: the round falls back to scanning the rows)
+__host__ __device__ __forceinline__ uint32_t cell_dec(unsigned long long v) { return (uint32_t)(v & R_FMASK); }
+__host__ __device__ __forceinline__ uint32_t cell_len(unsigned long long v) { return (uint32_t)((v >> R_FIELD) & R_FMASK); }
+__host__ __device__ __forceinline__ uint32_t cell_cnt(unsigned long long v) { return (uint32_t)((v >> (2 * R_FIELD)) & R_FMASK); }
+constexpr uint32_t LOOP_NEED_LEGACY = 7;  // the winner is too big for the packed cells: k_merge_loop takes the merges above R_HUGE
 constexpr uint32_t R_QCAP = 384;         // per-block top-2 entries a decision can fold (2 x blocks)
-constexpr uint32_t R_LOW = 1024;         // tokens below this are frequent neighbours: their bitmap bits are set once per BLOCK (shared-memory filter)
-constexpr uint32_t R_CHUNK = 128;        // bitmap words a block expands per pass of P2's job 1
-constexpr uint32_t R_CELLS = R_CHUNK * 32;  // ... and the touched cells they can hold
+
 constexpr uint32_t ERR_ROUND_MISMATCH = 2048u;  // a merge of a round found a different number of sites than its count
 
 struct RoundState {
-  uint32_t n_sites[2][RB];
-  uint32_t ub[2][RB][2];  // U bounds (left / right born pairs) per merge
+  // counters the site passes bump once per warp-iteration: one 128-byte line each, so that they spread over L2 slices instead
+  // of queueing at one (same-sector atomics serialise)
+  struct alignas(128) Line {
+    uint32_t v;
+    uint32_t pad[31];
+  };
+  struct alignas(128) Line64 {
+    unsigned long long v;  // U bound of the left born pairs | of the right born pairs << 32
+    unsigned long long pad[15];
+  };
+  Line n_sites[2][RB];
+  Line64 ub[2][RB];
+  uint32_t overflow[2];   // a block's list of touched cells was full: the round scans the rows instead
   unsigned long long rounds, round_merges, rounds_cut_born, rounds_single, tried;
-  unsigned long long stop_reason[8];  // why a batch was not extended: 0 cap, 1 no exact candidate, 2 tie, 3 big, 4 token, 5 fresh token, 6 limits
+  unsigned long long stop_reason[8];
+  unsigned long long iters_small, iters_big, cells_small, cells_big, sites_small, sites_big;  // P1 warp-iterations, touched cells, sites  // why a batch was not extended: 0 cap, 1 no exact candidate, 2 tie, 3 big, 4 token, 5 fresh token, 6 limits
 };
 
 struct RoundArgs {
   LoopArgs L;
-  uint32_t* rows;    // [2][RB][RW_ROWS][ND_STRIDE]
+  unsigned long long* cells;  // [2][RB][2][ND_STRIDE] packed delta cells (see R_FIELD)
+  uint32_t* slotrows;         // [2][RB][2][ND_STRIDE] table slot of the born pair (tok, c) / (c, tok), for the list filling
+  uint32_t* lists;            // [2][blocks][R_LISTCAP] cells each block touched first: (merge * 2 + side) << 16 | token
   SiteRec* bsites;   // [2][RB][R_SMALL]: merges 1.. of a round (merge 0 uses L.A.sites / L.sites2, which the host sizes)
-  uint32_t* bits;    // [2][RB][2][R_BW]: tokens whose cells of a merge's left / right rows were touched by the site pass
   int bar_mode;      // 0: k_merge_loop's barrier (two sequentially consistent fences); 1: release arrival + acquire poll
   uint4* gp;         // [2 * blocks] per-block top-2: (primary lo, primary hi, slot, mult)
   uint32_t* gk;      // [2 * blocks] ... and the pair key of that slot
@@ -76,11 +96,18 @@ struct RoundArgs {
   uint32_t kmax;     // merges per round (1 .. RB)
 };
 
-__device__ __forceinline__ uint32_t* round_row(const RoundArgs& R, uint32_t par, uint32_t j, int row) {
-  return R.rows + (((size_t)par * RB + j) * RW_ROWS + (size_t)row) * ND_STRIDE;
+__device__ __forceinline__ unsigned long long* round_cells(const RoundArgs& R, uint32_t par, uint32_t j, uint32_t side) {
+  return R.cells + (((size_t)par * RB + j) * 2u + side) * ND_STRIDE;
 }
-__device__ __forceinline__ uint32_t* round_bits(const RoundArgs& R, uint32_t par, uint32_t j, uint32_t side) {
-  return R.bits + (((size_t)par * RB + j) * 2u + side) * R_BW;
+__device__ __forceinline__ uint32_t* round_slotrow(const RoundArgs& R, uint32_t par, uint32_t j, uint32_t side) {
+  return R.slotrows + (((size_t)par * RB + j) * 2u + side) * ND_STRIDE;
+}
+__device__ __forceinline__ uint32_t* round_list(const RoundArgs& R, uint32_t par) {
+  return R.lists + ((size_t)par * gridDim.x + blockIdx.x) * R_LISTCAP;
+}
+// decrements of the old pair a later merge holds in ITS cell of token `tok` (cross-reads of P2: nobody writes the cells then)
+__device__ __forceinline__ uint32_t round_dec_of(const RoundArgs& R, uint32_t par, uint32_t j, uint32_t side, uint32_t tok) {
+  return cell_dec(ld_cg(round_cells(R, par, j, side) + tok));
 }
 
 // Site record of a round: x = p, y = position of the left token of the born left adjacency (NOPOS: none),
@@ -112,6 +139,10 @@ __device__ __forceinline__ void grid_barrier_ra(unsigned long long* ctr, unsigne
   }
   __syncthreads();
 }
+
+// 256-bit filter over token indices (bit = index mod 256): "is this token the a / the b of a merge of the batch?" costs one
+// shared-memory word for the 15 of 16 tokens that are not
+__device__ __forceinline__ bool role_maybe(const uint32_t* filt, uint32_t tok) { return (filt[(tok >> 5) & 7u] >> (tok & 31u)) & 1u; }
 
 // ---- top-2 groups: the two largest DISTINCT primaries, each with the number of pairs that share it and the smallest slot ----
 struct Top2 {
@@ -160,9 +191,11 @@ struct RoundSm {
   uint32_t qs[R_QCAP], qm[R_QCAP], qk[R_QCAP];
   unsigned long long cp[RB];
   uint32_t cs[RB], cm[RB], ck[RB], cls[RB], cll[RB], clen[RB];
-  uint32_t g_n_keys, g_pool_cursor, g_snap_err, ncell;
-  uint32_t lowbits[RB][2][R_LOW / 32];  // bits of the touched-token bitmaps this block has already set (tokens < R_LOW)
-  uint32_t cell[R_CELLS];               // P2 job 1: (merge * 2 + side) << 16 | token of the touched cells of the current chunk
+  uint32_t g_n_keys, g_pool_cursor, g_snap_err, pad1;
+  uint32_t ncell[2];  // cells this block touched first in the round of either parity (entries of its list)
+  uint32_t pool_next, pool_end;  // this block's private chunk of the occurrence pool (list space without a grid-wide atomic)
+  uint32_t keys_ins;             // keys this block inserted in the current P2 (one n_keys atomic per block and round)
+  uint32_t filt_a[8], filt_b[8]; // role_maybe filters: the a's / the b's of the batch
   Top2 t2[32];
   unsigned long long red[32];
   uint32_t s_max[32];
@@ -198,42 +231,46 @@ __device__ __forceinline__ Top2 top2_block_reduce(Top2 v, Top2* s_t2) {
   return top2_warp_reduce(u);
 }
 
-// all 32 lanes call; `has` lanes add one to row[tok]; lanes that agree on tok elect a leader which issues ONE atomic.
-// Returns, in the leader lane, the number of lanes it stands for (0 elsewhere).
-// set the token's bit in the merge's touched-token bitmap.  Frequent neighbours (low token indices) would receive one
-// atomic per warp of every site pass on a handful of words: each block sets those bits once (shared-memory filter).
-__device__ __forceinline__ void round_mark(uint32_t* bits, uint32_t* low, uint32_t tok) {
-  const uint32_t m = 1u << (tok & 31u);
-  if (tok < R_LOW) {
-    uint32_t* lw = low + (tok >> 5);
-    if (*reinterpret_cast<volatile uint32_t*>(lw) & m) return;
-    atomicOr(lw, m);
+// All 32 lanes call; `has` lanes contribute to the cell of `tok`: a decrement (dec), an occurrence of the born pair (newp),
+// a counted occurrence (counted).  Lanes that agree on tok elect a leader which issues ONE 64-bit atomic for all of them; the
+// lane that finds the cell empty lists it for P2 (one shared-memory counter bump per warp).  Returns the leader's counted
+// occurrences (0 elsewhere): the ingredient of the born-pair bound.
+__device__ __forceinline__ uint32_t cell_add_warp(const RoundArgs& R, RoundSm& S, uint32_t par, uint32_t js, unsigned long long* cells, uint32_t tok, bool has,
+                                                  bool dec, bool newp, bool counted, uint32_t c, uint32_t partner) {
+  const uint32_t lane = lane_id();
+  const uint32_t peers = __match_any_sync(0xFFFFFFFFu, has ? tok : (0xFFFFFF00u + lane));
+  const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, has && dec);
+  const uint32_t nmask = __ballot_sync(0xFFFFFFFFu, has && newp);
+  const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, has && newp && counted);
+  const bool leader = has && lane == (uint32_t)(__ffs(peers) - 1);
+  uint32_t nc = 0;
+  bool first = false;
+  if (leader) {
+    nc = (uint32_t)__popc(peers & cmask);
+    const unsigned long long add = (unsigned long long)__popc(peers & dmask) | ((unsigned long long)__popc(peers & nmask) << R_FIELD) |
+                                   ((unsigned long long)nc << (2 * R_FIELD));
+    first = atomicAdd(cells + tok, add) == 0ull;
   }
-  atomicOr(bits + (tok >> 5), m);
-}
-
-__device__ __forceinline__ uint32_t row_add_warp(uint32_t* row, uint32_t* bits, uint32_t* low, uint32_t tok, bool has) {
-  const uint32_t lane = lane_id();
-  const uint32_t peers = __match_any_sync(0xFFFFFFFFu, has ? tok : (0xFFFFFF00u + lane));
-  const bool leader = has && lane == (uint32_t)(__ffs(peers) - 1);
-  if (!leader) return 0;
-  const uint32_t n = (uint32_t)__popc(peers);
-  atomicAdd(row + tok, n);
-  round_mark(bits, low, tok);
-  return n;
-}
-
-// the born pair (tok, c) / (c, tok): occurrences and counted occurrences; returns the leader's counted lanes (0 elsewhere)
-__device__ __forceinline__ uint32_t row_new_warp(uint32_t* len_row, uint32_t* cnt_row, uint32_t* bits, uint32_t* low, uint32_t tok, bool has, bool counted) {
-  const uint32_t lane = lane_id();
-  const uint32_t peers = __match_any_sync(0xFFFFFFFFu, has ? tok : (0xFFFFFF00u + lane));
-  const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, has && counted);
-  const bool leader = has && lane == (uint32_t)(__ffs(peers) - 1);
-  if (!leader) return 0;
-  atomicAdd(len_row + tok, (uint32_t)__popc(peers));
-  const uint32_t nc = (uint32_t)__popc(peers & cmask);
-  if (nc) atomicAdd(cnt_row + tok, nc);
-  round_mark(bits, low, tok);
+  const uint32_t fm = __ballot_sync(0xFFFFFFFFu, first);
+  if (fm) {
+    uint32_t base = 0;
+    const int src = __ffs(fm) - 1;
+    if ((int)lane == src) base = atomicAdd(&S.ncell[par], (uint32_t)__popc(fm));
+    base = __shfl_sync(0xFFFFFFFFu, base, src);
+    if (first) {
+      const uint32_t k = base + __popc(fm & ((1u << lane) - 1u));
+      if (k < R_LISTCAP) round_list(R, par)[k] = (js << 16) | tok;
+      else R.rs->overflow[par] = 1;
+      // P2 will probe the pair table for the born pair (tok, c) / (c, tok) and for the old pair (tok, a) / (b, tok): ask for
+      // their home slots now, so that they sit in L2 by then (hints only)
+      const PairTable& t = R.L.A.t;
+      const uint32_t side = js & 1u;
+      prefetch_l2(t.keys + tbl_hash(t, side ? pair_key(c, tok) : pair_key(tok, c)));
+      const uint32_t h2 = tbl_hash(t, side ? pair_key(partner, tok) : pair_key(tok, partner));
+      prefetch_l2(t.keys + h2);
+      prefetch_l2(t.cnt + h2);
+    }
+  }
   return nc;
 }
 
@@ -249,8 +286,8 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S,
   const uint32_t a = S.a[j], b = S.b[j], c = c_first + j;
   const uint32_t total = S.llen[j];
   const uint32_t lane = lane_id();
-  uint32_t* const dec_l = round_row(R, par, j, RW_DEC_L);
-  uint32_t* const dec_r = round_row(R, par, j, RW_DEC_R);
+  unsigned long long* const cells_l = round_cells(R, par, j, 0);
+  unsigned long long* const cells_r = round_cells(R, par, j, 1);
   bool site = false;
   uint32_t p = 0, w = 0, q = 0, koff = 0;
   if (i < total) {
@@ -267,7 +304,7 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S,
   const uint32_t smask = __ballot_sync(0xFFFFFFFFu, site);
   if (!smask) return;
   uint32_t site_base = 0;
-  if (lane == (uint32_t)(__ffs(smask) - 1)) site_base = atomicAdd(&R.rs->n_sites[par][j], (uint32_t)__popc(smask));
+  if (lane == (uint32_t)(__ffs(smask) - 1)) site_base = atomicAdd(&R.rs->n_sites[par][j].v, (uint32_t)__popc(smask));
   SiteRec rec{p, NOPOS, R_NOTOK, R_NOTOK};
   // ---- adjacency on the left of the new token ----
   uint32_t dec1_tok = 0, new1_tok = 0;
@@ -310,7 +347,7 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S,
         // is the left neighbour the right half of a site of an EARLIER merge of this batch?  Then it is c_i by now.
         int vi = -1;
         uint32_t vpos = NOPOS;
-        for (uint32_t i2 = 0; i2 < j; i2++) {
+        for (uint32_t i2 = 0; i2 < (role_maybe(S.filt_b, (uint32_t)x) ? j : 0u); i2++) {
           if ((uint32_t)x != S.b[i2]) continue;
           const uint32_t wl = ld_slot(slots + lpos);
           if (S.a[i2] != S.b[i2]) {
@@ -345,11 +382,11 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S,
       }
     }
   }
-  uint32_t* const bits_l = round_bits(R, par, j, 0);
-  uint32_t* const bits_r = round_bits(R, par, j, 1);
-  uint32_t* const low_l = S.lowbits[j][0];
-  uint32_t* const low_r = S.lowbits[j][1];
-  const uint32_t nc1 = row_new_warp(round_row(R, par, j, RW_NL_LEN), round_row(R, par, j, RW_NL_CNT), bits_l, low_l, new1_tok, new1, new1_counted);
+  // one atomic per distinct left neighbour: the born pair (new1_tok, c), with the decrement when it concerns the same token
+  // (it does unless the site is chained to the one on its left: then the decrement is (b,a)'s and goes out on its own)
+  const bool dec1_same = dec1 && dec1_tok == new1_tok;
+  const uint32_t nc1 = cell_add_warp(R, S, par, j * 2u, cells_l, new1_tok, new1, dec1_same, true, new1_counted, c, a);
+  if (__any_sync(0xFFFFFFFFu, dec1 && !dec1_same)) cell_add_warp(R, S, par, j * 2u, cells_l, dec1_tok, dec1 && !dec1_same, true, false, false, c, a);
   rec.lslot = new1 ? new1_tok : R_NOTOK;
 
   // ---- adjacency on the right of the new token (left to the next site when that one is chained) ----
@@ -367,7 +404,7 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S,
       }
       if (!chained_right) {
         int vi = -1;
-        for (uint32_t i2 = 0; i2 < j; i2++) {
+        for (uint32_t i2 = 0; i2 < (role_maybe(S.filt_a, (uint32_t)y) ? j : 0u); i2++) {
           if ((uint32_t)y != S.a[i2]) continue;
           uint32_t r2;
           if (right_token(slots, n, r, &r2) == (int)S.b[i2]) vi = (int)i2;  // y starts a site of merge i (for a_i == b_i: offset 0 of its run)
@@ -393,15 +430,14 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S,
       }
     }
   }
-  row_add_warp(dec_l, bits_l, low_l, dec1_tok, dec1);
-  row_add_warp(dec_r, bits_r, low_r, dec2_tok, dec2);
-  const uint32_t nc2 = row_new_warp(round_row(R, par, j, RW_NR_LEN), round_row(R, par, j, RW_NR_CNT), bits_r, low_r, new2_tok, new2, true);
+  const bool dec2_same = dec2 && new2 && dec2_tok == new2_tok;  // (always, when there is a decrement: kept general)
+  const uint32_t nc2 = cell_add_warp(R, S, par, j * 2u + 1u, cells_r, new2_tok, new2, dec2_same, true, true, c, b);
+  if (__any_sync(0xFFFFFFFFu, dec2 && !dec2_same)) cell_add_warp(R, S, par, j * 2u + 1u, cells_r, dec2_tok, dec2 && !dec2_same, true, false, false, c, b);
   rec.rslot = new2 ? new2_tok : R_NOTOK;
   // upper bounds of the born pairs' counts: the largest group of lanes that share a neighbour, summed over the warps
   const uint32_t u1 = __reduce_max_sync(0xFFFFFFFFu, nc1), u2 = __reduce_max_sync(0xFFFFFFFFu, nc2);
   if (lane == 0) {
-    if (u1) atomicAdd(&R.rs->ub[par][j][0], u1);
-    if (u2) atomicAdd(&R.rs->ub[par][j][1], u2);
+    if (u1 | u2) atomicAdd(&R.rs->ub[par][j].v, (unsigned long long)u1 | ((unsigned long long)u2 << 32));
   }
   // ---- record the site ----
   const uint32_t base = __shfl_sync(0xFFFFFFFFu, site_base, __ffs(smask) - 1);
@@ -412,26 +448,6 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S,
   }
 }
 
-// phase_fill with the slot rows of a round's merge
-__device__ __forceinline__ void round_fill(const ApplyArgs& A, const uint32_t* lrow, const uint32_t* rrow, const SiteRec* sites, uint32_t n_sites,
-                                           uint32_t vt, uint32_t nvt) {
-  const PairTable& t = A.t;
-  const uint32_t round = (n_sites + 31u) & ~31u;
-  for (uint32_t i = vt; i < round; i += nvt) {
-    const bool has = i < n_sites;
-    const uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(sites) + i) : make_uint4(0, NOPOS, R_NOTOK | (R_NOTOK << 16), 0);
-    const uint32_t ltok = rv.z & 0xFFFFu, rtok = rv.z >> 16;
-    const uint32_t lslot = (has && ltok != R_NOTOK) ? ld_cg(lrow + ltok) : NOSLOT;
-    const uint32_t rslot = (has && rtok != R_NOTOK) ? ld_cg(rrow + rtok) : NOSLOT;
-    const bool hl = has && lslot != NOSLOT && t.occ_len[lslot];
-    const bool hr = has && rslot != NOSLOT && t.occ_len[rslot];
-    const uint32_t il = agg_cursor(t, lslot, hl);
-    const uint32_t ir = agg_cursor(t, rslot, hr);
-    if (hl) A.pool[il] = rv.y;
-    if (hr) A.pool[ir] = rv.x;
-  }
-}
-
 __device__ __forceinline__ SiteRec* round_sites_buf(const RoundArgs& R, uint32_t par, uint32_t j) {
   if (j == 0) return par ? R.L.sites2 : R.L.A.sites;
   return R.bsites + ((size_t)par * RB + j) * R_SMALL;
@@ -439,6 +455,7 @@ __device__ __forceinline__ SiteRec* round_sites_buf(const RoundArgs& R, uint32_t
 
 struct RoundFill {  // what the previous round left to do
   uint32_t v, par, k, c_first;  // merges committed / row parity / merges tried (rows to clear) / first token it created
+  uint32_t overflow;            // a list of touched cells overflowed in that round: clear by scanning
 };
 
 // the lists of the pairs born by the previous round's merges, as ONE index space over all their sites (32-aligned per merge),
@@ -458,8 +475,8 @@ __device__ __forceinline__ void round_fill_all(const RoundArgs& R, const RoundSm
     const bool has = off < S.fill_n[j];
     const uint4 rv = has ? ld_cg4(reinterpret_cast<const uint4*>(round_sites_buf(R, F.par, j)) + off) : make_uint4(0, NOPOS, R_NOTOK | (R_NOTOK << 16), 0);
     const uint32_t ltok = rv.z & 0xFFFFu, rtok = rv.z >> 16;
-    const uint32_t lslot = (has && ltok != R_NOTOK) ? ld_cg(round_row(R, F.par, j, RW_NL_SLOT) + ltok) : NOSLOT;
-    const uint32_t rslot = (has && rtok != R_NOTOK) ? ld_cg(round_row(R, F.par, j, RW_NR_SLOT) + rtok) : NOSLOT;
+    const uint32_t lslot = (has && ltok != R_NOTOK) ? ld_cg(round_slotrow(R, F.par, j, 0) + ltok) : NOSLOT;
+    const uint32_t rslot = (has && rtok != R_NOTOK) ? ld_cg(round_slotrow(R, F.par, j, 1) + rtok) : NOSLOT;
     const bool hl = has && lslot != NOSLOT && t.occ_len[lslot];
     const bool hr = has && rslot != NOSLOT && t.occ_len[rslot];
     const uint32_t il = agg_cursor(t, lslot, hl);
@@ -469,26 +486,22 @@ __device__ __forceinline__ void round_fill_all(const RoundArgs& R, const RoundSm
   }
 }
 
-// zero the cells a finished round touched (its bitmaps say which) and the bitmaps themselves; runs next to the site pass of
-// the following round -- which writes the rows of the OTHER parity -- or at kernel exit
-__device__ __forceinline__ void round_clear_rows(const RoundArgs& R, uint32_t par, uint32_t k, uint32_t c_hi, uint32_t vt, uint32_t nvt) {
-  const uint32_t W = (c_hi + 31u) >> 5;  // bitmap words in use
-  const uint32_t total = k * 2u * W;
-  for (uint32_t i = vt; i < total; i += nvt) {
-    const uint32_t js = i / W, wi = i - js * W, j = js >> 1, side = js & 1u;
-    uint32_t* bw = round_bits(R, par, j, side) + wi;
-    uint32_t word = ld_cg(bw);
-    if (!word) continue;
-    *bw = 0;
-    uint32_t* r0 = round_row(R, par, j, side ? RW_DEC_R : RW_DEC_L) + wi * 32u;
-    uint32_t* r1 = round_row(R, par, j, side ? RW_NR_LEN : RW_NL_LEN) + wi * 32u;
-    uint32_t* r2 = round_row(R, par, j, side ? RW_NR_CNT : RW_NL_CNT) + wi * 32u;
-    while (word) {
-      const uint32_t bpos = (uint32_t)__ffs(word) - 1u;
-      word &= word - 1u;
-      r0[bpos] = 0;
-      r1[bpos] = 0;
-      r2[bpos] = 0;
+// zero the cells a finished round touched: every block clears the cells of its own list (or, after an overflow, everybody
+// scans the rows); runs next to the site pass of the following round -- which writes the cells of the OTHER parity -- or at exit
+__device__ __forceinline__ void round_clear_cells(const RoundArgs& R, const RoundSm& S, const RoundFill& F, uint32_t lt, uint32_t nlt, uint32_t vt, uint32_t nvt) {
+  if (!F.overflow) {
+    const uint32_t n = min(S.ncell[F.par], R_LISTCAP);
+    const uint32_t* list = round_list(R, F.par);
+    for (uint32_t i = lt; i < n; i += nlt) {
+      const uint32_t ent = ld_cg(list + i);
+      round_cells(R, F.par, (ent >> 17) & (RB - 1u), (ent >> 16) & 1u)[ent & 0xFFFFu] = 0ull;
+    }
+  } else {
+    const uint32_t T = F.c_first + F.k;
+    const uint32_t total = F.k * 2u * T;
+    for (uint32_t i = vt; i < total; i += nvt) {
+      const uint32_t js = i / T, tok = i - js * T;
+      round_cells(R, F.par, js >> 1, js & 1u)[tok] = 0ull;
     }
   }
 }
@@ -497,29 +510,28 @@ __global__ void k_rounds_prepare(RoundState* rs) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     for (int p = 0; p < 2; p++)
       for (int j = 0; j < RB; j++) {
-        rs->n_sites[p][j] = 0;
-        rs->ub[p][j][0] = rs->ub[p][j][1] = 0;
+        rs->n_sites[p][j].v = 0;
+        rs->ub[p][j].v = 0;
       }
+    rs->overflow[0] = rs->overflow[1] = 0;
   }
 }
 
-// how the 16 warps of a block share three independent, latency-bound jobs of n1/n2/n3 items whose dependent chains cost
-// about l1/l2/l3 (same unit): greedy on the number of passes each job needs
-__device__ __forceinline__ void round_split(uint32_t n1, uint32_t n2, uint32_t n3, uint32_t l1, uint32_t l2, uint32_t l3, uint32_t lanes_per_warp_grid,
-                                            uint32_t nwarps, uint32_t* w1, uint32_t* w2, uint32_t* w3) {
-  uint32_t a = 1, b = 1, c = 1;
+// how the warps of a block share three independent, latency-bound jobs whose items need q1/q2/q3 passes of ONE warp per
+// block (q = items / (32 x blocks), rounded up) and whose dependent chains cost about l1/l2/l3 (same unit): greedy on the
+// cost of each job, in float arithmetic (every thread of the grid runs this once per round: it has to be cheap)
+__device__ __forceinline__ void round_split(float q1, float q2, float q3, float l1, float l2, float l3, uint32_t nwarps, uint32_t* w1, uint32_t* w2,
+                                            uint32_t* w3) {
+  float a = 1.f, b = 1.f, c = 1.f;
   for (uint32_t i = 3; i < nwarps; i++) {
-    const uint32_t ca = ((n1 + lanes_per_warp_grid * a - 1) / (lanes_per_warp_grid * a)) * l1;
-    const uint32_t cb = ((n2 + lanes_per_warp_grid * b - 1) / (lanes_per_warp_grid * b)) * l2;
-    const uint32_t cc = ((n3 + lanes_per_warp_grid * c - 1) / (lanes_per_warp_grid * c)) * l3;
-    // the job that would gain most from one more warp: largest cost first; among equals the one with most items per warp
-    if (ca >= cb && ca >= cc) a++;
-    else if (cb >= cc) b++;
-    else c++;
+    const float ca = ceilf(__fdividef(q1, a)) * l1, cb = ceilf(__fdividef(q2, b)) * l2, cc = ceilf(__fdividef(q3, c)) * l3;
+    if (ca >= cb && ca >= cc) a += 1.f;
+    else if (cb >= cc) b += 1.f;
+    else c += 1.f;
   }
-  *w1 = a;
-  *w2 = b;
-  *w3 = c;
+  *w1 = (uint32_t)a;
+  *w2 = (uint32_t)b;
+  *w3 = (uint32_t)c;
 }
 
 __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
@@ -563,6 +575,8 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
       R.gk[2 * bid + 1] = v.k1;
     }
     if (tid < RB) S.fill_n[tid] = 0;
+    if (tid < 2) S.ncell[tid] = 0;
+    if (tid == 0) S.pool_next = S.pool_end = S.keys_ins = 0;
   }
   RBARRIER();
 
@@ -578,7 +592,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     if ((i) < 5) st->fine_ns[(prof_big ? 6 : 0) + (i)] += tp1 - tp0; \
     tp0 = tp1;                                                \
   }
-  RoundFill F{0, 0, 0, 0};
+  RoundFill F{0, 0, 0, 0, 0};
   uint32_t it = 0;  // merges committed by this launch
   for (uint32_t round = 0;; round++) {
     const uint32_t par = round & 1u;
@@ -600,7 +614,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         S.cp[tid] = 0;
         S.cm[tid] = 0;
       }
-      for (uint32_t i = tid; i < RB * 2u * (R_LOW / 32u); i += blockDim.x) (&S.lowbits[0][0][0])[i] = 0;
+      if (tid == 1) S.ncell[par] = 0;  // (the cells the round before last listed were cleared next to the last P1)
       if (tid == 320) S.g_n_keys = ld_cg(&st->n_keys);  // (stable here: they only change in P2)
       if (tid == 321) S.g_pool_cursor = ld_cg(&st->pool_cursor);
       if (tid == 322) S.g_snap_err = ld_cg(&st->snap_err);
@@ -656,6 +670,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         else if (w0 < L.min_weight) status = LOOP_DONE;  // core.ts:313
         else if (it >= L.log_cap) status = LOOP_LIMIT;
         else if (c_first >= L.max_tokens) status = LOOP_NEED_HOST;
+        else if (w0 > R_HUGE) status = LOOP_NEED_LEGACY;
         const unsigned long long pj = (j < RB) ? S.cp[j] : 0ull;
         const uint32_t wj = (uint32_t)(pj >> 20), key = (j < RB) ? S.ck[j] : 0u;
         const uint32_t aj = key >> 16, bj = key & 0xFFFFu, cj = c_first + j;
@@ -672,7 +687,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         // capacity the host guarantees (k_merge_loop's checks, cumulative over the batch)
         uint32_t cap_fail = 0;  // 0 fine, else the status it would mean for candidate 0
         if ((unsigned long long)n_keys + keys_incl > (unsigned long long)(L.tbl_cap >> 1)) cap_fail = LOOP_NEED_HOST;
-        else if ((unsigned long long)pool_cursor + 2ull * w_incl > L.pool_cap) cap_fail = LOOP_NEED_HOST;
+        else if ((unsigned long long)pool_cursor + 2ull * w_incl + (unsigned long long)nblk * R_POOL_CHUNK > L.pool_cap) cap_fail = LOOP_NEED_HOST;
         else if (j == 0 && wj > A.sites_cap) cap_fail = LOOP_NEED_HOST;
         else if ((unsigned long long)hot_pre + keys_incl > min(L.hot_cap, L.hot_limit)) cap_fail = LOOP_NEED_REBUILD;
         else if (cj + 1 > L.len16_cap) cap_fail = LOOP_NEED_HOST;
@@ -703,7 +718,11 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         uint32_t k = objections ? (uint32_t)__ffs(objections) - 1u : 32u;  // first candidate that cannot join
         const uint32_t why = __shfl_sync(0xFFFFFFFFu, stop, k & 31u);
         if (status != LOOP_RUNNING) k = 0;
+        if (j < 8) S.filt_a[j] = S.filt_b[j] = 0;
+        __syncwarp();
         if (j < k) {
+          atomicOr(&S.filt_a[(aj >> 5) & 7u], 1u << (aj & 31u));
+          atomicOr(&S.filt_b[(bj >> 5) & 7u], 1u << (bj & 31u));
           S.a[j] = aj;
           S.b[j] = bj;
           S.w[j] = wj;
@@ -737,6 +756,11 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     uint32_t status = S.status;
     uint32_t k = S.k;
     prof_big = (status == LOOP_RUNNING && S.w[0] > R_LAT) ? 1u : 0u;
+    const bool prof_big_all = prof_big != 0;
+    if (lead && status == LOOP_RUNNING) {
+      if (prof_big) rs->iters_big += S.iter0[k];
+      else rs->iters_small += S.iter0[k];
+    }
     if (prof && status == LOOP_RUNNING) st->fine_ns[prof_big ? 11 : 5] += 1;
     RPROF(0)
     // ---- tie on (weight, a.index+b.index): the pair whose last counted occurrence comes first wins (core.ts:294-305) ----
@@ -762,6 +786,9 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         S.slot[0] = s;
         S.a[0] = key >> 16;
         S.b[0] = key & 0xFFFFu;
+        for (int i = 0; i < 8; i++) S.filt_a[i] = S.filt_b[i] = 0;
+        S.filt_a[((key >> 16) >> 5) & 7u] = 1u << ((key >> 16) & 31u);
+        S.filt_b[((key & 0xFFFFu) >> 5) & 7u] = 1u << (key & 31u);
         S.lstart[0] = t.occ_start[s];
         S.llen[0] = t.occ_len[s];
         S.lenc[0] = A.len16[key >> 16] + A.len16[key & 0xFFFFu];
@@ -773,7 +800,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     if (status != LOOP_RUNNING) {
       // the kernel leaves every list complete and every row zero
       round_fill_all(R, S, F, gt, gn);
-      if (F.k) round_clear_rows(R, F.par, F.k, F.c_first + F.k, gt, gn);
+      if (F.k) round_clear_cells(R, S, F, tid, blockDim.x, gt, gn);
       if (lead) {
         st->status = status;
         st->iters_done = it;
@@ -794,13 +821,13 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
       RBARRIER();
     }
     // ================= P1: the site passes of the batch, next to the list filling of the previous round =================
-    if (lead) {
-      for (uint32_t j = 0; j < k; j++) A.len16[c_first + j] = S.lenc[j];  // chars = a.chars + b.chars (:318)
-      for (uint32_t j = 0; j < RB; j++) {
-        rs->n_sites[par ^ 1u][j] = 0;
-        rs->ub[par ^ 1u][j][0] = rs->ub[par ^ 1u][j][1] = 0;
+    if (bid == 0 && warp == 0) {
+      if (lane < k) A.len16[c_first + lane] = S.lenc[lane];  // chars = a.chars + b.chars (:318)
+      if (lane < RB) {
+        rs->n_sites[par ^ 1u][lane].v = 0;
+        rs->ub[par ^ 1u][lane].v = 0;
       }
-      if (S.mult0 > 1) st->tie_breaks++;
+      if (lane == 0 && S.mult0 > 1) st->tie_breaks++;
     }
     {
       const uint32_t iters = S.iter0[k];
@@ -819,12 +846,12 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         }
         if (!split) {
           if (F.v) round_fill_all(R, S, F, gt, gn);
-          if (F.k) round_clear_rows(R, F.par, F.k, F.c_first + F.k, gt, gn);
+          if (F.k) round_clear_cells(R, S, F, tid, blockDim.x, gt, gn);
         }
       } else {
         const uint32_t hvt = (bid * wh + warp - ws) * 32u + lane, hnvt = nblk * wh * 32u;
         if (F.v) round_fill_all(R, S, F, hvt, hnvt);
-        if (F.k) round_clear_rows(R, F.par, F.k, F.c_first + F.k, hvt, hnvt);
+        if (F.k) round_clear_cells(R, S, F, (warp - ws) * 32u + lane, wh * 32u, hvt, hnvt);
       }
     }
     RPROF(1)
@@ -833,11 +860,14 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     // ================= P2 =================
     // valid prefix: no pair born by an earlier merge of the batch may reach the count of a later one
     uint32_t v = k;
+    const uint32_t ns_all = (lane < k) ? ld_cg(&rs->n_sites[par][lane].v) : 0u;  // (requested together with the bounds and the flag)
+    const uint32_t overflow = ld_cg(&rs->overflow[par]);                         // (set during P1 only)
     {
-      const uint32_t ubv = (lane < 2 * k) ? ld_cg(&rs->ub[par][lane >> 1][lane & 1u]) : 0u;
+      const unsigned long long ub2 = (lane < k) ? ld_cg(&rs->ub[par][lane].v) : 0ull;
+      const uint32_t ubv = max((uint32_t)ub2, (uint32_t)(ub2 >> 32));  // lane j: the larger of merge j's two bounds
       uint32_t run = 0;
       for (uint32_t j = 0; j + 1 < k; j++) {
-        run = max(run, max(__shfl_sync(0xFFFFFFFFu, ubv, 2 * j), __shfl_sync(0xFFFFFFFFu, ubv, 2 * j + 1)));
+        run = max(run, __shfl_sync(0xFFFFFFFFu, ubv, j));
         if (run >= S.w[j + 1]) {
           v = j + 1;
           break;
@@ -845,209 +875,269 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
       }
     }
     // sites per merge (lane j of every warp holds merge j's), their sum
-    const uint32_t ns_lane = (lane < v) ? ld_cg(&rs->n_sites[par][lane]) : 0u;
+    const uint32_t ns_lane = (lane < v) ? ns_all : 0u;
     uint32_t sites_all = ns_lane;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sites_all += __shfl_xor_sync(0xFFFFFFFFu, sites_all, o);
-    if (lead) {
-      uint32_t bad = 0;
-      for (uint32_t j = 0; j < v; j++) {
+    if (bid == 0 && warp == 0) {  // lane j commits merge j of the batch (a serial loop here would sit on every round's critical path)
+      const bool mine_j = lane < v;
+      if (mine_j) {
         MergeRec r;
-        r.a = (int32_t)S.a[j];
-        r.b = (int32_t)S.b[j];
-        r.c = (int32_t)(c_first + j);
+        r.a = (int32_t)S.a[lane];
+        r.b = (int32_t)S.b[lane];
+        r.c = (int32_t)(c_first + lane);
         r.reserved = 0;
-        r.weight = (long long)S.w[j];
-        L.log[it + j] = r;
-        t.cnt[S.slot[j]] = 0;  // every counted occurrence of the winner is being replaced
-        bad |= ld_cg(&rs->n_sites[par][j]) != S.w[j];
+        r.weight = (long long)S.w[lane];
+        L.log[it + lane] = r;
+        t.cnt[S.slot[lane]] = 0;  // every counted occurrence of the winner is being replaced
       }
-      st->live_tokens -= sites_all;
-      st->sites_total += sites_all;
-      st->n_cand = 0;
-      st->tie_pos = ~0ull;
-      if (bad) atomicOr(&st->err, ERR_ROUND_MISMATCH);
-      st->snap_err = st->err;
-      rs->round_merges += v;
-      if (v < k) rs->rounds_cut_born++;
+      const uint32_t bad = __ballot_sync(0xFFFFFFFFu, mine_j && ns_lane != S.w[lane]);
+      if (lane == 0) {
+        st->live_tokens -= sites_all;
+        st->sites_total += sites_all;
+        st->n_cand = 0;
+        st->tie_pos = ~0ull;
+        if (bad) atomicOr(&st->err, ERR_ROUND_MISMATCH);
+        st->snap_err = st->err;
+        rs->round_merges += v;
+        if (S.w[0] > R_LAT) rs->sites_big += sites_all; else rs->sites_small += sites_all;
+        if (v < k) rs->rounds_cut_born++;
+      }
     }
     Top2 mine = top2_empty();
-    {
-      const bool split = sites_all <= 8u * R_LAT;
-      const uint32_t NW = blockDim.x >> 5;
-      uint32_t wn = NW, wr = NW, wm = NW;
-      if (split) round_split(sites_all, sites_all, hot_pre, 8, 2, 5, nblk * 32u, NW, &wn, &wr, &wm);
-      // ---- job 1: the cells the site passes touched -> born pairs and decrements of the valid merges.  Block b owns the
-      // bitmap words f = b, b + blocks, ... of the flattened (merge, side, word) space (interleaved: the dense low-token words
-      // spread over all blocks), expands R_CHUNK of them at a time into a shared-memory list and hands one cell to each lane ----
-      if (!split || warp < wn) {
-        const uint32_t n1t = split ? wn * 32u : blockDim.x;  // threads of this block on the job
-        const uint32_t lt = tid;                              // (job 1 owns the first warps)
-        const uint32_t c_hi = c_first + k;
-        const uint32_t W = (c_hi + 31u) >> 5;
-        const uint32_t nwords = v * 2u * W;
-        const uint32_t M = nwords > bid ? (nwords - bid + nblk - 1u) / nblk : 0u;  // words this block owns
-        for (uint32_t m0 = 0; m0 < M; m0 += R_CHUNK) {
-          if (lt == 0) S.ncell = 0;
-          asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");
-          for (uint32_t m = m0 + lt; m < min(M, m0 + R_CHUNK); m += n1t) {
-            const uint32_t f = bid + nblk * m;
-            const uint32_t js = f / W, wi = f - js * W;
-            uint32_t word = ld_cg(round_bits(R, par, js >> 1, js & 1u) + wi);
-            if (!word) continue;
-            uint32_t pos = atomicAdd(&S.ncell, (uint32_t)__popc(word));
-            while (word) {
-              const uint32_t bpos = (uint32_t)__ffs(word) - 1u;
-              word &= word - 1u;
-              S.cell[pos++] = (js << 16) | (wi * 32u + bpos);
-            }
-          }
-          asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");
-          const uint32_t ncell = S.ncell;
-          for (uint32_t base = 0; base < ncell; base += n1t) {
-            const uint32_t idx = base + lt;
-            const bool act = idx < ncell;
-            const uint32_t ent = act ? S.cell[idx] : 0u;
-            const uint32_t jj = (ent >> 17) & (RB - 1u), side = (ent >> 16) & 1u, tok = ent & 0xFFFFu;
-            const uint32_t cj = c_first + jj;
-            const uint32_t ajj = S.a[jj], bjj = S.b[jj];
-            uint32_t dec = 0, len = 0, cntv = 0;
-            if (act) {
-              dec = ld_cg(round_row(R, par, jj, side ? RW_DEC_R : RW_DEC_L) + tok);
-              len = ld_cg(round_row(R, par, jj, side ? RW_NR_LEN : RW_NL_LEN) + tok);
-              cntv = ld_cg(round_row(R, par, jj, side ? RW_NR_CNT : RW_NL_CNT) + tok);
-            }
-            // ---- a pair born by merge jj: (tok, c) or (c, tok) ----
-            {
-              const bool born = len != 0;
-              // list space first (one cursor atomic per warp): its round trip overlaps the table probe below
-              uint32_t mylen = born ? len : 0u;
-              uint32_t inc = mylen;
-#pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                if ((int)lane >= o) inc += x;
-              }
-              const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, inc, 31);
-              uint32_t wbase = 0;
-              if (lane == 31 && wtotal) wbase = atomicAdd(&st->pool_cursor, wtotal);
-              uint32_t s = NOSLOT;
-              bool ins = false;
-              if (born) {
-                // adjacencies a LATER valid merge of the batch took away again (its virtual neighbour c_jj)
-                for (uint32_t j2 = jj + 1; j2 < v; j2++) {
-                  if (side) {
-                    if (tok == S.a[j2]) cntv -= ld_cg(round_row(R, par, j2, RW_DEC_L) + cj);
-                  } else {
-                    if (tok == S.b[j2]) cntv -= ld_cg(round_row(R, par, j2, RW_DEC_R) + cj);
-                  }
-                }
-                // the key is new (it holds a token this round creates): claim the home slot with one CAS, probe on only when taken
-                const uint32_t key = side ? pair_key(cj, tok) : pair_key(tok, cj);
-                const uint32_t h = tbl_hash(t, key);
-                const uint32_t was = atomicCAS(t.keys + h, EMPTY_KEY, key);
-                if (was == EMPTY_KEY) {
-                  s = h;
-                  ins = true;
-                } else {
-                  s = tbl_find_or_insert_ex(t, key, &ins);
-                }
-                if (s == NOSLOT) atomicOr(&st->err, ERR_TABLE_FULL);
-              }
-              const uint32_t im = __ballot_sync(0xFFFFFFFFu, ins);
-              if (im && lane == (uint32_t)(__ffs(im) - 1)) atomicAdd(&st->n_keys, (uint32_t)__popc(im));
-              wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
-              if (born && s != NOSLOT) {
-                uint32_t start = wbase + (inc - mylen);
-                if (start > L.pool_cap || mylen > L.pool_cap - start) {
-                  atomicOr(&st->err, ERR_POOL_FULL);
-                  start = 0;
-                  mylen = 0;
-                }
-                t.occ_start[s] = start;
-                t.occ_len[s] = mylen;
-                t.occ_fill[s] = 0;
-                round_row(R, par, jj, side ? RW_NR_SLOT : RW_NL_SLOT)[tok] = s;
-                t.cnt[s] = cntv;  // the key is new: nobody else touches its count in this phase
-                const uint32_t pa = side ? cj : tok, pb = side ? tok : cj;
-                const uint32_t la = (pa >= c_first) ? S.lenc[pa - c_first] : A.len16[pa], lb = (pb >= c_first) ? S.lenc[pb - c_first] : A.len16[pb];
-                const unsigned long long pr = (cntv && !(L.max_length && la + lb > L.max_length)) ? make_primary(cntv, pa, pb) : 0ull;
-                if (pr && (uint32_t)(pr >> 20) >= thresh) {
-                  const uint32_t hk = atomicAdd(&st->hot_n, 1u);
-                  if (hk < L.hot_cap) L.hot[hk] = s;
-                  else atomicOr(&st->err, ERR_HOT_OVERFLOW);
-                  top2_add(mine, pr, s, 1, pair_key(pa, pb));
-                }
-              }
-            }
-            // ---- decrements of an OLD pair: (tok, a_jj) on the left side, (b_jj, tok) on the right side ----
-            if (dec != 0 && tok < c_first) {
-              uint32_t totald = dec;
-              bool handle = true;
-              if (side) {  // (b_jj, tok): also decremented from the left side of the valid merge whose a is tok
-                for (uint32_t j2 = 0; j2 < v; j2++)
-                  if (tok == S.a[j2]) totald += ld_cg(round_row(R, par, j2, RW_DEC_L) + bjj);
-              } else {     // (tok, a_jj): when tok is the b of a valid merge whose right side holds the pair too, that side handles both
-                for (uint32_t j2 = 0; j2 < v; j2++)
-                  if (tok == S.b[j2] && ld_cg(round_row(R, par, j2, RW_DEC_R) + ajj) != 0) handle = false;
-              }
-              if (handle) {
-                const uint32_t pa = side ? bjj : tok, pb = side ? tok : ajj;
-                // home slot: key and count are requested together (one round trip when the first probe hits)
-                const uint32_t key = pair_key(pa, pb), h = tbl_hash(t, key);
-                const uint32_t k0 = t.keys[h];
-                uint32_t old = t.cnt[h];
-                uint32_t s = h;
-                if (k0 != key) {
-                  s = (k0 == EMPTY_KEY) ? NOSLOT : tbl_find(t, key);
-                  if (s != NOSLOT) old = t.cnt[s];
-                }
-                if (s == NOSLOT) {
-                  atomicOr(&st->err, ERR_MISSING_KEY);
-                } else {
-                  if (old < totald) atomicOr(&st->err, ERR_ROUND_MISMATCH);
-                  const uint32_t nv = old - totald;
-                  t.cnt[s] = nv;  // this thread is the only one that touches the pair in this phase
-                  if (nv && !(L.max_length && A.len16[pa] + A.len16[pb] > L.max_length)) top2_add(mine, make_primary(nv, pa, pb), s, 1, pair_key(pa, pb));
-                }
-              }
-            }
-          }
-          asm volatile("bar.sync 1, %0;" ::"r"(n1t) : "memory");  // the list is reused by the next chunk
+    if (tid == 0) {
+      S.keys_ins = 0;
+      if (S.pool_next + R_POOL_CHUNK / 4u > S.pool_end || S.pool_next > S.pool_end) {  // the chunk is (nearly) used up: take a fresh one
+        const uint32_t at = atomicAdd(&st->pool_cursor, R_POOL_CHUNK);
+        if (at <= L.pool_cap && R_POOL_CHUNK <= L.pool_cap - at) {
+          S.pool_next = at;
+          S.pool_end = at + R_POOL_CHUNK;
+        } else {
+          S.pool_next = S.pool_end = 0;  // (the decision keeps this from happening; lists then come from the cursor and fail its check)
         }
       }
+    }
+    __syncthreads();
+    const bool jprof = bid == 0 && lane == 0 && !prof_big_all;  // block 0, rounds of small merges: when each job of P2 ends
+    const unsigned long long jt0 = jprof ? now_ns() : 0;
+    {
+      const bool split = sites_all <= (1u << 20);
+      const uint32_t NW = blockDim.x >> 5;
+      uint32_t wn = NW, wr = NW, wm = NW;
+      if (split) {
+        const float rg = __fdividef(1.f, (float)(nblk * 32u));
+        round_split(ceilf((float)sites_all * 0.5f * rg), ceilf((float)sites_all * rg), ceilf((float)hot_pre * rg), 8.f, 2.f, 5.f, NW, &wn, &wr, &wm);
+      }
+      // ---- job 1: the cells the site passes touched -> born pairs and decrements of the valid merges.  Every block works
+      // through the list of the cells IT touched first, one cell per lane (after a list overflow: everybody scans the rows) ----
+      if (!split || warp < wn) {
+        const uint32_t n1t = split ? wn * 32u : blockDim.x;  // threads of this block on the job (its first warps)
+        const uint32_t lt = tid;
+        // one touched cell: warp-collective (inactive lanes pass act = false)
+        auto process = [&](bool act, uint32_t jj, uint32_t side, uint32_t tok, unsigned long long cellv) {
+          const uint32_t cj = c_first + jj;
+          const uint32_t ajj = S.a[jj], bjj = S.b[jj];
+          const uint32_t dec = act ? cell_dec(cellv) : 0u, len = act ? cell_len(cellv) : 0u;
+          uint32_t cntv = cell_cnt(cellv);
+          // the old pair's home slot (key, count) is requested NOW: its round trip runs next to the born pair's insertion
+          const bool has_dec = dec != 0 && tok < c_first;
+          const uint32_t dpa = side ? bjj : tok, dpb = side ? tok : ajj;
+          const uint32_t dkey = pair_key(dpa, dpb), dh = tbl_hash(t, dkey);
+          uint32_t dk0 = EMPTY_KEY, dold = 0;
+          if (has_dec) {
+            dk0 = t.keys[dh];
+            dold = t.cnt[dh];
+          }
+          // ---- a pair born by merge jj: (tok, c) or (c, tok) ----
+          {
+            const bool born = len != 0;
+            // list space first (one cursor atomic per warp): its round trip overlaps the table probe below
+            uint32_t mylen = born ? len : 0u;
+            uint32_t inc = mylen;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t x = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+              if ((int)lane >= o) inc += x;
+            }
+            const uint32_t wtotal = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            // the warp's list cells come out of the block's private chunk of the pool (a shared-memory bump); only a warp that
+            // needs more than a chunk holds, or finds the chunk used up, goes to the grid-wide cursor
+            uint32_t wbase = 0;
+            if (lane == 31 && wtotal) {
+              bool got = false;
+              if (wtotal <= R_POOL_CHUNK / 4u) {
+                const uint32_t at = atomicAdd(&S.pool_next, wtotal);
+                if (at + wtotal <= S.pool_end) {
+                  wbase = at;
+                  got = true;
+                }
+              }
+              if (!got) {
+                // (a failed bump leaves pool_next past pool_end: every later warp of the round takes this path too, and the
+                // block fetches a fresh chunk at the start of its next P2)
+                wbase = atomicAdd(&st->pool_cursor, wtotal);
+              }
+            }
+            uint32_t s = NOSLOT, hot_s = NOSLOT, hot_key = 0;
+            unsigned long long hot_pr = 0ull;
+            bool ins = false;
+            if (born) {
+              // adjacencies a LATER valid merge of the batch took away again (its virtual neighbour c_jj)
+              if (role_maybe(side ? S.filt_a : S.filt_b, tok)) {
+                for (uint32_t j2 = jj + 1; j2 < v; j2++) {
+                  if (side) {
+                    if (tok == S.a[j2]) cntv -= round_dec_of(R, par, j2, 0, cj);
+                  } else {
+                    if (tok == S.b[j2]) cntv -= round_dec_of(R, par, j2, 1, cj);
+                  }
+                }
+              }
+              // the key is new (it holds a token this round creates): claim the home slot with one CAS, probe on only when taken
+              const uint32_t key = side ? pair_key(cj, tok) : pair_key(tok, cj);
+              const uint32_t h = tbl_hash(t, key);
+              const uint32_t was = atomicCAS(t.keys + h, EMPTY_KEY, key);
+              if (was == EMPTY_KEY) {
+                s = h;
+                ins = true;
+              } else {
+                s = tbl_find_or_insert_ex(t, key, &ins);
+              }
+              if (s == NOSLOT) atomicOr(&st->err, ERR_TABLE_FULL);
+            }
+            const uint32_t im = __ballot_sync(0xFFFFFFFFu, ins);
+            if (im && lane == (uint32_t)(__ffs(im) - 1)) atomicAdd(&S.keys_ins, (uint32_t)__popc(im));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+            if (born && s != NOSLOT) {
+              uint32_t start = wbase + (inc - mylen);
+              if (start > L.pool_cap || mylen > L.pool_cap - start) {
+                atomicOr(&st->err, ERR_POOL_FULL);
+                start = 0;
+                mylen = 0;
+              }
+              t.occ_start[s] = start;
+              t.occ_len[s] = mylen;
+              t.occ_fill[s] = 0;
+              round_slotrow(R, par, jj, side)[tok] = s;
+              t.cnt[s] = cntv;  // the key is new: nobody else touches its count in this phase
+              const uint32_t pa = side ? cj : tok, pb = side ? tok : cj;
+              const uint32_t la = (pa >= c_first) ? S.lenc[pa - c_first] : A.len16[pa], lb = (pb >= c_first) ? S.lenc[pb - c_first] : A.len16[pb];
+              const unsigned long long pr = (cntv && !(L.max_length && la + lb > L.max_length)) ? make_primary(cntv, pa, pb) : 0ull;
+              hot_pr = (pr && (uint32_t)(pr >> 20) >= thresh) ? pr : 0ull;
+              hot_s = s;
+              hot_key = pair_key(pa, pb);
+            }
+            // pairs that join the hot list: one hot_n atomic per warp
+            const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hot_pr != 0ull);
+            if (hm) {
+              uint32_t hbase = 0;
+              const int src = __ffs(hm) - 1;
+              if ((int)lane == src) hbase = atomicAdd(&st->hot_n, (uint32_t)__popc(hm));
+              hbase = __shfl_sync(0xFFFFFFFFu, hbase, src);
+              if (hot_pr) {
+                const uint32_t hk = hbase + __popc(hm & ((1u << lane) - 1u));
+                if (hk < L.hot_cap) L.hot[hk] = hot_s;
+                else atomicOr(&st->err, ERR_HOT_OVERFLOW);
+                top2_add(mine, hot_pr, hot_s, 1, hot_key);
+              }
+            }
+          }
+          // ---- decrements of an OLD pair: (tok, a_jj) on the left side, (b_jj, tok) on the right side ----
+          if (has_dec) {
+            uint32_t totald = dec;
+            bool handle = true;
+            if (side) {  // (b_jj, tok): also decremented from the left side of the valid merge whose a is tok
+              if (role_maybe(S.filt_a, tok))
+                for (uint32_t j2 = 0; j2 < v; j2++)
+                  if (tok == S.a[j2]) totald += round_dec_of(R, par, j2, 0, bjj);
+            } else {     // (tok, a_jj): when tok is the b of a valid merge whose right side holds the pair too, that side handles both
+              if (role_maybe(S.filt_b, tok))
+                for (uint32_t j2 = 0; j2 < v; j2++)
+                  if (tok == S.b[j2] && round_dec_of(R, par, j2, 1, ajj) != 0) handle = false;
+            }
+            if (handle) {
+              const uint32_t pa = dpa, pb = dpb, key = dkey, h = dh, k0 = dk0;
+              uint32_t old = dold;
+              uint32_t s = h;
+              if (k0 != key) {
+                s = (k0 == EMPTY_KEY) ? NOSLOT : tbl_find(t, key);
+                if (s != NOSLOT) old = t.cnt[s];
+              }
+              if (s == NOSLOT) {
+                atomicOr(&st->err, ERR_MISSING_KEY);
+              } else {
+                if (old < totald) atomicOr(&st->err, ERR_ROUND_MISMATCH);
+                const uint32_t nv = old - totald;
+                t.cnt[s] = nv;  // this thread is the only one that touches the pair in this phase
+                if (nv && !(L.max_length && A.len16[pa] + A.len16[pb] > L.max_length)) top2_add(mine, make_primary(nv, pa, pb), s, 1, pair_key(pa, pb));
+              }
+            }
+          }
+        };
+        if (!overflow) {
+          const uint32_t ncell = S.ncell[par];
+          const uint32_t* list = round_list(R, par);
+          if (lt == 0 && ncell) atomicAdd(S.w[0] > R_LAT ? &rs->cells_big : &rs->cells_small, (unsigned long long)ncell);
+          for (uint32_t base = 0; base < ncell; base += n1t) {
+            const uint32_t idx = base + lt;
+            const uint32_t ent = idx < ncell ? ld_cg(list + idx) : 0u;
+            const uint32_t jj = (ent >> 17) & (RB - 1u), side = (ent >> 16) & 1u, tok = ent & 0xFFFFu;
+            const bool act = idx < ncell && jj < v;
+            const unsigned long long cellv = act ? ld_cg(round_cells(R, par, jj, side) + tok) : 0ull;
+            process(act, jj, side, tok, cellv);
+          }
+        } else {
+          // a list was full: every cell of the valid merges' rows, shared by the job's threads of the whole grid
+          const uint32_t T = (c_first + k + 31u) & ~31u;
+          const uint32_t total = v * 2u * T;
+          for (uint32_t i = bid * n1t + lt; i < total; i += nblk * n1t) {
+            const uint32_t js = i / T, tok = i - js * T;
+            const unsigned long long cellv = ld_cg(round_cells(R, par, js >> 1, js & 1u) + tok);
+            if (!__any_sync(0xFFFFFFFFu, cellv != 0ull)) continue;
+            process(cellv != 0ull, js >> 1, js & 1u, tok, cellv);
+          }
+        }
+      }
+      if (jprof && warp == 0) st->mg_prof_ns[0] += now_ns() - jt0;
       // ---- job 2: rewrite the corpus at the sites of the valid merges (the records carry the spans) ----
       if (!split || (warp >= wn && warp < wn + wr)) {
         const uint32_t vt = split ? (bid * wr + warp - wn) * 32u + lane : gt, nvt = split ? nblk * wr * 32u : gn;
         uint32_t* slots = A.slots;
-        for (uint32_t j = 0; j < v; j++) {
-          const uint4* sites = reinterpret_cast<const uint4*>(round_sites_buf(R, par, j));
-          const uint32_t nsj = __shfl_sync(0xFFFFFFFFu, ns_lane, j);
+        // one index space over the sites of all valid merges (32-aligned per merge): every thread of the job gets its share
+        uint32_t total = 0;
+        for (uint32_t j = 0; j < v; j++) total += (__shfl_sync(0xFFFFFFFFu, ns_lane, j) + 31u) & ~31u;
+        for (uint32_t i = vt; i < total; i += nvt) {
+          uint32_t j = 0, off = i;
+          for (;;) {  // (warp-uniform)
+            const uint32_t nj = (__shfl_sync(0xFFFFFFFFu, ns_lane, j) + 31u) & ~31u;
+            if (off < nj) break;
+            off -= nj;
+            j++;
+          }
+          if (off >= __shfl_sync(0xFFFFFFFFu, ns_lane, j)) continue;
+          const uint4 rv = ld_cg4(reinterpret_cast<const uint4*>(round_sites_buf(R, par, j)) + off);
           const uint32_t cj = c_first + j;
-          for (uint32_t i = vt; i < nsj; i += nvt) {
-            const uint4 rv = ld_cg4(sites + i);
-            const uint32_t p = rv.x;
-            uint32_t q, e;
-            if (rv.w & 0x40000000u) {  // span too long for the record: walk
-              q = next_pos(slots, A.n, p);
-              e = next_pos(slots, A.n, q) - 1;
-            } else {
-              q = p + ((rv.w >> 15) & 0x7FFFu);
-              e = p + (rv.w & 0x7FFFu);
-            }
-            const uint32_t span = e - p + 1;
-            if (span > VAL_MASK) atomicOr(&st->err, ERR_SPAN_OVERFLOW);
-            slots[p] = (rv.w & DOCSTART) | cj;
-            if (span == 2) {
-              slots[p + 1] = mk_back(1);
-            } else {
-              if (q != p + 1 && q != e) slots[q] = mk_hole();
-              slots[p + 1] = mk_span(span);
-              slots[e] = mk_back(span - 1);
-            }
+          const uint32_t p = rv.x;
+          uint32_t q, e;
+          if (rv.w & 0x40000000u) {  // span too long for the record: walk
+            q = next_pos(slots, A.n, p);
+            e = next_pos(slots, A.n, q) - 1;
+          } else {
+            q = p + ((rv.w >> 15) & 0x7FFFu);
+            e = p + (rv.w & 0x7FFFu);
+          }
+          const uint32_t span = e - p + 1;
+          if (span > VAL_MASK) atomicOr(&st->err, ERR_SPAN_OVERFLOW);
+          slots[p] = (rv.w & DOCSTART) | cj;
+          if (span == 2) {
+            slots[p + 1] = mk_back(1);
+          } else {
+            if (q != p + 1 && q != e) slots[q] = mk_hole();
+            slots[p + 1] = mk_span(span);
+            slots[e] = mk_back(span - 1);
           }
         }
       }
+      if (jprof && split && warp == wn) st->mg_prof_ns[1] += now_ns() - jt0;
       // ---- job 3: arg-max over the pairs that were already hot and that no valid merge touches ----
       if (!split || warp >= wn + wr) {
         const uint32_t vt = split ? (bid * wm + warp - wn - wr) * 32u + lane : gt, nvt = split ? nblk * wm * 32u : gn;
@@ -1058,10 +1148,12 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
           const uint32_t cv = t.cnt[hs];  // (in flight next to the role test)
           const uint32_t x = key >> 16, y = key & 0xFFFFu;
           bool skip = false;
-          for (uint32_t j2 = 0; j2 < v; j2++) {
-            if (hs == S.slot[j2]) skip = true;  // a winner: its count is being zeroed
-            if (y == S.a[j2] && ld_cg(round_row(R, par, j2, RW_DEC_L) + x) != 0) skip = true;  // job 1 hands in its new count
-            if (x == S.b[j2] && ld_cg(round_row(R, par, j2, RW_DEC_R) + y) != 0) skip = true;
+          if (role_maybe(S.filt_a, y) || role_maybe(S.filt_b, x) || role_maybe(S.filt_a, x)) {  // (a winner (a_j, b_j) passes the last test)
+            for (uint32_t j2 = 0; j2 < v; j2++) {
+              if (hs == S.slot[j2]) skip = true;  // a winner: its count is being zeroed
+              if (y == S.a[j2] && round_dec_of(R, par, j2, 0, x) != 0) skip = true;  // job 1 hands in its new count
+              if (x == S.b[j2] && round_dec_of(R, par, j2, 1, y) != 0) skip = true;
+            }
           }
           if (skip || !cv) continue;
           if (L.max_length && A.len16[x] + A.len16[y] > L.max_length) continue;
@@ -1069,20 +1161,28 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         }
       }
     }
+    if (jprof && warp == (blockDim.x >> 5) - 1u) st->mg_prof_ns[2] += now_ns() - jt0;
     {
       const Top2 tv = top2_block_reduce(mine, S.t2);
+      if (tid == 0 && S.keys_ins) atomicAdd(&st->n_keys, S.keys_ins);
       if (tid == 0) {
         R.gp[2 * bid] = make_uint4((uint32_t)tv.p0, (uint32_t)(tv.p0 >> 32), tv.s0, tv.m0);
         R.gp[2 * bid + 1] = make_uint4((uint32_t)tv.p1, (uint32_t)(tv.p1 >> 32), tv.s1, tv.m1);
         R.gk[2 * bid] = tv.k0;
         R.gk[2 * bid + 1] = tv.k1;
       }
-      if (tid < RB) S.fill_n[tid] = (tid < v) ? ld_cg(&rs->n_sites[par][tid]) : 0u;
+      if (tid < RB) S.fill_n[tid] = (tid < v) ? ld_cg(&rs->n_sites[par][tid].v) : 0u;
+    }
+    if (jprof && warp == 0) {
+      st->mg_prof_ns[3] += now_ns() - jt0;
+      st->mg_prof_ns[4] += 1;
     }
     F.v = v;
     F.par = par;
     F.k = k;
     F.c_first = c_first;
+    F.overflow = overflow;
+    if (lead) rs->overflow[par ^ 1u] = 0;  // (read by nobody before the next round's P2, set by nobody before its P1)
     it += v;
     RPROF(3)
     RBARRIER();
