@@ -921,7 +921,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_rounds, RD_THREADS, 0));
       if (per_sm < 1) return fail(e, BPE_E_CUDA, "k_merge_rounds does not fit on an SM");
       // (a decision folds two partial entries per block with one thread each)
-      const int most = std::min({e->sm_count * per_sm, (int)(R_QCAP / 2), RD_THREADS / 2});
+      const int most = std::min({e->sm_count * per_sm, (int)(R_QCAP / RT), RD_THREADS / RT});
       e->round_blocks = std::min(e->sm_count, most);
       if (const char* v = getenv("BPE_LOOP_BLOCKS")) e->round_blocks = std::max(1, std::min(atoi(v), most));
     }
@@ -935,8 +935,8 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       CK(e->r_state.reserve(1));
       CK(cudaMemsetAsync(e->r_state.p, 0, sizeof(RoundState), e->stream));
     }
-    CK(e->r_gp.reserve((size_t)2 * e->round_blocks));
-    CK(e->r_gk.reserve((size_t)2 * e->round_blocks));
+    CK(e->r_gp.reserve((size_t)RT * e->round_blocks));
+    CK(e->r_gk.reserve((size_t)RT * e->round_blocks));
   }
   CK(e->partials.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
   CK(e->partial_keys.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
@@ -1010,7 +1010,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       L.bar_ns = (uint32_t)std::max(32, std::min(ns, 4096));
     }
     const char* pf = getenv("BPE_LOOP_PREFETCH");  // read per launch: a tuning knob
-    L.prefetch = pf ? std::max(0, std::min(atoi(pf), 2)) : 1;
+    L.prefetch = pf ? std::max(0, std::min(atoi(pf), 2)) : (use_rounds ? 0 : 1);  // (k_merge_rounds: measured, the helper warps become the tail)
     L.replay = dev_replay ? dev_replay + 2 * done : nullptr;
     if (dev_replay) e->hot_valid = false;  // replayed merges do not feed the hot list
     static const bool trace = getenv("BPE_TRACE") != nullptr;
@@ -1111,6 +1111,9 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       uint64_t keys_after = (uint64_t)e->h_st->n_keys + new_keys;
       if (keys_after * 2 > e->tbl_cap) {
         uint64_t want = std::min<uint64_t>(keys_after * 5 / 2, 0x80000000ull);  // next power of two: load 0.2 .. 0.4
+        // a run over a big corpus ends with distinct pairs ~ 5 % of its positions (48 M for the 1 GB Zipf corpus): the first
+        // growth goes most of the way instead of doubling eleven times (a relaunch + rehash each)
+        want = std::max<uint64_t>(want, std::min<uint64_t>(e->n_slots / 16, 1ull << 27));
         if (keys_after * 2 > pow2_at_least(want)) {
           rc = fail(e, BPE_E_NOMEM, "pair table cannot grow further");
           break;

@@ -60,7 +60,7 @@ __host__ __device__ __forceinline__ uint32_t cell_dec(unsigned long long v) { re
 __host__ __device__ __forceinline__ uint32_t cell_len(unsigned long long v) { return (uint32_t)((v >> R_FIELD) & R_FMASK); }
 __host__ __device__ __forceinline__ uint32_t cell_cnt(unsigned long long v) { return (uint32_t)((v >> (2 * R_FIELD)) & R_FMASK); }
 constexpr uint32_t LOOP_NEED_LEGACY = 7;  // the winner is too big for the packed cells: k_merge_loop takes the merges above R_HUGE
-constexpr uint32_t R_QCAP = 384;         // per-block top-2 entries a decision can fold (2 x blocks)
+constexpr uint32_t R_QCAP = 512;         // per-block partial entries a decision can fold (RT x blocks)
 
 constexpr uint32_t ERR_ROUND_MISMATCH = 2048u;  // a merge of a round found a different number of sites than its count
 
@@ -90,8 +90,8 @@ struct RoundArgs {
   uint32_t* lists;            // [2][blocks][R_LISTCAP] cells each block touched first: (merge * 2 + side) << 16 | token
   SiteRec* bsites;   // [2][RB][R_SMALL]: merges 1.. of a round (merge 0 uses L.A.sites / L.sites2, which the host sizes)
   int bar_mode;      // 0: k_merge_loop's barrier (two sequentially consistent fences); 1: release arrival + acquire poll
-  uint4* gp;         // [2 * blocks] per-block top-2: (primary lo, primary hi, slot, mult)
-  uint32_t* gk;      // [2 * blocks] ... and the pair key of that slot
+  uint4* gp;         // [RT * blocks] per-block top groups: (primary lo, primary hi, slot, mult)
+  uint32_t* gk;      // [RT * blocks] ... and the pair key of that slot
   RoundState* rs;
   uint32_t kmax;     // merges per round (1 .. RB)
 };
@@ -144,38 +144,79 @@ __device__ __forceinline__ void grid_barrier_ra(unsigned long long* ctr, unsigne
 // shared-memory word for the 15 of 16 tokens that are not
 __device__ __forceinline__ bool role_maybe(const uint32_t* filt, uint32_t tok) { return (filt[(tok >> 5) & 7u] >> (tok & 31u)) & 1u; }
 
-// ---- top-2 groups: the two largest DISTINCT primaries, each with the number of pairs that share it and the smallest slot ----
+// ---- top-N groups: the RT largest DISTINCT primaries, each with the number of pairs that share it and the smallest slot ----
+// (what a block publishes for the next decision: the more groups per block, the deeper the exact candidate list reaches)
+#ifndef BPE_RT
+#define BPE_RT 2
+#endif
+constexpr int RT = BPE_RT;  // (3 reaches deeper -- 10 % fewer rounds on cfg3 -- but its reduction costs more than that saves: measured)
 struct Top2 {
-  unsigned long long p0, p1;
-  uint32_t s0, s1, m0, m1, k0, k1;
+  unsigned long long p[RT];
+  uint32_t s[RT], m[RT], k[RT];
 };
-__device__ __forceinline__ Top2 top2_empty() { return Top2{0ull, 0ull, NOSLOT, NOSLOT, 0u, 0u, 0u, 0u}; }
+__device__ __forceinline__ Top2 top2_empty() {
+  Top2 t;
+#pragma unroll
+  for (int i = 0; i < RT; i++) {
+    t.p[i] = 0ull;
+    t.s[i] = NOSLOT;
+    t.m[i] = 0u;
+    t.k[i] = 0u;
+  }
+  return t;
+}
 __device__ __forceinline__ void top2_add(Top2& t, unsigned long long p, uint32_t slot, uint32_t mult, uint32_t key) {
   if (!p) return;
-  if (p > t.p0) {
-    t.p1 = t.p0; t.s1 = t.s0; t.m1 = t.m0; t.k1 = t.k0;
-    t.p0 = p; t.s0 = slot; t.m0 = mult; t.k0 = key;
-  } else if (p == t.p0) {
-    t.m0 += mult;
-    if (slot < t.s0) { t.s0 = slot; t.k0 = key; }
-  } else if (p > t.p1) {
-    t.p1 = p; t.s1 = slot; t.m1 = mult; t.k1 = key;
-  } else if (p == t.p1) {
-    t.m1 += mult;
-    if (slot < t.s1) { t.s1 = slot; t.k1 = key; }
+  bool done = false;
+#pragma unroll
+  for (int i = 0; i < RT; i++) {
+    if (!done && p == t.p[i]) {
+      t.m[i] += mult;
+      if (slot < t.s[i]) {
+        t.s[i] = slot;
+        t.k[i] = key;
+      }
+      done = true;
+    }
+    if (!done && p > t.p[i]) {  // insert here, the smaller groups move down (the last one drops out)
+#pragma unroll
+      for (int j = RT - 1; j > i; j--) {
+        t.p[j] = t.p[j - 1];
+        t.s[j] = t.s[j - 1];
+        t.m[j] = t.m[j - 1];
+        t.k[j] = t.k[j - 1];
+      }
+      t.p[i] = p;
+      t.s[i] = slot;
+      t.m[i] = mult;
+      t.k[i] = key;
+      done = true;
+    }
   }
 }
 __device__ __forceinline__ Top2 top2_warp_reduce(Top2 v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long q0 = __shfl_xor_sync(0xFFFFFFFFu, v.p0, o), q1 = __shfl_xor_sync(0xFFFFFFFFu, v.p1, o);
-    uint32_t s0 = __shfl_xor_sync(0xFFFFFFFFu, v.s0, o), s1 = __shfl_xor_sync(0xFFFFFFFFu, v.s1, o);
-    uint32_t m0 = __shfl_xor_sync(0xFFFFFFFFu, v.m0, o), m1 = __shfl_xor_sync(0xFFFFFFFFu, v.m1, o);
-    uint32_t k0 = __shfl_xor_sync(0xFFFFFFFFu, v.k0, o), k1 = __shfl_xor_sync(0xFFFFFFFFu, v.k1, o);
-    top2_add(v, q0, s0, m0, k0);
-    top2_add(v, q1, s1, m1, k1);
+    Top2 w;
+#pragma unroll
+    for (int i = 0; i < RT; i++) {
+      w.p[i] = __shfl_xor_sync(0xFFFFFFFFu, v.p[i], o);
+      w.s[i] = __shfl_xor_sync(0xFFFFFFFFu, v.s[i], o);
+      w.m[i] = __shfl_xor_sync(0xFFFFFFFFu, v.m[i], o);
+      w.k[i] = __shfl_xor_sync(0xFFFFFFFFu, v.k[i], o);
+    }
+#pragma unroll
+    for (int i = 0; i < RT; i++) top2_add(v, w.p[i], w.s[i], w.m[i], w.k[i]);
   }
   return v;
+}
+// a block's groups -> its RT entries of the partial arrays
+__device__ __forceinline__ void top2_publish(const Top2& v, uint4* gp, uint32_t* gk, uint32_t bid) {
+#pragma unroll
+  for (int i = 0; i < RT; i++) {
+    gp[RT * bid + i] = make_uint4((uint32_t)v.p[i], (uint32_t)(v.p[i] >> 32), v.s[i], v.m[i]);
+    gk[RT * bid + i] = v.k[i];
+  }
 }
 
 // shared memory of one block of k_merge_rounds
@@ -569,10 +610,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     }
     const Top2 v = top2_block_reduce(mine, S.t2);
     if (tid == 0) {
-      R.gp[2 * bid] = make_uint4((uint32_t)v.p0, (uint32_t)(v.p0 >> 32), v.s0, v.m0);
-      R.gp[2 * bid + 1] = make_uint4((uint32_t)v.p1, (uint32_t)(v.p1 >> 32), v.s1, v.m1);
-      R.gk[2 * bid] = v.k0;
-      R.gk[2 * bid + 1] = v.k1;
+      top2_publish(v, R.gp, R.gk, bid);
     }
     if (tid < RB) S.fill_n[tid] = 0;
     if (tid < 2) S.ncell[tid] = 0;
@@ -602,7 +640,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     {
       unsigned long long myp = 0;
       uint32_t mys = NOSLOT, mym = 0, myk = 0;
-      if (tid < 2 * nblk) {
+      if (tid < RT * nblk) {
         const uint4 v = ld_cg4(R.gp + tid);
         myp = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
         mys = v.z;
@@ -618,8 +656,8 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
       if (tid == 320) S.g_n_keys = ld_cg(&st->n_keys);  // (stable here: they only change in P2)
       if (tid == 321) S.g_pool_cursor = ld_cg(&st->pool_cursor);
       if (tid == 322) S.g_snap_err = ld_cg(&st->snap_err);
-      // the list of candidates is exact down to the largest second-best primary any block published
-      const unsigned long long Lcut = block_max_u64((tid & 1u) ? myp : 0ull, S.red);  // (syncs inside: qn / cp are visible)
+      // the list of candidates is exact down to the largest LAST (RT-th best) primary any block published
+      const unsigned long long Lcut = block_max_u64((tid % RT == RT - 1) ? myp : 0ull, S.red);  // (syncs inside: qn / cp are visible)
       if (myp && myp >= Lcut) {
         const uint32_t k = atomicAdd(&S.qn, 1u);
         S.qp[k] = myp;
@@ -852,6 +890,25 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         const uint32_t hvt = (bid * wh + warp - ws) * 32u + lane, hnvt = nblk * wh * 32u;
         if (F.v) round_fill_all(R, S, F, hvt, hnvt);
         if (F.k) round_clear_cells(R, S, F, (warp - ws) * 32u + lane, wh * 32u, hvt, hnvt);
+        // Speculation: the candidates the batch left behind are the most likely members of the next one.  The helper warps
+        // pull their occurrence lists and the corpus lines around the occurrences into L2, so that the next site pass -- a chain
+        // of dependent loads -- finds them there instead of in DRAM.  Hints only: nothing depends on them.
+        if (L.prefetch) {
+          uint32_t budget = 32768u;
+          for (uint32_t j = k; j < RB && budget; j++) {
+            if (!S.cp[j]) break;
+            const uint32_t len = min(S.cll[j], budget), start = S.cls[j];
+            for (uint32_t i = hvt; i < len; i += hnvt) {
+              const uint32_t pp = ld_cg(A.pool + start + i);
+              if (pp >= A.n) continue;
+              const uint32_t* q = A.slots + pp;
+              prefetch_l2(q);
+              if (pp >= 12u) prefetch_l2(q - 12);
+              if (pp + 28u < A.n) prefetch_l2(q + 28);
+            }
+            budget -= len;
+          }
+        }
       }
     }
     RPROF(1)
@@ -1165,11 +1222,15 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     {
       const Top2 tv = top2_block_reduce(mine, S.t2);
       if (tid == 0 && S.keys_ins) atomicAdd(&st->n_keys, S.keys_ins);
+      if (tid < 2 && tv.p[0]) {  // the next decision reads the list fields of its candidates: ask for them now
+        const uint32_t ps = tid == 0 ? tv.s[0] : tv.s[RT - 1];
+        if (ps != NOSLOT) {
+          prefetch_l2(t.occ_start + ps);
+          prefetch_l2(t.occ_len + ps);
+        }
+      }
       if (tid == 0) {
-        R.gp[2 * bid] = make_uint4((uint32_t)tv.p0, (uint32_t)(tv.p0 >> 32), tv.s0, tv.m0);
-        R.gp[2 * bid + 1] = make_uint4((uint32_t)tv.p1, (uint32_t)(tv.p1 >> 32), tv.s1, tv.m1);
-        R.gk[2 * bid] = tv.k0;
-        R.gk[2 * bid + 1] = tv.k1;
+        top2_publish(tv, R.gp, R.gk, bid);
       }
       if (tid < RB) S.fill_n[tid] = (tid < v) ? ld_cg(&rs->n_sites[par][tid].v) : 0u;
     }
