@@ -189,6 +189,8 @@ struct bpe_engine {
   DevBuf<uint4> r_gp;
   DevBuf<uint32_t> r_gk;
   DevBuf<RoundState> r_state;
+  DevBuf<unsigned long long> r_gcells;  // sharded rounds: the deltas summed over the ranks
+  DevBuf<uint32_t> r_glists;
   int round_blocks = 0;  // co-resident grid of k_merge_rounds
   int host_loop = 0;     // debug: drive mergeUntil from the host, one launch per phase
   int scan_mode = 0;     // debug: walk all slots instead of occurrence lists
@@ -890,6 +892,63 @@ int append_docs_dev(bpe_engine* e, const int32_t* dev_ids, const int64_t* host_o
 }
 
 
+// buffers of k_merge_rounds (round_kernels.cuh): delta cells, slot rows, per-block cell lists, site buffers, partials
+int ensure_round_buffers(bpe_engine* e) {
+  if (!e->round_blocks) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_rounds, RD_THREADS, 0));
+    if (per_sm < 1) return fail(e, BPE_E_CUDA, "k_merge_rounds does not fit on an SM");
+    // (a decision folds RT partial entries per block with one thread each)
+    const int most = std::min({e->sm_count * per_sm, (int)(R_QCAP / RT), RD_THREADS / RT});
+    e->round_blocks = std::min(e->sm_count, most);
+    if (const char* v = getenv("BPE_LOOP_BLOCKS")) e->round_blocks = std::max(1, std::min(atoi(v), most));
+  }
+  const size_t cells = (size_t)2 * RB * 2 * ND_STRIDE;
+  if (!e->r_cells.p) {
+    CK(e->r_cells.reserve(cells));
+    CK(cudaMemsetAsync(e->r_cells.p, 0, cells * 8, e->stream));  // the kernel keeps the cells zero between launches
+    CK(e->r_slotrows.reserve(cells));
+    CK(e->r_lists.reserve((size_t)2 * e->round_blocks * R_LISTCAP));
+    CK(e->r_bsites.reserve((size_t)2 * RB * R_SMALL));
+    CK(e->r_state.reserve(1));
+    CK(cudaMemsetAsync(e->r_state.p, 0, sizeof(RoundState), e->stream));
+  }
+  if (e->mg_world > 1 && !e->r_gcells.p) {
+    CK(e->r_gcells.reserve(cells));
+    CK(cudaMemsetAsync(e->r_gcells.p, 0, cells * 8, e->stream));
+    CK(e->r_glists.reserve((size_t)2 * e->round_blocks * R_LISTCAP));
+  }
+  CK(e->r_gp.reserve((size_t)RT * e->round_blocks));
+  CK(e->r_gk.reserve((size_t)RT * e->round_blocks));
+  return BPE_OK;
+}
+
+RoundArgs round_args(bpe_engine* e, const LoopArgs& L, int round_k) {
+  RoundArgs RA{};
+  RA.L = L;
+  RA.cells = e->r_cells.p;
+  RA.slotrows = e->r_slotrows.p;
+  RA.lists = e->r_lists.p;
+  RA.bsites = e->r_bsites.p;
+  RA.gp = e->r_gp.p;
+  RA.gk = e->r_gk.p;
+  RA.rs = e->r_state.p;
+  RA.kmax = (uint32_t)round_k;
+  RA.bar_mode = 1;
+  if (const char* v = getenv("BPE_LOOP_BAR")) RA.bar_mode = atoi(v) ? 1 : 0;
+  RA.mg_on = 0;
+  RA.gcells = e->r_gcells.p;
+  RA.glists = e->r_glists.p;
+  return RA;
+}
+
+void round_stats(bpe_engine* e, const RoundState& hrs) {
+  e->stats.loop_rounds = (int64_t)hrs.rounds;
+  e->stats.loop_round_merges = (int64_t)hrs.round_merges;
+  e->stats.loop_round_tried = (int64_t)hrs.tried;
+  e->stats.loop_rounds_cut = (int64_t)hrs.rounds_cut_born;
+}
+
 // ---- mergeUntil: persistent cooperative kernel, the host only grows buffers / rebuilds the hot list -----------
 int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_t max_iterations, bpe_merge* log,
                        int64_t log_cap, int64_t* n_done, const int32_t* dev_replay = nullptr) {
@@ -915,29 +974,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
   int round_k = RB;
   if (const char* v = getenv("BPE_LOOP_ROUNDS")) use_rounds = use_rounds && atoi(v) != 0;
   if (const char* v = getenv("BPE_LOOP_K")) round_k = std::max(1, std::min(atoi(v), (int)RB));
-  if (use_rounds) {
-    if (!e->round_blocks) {
-      int per_sm = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_merge_rounds, RD_THREADS, 0));
-      if (per_sm < 1) return fail(e, BPE_E_CUDA, "k_merge_rounds does not fit on an SM");
-      // (a decision folds two partial entries per block with one thread each)
-      const int most = std::min({e->sm_count * per_sm, (int)(R_QCAP / RT), RD_THREADS / RT});
-      e->round_blocks = std::min(e->sm_count, most);
-      if (const char* v = getenv("BPE_LOOP_BLOCKS")) e->round_blocks = std::max(1, std::min(atoi(v), most));
-    }
-    if (!e->r_cells.p) {
-      const size_t cells = (size_t)2 * RB * 2 * ND_STRIDE;
-      CK(e->r_cells.reserve(cells));
-      CK(cudaMemsetAsync(e->r_cells.p, 0, cells * 8, e->stream));  // the kernel keeps the cells zero between launches
-      CK(e->r_slotrows.reserve(cells));
-      CK(e->r_lists.reserve((size_t)2 * e->round_blocks * R_LISTCAP));
-      CK(e->r_bsites.reserve((size_t)2 * RB * R_SMALL));
-      CK(e->r_state.reserve(1));
-      CK(cudaMemsetAsync(e->r_state.p, 0, sizeof(RoundState), e->stream));
-    }
-    CK(e->r_gp.reserve((size_t)RT * e->round_blocks));
-    CK(e->r_gk.reserve((size_t)RT * e->round_blocks));
-  }
+  if (use_rounds) TRY(ensure_round_buffers(e));
   CK(e->partials.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
   CK(e->partial_keys.reserve((size_t)std::max(e->loop_blocks, e->grid(8))));
   CK(e->sites.reserve(1u << 16, 0, e->stream, 1.0));
@@ -1024,18 +1061,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       void* args[] = {&L};
       ce = cudaLaunchCooperativeKernel((void*)k_merge_loop, dim3(e->loop_blocks), dim3(ML_THREADS), args, 0, e->stream);
     } else if (use_rounds) {
-      RoundArgs RA;
-      RA.L = L;
-      RA.cells = e->r_cells.p;
-      RA.slotrows = e->r_slotrows.p;
-      RA.lists = e->r_lists.p;
-      RA.bsites = e->r_bsites.p;
-      RA.gp = e->r_gp.p;
-      RA.gk = e->r_gk.p;
-      RA.rs = e->r_state.p;
-      RA.kmax = (uint32_t)round_k;
-      RA.bar_mode = 1;
-      if (const char* v = getenv("BPE_LOOP_BAR")) RA.bar_mode = atoi(v) ? 1 : 0;
+      RoundArgs RA = round_args(e, L, round_k);
       k_rounds_prepare<<<1, 32, 0, e->stream>>>(e->r_state.p);
       e->stats.kernel_launches++;
       void* rargs[] = {&RA};
@@ -1155,10 +1181,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       RoundState hrs;
       CK(cudaMemcpyAsync(&hrs, e->r_state.p, sizeof(RoundState), cudaMemcpyDeviceToHost, e->stream));
       CK(cudaStreamSynchronize(e->stream));
-      e->stats.loop_rounds = (int64_t)hrs.rounds;
-      e->stats.loop_round_merges = (int64_t)hrs.round_merges;
-      e->stats.loop_round_tried = (int64_t)hrs.tried;
-      e->stats.loop_rounds_cut = (int64_t)hrs.rounds_cut_born;
+      round_stats(e, hrs);
       static const bool trace_r = getenv("BPE_TRACE") != nullptr;
       if (trace_r)
         fprintf(stderr, "[bpe] rounds %llu, merges %llu (tried %llu), cut by the born-pair bound %llu, single %llu; batch ends: cap %llu, no-candidate %llu, tie %llu, big %llu, "
@@ -1235,6 +1258,16 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
   CK(e->mg_touched.reserve((size_t)4 * BPE_MAX_TOKENS + 64));
   CK(e->mg_tie_sorted.reserve(e->mg_tie_cap));
   CK(e->mg_newpair.reserve((size_t)2 * BPE_MAX_TOKENS + 64));
+  // several exact merges per barrier round and ONE exchange per round (round_kernels.cuh); BPE_LOOP_ROUNDS=0 keeps k_merge_loop_mg
+  bool use_rounds = true;
+  int round_k = RB;
+  if (const char* v = getenv("BPE_LOOP_ROUNDS")) use_rounds = atoi(v) != 0;
+  if (const char* v = getenv("BPE_LOOP_K")) round_k = std::max(1, std::min(atoi(v), (int)RB));
+  if (use_rounds) {
+    TRY(ensure_round_buffers(e));
+    CK(e->sites2.reserve(std::max<size_t>(e->sites.cap, 1u << 16), 0, e->stream, 1.0));
+  }
+  bool legacy_above = false;
   cudaEvent_t t0, t1;
   CK(cudaEventCreate(&t0));
   CK(cudaEventCreate(&t1));
@@ -1298,10 +1331,30 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
     auto tw0 = std::chrono::steady_clock::now();
     k_loop_prepare<<<1, 32, 0, e->stream>>>(e->d_st.p, (uint32_t)e->n_tokens, e->barrier.p);
     e->stats.kernel_launches++;
-    void* args[] = {&P};
-    ce = cudaLaunchCooperativeKernel((void*)k_merge_loop_mg, dim3(e->mg_loop_blocks), dim3(ML_THREADS), args, 0, e->stream);
+    if (use_rounds && !legacy_above) {
+      L.sites2 = e->sites2.p;
+      L.A.sites_cap = (uint32_t)std::min<size_t>(L.A.sites_cap, e->sites2.cap);
+      L.p1_sites = 12;
+      L.p2_new = 10;
+      L.p2_rw = 2;
+      L.bar_ns = 256;
+      L.prefetch = 0;
+      RoundArgs RA = round_args(e, L, round_k);
+      RA.mg_on = 1;
+      RA.mg = P.M;
+      k_rounds_prepare<<<1, 32, 0, e->stream>>>(e->r_state.p);
+      e->stats.kernel_launches++;
+      void* rargs[] = {&RA};
+      ce = cudaLaunchCooperativeKernel((void*)k_merge_rounds, dim3(e->round_blocks), dim3(RD_THREADS), rargs, 0, e->stream);
+    } else {
+      // (rounds: the winner has more sites than the packed delta cells can count -- k_merge_loop_mg takes the merges above
+      // R_HUGE, it stops, "done", at the first winner at or below it)
+      if (use_rounds) L.min_weight = (uint32_t)std::max<int64_t>(mw, (int64_t)R_HUGE + 1);
+      void* args[] = {&P};
+      ce = cudaLaunchCooperativeKernel((void*)k_merge_loop_mg, dim3(e->mg_loop_blocks), dim3(ML_THREADS), args, 0, e->stream);
+    }
     if (ce != cudaSuccess) {
-      rc = fail(e, BPE_E_CUDA, "cooperative launch of k_merge_loop_mg: %s", cudaGetErrorString(ce));
+      rc = fail(e, BPE_E_CUDA, "cooperative launch of the sharded mergeUntil kernel: %s", cudaGetErrorString(ce));
       break;
     }
     e->stats.kernel_launches++;
@@ -1344,6 +1397,14 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
     }
     host_ms[3] += since(tl);
     uint32_t status = e->h_st->status;
+    if (use_rounds && legacy_above && status == LOOP_DONE && (int64_t)e->h_st->best_cnt >= mw) {
+      legacy_above = false;  // below R_HUGE now: back to the rounds
+      continue;
+    }
+    if (status == LOOP_NEED_LEGACY) {
+      legacy_above = true;
+      continue;
+    }
     if (status == LOOP_DONE || status == LOOP_EMPTY) break;
     if (status == LOOP_LIMIT) continue;
     if (status == LOOP_NEED_REBUILD) {
@@ -1370,6 +1431,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
       uint64_t keys_after = (uint64_t)e->h_st->n_keys + new_keys;
       if (keys_after * 2 > e->tbl_cap) {
         uint64_t want = std::min<uint64_t>(keys_after * 5 / 2, 0x80000000ull);
+        want = std::max<uint64_t>(want, std::min<uint64_t>((uint64_t)e->n_slots * e->mg_world / 16, 1ull << 27));  // (the keys are global)
         if (keys_after * 2 > pow2_at_least(want)) {
           rc = fail(e, BPE_E_NOMEM, "pair table cannot grow further");
           break;
@@ -1379,6 +1441,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
         if (trace) fprintf(stderr, "[bpe r%d] grow_table -> %u slots: %.1f ms\n", e->mg_rank, e->tbl_cap, since(tt));
       }
       uint64_t pool_after = (uint64_t)e->h_st->pool_cursor + 4 * w;  // the in-kernel test is one merge conservative
+      if (use_rounds) pool_after += (uint64_t)(2 * RB) * w + 2ull * e->round_blocks * R_POOL_CHUNK;  // ... one ROUND conservative there
       auto tp = clk();
       if (pool_after > 0xFFFFFFF0ull) {
         rc = fail(e, BPE_E_DOMAIN, "occurrence pool exceeds 2^32 cells");
@@ -1386,6 +1449,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
       }
       if ((ce = e->pool.reserve((size_t)pool_after, e->h_st->pool_cursor, e->stream, 1.5)) != cudaSuccess ||
           (ce = e->sites.reserve((size_t)w, 0, e->stream, 1.25)) != cudaSuccess ||
+          (use_rounds && (ce = e->sites2.reserve(e->sites.cap, 0, e->stream, 1.0)) != cudaSuccess) ||
           (ce = e->newslots.reserve((size_t)new_keys, 0, e->stream, 1.25)) != cudaSuccess ||
           (ce = e->hot.reserve((size_t)e->h_st->hot_n + 2 * new_keys, e->h_st->hot_n, e->stream, 1.5)) != cudaSuccess ||
           (ce = e->cands.reserve((size_t)e->h_st->best_mult, 0, e->stream, 1.5)) != cudaSuccess) {
@@ -1413,6 +1477,20 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
     e->live_tokens = e->h_st->live_tokens;
     e->stats.sites_merged = (int64_t)e->h_st->sites_total;
     e->stats.tie_breaks = e->h_st->tie_breaks;
+    if (use_rounds) {
+      RoundState hrs;
+      CK(cudaMemcpyAsync(&hrs, e->r_state.p, sizeof(RoundState), cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      round_stats(e, hrs);
+      if (getenv("BPE_TRACE") && e->mg_rank == 0) {
+        const unsigned long long* f = e->h_st->fine_ns;
+        const double ns = std::max(1.0, (double)f[5]), nb = std::max(1.0, (double)f[11]);
+        fprintf(stderr, "[bpe r0] rounds %llu, merges %llu (tried %llu); block 0, us per round of small merges (%.0f): decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f; "
+                        "of big merges (%.0f): decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f; exchange (emit..summed) ms %.1f\n", hrs.rounds, hrs.round_merges, hrs.tried,
+                (double)f[5], f[0] / ns * 1e-3, f[1] / ns * 1e-3, f[2] / ns * 1e-3, f[3] / ns * 1e-3, f[4] / ns * 1e-3, (double)f[11], f[6] / nb * 1e-3, f[7] / nb * 1e-3,
+                f[8] / nb * 1e-3, f[9] / nb * 1e-3, f[10] / nb * 1e-3, (double)e->h_st->prof_ns[5] * 1e-6);
+      }
+    }
     if (getenv("BPE_TRACE") && e->mg_rank == 0) {
       fprintf(stderr, "[bpe r0] mg phases ms (decide, P1, wait, M1, wait, send+local P2, barrier+peer wait, apply, wait, P3, wait, tie):");
       for (int i = 0; i < 12; i++) fprintf(stderr, " %.1f", (double)e->h_st->mg_prof_ns[i] * 1e-6);
@@ -1827,7 +1905,8 @@ int bpe_mg_init(bpe_engine* e, int rank, int world, void* handle_out64) {
   if (e->mg_mailbox) return fail(e, BPE_E_INVALID, "bpe_mg_init called twice");
   e->mg_rank = rank;
   e->mg_world = world;
-  e->mg_inbox_stride = MG_HDR + 4u * BPE_MAX_TOKENS + 64u;
+  // records one rank can send per exchange (k_merge_rounds: the cells of up to 16 merges a round; k_merge_loop_mg: of one merge)
+  e->mg_inbox_stride = 1u << 20;
   e->mg_tie_cap = 4096;
   size_t bytes = (size_t)2 * MG_MAX_WORLD * 128 + (size_t)2 * world * e->mg_inbox_stride * 8 + (size_t)2 * world * e->mg_tie_cap * 4;
   CK(cudaMalloc(&e->mg_mailbox, bytes));

@@ -37,6 +37,7 @@
 // count is unchanged; equal keys never enter a batch (position tie-breaks run alone, through the path k_merge_loop uses).
 #pragma once
 #include "train_kernels.cuh"
+#include "mg_kernels.cuh"
 
 namespace bpe {
 
@@ -78,6 +79,13 @@ struct RoundState {
   Line n_sites[2][RB];
   Line64 ub[2][RB];
   uint32_t overflow[2];   // a block's list of touched cells was full: the round scans the rows instead
+  // sharded corpus: what the exchange of a round folds out of the ranks' message headers (same values on every rank)
+  uint32_t goverflow[2];            // a block's list of GLOBAL cells was full
+  uint32_t mg_n[MG_MAX_WORLD];      // records each rank sent
+  unsigned long long mg_ub[RB];     // sum over ranks of the U bounds (left | right << 32): bounds of the global counts
+  uint32_t mg_ns[RB];               // sites of merge j on all ranks
+  uint32_t mg_k;                    // merges every rank tried (the smallest batch)
+  uint32_t mg_pad;
   unsigned long long rounds, round_merges, rounds_cut_born, rounds_single, tried;
   unsigned long long stop_reason[8];
   unsigned long long iters_small, iters_big, cells_small, cells_big, sites_small, sites_big;  // P1 warp-iterations, touched cells, sites  // why a batch was not extended: 0 cap, 1 no exact candidate, 2 tie, 3 big, 4 token, 5 fresh token, 6 limits
@@ -94,6 +102,13 @@ struct RoundArgs {
   uint32_t* gk;      // [RT * blocks] ... and the pair key of that slot
   RoundState* rs;
   uint32_t kmax;     // merges per round (1 .. RB)
+  // corpus sharded by document over several GPUs (mg_kernels.cuh): the counts of the pair table are global and replicated, the
+  // cells above hold THIS shard's deltas; once per round every rank stores its non-empty cells as records into every rank's
+  // inbox over NVLink, and every rank sums all records into gcells -- the global deltas P2 then works from
+  int mg_on;
+  MgArgs mg;
+  unsigned long long* gcells;  // [2][RB][2][ND_STRIDE]: decrements | counted occurrences << 21, summed over the ranks
+  uint32_t* glists;            // [2][blocks][R_LISTCAP]: global cells each block touched first while summing
 };
 
 __device__ __forceinline__ unsigned long long* round_cells(const RoundArgs& R, uint32_t par, uint32_t j, uint32_t side) {
@@ -106,8 +121,14 @@ __device__ __forceinline__ uint32_t* round_list(const RoundArgs& R, uint32_t par
   return R.lists + ((size_t)par * gridDim.x + blockIdx.x) * R_LISTCAP;
 }
 // decrements of the old pair a later merge holds in ITS cell of token `tok` (cross-reads of P2: nobody writes the cells then)
+__device__ __forceinline__ unsigned long long* round_gcells(const RoundArgs& R, uint32_t par, uint32_t j, uint32_t side) {
+  return R.gcells + (((size_t)par * RB + j) * 2u + side) * ND_STRIDE;
+}
+__device__ __forceinline__ uint32_t* round_glist(const RoundArgs& R, uint32_t par) {
+  return R.glists + ((size_t)par * gridDim.x + blockIdx.x) * R_LISTCAP;
+}
 __device__ __forceinline__ uint32_t round_dec_of(const RoundArgs& R, uint32_t par, uint32_t j, uint32_t side, uint32_t tok) {
-  return cell_dec(ld_cg(round_cells(R, par, j, side) + tok));
+  return cell_dec(ld_cg((R.mg_on ? round_gcells(R, par, j, side) : round_cells(R, par, j, side)) + tok));  // (both layouts keep it in the low bits)
 }
 
 // Site record of a round: x = p, y = position of the left token of the born left adjacency (NOPOS: none),
@@ -232,8 +253,10 @@ struct RoundSm {
   uint32_t qs[R_QCAP], qm[R_QCAP], qk[R_QCAP];
   unsigned long long cp[RB];
   uint32_t cs[RB], cm[RB], ck[RB], cls[RB], cll[RB], clen[RB];
-  uint32_t g_n_keys, g_pool_cursor, g_snap_err, pad1;
+  uint32_t g_n_keys, g_pool_cursor, g_snap_err, g_abort;
+  uint32_t gv[8];  // sharded: the folded header values (OR of the ranks' error flags, minima of their capacities)
   uint32_t ncell[2];  // cells this block touched first in the round of either parity (entries of its list)
+  uint32_t gncell[2]; // sharded: global cells this block touched first while summing the ranks' records
   uint32_t pool_next, pool_end;  // this block's private chunk of the occurrence pool (list space without a grid-wide atomic)
   uint32_t keys_ins;             // keys this block inserted in the current P2 (one n_keys atomic per block and round)
   uint32_t filt_a[8], filt_b[8]; // role_maybe filters: the a's / the b's of the batch
@@ -313,6 +336,193 @@ __device__ __forceinline__ uint32_t cell_add_warp(const RoundArgs& R, RoundSm& S
     }
   }
   return nc;
+}
+
+// ---- sharded corpus: the message of a round ----
+// u64 words of one (parity, sender) area of an inbox: MGR_HDR words of header, then the records.
+//   [0..5]   the twelve u32 of mg_kernels' header (H_N records, H_ERR, capacities)
+//   [8 + j]  U bounds of merge j on the sender (left | right << 32)       [24 + j]  sites of merge j on the sender
+//   [40]     merges the sender tried (its batch; every rank commits at most the smallest)
+// record: ((merge * 2 + side) << 16 | token) << 42 | counted occurrences << 21 | decrements
+constexpr uint32_t MGR_HDR = 64;
+
+// X1: this rank's touched cells -> records in every rank's inbox (every block: the cells of its own list)
+__device__ __forceinline__ void mgr_emit(const RoundArgs& R, const RoundSm& S, uint32_t par, uint32_t epar, uint32_t k, uint32_t c_hi) {
+  const MgArgs& M = R.mg;
+  DevState* st = R.L.A.st;
+  const uint32_t cap = M.inbox_stride - MGR_HDR;
+  const uint32_t lane = lane_id();
+  auto emit = [&](bool has, uint32_t js, uint32_t tok, unsigned long long cellv) {
+    has = has && (cell_dec(cellv) | cell_cnt(cellv)) != 0u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
+    if (!m) return;
+    uint32_t base = 0;
+    const int src = __ffs(m) - 1;
+    if ((int)lane == src) base = atomicAdd(&st->n_out, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, src);
+    if (has) {
+      const uint32_t at = base + __popc(m & ((1u << lane) - 1u));
+      if (at < cap) {
+        const unsigned long long rec = ((unsigned long long)((js << 16) | tok) << 42) | ((unsigned long long)cell_cnt(cellv) << R_FIELD) | cell_dec(cellv);
+        for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MGR_HDR + at] = rec;
+      } else {
+        atomicOr(&st->err, ERR_INBOX_OVERFLOW);
+      }
+    }
+  };
+  if (!ld_cg(&R.rs->overflow[par])) {
+    const uint32_t n = S.ncell[par];
+    const uint32_t* list = round_list(R, par);
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+      const uint32_t idx = base + threadIdx.x;
+      const uint32_t ent = idx < n ? ld_cg(list + idx) : 0u;
+      const uint32_t js = (ent >> 16) & (2u * RB - 1u), tok = ent & 0xFFFFu;
+      emit(idx < n, js, tok, idx < n ? ld_cg(round_cells(R, par, js >> 1, js & 1u) + tok) : 0ull);
+    }
+  } else {
+    const uint32_t T = (c_hi + 31u) & ~31u;
+    const uint32_t total = k * 2u * T;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const uint32_t js = i / T, tok = i - js * T;
+      emit(true, js, tok, ld_cg(round_cells(R, par, js >> 1, js & 1u) + tok));
+    }
+  }
+}
+
+// warp 0 of block 0, lane q talks to rank q: header of this rank's message, then the flag
+__device__ __forceinline__ void mgr_send_warp(const RoundArgs& R, uint32_t par, uint32_t epar, uint32_t k, unsigned long long epoch) {
+  const MgArgs& M = R.mg;
+  const LoopArgs& L = R.L;
+  DevState* st = L.A.st;
+  const int q = (int)lane_id();
+  if (q < M.world) {
+    const uint32_t cur = ld_cg(&st->pool_cursor);
+    uint32_t h[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) h[i] = 0;
+    h[H_N] = min(ld_cg(&st->n_out), M.inbox_stride - MGR_HDR);
+    h[H_ERR] = ld_cg(&st->err);
+    h[H_POOL_FREE] = L.pool_cap > cur ? L.pool_cap - cur : 0;
+    h[H_SITES_CAP] = L.A.sites_cap;
+    h[H_NEW_CAP] = 0xFFFFFFFFu;
+    h[H_HOT_CAP] = min(L.hot_cap, L.hot_limit);
+    h[H_LEN16_CAP] = L.len16_cap;
+    h[H_TBL_CAP] = L.tbl_cap;
+    h[H_CAND_CAP] = min(L.cand_cap, M.tie_cap);
+    unsigned long long* dst = mg_area(M, q, epar, M.rank);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 3; i++) d4[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+    for (uint32_t j = 0; j < RB; j++) {
+      dst[8 + j] = j < k ? ld_cg(&R.rs->ub[par][j].v) : 0ull;
+      dst[24 + j] = j < k ? (unsigned long long)ld_cg(&R.rs->n_sites[par][j].v) : 0ull;
+    }
+    dst[40] = k;
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (q < M.world && q != M.rank) st_release_sys(M.flag_data[q] + 16 * M.rank, epoch);
+}
+
+// ... wait for every peer's flag, then fold the headers: OR of the error flags, minima of the capacities (st->g_vals, as
+// mg_kernels.cuh), sums of the per-merge bounds and site counts, the smallest batch
+__device__ __forceinline__ void mgr_wait_fold_warp(const RoundArgs& R, uint32_t epar, unsigned long long epoch) {
+  const MgArgs& M = R.mg;
+  DevState* st = R.L.A.st;
+  RoundState* rs = R.rs;
+  const int q = (int)lane_id();
+  if (q < M.world && q != M.rank) {
+    const unsigned long long* f = M.flag_data[M.rank] + 16 * q;
+    const unsigned long long t0 = now_ns();
+    uint32_t ns = 16;
+    while (ld_acquire_sys(f) < epoch) {
+      __nanosleep(ns);
+      if (ns < 128) ns <<= 1;
+      if (now_ns() - t0 > MG_TIMEOUT_NS) {
+        atomicOr(&st->err, ERR_PEER_TIMEOUT);
+        st->mg_abort = 1;
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  uint32_t w[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) w[i] = (i == H_ERR) ? 0u : 0xFFFFFFFFu;
+  uint32_t kq = 0xFFFFFFFFu;
+  if (q < M.world) {
+    const unsigned long long* hq = mg_area(M, M.rank, epar, q);
+    const uint4* h4 = reinterpret_cast<const uint4*>(hq);
+    const uint4 v0 = ld_cg4(h4), v1 = ld_cg4(h4 + 1), v2 = ld_cg4(h4 + 2);
+    w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w; w[8] = v2.x; w[9] = v2.y; w[10] = v2.z; w[11] = v2.w;
+    rs->mg_n[q] = w[H_N];
+    kq = (uint32_t)ld_cg(hq + 40);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = H_ERR; i <= H_CAND_CAP; i++) {
+      const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, w[i], o);
+      w[i] = (i == H_ERR) ? (w[i] | other) : min(w[i], other);
+    }
+    kq = min(kq, __shfl_xor_sync(0xFFFFFFFFu, kq, o));
+  }
+  if (q == 0) {
+    uint4* g = reinterpret_cast<uint4*>(st->g_vals);
+    g[0] = make_uint4(w[H_ERR], w[H_POOL_FREE], w[H_SITES_CAP], w[H_NEW_CAP]);
+    g[1] = make_uint4(w[H_HOT_CAP], w[H_LEN16_CAP], w[H_TBL_CAP], w[H_CAND_CAP]);
+    rs->mg_k = kq;
+  }
+  if (q < RB) {  // lane j sums merge j's bounds and sites over the senders
+    unsigned long long ul = 0, ur = 0;
+    uint32_t nsum = 0;
+    for (int s = 0; s < M.world; s++) {
+      const unsigned long long* hs = mg_area(M, M.rank, epar, s);
+      const unsigned long long u = ld_cg(hs + 8 + q);
+      ul += (uint32_t)u;
+      ur += (uint32_t)(u >> 32);
+      nsum += (uint32_t)ld_cg(hs + 24 + q);
+    }
+    rs->mg_ub[q] = min(ul, 0xFFFFFFFFull) | (min(ur, 0xFFFFFFFFull) << 32);
+    rs->mg_ns[q] = nsum;
+  }
+}
+
+// X2: the records of all ranks, one index space -> summed into the global cells; the thread that finds a cell empty lists it
+__device__ __forceinline__ void mgr_accumulate(const RoundArgs& R, RoundSm& S, uint32_t par, uint32_t epar) {
+  const MgArgs& M = R.mg;
+  RoundState* rs = R.rs;
+  const uint32_t lane = lane_id();
+  uint32_t pre[MG_MAX_WORLD + 1];
+  pre[0] = 0;
+#pragma unroll
+  for (int q = 0; q < MG_MAX_WORLD; q++) pre[q + 1] = pre[q] + (q < M.world ? ld_cg(&rs->mg_n[q]) : 0u);
+  const uint32_t total = pre[MG_MAX_WORLD];
+  for (uint32_t jx = blockIdx.x * blockDim.x + threadIdx.x; jx < ((total + 31u) & ~31u); jx += gridDim.x * blockDim.x) {
+    bool first = false;
+    uint32_t ent = 0;
+    if (jx < total) {
+      int q = 0;
+#pragma unroll
+      for (int r = 1; r < MG_MAX_WORLD; r++) q += (jx >= pre[r]) ? 1 : 0;
+      const unsigned long long rec = ld_cg(mg_area(M, M.rank, epar, q) + MGR_HDR + (jx - pre[q]));
+      ent = (uint32_t)(rec >> 42);
+      const uint32_t js = (ent >> 16) & (2u * RB - 1u), tok = ent & 0xFFFFu;
+      first = atomicAdd(round_gcells(R, par, js >> 1, js & 1u) + tok, rec & ((1ull << (2 * R_FIELD)) - 1ull)) == 0ull;
+    }
+    const uint32_t fm = __ballot_sync(0xFFFFFFFFu, first);
+    if (fm) {
+      uint32_t base = 0;
+      const int src = __ffs(fm) - 1;
+      if ((int)lane == src) base = atomicAdd(&S.gncell[par], (uint32_t)__popc(fm));
+      base = __shfl_sync(0xFFFFFFFFu, base, src);
+      if (first) {
+        const uint32_t at = base + __popc(fm & ((1u << lane) - 1u));
+        if (at < R_LISTCAP) round_glist(R, par)[at] = ent;
+        else rs->goverflow[par] = 1;
+      }
+    }
+  }
 }
 
 // One warp-iteration of the site pass of merge j of the round: 32 entries of its occurrence list.
@@ -497,6 +707,7 @@ __device__ __forceinline__ SiteRec* round_sites_buf(const RoundArgs& R, uint32_t
 struct RoundFill {  // what the previous round left to do
   uint32_t v, par, k, c_first;  // merges committed / row parity / merges tried (rows to clear) / first token it created
   uint32_t overflow;            // a list of touched cells overflowed in that round: clear by scanning
+  uint32_t goverflow;           // sharded: the same for the lists of global cells
 };
 
 // the lists of the pairs born by the previous round's merges, as ONE index space over all their sites (32-aligned per merge),
@@ -545,6 +756,22 @@ __device__ __forceinline__ void round_clear_cells(const RoundArgs& R, const Roun
       round_cells(R, F.par, js >> 1, js & 1u)[tok] = 0ull;
     }
   }
+  if (!R.mg_on) return;
+  if (!F.goverflow) {  // sharded: the global cells this block listed while summing
+    const uint32_t n = min(S.gncell[F.par], R_LISTCAP);
+    const uint32_t* list = round_glist(R, F.par);
+    for (uint32_t i = lt; i < n; i += nlt) {
+      const uint32_t ent = ld_cg(list + i);
+      round_gcells(R, F.par, (ent >> 17) & (RB - 1u), (ent >> 16) & 1u)[ent & 0xFFFFu] = 0ull;
+    }
+  } else {
+    const uint32_t T = F.c_first + F.k;
+    const uint32_t total = F.k * 2u * T;
+    for (uint32_t i = vt; i < total; i += nvt) {
+      const uint32_t js = i / T, tok = i - js * T;
+      round_gcells(R, F.par, js >> 1, js & 1u)[tok] = 0ull;
+    }
+  }
 }
 
 __global__ void k_rounds_prepare(RoundState* rs) {
@@ -555,6 +782,7 @@ __global__ void k_rounds_prepare(RoundState* rs) {
         rs->ub[p][j].v = 0;
       }
     rs->overflow[0] = rs->overflow[1] = 0;
+    rs->goverflow[0] = rs->goverflow[1] = 0;
   }
 }
 
@@ -613,8 +841,21 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
       top2_publish(v, R.gp, R.gk, bid);
     }
     if (tid < RB) S.fill_n[tid] = 0;
-    if (tid < 2) S.ncell[tid] = 0;
+    if (tid < 2) S.ncell[tid] = S.gncell[tid] = 0;
     if (tid == 0) S.pool_next = S.pool_end = S.keys_ins = 0;
+  }
+  // sharded: exchanges completed so far (the peers' flags keep counting across launches), what the previous round may have
+  // taken from the pool since the headers were written
+  unsigned long long mg_epoch = R.mg_on ? ld_cg(&st->mg_epoch) : 0ull, tie_epoch = R.mg_on ? ld_cg(&st->mg_tie_epoch) : 0ull;
+  unsigned long long mg_prev_alloc = 0;
+  if (R.mg_on) {
+    // hello exchange: headers only (capacities, errors), so that the first decision is taken on global minima
+    if (lead) st->mg_abort = 0;
+    if (bid == 0 && warp == 0) {
+      mgr_send_warp(R, 0, (uint32_t)((mg_epoch + 1) & 1u), 0, mg_epoch + 1);
+      mgr_wait_fold_warp(R, (uint32_t)((mg_epoch + 1) & 1u), mg_epoch + 1);
+    }
+    mg_epoch++;
   }
   RBARRIER();
 
@@ -630,7 +871,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     if ((i) < 5) st->fine_ns[(prof_big ? 6 : 0) + (i)] += tp1 - tp0; \
     tp0 = tp1;                                                \
   }
-  RoundFill F{0, 0, 0, 0, 0};
+  RoundFill F{0, 0, 0, 0, 0, 0};
   uint32_t it = 0;  // merges committed by this launch
   for (uint32_t round = 0;; round++) {
     const uint32_t par = round & 1u;
@@ -656,6 +897,9 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
       if (tid == 320) S.g_n_keys = ld_cg(&st->n_keys);  // (stable here: they only change in P2)
       if (tid == 321) S.g_pool_cursor = ld_cg(&st->pool_cursor);
       if (tid == 322) S.g_snap_err = ld_cg(&st->snap_err);
+      if (tid == 323) S.g_abort = R.mg_on ? ld_cg(&st->mg_abort) : 0u;
+      if (tid >= 324 && tid < 332) S.gv[tid - 324] = R.mg_on ? ld_cg(&st->g_vals[tid - 324]) : 0u;
+      if (tid == 2) S.gncell[par] = 0;
       // the list of candidates is exact down to the largest LAST (RT-th best) primary any block published
       const unsigned long long Lcut = block_max_u64((tid % RT == RT - 1) ? myp : 0ull, S.red);  // (syncs inside: qn / cp are visible)
       if (myp && myp >= Lcut) {
@@ -702,7 +946,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         const uint32_t w0 = (uint32_t)(p0 >> 20);
         const uint32_t n_keys = S.g_n_keys, pool_cursor = S.g_pool_cursor;
         uint32_t status = LOOP_RUNNING;
-        if (S.g_snap_err) status = LOOP_ERROR;
+        if (S.g_snap_err || (R.mg_on && (S.g_abort || S.gv[0]))) status = LOOP_ERROR;
         else if (!p0) status = (thresh <= 1) ? LOOP_EMPTY : LOOP_NEED_REBUILD;
         else if (w0 < thresh) status = LOOP_NEED_REBUILD;
         else if (w0 < L.min_weight) status = LOOP_DONE;  // core.ts:313
@@ -724,6 +968,16 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         }
         // capacity the host guarantees (k_merge_loop's checks, cumulative over the batch)
         uint32_t cap_fail = 0;  // 0 fine, else the status it would mean for candidate 0
+        if (R.mg_on) {
+          // sharded: the minima over the ranks that the last exchange carried (so that every rank takes the same decision);
+          // the pool figure is one round old
+          const unsigned long long pool_free = S.gv[1] > mg_prev_alloc ? S.gv[1] - mg_prev_alloc : 0ull;
+          if ((unsigned long long)n_keys + keys_incl > (unsigned long long)(S.gv[6] >> 1)) cap_fail = LOOP_NEED_HOST;
+          else if (2ull * w_incl + (unsigned long long)nblk * R_POOL_CHUNK > pool_free) cap_fail = LOOP_NEED_HOST;
+          else if (j == 0 && wj > S.gv[2]) cap_fail = LOOP_NEED_HOST;
+          else if ((unsigned long long)hot_pre + keys_incl > S.gv[4]) cap_fail = LOOP_NEED_REBUILD;
+          else if (cj + 1 > S.gv[5]) cap_fail = LOOP_NEED_HOST;
+        } else
         if ((unsigned long long)n_keys + keys_incl > (unsigned long long)(L.tbl_cap >> 1)) cap_fail = LOOP_NEED_HOST;
         else if ((unsigned long long)pool_cursor + 2ull * w_incl + (unsigned long long)nblk * R_POOL_CHUNK > L.pool_cap) cap_fail = LOOP_NEED_HOST;
         else if (j == 0 && wj > A.sites_cap) cap_fail = LOOP_NEED_HOST;
@@ -733,7 +987,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         if (status == LOOP_RUNNING) {
           const uint32_t cf0 = __shfl_sync(0xFFFFFFFFu, cap_fail, 0);
           if (cf0) status = cf0;
-          else if (mult0 > 1 && mult0 > L.cand_cap) status = LOOP_NEED_HOST;
+          else if (mult0 > 1 && mult0 > (R.mg_on ? S.gv[7] : L.cand_cap)) status = LOOP_NEED_HOST;
         }
         // why candidate j >= 1 cannot join (0: it can); same codes as RoundState::stop_reason
         uint32_t stop = 0;
@@ -812,14 +1066,79 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
       }
       phase_collect(t, A.len16, L.max_length, 1, L.hot, hot_pre, S.cp[0], L.cands, L.cand_cap, st, bid, nblk);
       RBARRIER();
-      phase_tie(A.slots, A.n, t, A.pool, L.cands, ld_cg(&st->n_cand), st, S.s_max, bid, nblk);
-      RBARRIER();
-      const unsigned long long tp = ld_cg(&st->tie_pos);
+      unsigned long long tp;
+      uint32_t tie_slot = NOSLOT;
+      if (!R.mg_on) {
+        phase_tie(A.slots, A.n, t, A.pool, L.cands, ld_cg(&st->n_cand), st, S.s_max, bid, nblk);
+        RBARRIER();
+        tp = ld_cg(&st->tie_pos);
+        tie_slot = (uint32_t)(tp & 0xFFFFFFFFu);
+      } else {
+        // sharded: last counted occurrence in GLOBAL scan order = (rank, local position); the candidates go in canonical
+        // (pair key) order so that every rank talks about the same one, and each rank tells every other where ITS last
+        // counted occurrence of each candidate is (mg_kernels.cuh)
+        const MgArgs& M = R.mg;
+        const uint32_t tpar = (uint32_t)((tie_epoch + 1) & 1u);
+        const uint32_t nc = ld_cg(&st->n_cand);  // == mult0 on every rank
+        for (uint32_t i = gt; i < nc; i += gn) {
+          const uint32_t si = ld_cg(&L.cands[i]);
+          const uint32_t ki = t.keys[si];
+          uint32_t r = 0;
+          for (uint32_t j2 = 0; j2 < nc; j2++) r += t.keys[ld_cg(&L.cands[j2])] < ki;
+          M.tie_sorted[r] = si;
+        }
+        RBARRIER();
+        for (uint32_t cnd = bid; cnd < nc; cnd += nblk) {  // one block per candidate
+          const uint32_t sc = ld_cg(&M.tie_sorted[cnd]);
+          const uint32_t key = t.keys[sc];
+          const uint32_t ca = key >> 16, cb = key & 0xFFFFu;
+          const uint32_t start = t.occ_start[sc], len = t.occ_len[sc];
+          uint32_t vmax = 0;
+          for (uint32_t i = tid; i < len; i += blockDim.x) {
+            const uint32_t pp = A.pool[start + i];
+            if (counted_occurrence(A.slots, A.n, pp, ca, cb)) vmax = max(vmax, pp + 1);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) vmax = max(vmax, __shfl_xor_sync(0xFFFFFFFFu, vmax, o));
+          __syncthreads();
+          if (lane == 0) S.s_max[warp] = vmax;
+          __syncthreads();
+          if (tid == 0) {
+            uint32_t m = 0;
+            for (uint32_t i = 0; i < (blockDim.x >> 5); i++) m = max(m, S.s_max[i]);
+            for (int q = 0; q < M.world; q++) M.tiebox[q][((size_t)tpar * M.world + M.rank) * M.tie_cap + cnd] = m;
+            __threadfence_system();
+          }
+        }
+        RBARRIER();
+        if (lead) {
+          st->tie_pos = ~0ull;
+          mg_signal_and_wait(M, M.flag_tie, tie_epoch + 1, st);
+        }
+        tie_epoch++;
+        RBARRIER();
+        if (bid == 0) {
+          const uint32_t* box = M.tiebox[M.rank] + (size_t)tpar * M.world * M.tie_cap;
+          for (uint32_t i = tid; i < nc; i += blockDim.x) {
+            for (int q = M.world - 1; q >= 0; q--) {  // the highest rank holding the pair owns its last occurrence
+              const uint32_t vq = ld_cg(box + (size_t)q * M.tie_cap + i);
+              if (vq) {
+                atomicMin(&st->tie_pos, ((((unsigned long long)q << 32) | (vq - 1)) << 16) | i);
+                break;
+              }
+            }
+          }
+        }
+        RBARRIER();
+        tp = ld_cg(&st->tie_pos);
+        if (ld_cg(&st->mg_abort)) tp = ~0ull;
+        if (tp != ~0ull) tie_slot = ld_cg(&M.tie_sorted[(uint32_t)(tp & 0xFFFFu)]);
+      }
       __syncthreads();
       if (tp == ~0ull) {
         status = LOOP_ERROR;
       } else if (tid == 0) {
-        const uint32_t s = (uint32_t)(tp & 0xFFFFFFFFu);
+        const uint32_t s = tie_slot;
         const uint32_t key = t.keys[s];
         S.slot[0] = s;
         S.a[0] = key >> 16;
@@ -843,6 +1162,10 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         st->status = status;
         st->iters_done = it;
         st->n_tokens = n_tokens0 + it;
+        if (R.mg_on) {
+          st->mg_epoch = mg_epoch;
+          st->mg_tie_epoch = tie_epoch;
+        }
         Best wb{S.cp[0], S.cp[0] ? S.cs[0] : NOSLOT, S.cm[0]};
         publish_best(t, st, wb);
         st->n_cand = 0;
@@ -914,16 +1237,47 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     RPROF(1)
     RBARRIER();
     RPROF(2)
+    if (R.mg_on) {
+      // ================= sharded: one exchange per round =================
+      const uint32_t epar = (uint32_t)((mg_epoch + 1) & 1u);
+      mgr_emit(R, S, par, epar, k, c_first + k);  // this shard's deltas -> records in every rank's inbox (NVLink stores)
+      __threadfence_system();
+      RBARRIER();
+      if (bid == 0 && warp == 0) {
+        mgr_send_warp(R, par, epar, k, mg_epoch + 1);
+        mgr_wait_fold_warp(R, epar, mg_epoch + 1);
+        if (lane == 0) st->n_out = 0;  // nobody appends before the next round's emit
+      }
+      mg_epoch++;
+      RBARRIER();
+      if (ld_cg(&st->mg_abort)) {  // a peer did not answer: every block of every rank that still runs leaves
+        if (lead) {
+          st->status = LOOP_ERROR;
+          st->iters_done = it;
+          st->n_tokens = n_tokens0 + it;
+          st->mg_epoch = mg_epoch;
+          st->mg_tie_epoch = tie_epoch;
+        }
+        return;
+      }
+      mgr_accumulate(R, S, par, epar);  // all ranks' records summed into the global cells
+      RBARRIER();
+      RPROF(5)
+    }
     // ================= P2 =================
     // valid prefix: no pair born by an earlier merge of the batch may reach the count of a later one
-    uint32_t v = k;
+    // (sharded: every rank commits at most the smallest batch any rank tried, bounds and site counts are sums over the ranks)
+    const uint32_t k_all = R.mg_on ? min(k, ld_cg(&rs->mg_k)) : k;
+    uint32_t v = k_all;
     const uint32_t ns_all = (lane < k) ? ld_cg(&rs->n_sites[par][lane].v) : 0u;  // (requested together with the bounds and the flag)
+    const uint32_t ns_glob = R.mg_on ? ((lane < k_all) ? ld_cg(&rs->mg_ns[lane]) : 0u) : ns_all;
     const uint32_t overflow = ld_cg(&rs->overflow[par]);                         // (set during P1 only)
+    const uint32_t goverflow = R.mg_on ? ld_cg(&rs->goverflow[par]) : 0u;
     {
-      const unsigned long long ub2 = (lane < k) ? ld_cg(&rs->ub[par][lane].v) : 0ull;
+      const unsigned long long ub2 = (lane < k_all) ? (R.mg_on ? ld_cg(&rs->mg_ub[lane]) : ld_cg(&rs->ub[par][lane].v)) : 0ull;
       const uint32_t ubv = max((uint32_t)ub2, (uint32_t)(ub2 >> 32));  // lane j: the larger of merge j's two bounds
       uint32_t run = 0;
-      for (uint32_t j = 0; j + 1 < k; j++) {
+      for (uint32_t j = 0; j + 1 < k_all; j++) {
         run = max(run, __shfl_sync(0xFFFFFFFFu, ubv, j));
         if (run >= S.w[j + 1]) {
           v = j + 1;
@@ -948,7 +1302,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         L.log[it + lane] = r;
         t.cnt[S.slot[lane]] = 0;  // every counted occurrence of the winner is being replaced
       }
-      const uint32_t bad = __ballot_sync(0xFFFFFFFFu, mine_j && ns_lane != S.w[lane]);
+      const uint32_t bad = __ballot_sync(0xFFFFFFFFu, mine_j && ns_glob != S.w[lane]);
       if (lane == 0) {
         st->live_tokens -= sites_all;
         st->sites_total += sites_all;
@@ -1007,9 +1361,9 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
           }
           // ---- a pair born by merge jj: (tok, c) or (c, tok) ----
           {
-            const bool born = len != 0;
+            const bool born = len != 0 || (act && cntv != 0);  // (sharded: counted on another shard only -> the key and its count, no list)
             // list space first (one cursor atomic per warp): its round trip overlaps the table probe below
-            uint32_t mylen = born ? len : 0u;
+            uint32_t mylen = len;
             uint32_t inc = mylen;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -1130,16 +1484,23 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
             }
           }
         };
-        if (!overflow) {
-          const uint32_t ncell = S.ncell[par];
-          const uint32_t* list = round_list(R, par);
+        // sharded: the global cell (decrements, counted occurrences: sums over the ranks) and this shard's (occurrences: its
+        // list space) of one (merge, side, token), in the layout `process` reads
+        auto cell_of = [&](uint32_t jj, uint32_t side, uint32_t tok) -> unsigned long long {
+          if (!R.mg_on) return ld_cg(round_cells(R, par, jj, side) + tok);
+          const unsigned long long g = ld_cg(round_gcells(R, par, jj, side) + tok), l = ld_cg(round_cells(R, par, jj, side) + tok);
+          return (g & R_FMASK) | ((unsigned long long)cell_len(l) << R_FIELD) | (((g >> R_FIELD) & R_FMASK) << (2 * R_FIELD));
+        };
+        if (!(R.mg_on ? goverflow : overflow)) {
+          const uint32_t ncell = R.mg_on ? S.gncell[par] : S.ncell[par];
+          const uint32_t* list = R.mg_on ? round_glist(R, par) : round_list(R, par);
           if (lt == 0 && ncell) atomicAdd(S.w[0] > R_LAT ? &rs->cells_big : &rs->cells_small, (unsigned long long)ncell);
           for (uint32_t base = 0; base < ncell; base += n1t) {
             const uint32_t idx = base + lt;
             const uint32_t ent = idx < ncell ? ld_cg(list + idx) : 0u;
             const uint32_t jj = (ent >> 17) & (RB - 1u), side = (ent >> 16) & 1u, tok = ent & 0xFFFFu;
             const bool act = idx < ncell && jj < v;
-            const unsigned long long cellv = act ? ld_cg(round_cells(R, par, jj, side) + tok) : 0ull;
+            const unsigned long long cellv = act ? cell_of(jj, side, tok) : 0ull;
             process(act, jj, side, tok, cellv);
           }
         } else {
@@ -1148,7 +1509,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
           const uint32_t total = v * 2u * T;
           for (uint32_t i = bid * n1t + lt; i < total; i += nblk * n1t) {
             const uint32_t js = i / T, tok = i - js * T;
-            const unsigned long long cellv = ld_cg(round_cells(R, par, js >> 1, js & 1u) + tok);
+            const unsigned long long cellv = cell_of(js >> 1, js & 1u, tok);
             if (!__any_sync(0xFFFFFFFFu, cellv != 0ull)) continue;
             process(cellv != 0ull, js >> 1, js & 1u, tok, cellv);
           }
@@ -1243,7 +1604,13 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     F.k = k;
     F.c_first = c_first;
     F.overflow = overflow;
-    if (lead) rs->overflow[par ^ 1u] = 0;  // (read by nobody before the next round's P2, set by nobody before its P1)
+    F.goverflow = goverflow;
+    if (lead) rs->overflow[par ^ 1u] = rs->goverflow[par ^ 1u] = 0;  // (read by nobody before the next round's P2, set by nobody before its P1)
+    if (R.mg_on) {  // what this round's P2 may take from the pool on any rank: the headers of the next exchange are written before
+      unsigned long long wsum = 0;
+      for (uint32_t j = 0; j < v; j++) wsum += S.w[j];
+      mg_prev_alloc = 2ull * wsum + (unsigned long long)nblk * R_POOL_CHUNK;
+    }
     it += v;
     RPROF(3)
     RBARRIER();
