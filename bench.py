@@ -135,6 +135,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # (keeps NCCL's version banner off stdout: one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _abi.load_library()
     train_bytes, merges, encode_bytes = WORKLOADS[args.workload]
@@ -248,8 +249,12 @@ def run_b200(args):
     # K1 alone (ingest + histogram + lists), for its own roofline line
     reset()
     check(lib.bpe_add_documents_dev(h, C.c_void_p(ids_dev.data_ptr()), p64(off_host), n_docs))
-    m, found = _abi.bpe_merge(), C.c_int()
-    check(lib.bpe_find_next_merge(h, 2, 0, C.byref(m), C.byref(found)))  # builds this shard's index (local counts)
+    if world == 1:
+        m, found = _abi.bpe_merge(), C.c_int()
+        check(lib.bpe_find_next_merge(h, 2, 0, C.byref(m), C.byref(found)))  # builds the index
+    else:  # (single steps are refused on a sharded engine) sizing the export builds this shard's index
+        npairs = C.c_int64()
+        check(lib.bpe_mg_export_counts(h, None, None, 0, C.byref(npairs)))
     k1_ms = stats().ms_index_build - s_before.ms_index_build
     if world > 1:  # every rank must hold the same merge log
         import hashlib

@@ -60,6 +60,8 @@ constexpr uint32_t R_LISTCAP = 32768;    // touched cells a block can list per r
 __host__ __device__ __forceinline__ uint32_t cell_dec(unsigned long long v) { return (uint32_t)(v & R_FMASK); }
 __host__ __device__ __forceinline__ uint32_t cell_len(unsigned long long v) { return (uint32_t)((v >> R_FIELD) & R_FMASK); }
 __host__ __device__ __forceinline__ uint32_t cell_cnt(unsigned long long v) { return (uint32_t)((v >> (2 * R_FIELD)) & R_FMASK); }
+constexpr uint32_t R_BRECCAP = 65536;    // sharded: records a block can buffer during one site pass
+constexpr uint32_t MGR_HDR = 64;          // sharded: u64 words of header in front of the records of a round's message
 constexpr uint32_t LOOP_NEED_LEGACY = 7;  // the winner is too big for the packed cells: k_merge_loop takes the merges above R_HUGE
 constexpr uint32_t R_QCAP = 512;         // per-block partial entries a decision can fold (RT x blocks)
 
@@ -109,6 +111,7 @@ struct RoundArgs {
   MgArgs mg;
   unsigned long long* gcells;  // [2][RB][2][ND_STRIDE]: decrements | counted occurrences << 21, summed over the ranks
   uint32_t* glists;            // [2][blocks][R_LISTCAP]: global cells each block touched first while summing
+  unsigned long long* brec;    // [blocks][R_BRECCAP]: the records a block's site pass produces, flushed into the inboxes at its end
 };
 
 __device__ __forceinline__ unsigned long long* round_cells(const RoundArgs& R, uint32_t par, uint32_t j, uint32_t side) {
@@ -257,6 +260,7 @@ struct RoundSm {
   uint32_t gv[8];  // sharded: the folded header values (OR of the ranks' error flags, minima of their capacities)
   uint32_t ncell[2];  // cells this block touched first in the round of either parity (entries of its list)
   uint32_t gncell[2]; // sharded: global cells this block touched first while summing the ranks' records
+  uint32_t nrec, rec_base;  // sharded: records this block buffered in the current site pass / where they go in the inboxes
   uint32_t pool_next, pool_end;  // this block's private chunk of the occurrence pool (list space without a grid-wide atomic)
   uint32_t keys_ins;             // keys this block inserted in the current P2 (one n_keys atomic per block and round)
   uint32_t filt_a[8], filt_b[8]; // role_maybe filters: the a's / the b's of the batch
@@ -300,20 +304,37 @@ __device__ __forceinline__ Top2 top2_block_reduce(Top2 v, Top2* s_t2) {
 // lane that finds the cell empty lists it for P2 (one shared-memory counter bump per warp).  Returns the leader's counted
 // occurrences (0 elsewhere): the ingredient of the born-pair bound.
 __device__ __forceinline__ uint32_t cell_add_warp(const RoundArgs& R, RoundSm& S, uint32_t par, uint32_t js, unsigned long long* cells, uint32_t tok, bool has,
-                                                  bool dec, bool newp, bool counted, uint32_t c, uint32_t partner) {
+                                                  bool dec, bool newp, bool counted, uint32_t c, uint32_t partner, uint32_t epar) {
   const uint32_t lane = lane_id();
   const uint32_t peers = __match_any_sync(0xFFFFFFFFu, has ? tok : (0xFFFFFF00u + lane));
   const uint32_t dmask = __ballot_sync(0xFFFFFFFFu, has && dec);
   const uint32_t nmask = __ballot_sync(0xFFFFFFFFu, has && newp);
   const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, has && newp && counted);
   const bool leader = has && lane == (uint32_t)(__ffs(peers) - 1);
-  uint32_t nc = 0;
+  uint32_t nc = 0, nd = 0;
   bool first = false;
   if (leader) {
     nc = (uint32_t)__popc(peers & cmask);
-    const unsigned long long add = (unsigned long long)__popc(peers & dmask) | ((unsigned long long)__popc(peers & nmask) << R_FIELD) |
-                                   ((unsigned long long)nc << (2 * R_FIELD));
+    nd = (uint32_t)__popc(peers & dmask);
+    const unsigned long long add = (unsigned long long)nd | ((unsigned long long)__popc(peers & nmask) << R_FIELD) | ((unsigned long long)nc << (2 * R_FIELD));
     first = atomicAdd(cells + tok, add) == 0ull;
+  }
+  if (R.mg_on) {
+    // sharded: what this warp adds to the GLOBAL counts becomes a record in the block's buffer (a shared-memory counter bump
+    // per warp); the block stores its records into every rank's inbox when its site pass ends (round_flush_records)
+    const bool has_rec = leader;  // (also a cell that only holds uncounted occurrences: every rank must come to know the pair)
+    const uint32_t rm = __ballot_sync(0xFFFFFFFFu, has_rec);
+    if (rm) {
+      uint32_t base = 0;
+      const int src = __ffs(rm) - 1;
+      if ((int)lane == src) base = atomicAdd(&S.nrec, (uint32_t)__popc(rm));
+      base = __shfl_sync(0xFFFFFFFFu, base, src);
+      if (has_rec) {
+        const uint32_t at = base + __popc(rm & ((1u << lane) - 1u));
+        if (at < R_BRECCAP) R.brec[(size_t)blockIdx.x * R_BRECCAP + at] = ((unsigned long long)((js << 16) | tok) << 42) | ((unsigned long long)nc << R_FIELD) | nd;
+        else atomicOr(&R.L.A.st->err, ERR_INBOX_OVERFLOW);
+      }
+    }
   }
   const uint32_t fm = __ballot_sync(0xFFFFFFFFu, first);
   if (fm) {
@@ -343,50 +364,32 @@ __device__ __forceinline__ uint32_t cell_add_warp(const RoundArgs& R, RoundSm& S
 //   [0..5]   the twelve u32 of mg_kernels' header (H_N records, H_ERR, capacities)
 //   [8 + j]  U bounds of merge j on the sender (left | right << 32)       [24 + j]  sites of merge j on the sender
 //   [40]     merges the sender tried (its batch; every rank commits at most the smallest)
-// record: ((merge * 2 + side) << 16 | token) << 42 | counted occurrences << 21 | decrements
-constexpr uint32_t MGR_HDR = 64;
+// record: ((merge * 2 + side) << 16 | token) << 42 | counted occurrences << 21 | decrements    (one per warp and distinct
+// neighbour of a site pass, written while the pass runs)
 
-// X1: this rank's touched cells -> records in every rank's inbox (every block: the cells of its own list)
-__device__ __forceinline__ void mgr_emit(const RoundArgs& R, const RoundSm& S, uint32_t par, uint32_t epar, uint32_t k, uint32_t c_hi) {
+// end of a block's site pass: its buffered records go into every rank's inbox (ONE slot reservation per block and round,
+// coalesced NVLink stores); every thread of the block calls
+__device__ __forceinline__ void round_flush_records(const RoundArgs& R, RoundSm& S, uint32_t epar) {
   const MgArgs& M = R.mg;
   DevState* st = R.L.A.st;
-  const uint32_t cap = M.inbox_stride - MGR_HDR;
-  const uint32_t lane = lane_id();
-  auto emit = [&](bool has, uint32_t js, uint32_t tok, unsigned long long cellv) {
-    has = has && (cell_dec(cellv) | cell_cnt(cellv)) != 0u;
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, has);
-    if (!m) return;
-    uint32_t base = 0;
-    const int src = __ffs(m) - 1;
-    if ((int)lane == src) base = atomicAdd(&st->n_out, (uint32_t)__popc(m));
-    base = __shfl_sync(0xFFFFFFFFu, base, src);
-    if (has) {
-      const uint32_t at = base + __popc(m & ((1u << lane) - 1u));
-      if (at < cap) {
-        const unsigned long long rec = ((unsigned long long)((js << 16) | tok) << 42) | ((unsigned long long)cell_cnt(cellv) << R_FIELD) | cell_dec(cellv);
-        for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MGR_HDR + at] = rec;
-      } else {
-        atomicOr(&st->err, ERR_INBOX_OVERFLOW);
-      }
-    }
-  };
-  if (!ld_cg(&R.rs->overflow[par])) {
-    const uint32_t n = S.ncell[par];
-    const uint32_t* list = round_list(R, par);
-    for (uint32_t base = 0; base < n; base += blockDim.x) {
-      const uint32_t idx = base + threadIdx.x;
-      const uint32_t ent = idx < n ? ld_cg(list + idx) : 0u;
-      const uint32_t js = (ent >> 16) & (2u * RB - 1u), tok = ent & 0xFFFFu;
-      emit(idx < n, js, tok, idx < n ? ld_cg(round_cells(R, par, js >> 1, js & 1u) + tok) : 0ull);
-    }
-  } else {
-    const uint32_t T = (c_hi + 31u) & ~31u;
-    const uint32_t total = k * 2u * T;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-      const uint32_t js = i / T, tok = i - js * T;
-      emit(true, js, tok, ld_cg(round_cells(R, par, js >> 1, js & 1u) + tok));
+  __syncthreads();
+  const uint32_t n = min(S.nrec, R_BRECCAP);
+  if (threadIdx.x == 0) S.rec_base = n ? atomicAdd(&st->n_out, n) : 0u;
+  __syncthreads();
+  const uint32_t base = S.rec_base, cap = M.inbox_stride - MGR_HDR;
+  const unsigned long long* mine = R.brec + (size_t)blockIdx.x * R_BRECCAP;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long rec = mine[i];
+    const uint32_t at = base + i;
+    if (at < cap) {
+      for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MGR_HDR + at] = rec;
+    } else {
+      atomicOr(&st->err, ERR_INBOX_OVERFLOW);
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) S.nrec = 0;
+  __threadfence_system();
 }
 
 // warp 0 of block 0, lane q talks to rank q: header of this rank's message, then the flag
@@ -395,6 +398,9 @@ __device__ __forceinline__ void mgr_send_warp(const RoundArgs& R, uint32_t par, 
   const LoopArgs& L = R.L;
   DevState* st = L.A.st;
   const int q = (int)lane_id();
+  // lane j fetches merge j's figures once; the lanes that write a header read them out of each other's registers
+  const unsigned long long ub_lane = ((uint32_t)q < k) ? ld_cg(&R.rs->ub[par][q].v) : 0ull;
+  const uint32_t ns_lane = ((uint32_t)q < k) ? ld_cg(&R.rs->n_sites[par][q].v) : 0u;
   if (q < M.world) {
     const uint32_t cur = ld_cg(&st->pool_cursor);
     uint32_t h[12];
@@ -413,15 +419,20 @@ __device__ __forceinline__ void mgr_send_warp(const RoundArgs& R, uint32_t par, 
     uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
     for (int i = 0; i < 3; i++) d4[i] = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-    for (uint32_t j = 0; j < RB; j++) {
-      dst[8 + j] = j < k ? ld_cg(&R.rs->ub[par][j].v) : 0ull;
-      dst[24 + j] = j < k ? (unsigned long long)ld_cg(&R.rs->n_sites[par][j].v) : 0ull;
-    }
     dst[40] = k;
-    __threadfence_system();
   }
+  for (uint32_t j = 0; j < RB; j++) {  // (every lane takes part in the shuffles; the lanes that talk to a rank store)
+    const unsigned long long u = __shfl_sync(0xFFFFFFFFu, ub_lane, j);
+    const uint32_t n = __shfl_sync(0xFFFFFFFFu, ns_lane, j);
+    if (q < M.world) {
+      unsigned long long* dst = mg_area(M, q, epar, M.rank);
+      dst[8 + j] = u;
+      dst[24 + j] = (unsigned long long)n;
+    }
+  }
+  if (q < M.world) __threadfence_system();
   __syncwarp();
-  if (q < M.world && q != M.rank) st_release_sys(M.flag_data[q] + 16 * M.rank, epoch);
+  if (q < M.world) st_release_sys(M.flag_data[q] + 16 * M.rank, epoch);  // (own rank included: every block of every rank polls all flags)
 }
 
 // ... wait for every peer's flag, then fold the headers: OR of the error flags, minima of the capacities (st->g_vals, as
@@ -431,7 +442,7 @@ __device__ __forceinline__ void mgr_wait_fold_warp(const RoundArgs& R, uint32_t 
   DevState* st = R.L.A.st;
   RoundState* rs = R.rs;
   const int q = (int)lane_id();
-  if (q < M.world && q != M.rank) {
+  if (q < M.world) {  // (warp 0 of EVERY block: no grid barrier between the exchange and the summing)
     const unsigned long long* f = M.flag_data[M.rank] + 16 * q;
     const unsigned long long t0 = now_ns();
     uint32_t ns = 16;
@@ -476,12 +487,15 @@ __device__ __forceinline__ void mgr_wait_fold_warp(const RoundArgs& R, uint32_t 
   if (q < RB) {  // lane j sums merge j's bounds and sites over the senders
     unsigned long long ul = 0, ur = 0;
     uint32_t nsum = 0;
-    for (int s = 0; s < M.world; s++) {
-      const unsigned long long* hs = mg_area(M, M.rank, epar, s);
-      const unsigned long long u = ld_cg(hs + 8 + q);
-      ul += (uint32_t)u;
-      ur += (uint32_t)(u >> 32);
-      nsum += (uint32_t)ld_cg(hs + 24 + q);
+#pragma unroll
+    for (int s = 0; s < MG_MAX_WORLD; s++) {  // (unrolled: the loads of all senders are in flight together)
+      if (s < M.world) {
+        const unsigned long long* hs = mg_area(M, M.rank, epar, s);
+        const unsigned long long u = ld_cg(hs + 8 + q);
+        ul += (uint32_t)u;
+        ur += (uint32_t)(u >> 32);
+        nsum += (uint32_t)ld_cg(hs + 24 + q);
+      }
     }
     rs->mg_ub[q] = min(ul, 0xFFFFFFFFull) | (min(ur, 0xFFFFFFFFull) << 32);
     rs->mg_ns[q] = nsum;
@@ -508,7 +522,8 @@ __device__ __forceinline__ void mgr_accumulate(const RoundArgs& R, RoundSm& S, u
       const unsigned long long rec = ld_cg(mg_area(M, M.rank, epar, q) + MGR_HDR + (jx - pre[q]));
       ent = (uint32_t)(rec >> 42);
       const uint32_t js = (ent >> 16) & (2u * RB - 1u), tok = ent & 0xFFFFu;
-      first = atomicAdd(round_gcells(R, par, js >> 1, js & 1u) + tok, rec & ((1ull << (2 * R_FIELD)) - 1ull)) == 0ull;
+      // (bit 42 up counts the records of the cell: the sum is never zero once a record arrived, whatever it carried)
+      first = atomicAdd(round_gcells(R, par, js >> 1, js & 1u) + tok, (rec & ((1ull << (2 * R_FIELD)) - 1ull)) + (1ull << (2 * R_FIELD))) == 0ull;
     }
     const uint32_t fm = __ballot_sync(0xFFFFFFFFu, first);
     if (fm) {
@@ -529,7 +544,7 @@ __device__ __forceinline__ void mgr_accumulate(const RoundArgs& R, RoundSm& S, u
 // The logic of the neighbourhoods is phase_sites' (train_kernels.cuh); what differs is where the deltas go (the merge's
 // dense rows) and the virtual neighbours c_i of the earlier merges of the batch.
 __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S, uint32_t par, uint32_t j, uint32_t c_first,
-                                                 uint32_t i, SiteRec* site_out, uint32_t sites_cap) {
+                                                 uint32_t i, SiteRec* site_out, uint32_t sites_cap, uint32_t epar) {
   const ApplyArgs& A = R.L.A;
   const uint32_t* slots = A.slots;
   const uint32_t n = A.n;
@@ -636,8 +651,8 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S,
   // one atomic per distinct left neighbour: the born pair (new1_tok, c), with the decrement when it concerns the same token
   // (it does unless the site is chained to the one on its left: then the decrement is (b,a)'s and goes out on its own)
   const bool dec1_same = dec1 && dec1_tok == new1_tok;
-  const uint32_t nc1 = cell_add_warp(R, S, par, j * 2u, cells_l, new1_tok, new1, dec1_same, true, new1_counted, c, a);
-  if (__any_sync(0xFFFFFFFFu, dec1 && !dec1_same)) cell_add_warp(R, S, par, j * 2u, cells_l, dec1_tok, dec1 && !dec1_same, true, false, false, c, a);
+  const uint32_t nc1 = cell_add_warp(R, S, par, j * 2u, cells_l, new1_tok, new1, dec1_same, true, new1_counted, c, a, epar);
+  if (__any_sync(0xFFFFFFFFu, dec1 && !dec1_same)) cell_add_warp(R, S, par, j * 2u, cells_l, dec1_tok, dec1 && !dec1_same, true, false, false, c, a, epar);
   rec.lslot = new1 ? new1_tok : R_NOTOK;
 
   // ---- adjacency on the right of the new token (left to the next site when that one is chained) ----
@@ -682,8 +697,8 @@ __device__ __forceinline__ void round_sites_iter(const RoundArgs& R, RoundSm& S,
     }
   }
   const bool dec2_same = dec2 && new2 && dec2_tok == new2_tok;  // (always, when there is a decrement: kept general)
-  const uint32_t nc2 = cell_add_warp(R, S, par, j * 2u + 1u, cells_r, new2_tok, new2, dec2_same, true, true, c, b);
-  if (__any_sync(0xFFFFFFFFu, dec2 && !dec2_same)) cell_add_warp(R, S, par, j * 2u + 1u, cells_r, dec2_tok, dec2 && !dec2_same, true, false, false, c, b);
+  const uint32_t nc2 = cell_add_warp(R, S, par, j * 2u + 1u, cells_r, new2_tok, new2, dec2_same, true, true, c, b, epar);
+  if (__any_sync(0xFFFFFFFFu, dec2 && !dec2_same)) cell_add_warp(R, S, par, j * 2u + 1u, cells_r, dec2_tok, dec2 && !dec2_same, true, false, false, c, b, epar);
   rec.rslot = new2 ? new2_tok : R_NOTOK;
   // upper bounds of the born pairs' counts: the largest group of lanes that share a neighbour, summed over the warps
   const uint32_t u1 = __reduce_max_sync(0xFFFFFFFFu, nc1), u2 = __reduce_max_sync(0xFFFFFFFFu, nc2);
@@ -851,10 +866,9 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
   if (R.mg_on) {
     // hello exchange: headers only (capacities, errors), so that the first decision is taken on global minima
     if (lead) st->mg_abort = 0;
-    if (bid == 0 && warp == 0) {
-      mgr_send_warp(R, 0, (uint32_t)((mg_epoch + 1) & 1u), 0, mg_epoch + 1);
-      mgr_wait_fold_warp(R, (uint32_t)((mg_epoch + 1) & 1u), mg_epoch + 1);
-    }
+    if (tid == 0) S.nrec = 0;
+    if (bid == 0 && warp == 0) mgr_send_warp(R, 0, (uint32_t)((mg_epoch + 1) & 1u), 0, mg_epoch + 1);
+    if (warp == 0) mgr_wait_fold_warp(R, (uint32_t)((mg_epoch + 1) & 1u), mg_epoch + 1);
     mg_epoch++;
   }
   RBARRIER();
@@ -1203,7 +1217,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         for (uint32_t wi = bid * ws + warp; wi < iters; wi += nblk * ws) {
           uint32_t j = 0;
           while (j + 1 < k && wi >= S.iter0[j + 1]) j++;
-          round_sites_iter(R, S, par, j, c_first, (wi - S.iter0[j]) * 32u + lane, round_sites_buf(R, par, j), j == 0 ? A.sites_cap : R_SMALL);
+          round_sites_iter(R, S, par, j, c_first, (wi - S.iter0[j]) * 32u + lane, round_sites_buf(R, par, j), j == 0 ? A.sites_cap : R_SMALL, (uint32_t)((mg_epoch + 1) & 1u));
         }
         if (!split) {
           if (F.v) round_fill_all(R, S, F, gt, gn);
@@ -1234,22 +1248,22 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         }
       }
     }
+    if (R.mg_on) round_flush_records(R, S, (uint32_t)((mg_epoch + 1) & 1u));  // this block's records -> every rank's inbox
     RPROF(1)
     RBARRIER();
     RPROF(2)
     if (R.mg_on) {
       // ================= sharded: one exchange per round =================
+      // block 0 publishes this rank's header and flags; EVERY block waits for the flags of all ranks and folds the headers
+      // itself (same values everywhere), so that the summing can start without another grid barrier
       const uint32_t epar = (uint32_t)((mg_epoch + 1) & 1u);
-      mgr_emit(R, S, par, epar, k, c_first + k);  // this shard's deltas -> records in every rank's inbox (NVLink stores)
-      __threadfence_system();
-      RBARRIER();
       if (bid == 0 && warp == 0) {
         mgr_send_warp(R, par, epar, k, mg_epoch + 1);
-        mgr_wait_fold_warp(R, epar, mg_epoch + 1);
-        if (lane == 0) st->n_out = 0;  // nobody appends before the next round's emit
+        if (lane == 0) st->n_out = 0;  // nobody reserves slots before the next round's flush
       }
+      if (warp == 0) mgr_wait_fold_warp(R, epar, mg_epoch + 1);
       mg_epoch++;
-      RBARRIER();
+      __syncthreads();
       if (ld_cg(&st->mg_abort)) {  // a peer did not answer: every block of every rank that still runs leaves
         if (lead) {
           st->status = LOOP_ERROR;
