@@ -430,7 +430,8 @@ __device__ __forceinline__ void mgr_send_warp(const RoundArgs& R, uint32_t par, 
       dst[24 + j] = (unsigned long long)n;
     }
   }
-  if (q < M.world) __threadfence_system();
+  // (no fence: lane q wrote rank q's header itself and its release store orders that; the records were fenced at system scope
+  // by the blocks that wrote them, before the grid barrier this warp came through)
   __syncwarp();
   if (q < M.world) st_release_sys(M.flag_data[q] + 16 * M.rank, epoch);  // (own rank included: every block of every rank polls all flags)
 }
@@ -1257,11 +1258,20 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
       // block 0 publishes this rank's header and flags; EVERY block waits for the flags of all ranks and folds the headers
       // itself (same values everywhere), so that the summing can start without another grid barrier
       const uint32_t epar = (uint32_t)((mg_epoch + 1) & 1u);
+      unsigned long long xt0 = prof ? now_ns() : 0, xt1;
+#define XPROF(i)                         \
+  if (prof) {                            \
+    xt1 = now_ns();                      \
+    st->mg_prof_ns[5 + (i)] += xt1 - xt0; \
+    xt0 = xt1;                           \
+  }
       if (bid == 0 && warp == 0) {
         mgr_send_warp(R, par, epar, k, mg_epoch + 1);
         if (lane == 0) st->n_out = 0;  // nobody reserves slots before the next round's flush
       }
+      XPROF(0)
       if (warp == 0) mgr_wait_fold_warp(R, epar, mg_epoch + 1);
+      XPROF(1)
       mg_epoch++;
       __syncthreads();
       if (ld_cg(&st->mg_abort)) {  // a peer did not answer: every block of every rank that still runs leaves
@@ -1275,7 +1285,10 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         return;
       }
       mgr_accumulate(R, S, par, epar);  // all ranks' records summed into the global cells
+      XPROF(2)
       RBARRIER();
+      XPROF(3)
+#undef XPROF
       RPROF(5)
     }
     // ================= P2 =================
