@@ -31,7 +31,7 @@ class bpe_stats(C.Structure):
         "kernel_launches", "merges_applied", "index_builds", "hot_rebuilds", "tie_breaks", "sites_merged",
         "corpus_positions", "corpus_tokens", "distinct_pairs", "pool_used")] + [(n, C.c_double) for n in (
         "ms_index_build", "ms_argmax", "ms_apply", "ms_encode", "ms_last_merge_until")] + [("ms_loop_phase", C.c_double * 8)] + [(n, C.c_int64) for n in (
-        "loop_rounds", "loop_round_merges", "loop_round_tried", "loop_rounds_cut")]
+        "loop_rounds", "loop_round_merges", "loop_round_tried", "loop_rounds_cut", "encode_path")]
 
 
 MERGE_DTYPE = np.dtype([("a", "<i4"), ("b", "<i4"), ("c", "<i4"), ("reserved", "<i4"), ("weight", "<i8")])

@@ -15,6 +15,7 @@
 
 #include "encode_kernels.cuh"
 #include "encode_lanes.cuh"
+#include "encode_dp.cuh"
 #include "train_kernels.cuh"
 #include "mg_kernels.cuh"
 #include "round_kernels.cuh"
@@ -122,6 +123,8 @@ struct EncodeScratch {
   DevBuf<uint32_t> range_first, tile_sums;
   DevBuf<uint64_t> tile_off;
   DevBuf<uint32_t> flags;  // [0] long documents left for the per-document kernel, [1] error, [2] next range to claim
+  DevBuf<uint16_t> dp_last;              // forward path (encode_dp.cuh): last[] of every document, per warp [position][lane]
+  DevBuf<unsigned long long> dp_cursor;  // ... and where the next warp's rows start
 };
 
 struct bpe_engine {
@@ -156,6 +159,12 @@ struct bpe_engine {
   DevBuf<uint16_t> d_rule_c;
   uint32_t lt_cap = 0;
   int32_t lt_c_affine = -1;
+  // forward path (encode_dp.cuh): Aho-Corasick automaton over the tokens' characters + merge trees
+  bool dp_dirty = true, dp_ok = false;
+  DevBuf<uint32_t> d_dfa, d_split;
+  DevBuf<uint16_t> d_out_tok, d_tok_len, d_shorter;
+  uint32_t dp_alpha = 0;
+  int enc_dp = 1;        // BPE_ENC_DP=0 keeps the lane path
   int enc_lmax = 32;     // rows per lane of the lane path (32 or 48); BPE_ENC_LMAX overrides
   int enc_lmax_forced = 0;
   int enc_force_old = 0; // debug: BPE_ENC_OLD=1 routes every document through the per-document kernel
@@ -569,7 +578,7 @@ int run_apply(bpe_engine* e, uint32_t a, uint32_t b, uint32_t c, uint32_t bound)
   e->h_merges.push_back((int32_t)a);
   e->h_merges.push_back((int32_t)b);
   e->h_merges.push_back((int32_t)c);
-  e->mt_dirty = e->lt_dirty = true;
+  e->mt_dirty = e->lt_dirty = e->dp_dirty = true;
   e->n_tokens++;
   e->stats.merges_applied++;
   return BPE_OK;
@@ -704,6 +713,109 @@ int ensure_lane_tables(bpe_engine* e) {
   return BPE_OK;
 }
 
+// ---- tables of the forward encode path (encode_dp.cuh): tokens ending at a position, longest first, and merge trees ----
+// Supported when the table is what mergeUntil / fromJSON produce: the single characters are the tokens 0 .. n_alpha-1, merge r
+// creates token n_alpha + r out of older tokens, no two tokens spell the same string, and the dense automaton fits.
+int ensure_dp_tables(bpe_engine* e) {
+  if (!e->dp_dirty) return BPE_OK;
+  e->dp_dirty = false;
+  e->dp_ok = false;
+  const size_t m = e->h_merges.size() / 3;
+  const int64_t n_tok = e->n_tokens;
+  const int64_t A = n_tok - (int64_t)m;
+  if (A <= 0 || A > 4096 || n_tok > 0xFFF0) return BPE_OK;
+  std::vector<uint32_t> split((size_t)n_tok), off((size_t)n_tok + 1, 0);
+  std::vector<uint16_t> tok_len((size_t)n_tok, 1);
+  for (int64_t t = 0; t < A; t++) split[(size_t)t] = (uint32_t)t | ((uint32_t)t << 16);
+  for (size_t r = 0; r < m; r++) {
+    const int64_t a = e->h_merges[3 * r], b = e->h_merges[3 * r + 1], c = e->h_merges[3 * r + 2];
+    if (c != A + (int64_t)r || a < 0 || b < 0 || a >= c || b >= c) return BPE_OK;  // (characters added after merges: lane path)
+    const uint32_t L = (uint32_t)tok_len[(size_t)a] + tok_len[(size_t)b];
+    if (L > 0xFFF0u) return BPE_OK;
+    tok_len[(size_t)c] = (uint16_t)L;
+    split[(size_t)c] = (uint32_t)a | ((uint32_t)b << 16);
+  }
+  // the tokens' characters, then the trie
+  for (int64_t t = 0; t < n_tok; t++) off[(size_t)t + 1] = off[(size_t)t] + tok_len[(size_t)t];
+  if (off[(size_t)n_tok] > (64u << 20)) return BPE_OK;
+  std::vector<uint16_t> text(off[(size_t)n_tok]);
+  for (int64_t t = 0; t < A; t++) text[off[(size_t)t]] = (uint16_t)t;
+  for (size_t r = 0; r < m; r++) {
+    const size_t a = (size_t)e->h_merges[3 * r], b = (size_t)e->h_merges[3 * r + 1], c = (size_t)e->h_merges[3 * r + 2];
+    std::copy(text.begin() + off[a], text.begin() + off[a + 1], text.begin() + off[c]);
+    std::copy(text.begin() + off[b], text.begin() + off[b + 1], text.begin() + off[c] + tok_len[a]);
+  }
+  std::unordered_map<uint64_t, uint32_t> child;  // (node << 16 | char) -> node
+  child.reserve(text.size() * 2);
+  std::vector<uint16_t> node_tok(1, (uint16_t)DP_NONE);
+  std::vector<uint32_t> node_of((size_t)n_tok), parent(1, 0);
+  std::vector<uint16_t> pch(1, 0);
+  for (int64_t t = 0; t < n_tok; t++) {
+    uint32_t v = 0;
+    for (uint32_t i = off[(size_t)t]; i < off[(size_t)t + 1]; i++) {
+      const uint64_t key = ((uint64_t)v << 16) | text[i];
+      auto it = child.find(key);
+      if (it == child.end()) {
+        const uint32_t nv = (uint32_t)node_tok.size();
+        child.emplace(key, nv);
+        node_tok.push_back((uint16_t)DP_NONE);
+        parent.push_back(v);
+        pch.push_back(text[i]);
+        v = nv;
+      } else {
+        v = it->second;
+      }
+    }
+    if (node_tok[v] != DP_NONE) return BPE_OK;  // two tokens spell the same string: the string does not identify the token
+    node_tok[v] = (uint16_t)t;
+    node_of[(size_t)t] = v;
+  }
+  const size_t S = node_tok.size();
+  if (S * (size_t)A > (64u << 20)) return BPE_OK;  // dense automaton too large (huge alphabets): lane path
+  // Aho-Corasick as a dense automaton, nodes in order of depth: the row of a node is the row of its failure node (shallower,
+  // hence complete) with its own children written over it; the failure node of a child u = (v, ch) is row[fail(v)][ch]
+  std::vector<uint32_t> depth(S, 0), order(S);
+  for (size_t v = 1; v < S; v++) depth[v] = depth[parent[v]] + 1;  // (a parent's index is smaller than its children's)
+  for (size_t v = 0; v < S; v++) order[v] = (uint32_t)v;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return depth[x] < depth[y]; });
+  std::vector<uint32_t> kid_begin(S + 1, 0), kids(S > 0 ? S - 1 : 0);
+  for (size_t v = 1; v < S; v++) kid_begin[parent[v] + 1]++;
+  for (size_t v = 0; v < S; v++) kid_begin[v + 1] += kid_begin[v];
+  {
+    std::vector<uint32_t> fill(kid_begin.begin(), kid_begin.end() - 1);
+    for (size_t v = 1; v < S; v++) kids[fill[parent[v]]++] = (uint32_t)v;
+  }
+  std::vector<uint32_t> dfa(S * (size_t)A, 0), fail_(S, 0);
+  std::vector<uint16_t> out_tok(S, (uint16_t)DP_NONE);
+  for (uint32_t v : order) {
+    if (v != 0) {
+      out_tok[v] = node_tok[v] != DP_NONE ? node_tok[v] : out_tok[fail_[v]];
+      std::copy(dfa.begin() + (size_t)fail_[v] * A, dfa.begin() + (size_t)(fail_[v] + 1) * A, dfa.begin() + (size_t)v * A);
+    }
+    for (uint32_t i = kid_begin[v]; i < kid_begin[v + 1]; i++) {
+      const uint32_t u = kids[i];
+      fail_[u] = v == 0 ? 0u : dfa[(size_t)fail_[v] * A + pch[u]];
+      dfa[(size_t)v * A + pch[u]] = u;
+    }
+  }
+  std::vector<uint16_t> shorter((size_t)n_tok, (uint16_t)DP_NONE);
+  for (int64_t t = 0; t < n_tok; t++) shorter[(size_t)t] = out_tok[fail_[node_of[(size_t)t]]];
+  CK(e->d_dfa.reserve(dfa.size()));
+  CK(cudaMemcpyAsync(e->d_dfa.p, dfa.data(), dfa.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(e->d_out_tok.reserve(S));
+  CK(cudaMemcpyAsync(e->d_out_tok.p, out_tok.data(), S * 2, cudaMemcpyHostToDevice, e->stream));
+  CK(e->d_tok_len.reserve((size_t)n_tok));
+  CK(cudaMemcpyAsync(e->d_tok_len.p, tok_len.data(), (size_t)n_tok * 2, cudaMemcpyHostToDevice, e->stream));
+  CK(e->d_shorter.reserve((size_t)n_tok));
+  CK(cudaMemcpyAsync(e->d_shorter.p, shorter.data(), (size_t)n_tok * 2, cudaMemcpyHostToDevice, e->stream));
+  CK(e->d_split.reserve((size_t)n_tok));
+  CK(cudaMemcpyAsync(e->d_split.p, split.data(), (size_t)n_tok * 4, cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->dp_alpha = (uint32_t)A;
+  e->dp_ok = true;
+  return BPE_OK;
+}
+
 template <int LMAX, int WARPS>
 int launch_encode_lanes(bpe_engine* e, const int32_t* dev_ids, const int64_t* dev_doc_off, int64_t n_docs, const uint32_t* range_first,
                         uint32_t n_ranges, const LaneTables& lt, int32_t* out_tmp, uint32_t* out_len, uint32_t* n_long, uint32_t* err,
@@ -747,6 +859,7 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
   int overlap_rc = BPE_OK;
   if (e->h_merges.size() / 3 > EL_MAX_RANK + 1) return fail(e, BPE_E_DOMAIN, "merge list too long");
   TRY(ensure_lane_tables(e));
+  TRY(ensure_dp_tables(e));
   TRY(ensure_pipe(e));
   CK(sc.out_tmp.reserve((size_t)std::max<int64_t>(n_ids, 1)));
   CK(sc.out_len.reserve((size_t)n_docs + 1));
@@ -776,7 +889,23 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
                                                                                                              sc.range_first.p);
     CKL();
     LaneTables lt{e->d_lt.p, e->lt_cap - 1, (uint32_t)(32 - ilog2(e->lt_cap)), e->d_lt_dense.p, e->d_rule_c.p, e->lt_c_affine};
-    if (lmax == 16)
+    e->stats.encode_path = (e->enc_dp && e->dp_ok) ? 1 : 2;
+    if (e->enc_dp && e->dp_ok) {
+      // forward path: one left-to-right pass per document (encode_dp.cuh), one thread per document
+      constexpr int DPW = 8;
+      const unsigned long long cap_entries = 3ull * (unsigned long long)n_ids + (1ull << 20);  // (a warp of 32 documents needs 32 x its longest)
+      CK(sc.dp_last.reserve((size_t)cap_entries));
+      CK(sc.dp_cursor.reserve(1));
+      CK(cudaMemsetAsync(sc.dp_cursor.p, 0, 8, e->stream));
+      DpTables dt{e->d_dfa.p, e->d_out_tok.p, e->d_tok_len.p, e->d_shorter.p, e->d_split.p, e->dp_alpha};
+      int per_sm = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_dp<DPW>, DPW * 32, 0));
+      const int64_t want = (n_docs + DPW * 32 - 1) / (DPW * 32);
+      const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sm_count * std::max(per_sm, 1)));
+      k_encode_dp<DPW><<<blocks, DPW * 32, 0, e->stream>>>(dev_ids, dev_doc_off, n_docs, lt, dt, sc.dp_last.p, cap_entries, sc.dp_cursor.p, sc.out_tmp.p,
+                                                          sc.out_len.p, sc.flags.p, sc.flags.p + 1);
+      CKL();
+    } else if (lmax == 16)
       TRY((launch_encode_lanes<16, 20>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
     else if (lmax == 20)
       TRY((launch_encode_lanes<20, 16>(e, dev_ids, dev_doc_off, n_docs, sc.range_first.p, n_ranges, lt, sc.out_tmp.p, sc.out_len.p, sc.flags.p, sc.flags.p + 1, sc.flags.p + 2)));
@@ -798,6 +927,7 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
     if (hf[1]) return fail(e, BPE_E_INTERNAL, "encode rounds did not converge");
     run_old = hf[0] != 0;
   }
+  if (e->enc_force_old) e->stats.encode_path = 3;
   if (n_docs > 0 && run_old) {
     // per-document kernel: documents longer than a lane batch (marked EL_LONG), or everything when forced
     TRY(ensure_merge_table(e));
@@ -1107,7 +1237,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
         e->h_merges.push_back(r.c);
       }
       e->n_tokens += (int32_t)iters;
-      e->mt_dirty = e->lt_dirty = true;
+      e->mt_dirty = e->lt_dirty = e->dp_dirty = true;
       e->stats.merges_applied += iters;
     }
     uint32_t status = e->h_st->status;
@@ -1395,7 +1525,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
         e->h_merges.push_back(r.c);
       }
       e->n_tokens += (int32_t)iters;
-      e->mt_dirty = e->lt_dirty = true;
+      e->mt_dirty = e->lt_dirty = e->dp_dirty = true;
       e->stats.merges_applied += iters;
     }
     host_ms[3] += since(tl);
@@ -1600,6 +1730,8 @@ int bpe_create(int device, bpe_engine** out) {
   e->stream = e->own_stream;
   if (getenv("BPE_HOST_LOOP")) e->host_loop = 1;
   if (getenv("BPE_ENC_OLD")) e->enc_force_old = 1;
+  if (const char* v = getenv("BPE_ENC_DP")) e->enc_dp = atoi(v) != 0;
+  if (getenv("BPE_ENC_LMAX")) e->enc_dp = 0;  // (a forced lane geometry means the lane path is what is being tested)
   if (getenv("BPE_ENC_LMAX")) e->enc_lmax_forced = 1;
   if (const char* v = getenv("BPE_ENC_LMAX")) e->enc_lmax = (atoi(v) == 48 || atoi(v) == 24 || atoi(v) == 20 || atoi(v) == 16) ? atoi(v) : 32;
   *out = e;
@@ -1688,7 +1820,7 @@ int bpe_set_tokens(bpe_engine* e, const int32_t* utf16_len, int32_t n_tokens) {
   CK(cudaSetDevice(e->device));
   e->h_len16.assign(utf16_len, utf16_len + n_tokens);
   e->n_tokens = n_tokens;
-  e->mt_dirty = e->lt_dirty = true;
+  e->mt_dirty = e->lt_dirty = e->dp_dirty = true;
   TRY(sync_len16(e));
   e->hot_valid = false;
   return BPE_OK;
@@ -1705,7 +1837,7 @@ int bpe_load_merges(bpe_engine* e, const int32_t* abc, int64_t n_merges) {
   for (int64_t i = 0; i < 3 * n_merges; i++)
     if (abc[i] < 0 || abc[i] >= BPE_MAX_TOKENS) return fail(e, BPE_E_INVALID, "merge %lld holds index %d", (long long)(i / 3), abc[i]);
   e->h_merges.assign(abc, abc + 3 * n_merges);
-  e->mt_dirty = e->lt_dirty = true;
+  e->mt_dirty = e->lt_dirty = e->dp_dirty = true;
   return BPE_OK;
 }
 
@@ -1838,7 +1970,7 @@ int bpe_apply_merge(bpe_engine* e, int32_t a, int32_t b, int32_t c, int64_t* n_r
     e->h_merges.push_back(a);
     e->h_merges.push_back(b);
     e->h_merges.push_back(c);
-    e->mt_dirty = e->lt_dirty = true;
+    e->mt_dirty = e->lt_dirty = e->dp_dirty = true;
     e->n_tokens++;
     e->index_valid = false;
     return BPE_OK;
@@ -1878,7 +2010,7 @@ int bpe_apply_merges(bpe_engine* e, const int32_t* ab, int64_t n, int64_t* n_rep
       e->n_tokens++;
       if (n_replaced) n_replaced[i] = 0;
     }
-    e->mt_dirty = e->lt_dirty = true;
+    e->mt_dirty = e->lt_dirty = e->dp_dirty = true;
     TRY(sync_len16(e));
     return BPE_OK;
   }
@@ -2526,7 +2658,7 @@ int bpe_add_text(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_off
       e->h_len16.push_back(h_cp[k] >= 0x10000 ? 2 : 1);  // `chars.length` in UTF-16 units (core.ts:272)
     }
     e->n_tokens += (int32_t)nn;
-    e->mt_dirty = e->lt_dirty = true;
+    e->mt_dirty = e->lt_dirty = e->dp_dirty = true;
     TRY(sync_len16(e));
     DevBuf<int32_t> a, b;
     CK(a.reserve(nn));

@@ -82,6 +82,8 @@ typedef struct bpe_stats {
   int64_t loop_round_merges;   /* merges those rounds committed (/ loop_rounds = merges per round) */
   int64_t loop_round_tried;    /* merges whose site pass ran (committed + dropped by the born-pair bound) */
   int64_t loop_rounds_cut;     /* rounds that dropped a tail of their batch                       */
+  int64_t encode_path;         /* kernel the last encode call ran: 1 forward pass per document (csrc/encode_dp.cuh),
+                                  2 lane rounds (csrc/encode_lanes.cuh), 3 per-document kernel only                */
 } bpe_stats;
 
 int bpe_abi_version(void);

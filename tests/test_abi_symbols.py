@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert C.sizeof(_abi.bpe_merge) == 24
     assert _abi.MERGE_DTYPE.itemsize == 24
-    assert C.sizeof(_abi.bpe_stats) == 27 * 8
+    assert C.sizeof(_abi.bpe_stats) == 28 * 8
 
 
 def test_no_cpu_fallback_without_device():

@@ -408,12 +408,14 @@ def test_add_to_corpus_after_merges_appends_raw_ids():
     assert t.corpus_in_code == lit.corpus_in_code
 
 
-@pytest.mark.parametrize("lmax", ["48", "32", "24", "20", "16"])
+@pytest.mark.parametrize("lmax", ["dp", "48", "32", "24", "20", "16"])
 @pytest.mark.parametrize("seed", range(6))
 def test_encode_batch_lane_path_fuzz(seed, lmax, monkeypatch):
-    """K4 lane path (encode_lanes.cuh): batches of ragged documents -- empty, single-token, runs, documents longer than
-    one lane batch (per-document fallback) -- against the sequential replaceAll of core.ts:404-406."""
-    monkeypatch.setenv("BPE_ENC_LMAX", lmax)
+    """K4: the forward path (encode_dp.cuh, "dp": the default) and the lane path (encode_lanes.cuh, one forced geometry per
+    value) on batches of ragged documents -- empty, single-token, runs, documents longer than one lane batch (per-document
+    fallback) -- against the sequential replaceAll of core.ts:404-406."""
+    if lmax != "dp":
+        monkeypatch.setenv("BPE_ENC_LMAX", lmax)
     rng = random.Random(7000 + seed)
     alphabet = ["ab", "abc", "abcdef ", "ab", "abcdefghijklmnopqrstuvwxyz ", "xy "][seed]
     train = _random_docs(rng, alphabet, rng.randint(2, 10), rng.choice([50, 300, 2000]))
@@ -447,6 +449,8 @@ def test_encode_batch_lane_path_fuzz(seed, lmax, monkeypatch):
     for d, text in enumerate(docs):
         want = [ord(ch) - 1 for ch in lit.encodeToCode(text)]
         assert raw[roff[d]:roff[d + 1]].tolist() == want, (d, len(text))
+    if lmax == "dp":
+        assert gpu.stats()["encode_path"] == 1, "the forward path was expected to take this table"
     # the per-document kernel must agree with the lane path on every document
     monkeypatch.setenv("BPE_ENC_OLD", "1")
     old = make()
