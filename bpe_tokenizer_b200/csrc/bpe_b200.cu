@@ -161,10 +161,13 @@ struct bpe_engine {
   int32_t lt_c_affine = -1;
   // forward path (encode_dp.cuh): Aho-Corasick automaton over the tokens' characters + merge trees
   bool dp_dirty = true, dp_ok = false;
-  DevBuf<uint32_t> d_dfa, d_split;
-  DevBuf<uint16_t> d_out_tok, d_tok_len, d_shorter;
+  DevBuf<unsigned long long> d_dfa;
+  DevBuf<uint32_t> d_split;
+  DevBuf<uint16_t> d_tok_len, d_shorter;
+  bool dp_attr_set = false;
   uint32_t dp_alpha = 0;
-  int enc_dp = 1;        // BPE_ENC_DP=0 keeps the lane path
+  int enc_dp = 0;        // BPE_ENC_DP=1: forward path (exact, measured slower than the lane path: 8.5 vs 26.9 GB/s -- thread-per-document
+                         // keeps 5 of 32 lanes busy; kept as an independent second implementation)
   int enc_lmax = 32;     // rows per lane of the lane path (32 or 48); BPE_ENC_LMAX overrides
   int enc_lmax_forced = 0;
   int enc_force_old = 0; // debug: BPE_ENC_OLD=1 routes every document through the per-document kernel
@@ -800,10 +803,15 @@ int ensure_dp_tables(bpe_engine* e) {
   }
   std::vector<uint16_t> shorter((size_t)n_tok, (uint16_t)DP_NONE);
   for (int64_t t = 0; t < n_tok; t++) shorter[(size_t)t] = out_tok[fail_[node_of[(size_t)t]]];
-  CK(e->d_dfa.reserve(dfa.size()));
-  CK(cudaMemcpyAsync(e->d_dfa.p, dfa.data(), dfa.size() * 4, cudaMemcpyHostToDevice, e->stream));
-  CK(e->d_out_tok.reserve(S));
-  CK(cudaMemcpyAsync(e->d_out_tok.p, out_tok.data(), S * 2, cudaMemcpyHostToDevice, e->stream));
+  // one 8-byte entry per transition: next state | longest token ending there << 32 | its length << 48
+  std::vector<unsigned long long> dfa64(dfa.size());
+  for (size_t i = 0; i < dfa.size(); i++) {
+    const uint32_t nx = dfa[i];
+    const uint16_t ot = out_tok[nx];
+    dfa64[i] = (unsigned long long)nx | ((unsigned long long)ot << 32) | ((unsigned long long)(ot == DP_NONE ? 0 : tok_len[ot]) << 48);
+  }
+  CK(e->d_dfa.reserve(dfa64.size()));
+  CK(cudaMemcpyAsync(e->d_dfa.p, dfa64.data(), dfa64.size() * 8, cudaMemcpyHostToDevice, e->stream));
   CK(e->d_tok_len.reserve((size_t)n_tok));
   CK(cudaMemcpyAsync(e->d_tok_len.p, tok_len.data(), (size_t)n_tok * 2, cudaMemcpyHostToDevice, e->stream));
   CK(e->d_shorter.reserve((size_t)n_tok));
@@ -892,17 +900,22 @@ int encode_dev(bpe_engine* e, EncodeScratch& sc, const int32_t* dev_ids, const i
     e->stats.encode_path = (e->enc_dp && e->dp_ok) ? 1 : 2;
     if (e->enc_dp && e->dp_ok) {
       // forward path: one left-to-right pass per document (encode_dp.cuh), one thread per document
-      constexpr int DPW = 8;
+      constexpr int DPW = 16;
+      const size_t dp_smem_bytes = (size_t)DP_CACHE * 8 + (size_t)EL_DENSE * EL_DENSE * sizeof(uint2);
+      if (!e->dp_attr_set) {
+        CK(cudaFuncSetAttribute(k_encode_dp<DPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp_smem_bytes));
+        e->dp_attr_set = true;
+      }
       const unsigned long long cap_entries = 3ull * (unsigned long long)n_ids + (1ull << 20);  // (a warp of 32 documents needs 32 x its longest)
       CK(sc.dp_last.reserve((size_t)cap_entries));
       CK(sc.dp_cursor.reserve(1));
       CK(cudaMemsetAsync(sc.dp_cursor.p, 0, 8, e->stream));
-      DpTables dt{e->d_dfa.p, e->d_out_tok.p, e->d_tok_len.p, e->d_shorter.p, e->d_split.p, e->dp_alpha};
+      DpTables dt{e->d_dfa.p, e->d_tok_len.p, e->d_shorter.p, e->d_split.p, e->dp_alpha};
       int per_sm = 1;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_dp<DPW>, DPW * 32, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_dp<DPW>, DPW * 32, dp_smem_bytes));
       const int64_t want = (n_docs + DPW * 32 - 1) / (DPW * 32);
       const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sm_count * std::max(per_sm, 1)));
-      k_encode_dp<DPW><<<blocks, DPW * 32, 0, e->stream>>>(dev_ids, dev_doc_off, n_docs, lt, dt, sc.dp_last.p, cap_entries, sc.dp_cursor.p, sc.out_tmp.p,
+      k_encode_dp<DPW><<<blocks, DPW * 32, dp_smem_bytes, e->stream>>>(dev_ids, dev_doc_off, n_docs, lt, dt, sc.dp_last.p, cap_entries, sc.dp_cursor.p, sc.out_tmp.p,
                                                           sc.out_len.p, sc.flags.p, sc.flags.p + 1);
       CKL();
     } else if (lmax == 16)
@@ -1731,7 +1744,6 @@ int bpe_create(int device, bpe_engine** out) {
   if (getenv("BPE_HOST_LOOP")) e->host_loop = 1;
   if (getenv("BPE_ENC_OLD")) e->enc_force_old = 1;
   if (const char* v = getenv("BPE_ENC_DP")) e->enc_dp = atoi(v) != 0;
-  if (getenv("BPE_ENC_LMAX")) e->enc_dp = 0;  // (a forced lane geometry means the lane path is what is being tested)
   if (getenv("BPE_ENC_LMAX")) e->enc_lmax_forced = 1;
   if (const char* v = getenv("BPE_ENC_LMAX")) e->enc_lmax = (atoi(v) == 48 || atoi(v) == 24 || atoi(v) == 20 || atoi(v) == 16) ? atoi(v) : 32;
   *out = e;

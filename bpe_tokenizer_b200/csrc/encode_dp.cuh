@@ -30,9 +30,11 @@ constexpr uint32_t DP_MAX_LEN = 8192;   // characters of a document on this path
 constexpr uint32_t DP_NONE = 0xFFFFu;
 constexpr int DP_RING = 64;
 
+constexpr uint32_t DP_CACHE = 8192;   // entries of a block's cache of compatibility verdicts (shared memory, 8 bytes each)
+
 struct DpTables {
-  const uint32_t* dfa;        // [states][n_alpha] next state
-  const uint16_t* out_tok;    // [states] longest token that is a suffix of the state's string
+  const unsigned long long* dfa;  // [states][n_alpha]: next state | longest token that is a suffix of its string << 32 | that
+                                  // token's length << 48 -- one load per character gives all three
   const uint16_t* tok_len;    // [tokens] characters of the token
   const uint16_t* shorter;    // [tokens] longest token that is a proper suffix of the token's string (DP_NONE: a character)
   const uint32_t* split;      // [tokens] left part | right part << 16 (a character: itself twice)
@@ -57,13 +59,30 @@ __device__ __forceinline__ bool dp_compatible(const LaneTables& T, const uint2* 
   }
 }
 
+// ... with the verdict of a pair of tokens remembered per block: adjacent token pairs of natural text repeat (Zipf), and a
+// verdict read from shared memory replaces a walk of ~10 dependent table loads.  One 8-byte entry per slot (pair key << 1 |
+// verdict, written whole), direct mapped: a lost race or a collision only costs the walk.
+__device__ __forceinline__ bool dp_compatible_cached(const LaneTables& T, const uint2* s_dense, const DpTables& D, unsigned long long* s_cache, uint32_t t1,
+                                                     uint32_t t2) {
+  const uint32_t key = (t1 << 16) | t2;
+  unsigned long long* slot = s_cache + ((key * 0x9E3779B1u) >> 19);  // 13 bits
+  const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(slot);
+  if ((uint32_t)(e >> 1) == key && e != ~0ull) return (e & 1ull) != 0;
+  const bool ok = dp_compatible(T, s_dense, D, t1, t2);
+  *reinterpret_cast<volatile unsigned long long*>(slot) = ((unsigned long long)key << 1) | (ok ? 1ull : 0ull);
+  return ok;
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k_encode_dp(const int32_t* __restrict__ ids, const int64_t* __restrict__ doc_off, int64_t n_docs,
                                                            LaneTables T, DpTables D, uint16_t* __restrict__ scratch, unsigned long long scratch_cap,
                                                            unsigned long long* __restrict__ scratch_cursor, int32_t* __restrict__ out_tmp,
                                                            uint32_t* __restrict__ out_len, uint32_t* __restrict__ n_long, uint32_t* __restrict__ err) {
-  __shared__ uint2 s_dense[EL_DENSE * EL_DENSE];
+  extern __shared__ unsigned long long dp_smem[];
+  unsigned long long* s_cache = dp_smem;                                   // [DP_CACHE]
+  uint2* s_dense = reinterpret_cast<uint2*>(dp_smem + DP_CACHE);           // [EL_DENSE * EL_DENSE]
   for (int i = threadIdx.x; i < EL_DENSE * EL_DENSE; i += WARPS * 32) s_dense[i] = T.dense[i];
+  for (int i = threadIdx.x; i < (int)DP_CACHE; i += WARPS * 32) s_cache[i] = ~0ull;
   __syncthreads();
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = threadIdx.x & 31u;
@@ -102,19 +121,20 @@ __global__ void __launch_bounds__(WARPS * 32) k_encode_dp(const int32_t* __restr
     for (uint32_t i = 1; i <= maxlen; i++) {
       if (i <= len) {
         const uint32_t ch = (uint32_t)__ldg(ids + base + (i - 1));
-        state = __ldg(D.dfa + (size_t)state * D.n_alpha + ch);
-        uint32_t t = __ldg(D.out_tok + state);
+        const unsigned long long tr = __ldg(D.dfa + (size_t)state * D.n_alpha + ch);
+        state = (uint32_t)tr;
+        uint32_t t = (uint32_t)(tr >> 32) & 0xFFFFu, L = (uint32_t)(tr >> 48);
         for (;;) {
           if (t == DP_NONE) {  // (cannot happen: a character is a token and is compatible with whatever precedes it)
             atomicOr(err, 1u);
             t = ch;
             break;
           }
-          const uint32_t L = __ldg(D.tok_len + t);
           if (L >= i) break;  // the token starts the document (L == i)
           const uint32_t prev = (L < (uint32_t)DP_RING) ? (uint32_t)ring[(i - L) & (DP_RING - 1)] : (uint32_t)col[(size_t)(i - L) * 32];
-          if (dp_compatible(T, s_dense, D, prev, t)) break;
+          if (dp_compatible_cached(T, s_dense, D, s_cache, prev, t)) break;
           t = __ldg(D.shorter + t);
+          L = (t == DP_NONE) ? 0u : (uint32_t)__ldg(D.tok_len + t);
         }
         ring[i & (DP_RING - 1)] = (uint16_t)t;
         col[(size_t)i * 32] = (uint16_t)t;

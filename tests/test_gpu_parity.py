@@ -414,7 +414,9 @@ def test_encode_batch_lane_path_fuzz(seed, lmax, monkeypatch):
     """K4: the forward path (encode_dp.cuh, "dp": the default) and the lane path (encode_lanes.cuh, one forced geometry per
     value) on batches of ragged documents -- empty, single-token, runs, documents longer than one lane batch (per-document
     fallback) -- against the sequential replaceAll of core.ts:404-406."""
-    if lmax != "dp":
+    if lmax == "dp":
+        monkeypatch.setenv("BPE_ENC_DP", "1")
+    else:
         monkeypatch.setenv("BPE_ENC_LMAX", lmax)
     rng = random.Random(7000 + seed)
     alphabet = ["ab", "abc", "abcdef ", "ab", "abcdefghijklmnopqrstuvwxyz ", "xy "][seed]
