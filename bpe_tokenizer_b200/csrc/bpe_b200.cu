@@ -203,7 +203,6 @@ struct bpe_engine {
   DevBuf<RoundState> r_state;
   DevBuf<unsigned long long> r_gcells;  // sharded rounds: the deltas summed over the ranks
   DevBuf<uint32_t> r_glists;
-  DevBuf<unsigned long long> r_brec;
   int round_blocks = 0;  // co-resident grid of k_merge_rounds
   int host_loop = 0;     // debug: drive mergeUntil from the host, one launch per phase
   int scan_mode = 0;     // debug: walk all slots instead of occurrence lists
@@ -1061,7 +1060,6 @@ int ensure_round_buffers(bpe_engine* e) {
     CK(e->r_gcells.reserve(cells));
     CK(cudaMemsetAsync(e->r_gcells.p, 0, cells * 8, e->stream));
     CK(e->r_glists.reserve((size_t)2 * e->round_blocks * R_LISTCAP));
-    CK(e->r_brec.reserve((size_t)e->round_blocks * R_BRECCAP));
   }
   CK(e->r_gp.reserve((size_t)RT * e->round_blocks));
   CK(e->r_gk.reserve((size_t)RT * e->round_blocks));
@@ -1084,7 +1082,6 @@ RoundArgs round_args(bpe_engine* e, const LoopArgs& L, int round_k) {
   RA.mg_on = 0;
   RA.gcells = e->r_gcells.p;
   RA.glists = e->r_glists.p;
-  RA.brec = e->r_brec.p;
   return RA;
 }
 

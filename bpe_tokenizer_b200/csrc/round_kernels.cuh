@@ -60,7 +60,6 @@ constexpr uint32_t R_LISTCAP = 32768;    // touched cells a block can list per r
 __host__ __device__ __forceinline__ uint32_t cell_dec(unsigned long long v) { return (uint32_t)(v & R_FMASK); }
 __host__ __device__ __forceinline__ uint32_t cell_len(unsigned long long v) { return (uint32_t)((v >> R_FIELD) & R_FMASK); }
 __host__ __device__ __forceinline__ uint32_t cell_cnt(unsigned long long v) { return (uint32_t)((v >> (2 * R_FIELD)) & R_FMASK); }
-constexpr uint32_t R_BRECCAP = 65536;    // sharded: records a block can buffer during one site pass
 constexpr uint32_t MGR_HDR = 64;          // sharded: u64 words of header in front of the records of a round's message
 constexpr uint32_t LOOP_NEED_LEGACY = 7;  // the winner is too big for the packed cells: k_merge_loop takes the merges above R_HUGE
 constexpr uint32_t R_QCAP = 512;         // per-block partial entries a decision can fold (RT x blocks)
@@ -111,7 +110,6 @@ struct RoundArgs {
   MgArgs mg;
   unsigned long long* gcells;  // [2][RB][2][ND_STRIDE]: decrements | counted occurrences << 21, summed over the ranks
   uint32_t* glists;            // [2][blocks][R_LISTCAP]: global cells each block touched first while summing
-  unsigned long long* brec;    // [blocks][R_BRECCAP]: the records a block's site pass produces, flushed into the inboxes at its end
 };
 
 __device__ __forceinline__ unsigned long long* round_cells(const RoundArgs& R, uint32_t par, uint32_t j, uint32_t side) {
@@ -260,7 +258,7 @@ struct RoundSm {
   uint32_t gv[8];  // sharded: the folded header values (OR of the ranks' error flags, minima of their capacities)
   uint32_t ncell[2];  // cells this block touched first in the round of either parity (entries of its list)
   uint32_t gncell[2]; // sharded: global cells this block touched first while summing the ranks' records
-  uint32_t nrec, rec_base;  // sharded: records this block buffered in the current site pass / where they go in the inboxes
+  uint32_t rec_base, pad2;  // sharded: where this block's records go in the inboxes
   uint32_t pool_next, pool_end;  // this block's private chunk of the occurrence pool (list space without a grid-wide atomic)
   uint32_t keys_ins;             // keys this block inserted in the current P2 (one n_keys atomic per block and round)
   uint32_t filt_a[8], filt_b[8]; // role_maybe filters: the a's / the b's of the batch
@@ -319,23 +317,6 @@ __device__ __forceinline__ uint32_t cell_add_warp(const RoundArgs& R, RoundSm& S
     const unsigned long long add = (unsigned long long)nd | ((unsigned long long)__popc(peers & nmask) << R_FIELD) | ((unsigned long long)nc << (2 * R_FIELD));
     first = atomicAdd(cells + tok, add) == 0ull;
   }
-  if (R.mg_on) {
-    // sharded: what this warp adds to the GLOBAL counts becomes a record in the block's buffer (a shared-memory counter bump
-    // per warp); the block stores its records into every rank's inbox when its site pass ends (round_flush_records)
-    const bool has_rec = leader;  // (also a cell that only holds uncounted occurrences: every rank must come to know the pair)
-    const uint32_t rm = __ballot_sync(0xFFFFFFFFu, has_rec);
-    if (rm) {
-      uint32_t base = 0;
-      const int src = __ffs(rm) - 1;
-      if ((int)lane == src) base = atomicAdd(&S.nrec, (uint32_t)__popc(rm));
-      base = __shfl_sync(0xFFFFFFFFu, base, src);
-      if (has_rec) {
-        const uint32_t at = base + __popc(rm & ((1u << lane) - 1u));
-        if (at < R_BRECCAP) R.brec[(size_t)blockIdx.x * R_BRECCAP + at] = ((unsigned long long)((js << 16) | tok) << 42) | ((unsigned long long)nc << R_FIELD) | nd;
-        else atomicOr(&R.L.A.st->err, ERR_INBOX_OVERFLOW);
-      }
-    }
-  }
   const uint32_t fm = __ballot_sync(0xFFFFFFFFu, first);
   if (fm) {
     uint32_t base = 0;
@@ -367,28 +348,49 @@ __device__ __forceinline__ uint32_t cell_add_warp(const RoundArgs& R, RoundSm& S
 // record: ((merge * 2 + side) << 16 | token) << 42 | counted occurrences << 21 | decrements    (one per warp and distinct
 // neighbour of a site pass, written while the pass runs)
 
-// end of a block's site pass: its buffered records go into every rank's inbox (ONE slot reservation per block and round,
-// coalesced NVLink stores); every thread of the block calls
-__device__ __forceinline__ void round_flush_records(const RoundArgs& R, RoundSm& S, uint32_t epar) {
+// After the site passes of a round (grid barrier): every block turns the cells of ITS list -- the cells it touched first, now
+// complete -- into records in every rank's inbox: ONE record per touched cell and rank, one slot reservation per block,
+// coalesced NVLink stores.  (Records written while the passes run -- one per warp and neighbour -- were measured: the
+// frequent neighbours then receive hundreds of records each and the summing on the other side queues on those cells.)
+__device__ __forceinline__ void round_emit_records(const RoundArgs& R, RoundSm& S, uint32_t par, uint32_t epar, uint32_t k, uint32_t c_hi) {
   const MgArgs& M = R.mg;
   DevState* st = R.L.A.st;
-  __syncthreads();
-  const uint32_t n = min(S.nrec, R_BRECCAP);
-  if (threadIdx.x == 0) S.rec_base = n ? atomicAdd(&st->n_out, n) : 0u;
-  __syncthreads();
-  const uint32_t base = S.rec_base, cap = M.inbox_stride - MGR_HDR;
-  const unsigned long long* mine = R.brec + (size_t)blockIdx.x * R_BRECCAP;
-  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const unsigned long long rec = mine[i];
-    const uint32_t at = base + i;
-    if (at < cap) {
-      for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MGR_HDR + at] = rec;
-    } else {
-      atomicOr(&st->err, ERR_INBOX_OVERFLOW);
+  const uint32_t cap = M.inbox_stride - MGR_HDR;
+  if (!ld_cg(&R.rs->overflow[par])) {
+    const uint32_t n = min(S.ncell[par], R_LISTCAP);
+    if (threadIdx.x == 0) S.rec_base = n ? atomicAdd(&st->n_out, n) : 0u;
+    __syncthreads();
+    const uint32_t base = S.rec_base;
+    const uint32_t* list = round_list(R, par);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t ent = ld_cg(list + i);
+      const uint32_t js = (ent >> 16) & (2u * RB - 1u), tok = ent & 0xFFFFu;
+      const unsigned long long cellv = ld_cg(round_cells(R, par, js >> 1, js & 1u) + tok);
+      const unsigned long long rec = ((unsigned long long)ent << 42) | ((unsigned long long)cell_cnt(cellv) << R_FIELD) | cell_dec(cellv);
+      const uint32_t at = base + i;
+      if (at < cap) {
+        for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MGR_HDR + at] = rec;
+      } else {
+        atomicOr(&st->err, ERR_INBOX_OVERFLOW);
+      }
+    }
+  } else {
+    // a list was full: every non-empty cell of the round's rows (slots one by one: rare)
+    const uint32_t T = (c_hi + 31u) & ~31u;
+    const uint32_t total = k * 2u * T;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const uint32_t js = i / T, tok = i - js * T;
+      const unsigned long long cellv = ld_cg(round_cells(R, par, js >> 1, js & 1u) + tok);
+      if (!cellv) continue;
+      const uint32_t at = atomicAdd(&st->n_out, 1u);
+      if (at < cap) {
+        const unsigned long long rec = ((unsigned long long)((js << 16) | tok) << 42) | ((unsigned long long)cell_cnt(cellv) << R_FIELD) | cell_dec(cellv);
+        for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MGR_HDR + at] = rec;
+      } else {
+        atomicOr(&st->err, ERR_INBOX_OVERFLOW);
+      }
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) S.nrec = 0;
   __threadfence_system();
 }
 
@@ -867,7 +869,6 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
   if (R.mg_on) {
     // hello exchange: headers only (capacities, errors), so that the first decision is taken on global minima
     if (lead) st->mg_abort = 0;
-    if (tid == 0) S.nrec = 0;
     if (bid == 0 && warp == 0) mgr_send_warp(R, 0, (uint32_t)((mg_epoch + 1) & 1u), 0, mg_epoch + 1);
     if (warp == 0) mgr_wait_fold_warp(R, (uint32_t)((mg_epoch + 1) & 1u), mg_epoch + 1);
     mg_epoch++;
@@ -1249,15 +1250,17 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         }
       }
     }
-    if (R.mg_on) round_flush_records(R, S, (uint32_t)((mg_epoch + 1) & 1u));  // this block's records -> every rank's inbox
     RPROF(1)
     RBARRIER();
     RPROF(2)
     if (R.mg_on) {
       // ================= sharded: one exchange per round =================
-      // block 0 publishes this rank's header and flags; EVERY block waits for the flags of all ranks and folds the headers
-      // itself (same values everywhere), so that the summing can start without another grid barrier
+      // every block stores the cells it listed as records into every rank's inbox; after a grid barrier block 0 publishes
+      // this rank's header and flags; EVERY block waits for the flags of all ranks and folds the headers itself (same
+      // values everywhere), so that the summing can start without another grid barrier
       const uint32_t epar = (uint32_t)((mg_epoch + 1) & 1u);
+      round_emit_records(R, S, par, epar, k, c_first + k);
+      RBARRIER();
       unsigned long long xt0 = prof ? now_ns() : 0, xt1;
 #define XPROF(i)                         \
   if (prof) {                            \
