@@ -1212,7 +1212,9 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
       for (uint32_t j = 0; j < F.v; j++) fill_total += S.fill_n[j];
       // latency bound: some warps of every block walk the sites, the others fill the lists of the previous round's pairs and
       // zero the cells that round touched; throughput bound: everybody does everything
-      const bool split = iters <= 3u * nblk * ((L.p1_sites * (blockDim.x >> 5)) / 16u) && fill_total <= 65536u;
+      // (sharded: the list filling and cell clearing of the previous round run while this round's flags travel, see below;
+      // every warp walks sites)
+      const bool split = !R.mg_on && iters <= 3u * nblk * ((L.p1_sites * (blockDim.x >> 5)) / 16u) && fill_total <= 65536u;
       const uint32_t NW = blockDim.x >> 5;
       const uint32_t ws = split ? (L.p1_sites * NW) / 16u : NW, wh = NW - ws;
       if (warp < ws) {
@@ -1221,7 +1223,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
           while (j + 1 < k && wi >= S.iter0[j + 1]) j++;
           round_sites_iter(R, S, par, j, c_first, (wi - S.iter0[j]) * 32u + lane, round_sites_buf(R, par, j), j == 0 ? A.sites_cap : R_SMALL, (uint32_t)((mg_epoch + 1) & 1u));
         }
-        if (!split) {
+        if (!split && !R.mg_on) {
           if (F.v) round_fill_all(R, S, F, gt, gn);
           if (F.k) round_clear_cells(R, S, F, tid, blockDim.x, gt, gn);
         }
@@ -1273,6 +1275,9 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         if (lane == 0) st->n_out = 0;  // nobody reserves slots before the next round's flush
       }
       XPROF(0)
+      // while the flags of the other ranks travel: the occurrence lists of the previous round's born pairs, its cells
+      if (F.v) round_fill_all(R, S, F, gt, gn);
+      if (F.k) round_clear_cells(R, S, F, tid, blockDim.x, gt, gn);
       if (warp == 0) mgr_wait_fold_warp(R, epar, mg_epoch + 1);
       XPROF(1)
       mg_epoch++;
