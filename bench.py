@@ -24,6 +24,8 @@ import time
 
 import numpy as np
 
+_OUT = sys.stdout
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -453,7 +455,7 @@ def run_b200(args):
             line["encode"]["full_output"] = enc_full
         if enc_cpu is not None:
             line["encode"]["cpu_baseline"] = enc_cpu
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     lib.bpe_destroy(h)
     if world > 1:
         dist.destroy_process_group()
@@ -636,7 +638,7 @@ def run_reference(args):
         "config": {"workload": "%s: %d B Zipf-word corpus, mergeUntil to %d merges (bounded CPU sample, see cpu_baseline.sample)" % (args.workload, train_bytes, merges)},
         "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=_OUT, flush=True)
 
 
 def main():
@@ -648,6 +650,11 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("BPE_BENCH_WORKLOAD", "cfg3"), choices=sorted(WORKLOADS))
     ap.add_argument("--merges", type=int, default=0)
     args = ap.parse_args()
+    # stdout carries ONE JSON line: anything native code writes to descriptor 1 on the way (NCCL's version banner) goes to stderr
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1633,7 +1633,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
                 (double)f[5], f[0] / ns * 1e-3, f[1] / ns * 1e-3, f[2] / ns * 1e-3, f[3] / ns * 1e-3, f[4] / ns * 1e-3, (double)f[11], f[6] / nb * 1e-3, f[7] / nb * 1e-3,
                 f[8] / nb * 1e-3, f[9] / nb * 1e-3, f[10] / nb * 1e-3, (double)e->h_st->prof_ns[5] * 1e-6);
         const unsigned long long* m = e->h_st->mg_prof_ns;
-        fprintf(stderr, "[bpe r0] exchange, block 0, ms: send %.1f, wait for all flags + fold %.1f, sum the records %.1f, barrier %.1f\n", m[5] * 1e-6, m[6] * 1e-6, m[7] * 1e-6, m[8] * 1e-6);
+        fprintf(stderr, "[bpe r0] exchange, block 0, ms: header + records out + report %.1f, wait + sum as they arrive + fold %.1f, barrier %.1f\n", m[5] * 1e-6, m[6] * 1e-6, m[7] * 1e-6);
       }
     }
     if (getenv("BPE_TRACE") && e->mg_rank == 0) {

@@ -258,7 +258,8 @@ struct RoundSm {
   uint32_t gv[8];  // sharded: the folded header values (OR of the ranks' error flags, minima of their capacities)
   uint32_t ncell[2];  // cells this block touched first in the round of either parity (entries of its list)
   uint32_t gncell[2]; // sharded: global cells this block touched first while summing the ranks' records
-  uint32_t rec_base, pad2;  // sharded: where this block's records go in the inboxes
+  uint32_t rec_base, rec_cnt;  // sharded: where this block's records go in the inboxes, how many they are
+  uint32_t mg_mask, mg_cnt[MG_MAX_WORLD];  // sharded: senders whose message is complete and not summed yet, their records
   uint32_t pool_next, pool_end;  // this block's private chunk of the occurrence pool (list space without a grid-wide atomic)
   uint32_t keys_ins;             // keys this block inserted in the current P2 (one n_keys atomic per block and round)
   uint32_t filt_a[8], filt_b[8]; // role_maybe filters: the a's / the b's of the batch
@@ -348,18 +349,33 @@ __device__ __forceinline__ uint32_t cell_add_warp(const RoundArgs& R, RoundSm& S
 // record: ((merge * 2 + side) << 16 | token) << 42 | counted occurrences << 21 | decrements    (one per warp and distinct
 // neighbour of a site pass, written while the pass runs)
 
+// arrival counter of (receiver dst, parity, sender): words 2 and 3 of the sender's flag line on the receiver.  Every block of
+// the sender adds 1 << 32 | its records once its part of the message is out (fenced); the receiver resets it after use.
+__device__ __forceinline__ unsigned long long* mgr_counter(const MgArgs& M, int dst, uint32_t epar, int sender) {
+  return M.flag_data[dst] + 16 * sender + 2 + epar;
+}
+
+__device__ __forceinline__ void mgr_send_warp(const RoundArgs& R, uint32_t par, uint32_t epar, uint32_t k, unsigned long long epoch, bool with_flag);
+
 // After the site passes of a round (grid barrier): every block turns the cells of ITS list -- the cells it touched first, now
 // complete -- into records in every rank's inbox: ONE record per touched cell and rank, one slot reservation per block,
 // coalesced NVLink stores.  (Records written while the passes run -- one per warp and neighbour -- were measured: the
 // frequent neighbours then receive hundreds of records each and the summing on the other side queues on those cells.)
-__device__ __forceinline__ void round_emit_records(const RoundArgs& R, RoundSm& S, uint32_t par, uint32_t epar, uint32_t k, uint32_t c_hi) {
+__device__ __forceinline__ void round_emit_records(const RoundArgs& R, RoundSm& S, uint32_t par, uint32_t epar, uint32_t k, uint32_t c_hi, unsigned long long epoch) {
   const MgArgs& M = R.mg;
   DevState* st = R.L.A.st;
   const uint32_t cap = M.inbox_stride - MGR_HDR;
+  // (block 0: its last warp -- the records of a round keep the first warps busy, not that one -- also writes this rank's header)
+  const bool hdr_warp = blockIdx.x == 0 && (threadIdx.x >> 5) == (blockDim.x >> 5) - 1u;
+  if (threadIdx.x == 0) S.rec_cnt = 0;
   if (!ld_cg(&R.rs->overflow[par])) {
     const uint32_t n = min(S.ncell[par], R_LISTCAP);
-    if (threadIdx.x == 0) S.rec_base = n ? atomicAdd(&st->n_out, n) : 0u;
+    if (threadIdx.x == 0) {
+      S.rec_base = n ? atomicAdd(&st->n_out, n) : 0u;
+      S.rec_cnt = n;
+    }
     __syncthreads();
+    if (hdr_warp) mgr_send_warp(R, par, epar, k, epoch, false);
     const uint32_t base = S.rec_base;
     const uint32_t* list = round_list(R, par);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -376,13 +392,17 @@ __device__ __forceinline__ void round_emit_records(const RoundArgs& R, RoundSm& 
     }
   } else {
     // a list was full: every non-empty cell of the round's rows (slots one by one: rare)
+    __syncthreads();
+    if (hdr_warp) mgr_send_warp(R, par, epar, k, epoch, false);
     const uint32_t T = (c_hi + 31u) & ~31u;
     const uint32_t total = k * 2u * T;
+    uint32_t mine = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
       const uint32_t js = i / T, tok = i - js * T;
       const unsigned long long cellv = ld_cg(round_cells(R, par, js >> 1, js & 1u) + tok);
       if (!cellv) continue;
       const uint32_t at = atomicAdd(&st->n_out, 1u);
+      mine++;
       if (at < cap) {
         const unsigned long long rec = ((unsigned long long)((js << 16) | tok) << 42) | ((unsigned long long)cell_cnt(cellv) << R_FIELD) | cell_dec(cellv);
         for (int q = 0; q < M.world; q++) mg_area(M, q, epar, M.rank)[MGR_HDR + at] = rec;
@@ -390,12 +410,19 @@ __device__ __forceinline__ void round_emit_records(const RoundArgs& R, RoundSm& 
         atomicOr(&st->err, ERR_INBOX_OVERFLOW);
       }
     }
+    if (mine) atomicAdd(&S.rec_cnt, mine);
   }
-  __threadfence_system();
+  // this block's part of the message is out: one remote add per rank says so -- arrivals in the upper half of the counter, the
+  // block's records in the lower (the receiver needs their total, and only the sum over the blocks knows it)
+  __syncthreads();
+  if (threadIdx.x < (unsigned)M.world) {
+    __threadfence_system();  // (after the barrier: cumulative over the stores of the whole block, as in a grid barrier's arrive)
+    atomicAdd_system(mgr_counter(M, (int)threadIdx.x, epar, M.rank), (1ull << 32) | (unsigned long long)S.rec_cnt);
+  }
 }
 
 // warp 0 of block 0, lane q talks to rank q: header of this rank's message, then the flag
-__device__ __forceinline__ void mgr_send_warp(const RoundArgs& R, uint32_t par, uint32_t epar, uint32_t k, unsigned long long epoch) {
+__device__ __forceinline__ void mgr_send_warp(const RoundArgs& R, uint32_t par, uint32_t epar, uint32_t k, unsigned long long epoch, bool with_flag) {
   const MgArgs& M = R.mg;
   const LoopArgs& L = R.L;
   DevState* st = L.A.st;
@@ -435,31 +462,16 @@ __device__ __forceinline__ void mgr_send_warp(const RoundArgs& R, uint32_t par, 
   // (no fence: lane q wrote rank q's header itself and its release store orders that; the records were fenced at system scope
   // by the blocks that wrote them, before the grid barrier this warp came through)
   __syncwarp();
-  if (q < M.world) st_release_sys(M.flag_data[q] + 16 * M.rank, epoch);  // (own rank included: every block of every rank polls all flags)
+  if (with_flag && q < M.world) st_release_sys(M.flag_data[q] + 16 * M.rank, epoch);  // (own rank included: every block of every rank polls all flags)
 }
 
-// ... wait for every peer's flag, then fold the headers: OR of the error flags, minima of the capacities (st->g_vals, as
-// mg_kernels.cuh), sums of the per-merge bounds and site counts, the smallest batch
-__device__ __forceinline__ void mgr_wait_fold_warp(const RoundArgs& R, uint32_t epar, unsigned long long epoch) {
+// fold the headers of all senders (their messages are complete): OR of the error flags, minima of the capacities
+// (st->g_vals, as mg_kernels.cuh), sums of the per-merge bounds and site counts, the smallest batch
+__device__ __forceinline__ void mgr_fold_warp(const RoundArgs& R, uint32_t epar) {
   const MgArgs& M = R.mg;
   DevState* st = R.L.A.st;
   RoundState* rs = R.rs;
   const int q = (int)lane_id();
-  if (q < M.world) {  // (warp 0 of EVERY block: no grid barrier between the exchange and the summing)
-    const unsigned long long* f = M.flag_data[M.rank] + 16 * q;
-    const unsigned long long t0 = now_ns();
-    uint32_t ns = 16;
-    while (ld_acquire_sys(f) < epoch) {
-      __nanosleep(ns);
-      if (ns < 128) ns <<= 1;
-      if (now_ns() - t0 > MG_TIMEOUT_NS) {
-        atomicOr(&st->err, ERR_PEER_TIMEOUT);
-        st->mg_abort = 1;
-        break;
-      }
-    }
-  }
-  __syncwarp();
   uint32_t w[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) w[i] = (i == H_ERR) ? 0u : 0xFFFFFFFFu;
@@ -505,42 +517,108 @@ __device__ __forceinline__ void mgr_wait_fold_warp(const RoundArgs& R, uint32_t 
   }
 }
 
-// X2: the records of all ranks, one index space -> summed into the global cells; the thread that finds a cell empty lists it
-__device__ __forceinline__ void mgr_accumulate(const RoundArgs& R, RoundSm& S, uint32_t par, uint32_t epar) {
+
+// the hello exchange at the start of a launch: wait for every peer's flag, then fold the headers
+__device__ __forceinline__ void mgr_wait_fold_warp(const RoundArgs& R, uint32_t epar, unsigned long long epoch) {
   const MgArgs& M = R.mg;
-  RoundState* rs = R.rs;
-  const uint32_t lane = lane_id();
-  uint32_t pre[MG_MAX_WORLD + 1];
-  pre[0] = 0;
-#pragma unroll
-  for (int q = 0; q < MG_MAX_WORLD; q++) pre[q + 1] = pre[q] + (q < M.world ? ld_cg(&rs->mg_n[q]) : 0u);
-  const uint32_t total = pre[MG_MAX_WORLD];
-  for (uint32_t jx = blockIdx.x * blockDim.x + threadIdx.x; jx < ((total + 31u) & ~31u); jx += gridDim.x * blockDim.x) {
-    bool first = false;
-    uint32_t ent = 0;
-    if (jx < total) {
-      int q = 0;
-#pragma unroll
-      for (int r = 1; r < MG_MAX_WORLD; r++) q += (jx >= pre[r]) ? 1 : 0;
-      const unsigned long long rec = ld_cg(mg_area(M, M.rank, epar, q) + MGR_HDR + (jx - pre[q]));
-      ent = (uint32_t)(rec >> 42);
-      const uint32_t js = (ent >> 16) & (2u * RB - 1u), tok = ent & 0xFFFFu;
-      // (bit 42 up counts the records of the cell: the sum is never zero once a record arrived, whatever it carried)
-      first = atomicAdd(round_gcells(R, par, js >> 1, js & 1u) + tok, (rec & ((1ull << (2 * R_FIELD)) - 1ull)) + (1ull << (2 * R_FIELD))) == 0ull;
-    }
-    const uint32_t fm = __ballot_sync(0xFFFFFFFFu, first);
-    if (fm) {
-      uint32_t base = 0;
-      const int src = __ffs(fm) - 1;
-      if ((int)lane == src) base = atomicAdd(&S.gncell[par], (uint32_t)__popc(fm));
-      base = __shfl_sync(0xFFFFFFFFu, base, src);
-      if (first) {
-        const uint32_t at = base + __popc(fm & ((1u << lane) - 1u));
-        if (at < R_LISTCAP) round_glist(R, par)[at] = ent;
-        else rs->goverflow[par] = 1;
+  DevState* st = R.L.A.st;
+  const int q = (int)lane_id();
+  if (q < M.world) {  // (warp 0 of EVERY block)
+    const unsigned long long* f = M.flag_data[M.rank] + 16 * q;
+    const unsigned long long t0 = now_ns();
+    uint32_t ns = 16;
+    while (ld_acquire_sys(f) < epoch) {
+      __nanosleep(ns);
+      if (ns < 128) ns <<= 1;
+      if (now_ns() - t0 > MG_TIMEOUT_NS) {
+        atomicOr(&st->err, ERR_PEER_TIMEOUT);
+        st->mg_abort = 1;
+        break;
       }
     }
   }
+  __syncwarp();
+  mgr_fold_warp(R, epar);
+}
+
+// X2 of a round: the messages are summed as they complete.  Warp 0 of the block watches the arrival counters of all senders;
+// whenever some are complete (every block of the sender has reported) the whole block adds ITS share of those senders'
+// records to the global cells -- so what is left to do when the slowest rank reports is that rank's records alone.  The thread
+// that finds a cell empty lists it.  Sender q's records start at thread q * (threads / world) of the grid: a round's few
+// thousand records per sender spread over all blocks instead of queueing on the first ones.
+__device__ __forceinline__ void mgr_collect(const RoundArgs& R, RoundSm& S, uint32_t par, uint32_t epar) {
+  const MgArgs& M = R.mg;
+  DevState* st = R.L.A.st;
+  RoundState* rs = R.rs;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t G = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t shift = (G / (uint32_t)M.world) & ~31u;
+  const uint32_t cap = M.inbox_stride - MGR_HDR;
+  const uint32_t all = (1u << M.world) - 1u;
+  uint32_t done = 0;
+  const unsigned long long t0 = now_ns();
+  while (done != all) {
+    if (warp == 0) {
+      uint32_t mask = 0, ns = 16;
+      for (;;) {
+        unsigned long long v = 0;
+        if (lane < (uint32_t)M.world) v = ld_acquire_sys(mgr_counter(M, M.rank, epar, (int)lane));
+        const bool here = (uint32_t)(v >> 32) == gridDim.x && !((done >> lane) & 1u);
+        mask = __ballot_sync(0xFFFFFFFFu, here);
+        if (here) {
+          const uint32_t n = (uint32_t)v;
+          if (n > cap) atomicOr(&st->err, ERR_INBOX_OVERFLOW);
+          S.mg_cnt[lane] = min(n, cap);
+        }
+        if (mask) break;
+        __nanosleep(ns);
+        if (ns < 128) ns <<= 1;
+        if (now_ns() - t0 > MG_TIMEOUT_NS) {
+          atomicOr(&st->err, ERR_PEER_TIMEOUT);
+          st->mg_abort = 1;
+          mask = all & ~done;  // (leave the loop; the caller sees mg_abort)
+          if (lane < (uint32_t)M.world) S.mg_cnt[lane] = 0;
+          break;
+        }
+      }
+      if (lane == 0) S.mg_mask = mask;
+    }
+    __syncthreads();
+    const uint32_t mask = S.mg_mask;
+    for (int q = 0; q < M.world; q++) {
+      if (!((mask >> q) & 1u)) continue;
+      const uint32_t n = S.mg_cnt[q];
+      const unsigned long long* recs = mg_area(M, M.rank, epar, q) + MGR_HDR;
+      uint32_t jx = gtid + G - (uint32_t)q * shift;
+      if (jx >= G) jx -= G;
+      for (; jx < ((n + 31u) & ~31u); jx += G) {
+        bool first = false;
+        uint32_t ent = 0;
+        if (jx < n) {
+          const unsigned long long rec = ld_cg(recs + jx);
+          ent = (uint32_t)(rec >> 42);
+          const uint32_t js = (ent >> 16) & (2u * RB - 1u), tok = ent & 0xFFFFu;
+          // (bit 42 up counts the records of the cell: the sum is never zero once a record arrived, whatever it carried)
+          first = atomicAdd(round_gcells(R, par, js >> 1, js & 1u) + tok, (rec & ((1ull << (2 * R_FIELD)) - 1ull)) + (1ull << (2 * R_FIELD))) == 0ull;
+        }
+        const uint32_t fm = __ballot_sync(0xFFFFFFFFu, first);
+        if (fm) {
+          uint32_t base = 0;
+          const int src = __ffs(fm) - 1;
+          if ((int)lane == src) base = atomicAdd(&S.gncell[par], (uint32_t)__popc(fm));
+          base = __shfl_sync(0xFFFFFFFFu, base, src);
+          if (first) {
+            const uint32_t at = base + __popc(fm & ((1u << lane) - 1u));
+            if (at < R_LISTCAP) round_glist(R, par)[at] = ent;
+            else rs->goverflow[par] = 1;
+          }
+        }
+      }
+    }
+    done |= mask;
+    __syncthreads();  // (S.mg_mask and S.mg_cnt are rewritten by the next look at the counters)
+  }
+  if (warp == 0) mgr_fold_warp(R, epar);
 }
 
 // One warp-iteration of the site pass of merge j of the round: 32 entries of its occurrence list.
@@ -869,7 +947,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
   if (R.mg_on) {
     // hello exchange: headers only (capacities, errors), so that the first decision is taken on global minima
     if (lead) st->mg_abort = 0;
-    if (bid == 0 && warp == 0) mgr_send_warp(R, 0, (uint32_t)((mg_epoch + 1) & 1u), 0, mg_epoch + 1);
+    if (bid == 0 && warp == 0) mgr_send_warp(R, 0, (uint32_t)((mg_epoch + 1) & 1u), 0, mg_epoch + 1, true);
     if (warp == 0) mgr_wait_fold_warp(R, (uint32_t)((mg_epoch + 1) & 1u), mg_epoch + 1);
     mg_epoch++;
   }
@@ -1212,9 +1290,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
       for (uint32_t j = 0; j < F.v; j++) fill_total += S.fill_n[j];
       // latency bound: some warps of every block walk the sites, the others fill the lists of the previous round's pairs and
       // zero the cells that round touched; throughput bound: everybody does everything
-      // (sharded: the list filling and cell clearing of the previous round run while this round's flags travel, see below;
-      // every warp walks sites)
-      const bool split = !R.mg_on && iters <= 3u * nblk * ((L.p1_sites * (blockDim.x >> 5)) / 16u) && fill_total <= 65536u;
+      const bool split = iters <= 3u * nblk * ((L.p1_sites * (blockDim.x >> 5)) / 16u) && fill_total <= 65536u;
       const uint32_t NW = blockDim.x >> 5;
       const uint32_t ws = split ? (L.p1_sites * NW) / 16u : NW, wh = NW - ws;
       if (warp < ws) {
@@ -1223,7 +1299,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
           while (j + 1 < k && wi >= S.iter0[j + 1]) j++;
           round_sites_iter(R, S, par, j, c_first, (wi - S.iter0[j]) * 32u + lane, round_sites_buf(R, par, j), j == 0 ? A.sites_cap : R_SMALL, (uint32_t)((mg_epoch + 1) & 1u));
         }
-        if (!split && !R.mg_on) {
+        if (!split) {
           if (F.v) round_fill_all(R, S, F, gt, gn);
           if (F.k) round_clear_cells(R, S, F, tid, blockDim.x, gt, gn);
         }
@@ -1257,12 +1333,10 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     RPROF(2)
     if (R.mg_on) {
       // ================= sharded: one exchange per round =================
-      // every block stores the cells it listed as records into every rank's inbox; after a grid barrier block 0 publishes
-      // this rank's header and flags; EVERY block waits for the flags of all ranks and folds the headers itself (same
-      // values everywhere), so that the summing can start without another grid barrier
+      // block 0 writes this rank's header (bounds, site counts, capacities, batch) into every rank's inbox, every block the
+      // cells it listed as records; each block then reports to every rank's arrival counter.  No grid barrier on the way out:
+      // a receiver knows a message is complete when all blocks of the sender have reported.
       const uint32_t epar = (uint32_t)((mg_epoch + 1) & 1u);
-      round_emit_records(R, S, par, epar, k, c_first + k);
-      RBARRIER();
       unsigned long long xt0 = prof ? now_ns() : 0, xt1;
 #define XPROF(i)                         \
   if (prof) {                            \
@@ -1270,18 +1344,11 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
     st->mg_prof_ns[5 + (i)] += xt1 - xt0; \
     xt0 = xt1;                           \
   }
-      if (bid == 0 && warp == 0) {
-        mgr_send_warp(R, par, epar, k, mg_epoch + 1);
-        if (lane == 0) st->n_out = 0;  // nobody reserves slots before the next round's flush
-      }
+      round_emit_records(R, S, par, epar, k, c_first + k, mg_epoch + 1);
       XPROF(0)
-      // while the flags of the other ranks travel: the occurrence lists of the previous round's born pairs, its cells
-      if (F.v) round_fill_all(R, S, F, gt, gn);
-      if (F.k) round_clear_cells(R, S, F, tid, blockDim.x, gt, gn);
-      if (warp == 0) mgr_wait_fold_warp(R, epar, mg_epoch + 1);
+      mgr_collect(R, S, par, epar);  // all ranks' records summed into the global cells as they arrive, headers folded
       XPROF(1)
       mg_epoch++;
-      __syncthreads();
       if (ld_cg(&st->mg_abort)) {  // a peer did not answer: every block of every rank that still runs leaves
         if (lead) {
           st->status = LOOP_ERROR;
@@ -1292,10 +1359,12 @@ __global__ void __launch_bounds__(RD_THREADS, 1) k_merge_rounds(RoundArgs R) {
         }
         return;
       }
-      mgr_accumulate(R, S, par, epar);  // all ranks' records summed into the global cells
-      XPROF(2)
       RBARRIER();
-      XPROF(3)
+      if (bid == 0 && tid < (uint32_t)R.mg.world) {  // (used again two rounds on; the next round's records are reserved after more barriers)
+        *mgr_counter(R.mg, R.mg.rank, epar, (int)tid) = 0ull;
+        if (tid == 0) st->n_out = 0;
+      }
+      XPROF(2)
 #undef XPROF
       RPROF(5)
     }
