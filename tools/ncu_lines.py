@@ -1,11 +1,12 @@
 """Per-source-line instruction / stall-sample breakdown of one kernel from an .ncu-rep (SASS page joined with
-nvdisasm line info of the in-tree cubin).  usage: ncu_lines.py report.ncu-rep kernel_substring [min_pct]"""
+nvdisasm line info of the library's cubin).  usage: ncu_lines.py report.ncu-rep kernel_substring [min_pct]
+BPE_LIB = the library the report was taken with (default: the in-tree build; the join needs the very same SASS)."""
 import collections, csv, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, ksub = sys.argv[1], sys.argv[2]
 minp = float(sys.argv[3]) if len(sys.argv) > 3 else 0.5
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "bpe_tokenizer_b200", "libbpe_b200.so")], cwd=tmp, capture_output=True)
+subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("BPE_LIB") or os.path.join(ROOT, "bpe_tokenizer_b200", "libbpe_b200.so")], cwd=tmp, capture_output=True)
 sass = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, "bpe_b200.sm_100a.cubin")], capture_output=True, text=True).stdout.split("\n")
 start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and ksub in l)
 cur, insts = None, []
