@@ -17,7 +17,8 @@ def _merges(t):
     return [[a.index, b.index, c.weight] for a, b, c in t.merge_tokens]
 
 
-def run_checks(rank: int, world: int, zipf_bytes: int = 1_000_000, zipf_merges: int = 500, fuzz_cases: int = 10) -> None:
+def run_checks(rank: int, world: int, zipf_bytes: int = 1_000_000, zipf_merges: int = 500, fuzz_cases: int = 10, weak_bytes: int = 0,
+               weak_merges: int = 300) -> None:
     import torch
 
     from bpe_tokenizer_b200.sharded import ShardedBPETokenizer
@@ -82,6 +83,37 @@ def run_checks(rank: int, world: int, zipf_bytes: int = 1_000_000, zipf_merges: 
         s = gpu.stats()
         if rank == 0:
             print("mg parity ok: world %d, %d merges on %d B, ties %d, merge_until %.1f ms" % (world, n1, zipf_bytes, s["tie_breaks"], s["ms_last_merge_until"]), flush=True)
+        gpu.close()
+    # ---- weak construction (bench.py --workload cfg3w): every rank GENERATES its own shard (seed 43 + 1000 * rank), the corpus
+    # is the concatenation in rank order; token indices follow first appearance in that concatenation ----
+    if weak_bytes:
+        from bpe_tokenizer_b200.synth import first_appearance_ids, synth_corpus
+
+        shards = [synth_corpus(weak_bytes, seed=43 + 1000 * r) for r in range(world)]
+        text = np.concatenate([t for t, _ in shards])
+        base = np.cumsum([0] + [t.size for t, _ in shards])
+        off = np.concatenate([shards[0][1]] + [o[1:] + base[r] for r, (_, o) in enumerate(shards) if r > 0])
+        ids, alphabet = first_appearance_ids(text)
+        gpu, orc = ShardedBPETokenizer(dev), IntOracleTokenizer()
+        for t in (gpu, orc):
+            t.addToCorpus("".join(chr(c) for c in alphabet))
+            if hasattr(t, "_pending"):
+                t._pending = []
+            else:
+                t._o.clear_corpus()
+            for tk in t.token_table:
+                tk.weight = 0
+                tk.original_weight = 0
+        my_off = shards[rank][1]
+        gpu.addDocuments(ids[base[rank]:base[rank + 1]], my_off, local_shard=True)
+        orc.add_ids(ids, off)
+        n1 = gpu.mergeUntil({"max_iterations": weak_merges})
+        n2 = orc.mergeUntil({"max_iterations": weak_merges})
+        assert n1 == n2 == weak_merges, (n1, n2)
+        assert _merges(gpu) == _merges(orc), rank
+        assert gpu.toJSON() == orc.toJSON(), rank
+        if rank == 0:
+            print("mg weak parity ok: world %d, %d merges on %d x %d B" % (world, n1, world, weak_bytes), flush=True)
         gpu.close()
 
 

@@ -13,7 +13,7 @@ def test_sharded_training_matches_oracle_world2():
         pytest.skip("needs 2 GPUs")
     import mg_worker
 
-    mp.spawn(mg_worker._spawn_entry, args=(2, 29533, {"zipf_bytes": 400_000, "zipf_merges": 300, "fuzz_cases": 6}), nprocs=2, join=True)
+    mp.spawn(mg_worker._spawn_entry, args=(2, 29533, {"zipf_bytes": 400_000, "zipf_merges": 300, "fuzz_cases": 6, "weak_bytes": 250_000, "weak_merges": 250}), nprocs=2, join=True)
 
 
 def test_two_engines_on_two_devices_in_one_process():
