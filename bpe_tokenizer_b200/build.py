@@ -41,6 +41,9 @@ def build(force: bool = False, verbose: bool = False, out: str = LIB) -> str:
         extra.append("-DBPE_ML_THREADS=" + os.environ["BPE_ML_THREADS"])  # tuning: threads per block of the loop kernels
     if os.environ.get("BPE_TBL_STRIDE"):
         extra.append("-DBPE_TBL_STRIDE=" + os.environ["BPE_TBL_STRIDE"])  # tuning: 8 = one 32-byte entry per pair-table slot
+    for knob in ("BPE_R_SMALL_LOG", "BPE_R_BATCH_LOG"):  # tuning: size limits of a round's batch (round_kernels.cuh)
+        if os.environ.get(knob):
+            extra.append("-D%s=%s" % (knob, os.environ[knob]))
     if os.environ.get("BPE_RD_THREADS"):
         extra.append("-DBPE_RD_THREADS=" + os.environ["BPE_RD_THREADS"])  # tuning: threads per block of k_merge_rounds
     cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]

@@ -1586,7 +1586,7 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
       uint64_t pool_after = (uint64_t)e->h_st->pool_cursor + 4 * w;  // the in-kernel test is one merge conservative
       // ... one ROUND conservative there: the first merge of a round has at most R_HUGE sites (larger ones take the other kernel),
       // the previous round's batch -- whose allocation the figure in the header does not show yet -- at most as many
-      if (use_rounds) pool_after += 4ull * R_HUGE + 2ull * e->round_blocks * R_POOL_CHUNK;
+      if (use_rounds) pool_after += 2ull * R_HUGE + 2ull * std::max(R_HUGE, R_BATCH_SITES) + 2ull * e->round_blocks * R_POOL_CHUNK;
       auto tp = clk();
       if (pool_after > 0xFFFFFFF0ull) {
         rc = fail(e, BPE_E_DOMAIN, "occurrence pool exceeds 2^32 cells");

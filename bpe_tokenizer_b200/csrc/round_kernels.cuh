@@ -46,14 +46,23 @@ namespace bpe {
 #endif
 constexpr int RD_THREADS = BPE_RD_THREADS;  // threads per block of k_merge_rounds (one block per SM)
 constexpr int RB = 16;                   // merges per round at most
-constexpr uint32_t R_SMALL = 1u << 18;   // a merge with more counted occurrences than this runs alone
-constexpr uint32_t R_BATCH_SITES = 1u << 19;  // ... and a batch stops growing past this many sites (a dropped tail wastes its site pass)
+#ifndef BPE_R_SMALL_LOG
+#define BPE_R_SMALL_LOG 20
+#endif
+#ifndef BPE_R_BATCH_LOG
+#define BPE_R_BATCH_LOG 21
+#endif
+// (measured on cfg3, one GPU: 2^18 / 2^19 -> 498 ms per step, 2^19 / 2^20 -> 485, 2^20 / 2^21 -> 475: batching the big merges saves
+// their rounds' fixed costs, the dropped tails cost less than that)
+constexpr uint32_t R_SMALL = 1u << BPE_R_SMALL_LOG;   // a merge with more counted occurrences than this runs alone (<= R_HUGE)
+constexpr uint32_t R_BATCH_SITES = 1u << BPE_R_BATCH_LOG;  // ... and a batch stops growing past this many sites (a dropped tail wastes its site pass)
 constexpr uint32_t R_LAT = 16384;        // below this many sites a merge is latency bound (profile classes, warp splits)
 
 // One 64-bit cell per (merge of the round, side, other token): decrements of the old pair | occurrences of the born pair
 // << 21 | counted occurrences of the born pair << 42 -- ONE atomic per warp and distinct neighbour carries all three.
 constexpr uint32_t R_FIELD = 21;
 constexpr unsigned long long R_FMASK = (1ull << R_FIELD) - 1ull;
+static_assert(BPE_R_SMALL_LOG <= 20, "a batched merge must fit the 21-bit fields of the delta cells (R_HUGE)");
 constexpr uint32_t R_HUGE = 1u << 20;    // merges with more counted occurrences overflow the fields: they run through k_merge_loop
 constexpr uint32_t R_POOL_CHUNK = 1u << 16;  // occurrence-pool cells a block reserves at a time
 constexpr uint32_t R_LISTCAP = 32768;    // touched cells a block can list per round (more: the round falls back to scanning the rows)
