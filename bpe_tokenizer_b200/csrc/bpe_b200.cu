@@ -1342,7 +1342,7 @@ int merge_until_device(bpe_engine* e, int64_t min_weight, int32_t max_length, in
       if (trace_r) {
         const unsigned long long* f = e->h_st->fine_ns;
         const double ns = std::max(1.0, (double)f[5]), nb = std::max(1.0, (double)f[11]);
-        fprintf(stderr, "[bpe] block 0, us per round of small merges (%.0f rounds): decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f; per round of one big merge (%.0f): "
+        fprintf(stderr, "[bpe] block 0, us per round whose first merge has <= 16384 sites (%.0f rounds): decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f; per round whose first merge has more (%.0f): "
                         "decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f\n", (double)f[5], f[0] / ns * 1e-3, f[1] / ns * 1e-3, f[2] / ns * 1e-3, f[3] / ns * 1e-3, f[4] / ns * 1e-3,
                 (double)f[11], f[6] / nb * 1e-3, f[7] / nb * 1e-3, f[8] / nb * 1e-3, f[9] / nb * 1e-3, f[10] / nb * 1e-3);
       }
@@ -1630,8 +1630,8 @@ int merge_until_mg(bpe_engine* e, int64_t min_weight, int32_t max_length, int64_
       if (getenv("BPE_TRACE") && e->mg_rank == 0) {
         const unsigned long long* f = e->h_st->fine_ns;
         const double ns = std::max(1.0, (double)f[5]), nb = std::max(1.0, (double)f[11]);
-        fprintf(stderr, "[bpe r0] rounds %llu, merges %llu (tried %llu); block 0, us per round of small merges (%.0f): decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f; "
-                        "of big merges (%.0f): decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f; exchange (emit..summed) ms %.1f\n", hrs.rounds, hrs.round_merges, hrs.tried,
+        fprintf(stderr, "[bpe r0] rounds %llu, merges %llu (tried %llu); block 0, us per round whose first merge has <= 16384 sites (%.0f): decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f; "
+                        "whose first merge has more (%.0f): decide %.1f, P1 %.1f, wait %.1f, P2 %.1f, wait %.1f; exchange (emit..summed) ms %.1f\n", hrs.rounds, hrs.round_merges, hrs.tried,
                 (double)f[5], f[0] / ns * 1e-3, f[1] / ns * 1e-3, f[2] / ns * 1e-3, f[3] / ns * 1e-3, f[4] / ns * 1e-3, (double)f[11], f[6] / nb * 1e-3, f[7] / nb * 1e-3,
                 f[8] / nb * 1e-3, f[9] / nb * 1e-3, f[10] / nb * 1e-3, (double)e->h_st->prof_ns[5] * 1e-6);
         const unsigned long long* m = e->h_st->mg_prof_ns;
