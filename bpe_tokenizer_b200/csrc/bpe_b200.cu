@@ -434,7 +434,9 @@ int build_index(bpe_engine* e) {
   if (n) {
     k_alloc_lists<<<e->grid(4), 256, 0, e->stream>>>(e->table(), e->d_st.p, (uint32_t)e->pool.cap);
     CKL();
-    k_scatter<<<e->grid(8), K1_THREADS, 0, e->stream>>>(e->slots.p, (uint32_t)n, e->table(), e->pool.p, e->d_st.p);
+    int k1b_per_sm = 8;
+    if (const char* v = getenv("BPE_K1B_PER_SM")) k1b_per_sm = std::max(1, std::min(atoi(v), 8));  // tuning knob
+    k_scatter<<<e->grid(k1b_per_sm), K1_THREADS, 0, e->stream>>>(e->slots.p, (uint32_t)n, e->table(), e->pool.p, e->d_st.p);
     CKL();
   }
   CK(cudaEventRecord(e->ev1, e->stream));

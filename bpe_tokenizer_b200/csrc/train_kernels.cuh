@@ -146,7 +146,10 @@ __global__ void k_mark_docstarts(uint32_t* __restrict__ slots, const int64_t* __
 constexpr int K1_THREADS = 256;
 constexpr int K1_SMEM_SLOTS = 2048;  // 24 KB
 constexpr int K1_MAX_PROBE = 8;
-constexpr uint32_t K1B_CHUNK = 1u << 16;  // positions per block iteration of the scatter
+#ifndef BPE_K1B_CHUNK_LOG
+#define BPE_K1B_CHUNK_LOG 16
+#endif
+constexpr uint32_t K1B_CHUNK = 1u << BPE_K1B_CHUNK_LOG;  // positions per block iteration of the scatter
 
 struct SmemHist {
   uint32_t key[K1_SMEM_SLOTS];
