@@ -1,0 +1,65 @@
+"""CPU: the measurement contract of bench.py that needs no GPU.
+
+* `bench.py --impl reference` (the CPU restatement timed on host cores) prints exactly one JSON line on stdout with the keys the
+  driver reads, and the process never maps the CUDA product library (the reference arm must not depend on the thing it is
+  compared with).
+* The committed bench lines of this round (profiles/r02_bench_n*.json, produced on B200s by the same script) carry the merge
+  log's SHA-1 of the CPU oracle (tests/golden/cfg3_full_check.json) at every GPU count, the roofline / cpu_baseline / e2e objects
+  and a value that does not fall with N.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line_and_never_loads_the_product_library():
+    code = (
+        "import sys, runpy\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--workload', 'tiny']\n"
+        "try:\n"
+        "    runpy.run_path(%r, run_name='__main__')\n"
+        "finally:\n"
+        "    maps = open('/proc/self/maps').read()\n"
+        "    sys.stderr.write('PRODUCT_LIB_MAPPED=%%d\\n' %% ('libbpe_b200.so' in maps))\n" % os.path.join(ROOT, "bench.py")
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mergeUntil merges/sec" and d["unit"] == "merges/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "merges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "PRODUCT_LIB_MAPPED=0" in r.stderr, r.stderr[-500:]
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 8])
+def test_committed_bench_lines_of_this_round(n):
+    with open(os.path.join(ROOT, "profiles", "r02_bench_n%d.json" % n)) as f:
+        d = json.load(f)
+    with open(os.path.join(ROOT, "tests", "golden", "cfg3_full_check.json")) as f:
+        golden = json.load(f)
+    assert d["n_gpus"] == n and d["metric"] == "mergeUntil merges/sec" and d["scaling"] == "strong"
+    assert d["config"]["merges_done"] == 32000
+    assert d["config"]["merge_log_sha1"] == golden["sha1"] and d["config"]["merge_log_matches_cpu_golden"] is True
+    assert d["gpu_launches"] > 0 and d["clocks"]["reasons"] == []
+    assert d["e2e"]["h2d_bytes_per_step"] > 4_000_000_000 and 0 < d["e2e"]["value"] <= d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    enc = d["encode"]
+    assert enc["tokens_out"] == 176384677
+    full = enc["cpu_baseline"]["full_output"] if n == 1 else enc["full_output"]
+    assert full["matches_cpu_golden"] is True
+    if n == 1:
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline_incremental"]["value"] > d["cpu_baseline"]["value"]
+        assert 0 < r["real_frac"] < 1 and r["traffic"] > 1e11
+    else:
+        with open(os.path.join(ROOT, "profiles", "r02_bench_n1.json")) as f:
+            one = json.load(f)
+        assert d["value"] >= one["value"], "sharding must not make training slower than one GPU"
