@@ -175,6 +175,8 @@ def run_b200(args):
         b = shard_bounds(np.diff(off), world)
         lo, hi = b[rank], b[rank + 1]
     ids_host = torch.from_numpy(lut[text[off[lo]:off[hi]]]).pin_memory()
+    # the same shard as raw UTF-8 bytes (ASCII: 1 B per character), for the end-to-end step that enters through the text front end
+    text_host = torch.from_numpy(np.ascontiguousarray(text[off[lo]:off[hi]])).pin_memory() if world == 1 else None
     off_host = np.ascontiguousarray(off[lo:hi + 1] - off[lo])
     del text
     text2, off2 = synth(lib, encode_bytes, ENCODE_SEED)
@@ -283,10 +285,41 @@ def run_b200(args):
         digests = [None] * world
         dist.all_gather_object(digests, digest)
         assert all(d == digest for d in digests), "ranks disagree on the merge log: %r" % (digests,)
+    import hashlib
+
+    log_sha1_early = hashlib.sha1(log[:done].tobytes()).hexdigest()
     # ---- train: end to end from host buffers ----------------------------------------------------------
     e2e_steps = max(1, args.steps)
     train_step(True)
     ms_train_e2e = timed(lambda: train_step(True), e2e_steps)
+
+    # ... and from raw text, the form the reference's addToCorpus takes (core.ts:182-207): UTF-8 bytes in, code point -> token index,
+    # first-appearance token creation and weights on the device (bpe_add_text), then the same mergeUntil.  One GPU only (a sharded
+    # engine takes ids).  The merge log must be the one the id path produced.
+    e2e_text = None
+    if world == 1:
+        try:
+            new_cps = np.zeros(1 << 16, dtype=np.int32)
+            n_new = C.c_int32()
+
+            def train_step_text():
+                check(lib.bpe_clear_corpus(h))
+                check(lib.bpe_set_tokens(h, None, 0))
+                check(lib.bpe_set_chars(h, None, None, 0))
+                check(lib.bpe_load_merges(h, None, 0))
+                check(lib.bpe_add_text(h, C.cast(text_host.data_ptr(), _abi.u8p), p64(off_host), n_docs, p32(new_cps), new_cps.size, C.byref(n_new), None, 0))
+                assert n_new.value == len(alphabet) and new_cps[: n_new.value].tolist() == list(alphabet), "text front end found other characters"
+                check(lib.bpe_set_tokens(h, p32(len16), len(len16)))
+                check(lib.bpe_merge_until(h, 2, 0, merges, log.ctypes.data_as(C.c_void_p), merges, C.byref(n_done)))
+
+            train_step_text()
+            assert n_done.value == done and hashlib.sha1(log[:done].tobytes()).hexdigest() == log_sha1_early, "text path learned another merge log"
+            ms_text = timed(train_step_text, e2e_steps)
+            e2e_text = {"value": done * e2e_steps / (ms_text / 1e3), "unit": "merges/s", "h2d_bytes_per_step": int(text_host.numel() + off_host.nbytes),
+                        "d2h_bytes_per_step": int(done * MERGE_DTYPE.itemsize), "ms_per_step": ms_text / e2e_steps,
+                        "note": "bpe_add_text + bpe_merge_until: UTF-8 bytes in (1 B/char), characters -> token indices in first-appearance order on the device; same merge log"}
+        except Exception as ex:  # never take the line down
+            e2e_text = {"failed": repr(ex)}
 
     # ---- encode with the table just learned -------------------------------------------------------------
     tvi = np.arange(len(alphabet) + done, dtype=np.int32)  # raw-index-equivalent map without holes
@@ -436,6 +469,7 @@ def run_b200(args):
             },
             "e2e": {"value": e2e_value, "unit": "merges/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": int(done * MERGE_DTYPE.itemsize * world),
                     "ms_per_step": ms_train_e2e / e2e_steps},
+            "e2e_text": e2e_text,
             "gpu_launches": int(l1 - l0),
             "clocks": clocks,
             "rounds": rounds,

@@ -2638,7 +2638,12 @@ int bpe_add_text(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_off
   *n_new = 0;
   CK(cudaSetDevice(e->device));
   int64_t n_chars = 0;
+  const bool trace_t = getenv("BPE_TRACE") != nullptr;
+  auto clk = [] { return std::chrono::steady_clock::now(); };
+  auto since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(clk() - t).count(); };
+  auto tt0 = clk();
   TRY(text_to_ids(e, utf8, doc_byte_offsets, n_docs, true, &n_chars, nullptr));
+  const double ms_ids = since(tt0);
   // unknown code points become tokens in first-appearance order (core.ts:186-199)
   DevBuf<uint32_t> d_cp, d_pos, d_n;
   const uint32_t cap = 1u << 16;
@@ -2692,7 +2697,14 @@ int bpe_add_text(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_off
   }
   if (counts) CK(cudaMemcpyAsync(counts, e->x_counts.p, (size_t)e->n_tokens * 8, cudaMemcpyDeviceToHost, e->stream));
   CK(cudaStreamSynchronize(e->stream));
-  return append_docs_dev(e, e->x_ids.p, e->h_rel.data(), n_docs);
+  const double ms_fix = since(tt0) - ms_ids;
+  int rc_app = append_docs_dev(e, e->x_ids.p, e->h_rel.data(), n_docs);
+  if (trace_t) {
+    cudaStreamSynchronize(e->stream);
+    fprintf(stderr, "[bpe] add_text: %lld chars: copy in + decode %.1f ms, new characters + counts %.1f ms, append %.1f ms\n", (long long)n_chars, ms_ids, ms_fix,
+            since(tt0) - ms_ids - ms_fix);
+  }
+  return rc_app;
 }
 
 int bpe_encode_text_batch(bpe_engine* e, const uint8_t* utf8, const int64_t* doc_byte_offsets, int64_t n_docs, const int32_t* to_vector_index,

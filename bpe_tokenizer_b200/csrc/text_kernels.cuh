@@ -74,8 +74,13 @@ __global__ void __launch_bounds__(TX_THREADS) k_utf8_decode(const uint8_t* __res
       int32_t id = __ldg(cpmap + cp);
       if (id < 0) {
         id = -(int32_t)(cp + 1);
-        if (first_pos) atomicMin(first_pos + cp, (uint32_t)min(k, (uint64_t)0xFFFFFFFEu));
-        if (first_unknown) atomicMin(first_unknown, ((unsigned long long)k << 32) | cp);
+        // (look before the atomic: the entries only ever decrease, so a stale cached value can only let a superfluous atomic
+        // through, never hide a smaller position -- a fresh tokenizer's first gigabyte is ALL unknown characters, and 10^9
+        // atomics on the few dozen addresses of its alphabet were 200 ms)
+        const uint32_t k32 = (uint32_t)min(k, (uint64_t)0xFFFFFFFEu);
+        if (first_pos && k32 < first_pos[cp]) atomicMin(first_pos + cp, k32);
+        const unsigned long long fu = ((unsigned long long)k << 32) | cp;
+        if (first_unknown && fu < *first_unknown) atomicMin(first_unknown, fu);
       }
       ids[k] = id;
     }
@@ -143,9 +148,15 @@ __global__ void k_set_cpmap(int32_t* __restrict__ cpmap, const int32_t* __restri
     if ((uint32_t)cps[i] < CP_LIMIT) cpmap[cps[i]] = idx[i];
 }
 
+constexpr uint32_t FIX_SMEM_TOKENS = 2048;
 // resolve the -(cp + 1) placeholders after the new tokens got their indices; count every token (weights, core.ts:201-202)
 __global__ void k_fix_and_count(int32_t* __restrict__ ids, uint64_t n, const int32_t* __restrict__ cpmap, unsigned long long* __restrict__ counts,
                                 uint32_t n_tokens) {
+  // the counts of the low token indices -- every character of ordinary text -- are gathered per block in shared memory: a
+  // gigabyte of text would otherwise send some 10^8 atomics to the few dozen addresses of its alphabet
+  __shared__ uint32_t s_cnt[FIX_SMEM_TOKENS];
+  for (uint32_t t = threadIdx.x; t < FIX_SMEM_TOKENS; t += blockDim.x) s_cnt[t] = 0;
+  __syncthreads();
   uint64_t stride = (uint64_t)gridDim.x * blockDim.x;  // a multiple of 32: the loop is warp-uniform
   const uint32_t lane = threadIdx.x & 31;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((n + 31) & ~31ull); i += stride) {
@@ -158,8 +169,14 @@ __global__ void k_fix_and_count(int32_t* __restrict__ ids, uint64_t n, const int
       }
     }
     uint32_t peers = __match_any_sync(0xFFFFFFFFu, id);  // one atomic per distinct token per warp
-    if (lane == (uint32_t)(__ffs(peers) - 1) && id >= 0 && (uint32_t)id < n_tokens) atomicAdd(counts + id, (unsigned long long)__popc(peers));
+    if (lane == (uint32_t)(__ffs(peers) - 1) && id >= 0 && (uint32_t)id < n_tokens) {
+      if ((uint32_t)id < FIX_SMEM_TOKENS) atomicAdd(&s_cnt[id], (uint32_t)__popc(peers));  // (a block sees far fewer than 2^32 characters)
+      else atomicAdd(counts + id, (unsigned long long)__popc(peers));
+    }
   }
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < FIX_SMEM_TOKENS && t < n_tokens; t += blockDim.x)
+    if (s_cnt[t]) atomicAdd(counts + t, (unsigned long long)s_cnt[t]);
 }
 
 }  // namespace bpe
