@@ -11,9 +11,12 @@
 //               strictly decreasing (count, -(a+b)) keys, no tie inside the batch, pairwise disjoint tokens, no token born in
 //               the previous round (its occurrence lists are still being written), capacities.
 //   P1          site passes of all k merges over the corpus as it was at the decision.  A merge changes counts only of
-//               pairs that contain a, b or c, so ALL its count deltas live in dense per-token rows (no hashing in P1):
-//               DEC_L[x] = decrements of (x,a), DEC_R[y] of (b,y), NEW_L[x] / NEW_R[y] = occurrences and counted
-//               occurrences of the born pairs (x,c) / (c,y).  Token sets are disjoint, so the sites of m_j are the same
+//               pairs that contain a, b or c, so ALL its count deltas live in dense per-token rows (no hashing in P1): one
+//               packed 64-bit cell per (merge, side, other token x) = decrements of the old pair (x,a) / (b,x) | occurrences
+//               of the born pair (x,c) / (c,x) << 21 | its counted occurrences << 42; one ATOM.64 per warp and distinct
+//               neighbour carries all three, and the thread that finds a cell empty appends it to its block's list, so
+//               that P2 visits exactly the touched cells.  Token sets are disjoint
+ so the sites of m_j are the same
 //               before and after m_0..m_{j-1}; only a NEIGHBOUR of a site can have been rewritten by an earlier merge of the
 //               batch, and the site pass of m_j looks for exactly that: a left neighbour b_i preceded by a_i, or a right
 //               neighbour a_i followed by b_i (i < j), is the token c_i there (virtual neighbour), its pair with a_j / b_j
@@ -29,8 +32,13 @@
 //               thread per (pair), which hands the pair's new key to the arg-max --, the corpus is rewritten, and the
 //               arg-max runs over the old hot pairs that no valid merge touches.  -> per-block top-2 partials.
 //   -- barrier --
-//   The occurrence lists of the born pairs are filled next to P1 of the following round (as in k_merge_loop), and the rows
-//   of a round are zeroed by the scan of the following one (rows are double-buffered by round parity).
+//   The occurrence lists of the born pairs are filled next to P1 of the following round (as in k_merge_loop) on the helper
+//   warps, which also zero the cells the round touched (from the same lists; cells are double-buffered by round parity).
+//
+// Sharded corpus (mg_on): P1 runs on the local shard into local cells; after its barrier every block sends the cells it
+// listed as records to every rank (NVLink stores) and reports to a per-(receiver, parity, sender) arrival counter; every
+// block sums the records of the senders that are complete into the GLOBAL cells (mgr_collect), P2 runs over those.  The
+// decisions are replicated: U bounds and site counts are sums over the ranks, capacities minima (headers of the messages).
 //
 // Exactness argument for the order inside a batch (core.ts:294-305): counts of existing pairs never grow
 // under merging, so an old pair that ranked below m_j at the decision still does; born pairs are bounded by U; m_j's own
