@@ -15,8 +15,7 @@
 //               packed 64-bit cell per (merge, side, other token x) = decrements of the old pair (x,a) / (b,x) | occurrences
 //               of the born pair (x,c) / (c,x) << 21 | its counted occurrences << 42; one ATOM.64 per warp and distinct
 //               neighbour carries all three, and the thread that finds a cell empty appends it to its block's list, so
-//               that P2 visits exactly the touched cells.  Token sets are disjoint
- so the sites of m_j are the same
+//               that P2 visits exactly the touched cells.  Token sets are disjoint, so the sites of m_j are the same
 //               before and after m_0..m_{j-1}; only a NEIGHBOUR of a site can have been rewritten by an earlier merge of the
 //               batch, and the site pass of m_j looks for exactly that: a left neighbour b_i preceded by a_i, or a right
 //               neighbour a_i followed by b_i (i < j), is the token c_i there (virtual neighbour), its pair with a_j / b_j
