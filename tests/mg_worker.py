@@ -36,6 +36,19 @@ def run_checks(rank: int, world: int, zipf_bytes: int = 1_000_000, zipf_merges: 
         for d in docs:
             lit.addToCorpus(d)
             gpu.addToCorpus(d)
+        if case == 0 and world > 1:
+            # a shard alone cannot answer for the corpus: the single-step calls are refused, in the class and in the C ABI
+            import ctypes as C
+
+            from bpe_tokenizer_b200 import BpeError, _abi
+
+            try:
+                gpu.findNextMerge()
+                raise AssertionError("findNextMerge on a sharded corpus must raise")
+            except BpeError:
+                pass
+            m, found = _abi.bpe_merge(), C.c_int()
+            assert gpu._lib.bpe_find_next_merge(gpu._h, 2, 0, C.byref(m), C.byref(found)) == _abi.BPE_E_INVALID
         lit.mergeUntil(opts)
         gpu.mergeUntil(opts)
         assert _merges(gpu) == _merges(lit), (case, rank, _merges(gpu)[:8], _merges(lit)[:8])
